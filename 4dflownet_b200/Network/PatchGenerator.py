@@ -1,0 +1,65 @@
+"""Inference tiling with the reference's PatchGenerator interface (Network/PatchGenerator.py:6-154):
+zero-pad 2 voxels, pad the far side to fit, stride patch_size-4, crop 2*r per side on HR.
+Integer logic, bit-exact with the reference (pinned by tests/golden/patchgen_golden.npz);
+written on strided views instead of the reference's triple Python loop, and the stitch can
+run on the GPU (`Engine.stitch`) to avoid the host round trip."""
+import numpy as np
+
+
+class PatchGenerator:
+    def __init__(self, patch_size, res_increase):
+        self.patch_size = patch_size
+        self.effective_patch_size = patch_size - 4
+        self.res_increase = res_increase
+        self.padding = (0, 0, 0)
+        self.nr_x = self.nr_y = self.nr_z = 0
+
+    # -- geometry ---------------------------------------------------------------------------
+    def _plan(self, shape):
+        e = self.effective_patch_size
+        side = (self.patch_size - e) // 2
+        far, nr = [], []
+        for d in shape:
+            padded = d + 2 * side
+            rem = padded % e
+            extra = (self.patch_size - rem) if rem > 2 * side else (2 * side - rem)
+            far.append(extra)
+            nr.append((padded + extra - 2 * side) // e)
+        return side, tuple(far), tuple(nr)
+
+    def _pad_to_patch_size_with_overlap(self, img):
+        side, far, _ = self._plan(img.shape)
+        self.padding = tuple(f * self.res_increase for f in far)
+        return np.pad(img, [(side, side + f) for f in far], "constant")
+
+    def _generate_overlapping_patches(self, img):
+        side, far, nr = self._plan(img.shape)
+        padded = self._pad_to_patch_size_with_overlap(img)
+        P, e = self.patch_size, self.effective_patch_size
+        win = np.lib.stride_tricks.sliding_window_view(padded, (P, P, P))[::e, ::e, ::e]
+        win = win[:nr[0], :nr[1], :nr[2]]
+        return np.ascontiguousarray(win.reshape(-1, P, P, P)), nr[0], nr[1], nr[2]
+
+    def patchify(self, dataset):
+        stacks = []
+        for img in (dataset.u, dataset.v, dataset.w, dataset.mag_u, dataset.mag_v, dataset.mag_w):
+            s, i, j, k = self._generate_overlapping_patches(img)
+            stacks.append(s[..., None])
+        self.nr_x, self.nr_y, self.nr_z = i, j, k
+        return tuple(stacks[:3]), tuple(stacks[3:])
+
+    def unpatchify(self, results):
+        return tuple(self._patchup_with_overlap(results[..., c], self.nr_x, self.nr_y, self.nr_z) for c in range(3))
+
+    def _patchup_with_overlap(self, patches, x, y, z):
+        side_hr = (self.patch_size - self.effective_patch_size) // 2 * self.res_increase
+        n = patches.shape[1] - side_hr
+        core = patches[:, side_hr:n, side_hr:n, side_hr:n]
+        c = core.shape[1]
+        vol = core.reshape(x, y, z, c, c, c).transpose(0, 3, 1, 4, 2, 5).reshape(x * c, y * c, z * c)
+        px, py, pz = self.padding
+        return vol[:vol.shape[0] - px, :vol.shape[1] - py, :vol.shape[2] - pz]
+
+    def stitched_shape(self):
+        c = self.effective_patch_size * self.res_increase
+        return (self.nr_x * c - self.padding[0], self.nr_y * c - self.padding[1], self.nr_z * c - self.padding[2])

@@ -1,0 +1,532 @@
+// Backward kernels (fp32 CUDA cores): the gradients TF generates for
+// TrainerController.train_step (TrainerController.py:209-225) via tape.gradient --
+// Conv3DBackpropFilter (wgrad), BiasAddGrad, MirrorPadGrad (halo fold), Relu/LeakyReluGrad,
+// ResizeBilinearGrad (upsample) -- restated per SURVEY appendix C.  Conv3DBackpropInput for
+// the 64->64 layers is conv64 with dgrad=1 (conv_simt.cu).
+#include "kernels.h"
+
+namespace {
+
+__device__ __forceinline__ size_t g4_off(int D, int b, int x, int y, int z) {
+    const int dp = D + 4;
+    return ((((size_t)b * dp + (x + 2)) * dp + (y + 2)) * dp + (z + 2)) * 64;
+}
+__device__ __forceinline__ size_t raw_off(int D, int b, int px, int py, int pz) {
+    const int dp = D + 2;
+    return ((((size_t)b * dp + px) * dp + py) * dp + pz) * 64;
+}
+
+// deterministic second stage of every split reduction: out[j] = sum_r partial[r][j]
+__global__ void reduce_rows_kernel(const float* __restrict__ partial, int nrows, int ncols, float* __restrict__ out) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    float s = 0.f;
+    for (int r = 0; r < nrows; ++r) s += partial[(size_t)r * ncols + j];
+    out[j] = s;
+}
+
+// ---- 64->1 head conv, input gradient on the padded grid --------------------------------
+__global__ void __launch_bounds__(256) head2_dgrad_kernel(const float* __restrict__ g, int c,
+                                                          const float* __restrict__ w, float* __restrict__ raw,
+                                                          int B, int H) {
+    __shared__ float ws[27 * 64];
+    for (int i = threadIdx.x; i < 27 * 64; i += 256) ws[i] = w[i];
+    __syncthreads();
+    const int Hp = H + 2;
+    const size_t nvox = (size_t)B * Hp * Hp * Hp;
+    size_t vi = (size_t)blockIdx.x * 64 + (threadIdx.x >> 2);
+    if (vi >= nvox) return;
+    const int cq = (threadIdx.x & 3) * 16;
+    int pz = vi % Hp, py = (vi / Hp) % Hp, px = (vi / ((size_t)Hp * Hp)) % Hp, b = vi / ((size_t)Hp * Hp * Hp);
+    float acc[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) acc[n] = 0.f;
+    for (int tx = 0; tx < 3; ++tx) {
+        int x = px - tx;
+        if (x < 0 || x >= H) continue;
+        for (int ty = 0; ty < 3; ++ty) {
+            int y = py - ty;
+            if (y < 0 || y >= H) continue;
+            for (int tz = 0; tz < 3; ++tz) {
+                int z = pz - tz;
+                if (z < 0 || z >= H) continue;
+                float gv = g[((((size_t)b * H + x) * H + y) * H + z) * 3 + c];
+                const float* wp = ws + ((tx * 3 + ty) * 3 + tz) * 64 + cq;
+#pragma unroll
+                for (int n = 0; n < 16; ++n) acc[n] = fmaf(gv, wp[n], acc[n]);
+            }
+        }
+    }
+    float* o = raw + vi * 64 + cq;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(o + q * 4) = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+}
+
+// ---- 64->1 head conv, weight gradient: dw[t][ci] = sum_p hp[p][ci] * g[p - t] ------------
+// partial[blk][28][64]: rows 0..26 = dw taps, row 27 = (all 64 entries) sum of g (bias grad)
+constexpr int H2W_VOX_PER_BLOCK = 512;
+__global__ void __launch_bounds__(256) head2_wgrad_kernel(ActView h, const float* __restrict__ g, int c,
+                                                          float* __restrict__ partial) {
+    const int H = h.D, Hp = H + 2;
+    const size_t nvox = (size_t)h.B * Hp * Hp * Hp;
+    const int ci = threadIdx.x & 63, sub = threadIdx.x >> 6;
+    float acc[28];
+#pragma unroll
+    for (int t = 0; t < 28; ++t) acc[t] = 0.f;
+    const size_t nchunks = (nvox + H2W_VOX_PER_BLOCK - 1) / H2W_VOX_PER_BLOCK;
+    for (size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x)
+    for (int k = sub; k < H2W_VOX_PER_BLOCK; k += 4) {
+        size_t vi = chunk * H2W_VOX_PER_BLOCK + k;
+        if (vi >= nvox) break;
+        int pz = vi % Hp, py = (vi / Hp) % Hp, px = (vi / ((size_t)Hp * Hp)) % Hp, b = vi / ((size_t)Hp * Hp * Hp);
+        float hv = join_f16(h.hi[vi * 64 + ci], h.lo[vi * 64 + ci]);
+#pragma unroll
+        for (int tx = 0; tx < 3; ++tx) {
+            int x = px - tx;
+#pragma unroll
+            for (int ty = 0; ty < 3; ++ty) {
+                int y = py - ty;
+#pragma unroll
+                for (int tz = 0; tz < 3; ++tz) {
+                    int z = pz - tz;
+                    float gv = 0.f;
+                    if (x >= 0 && x < H && y >= 0 && y < H && z >= 0 && z < H)
+                        gv = g[((((size_t)b * H + x) * H + y) * H + z) * 3 + c];
+                    acc[(tx * 3 + ty) * 3 + tz] = fmaf(hv, gv, acc[(tx * 3 + ty) * 3 + tz]);
+                }
+            }
+        }
+        // bias gradient: count g once per interior voxel (padded coords 1..H)
+        if (px >= 1 && px <= H && py >= 1 && py <= H && pz >= 1 && pz <= H)
+            acc[27] += g[((((size_t)b * H + px - 1) * H + py - 1) * H + pz - 1) * 3 + c];
+    }
+    __shared__ float red[4][28][64];
+#pragma unroll
+    for (int t = 0; t < 28; ++t) red[sub][t][ci] = acc[t];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 28 * 64; i += 256) {
+        int t = i >> 6, cc = i & 63;
+        partial[(size_t)blockIdx.x * 28 * 64 + i] = red[0][t][cc] + red[1][t][cc] + red[2][t][cc] + red[3][t][cc];
+    }
+}
+
+// ---- halo fold (MirrorPadGrad) + add + activation gradient -------------------------------
+__global__ void __launch_bounds__(256) fold_act_kernel(const float* __restrict__ r0, const float* __restrict__ r1,
+                                                       const float* __restrict__ r2, const float* __restrict__ add,
+                                                       const __half* __restrict__ shi, const __half* __restrict__ slo,
+                                                       float slope, float* __restrict__ out, int B, int D) {
+    const size_t n = (size_t)B * D * D * D * 16;
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    size_t vi = i >> 4;
+    const int c = (i & 15) * 4;
+    int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+        if (dx == -1 && x != 0) continue;
+        if (dx == 1 && x != D - 1) continue;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            if (dy == -1 && y != 0) continue;
+            if (dy == 1 && y != D - 1) continue;
+#pragma unroll
+            for (int dz = -1; dz <= 1; ++dz) {
+                if (dz == -1 && z != 0) continue;
+                if (dz == 1 && z != D - 1) continue;
+                size_t o = raw_off(D, b, x + 1 + dx, y + 1 + dy, z + 1 + dz) + c;
+                float4 a = *reinterpret_cast<const float4*>(r0 + o);
+                s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+                if (r1) { a = *reinterpret_cast<const float4*>(r1 + o); s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w; }
+                if (r2) { a = *reinterpret_cast<const float4*>(r2 + o); s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w; }
+            }
+        }
+    }
+    size_t go = g4_off(D, b, x, y, z) + c;
+    if (add) {
+        float4 a = *reinterpret_cast<const float4*>(add + go);
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+    if (shi) {
+        float sv[4];
+        act_load4(shi, slo, act_off(D, b, x, y, z) + c, sv);
+        s.x *= act_grad_from_out(sv[0], slope);
+        s.y *= act_grad_from_out(sv[1], slope);
+        s.z *= act_grad_from_out(sv[2], slope);
+        s.w *= act_grad_from_out(sv[3], slope);
+    }
+    *reinterpret_cast<float4*>(out + go) = s;
+}
+
+// ---- 64->64 3x3x3 weight gradient: dW[t][ci][co] = sum_{b,v} Xp[b,v+t][ci] dY[b,v][co] ------
+// grid (9 (dx,dy) pairs, nchunk); block 256 = 16 ci-quads x 16 co-quads, 3 dz taps each.
+constexpr int WG_ZS = 32;
+__global__ void __launch_bounds__(256) wgrad64_kernel(ActView xin, const float* __restrict__ dy, float* __restrict__ partial) {
+    __shared__ __align__(16) float xrow[(WG_ZS + 2) * 64];
+    __shared__ __align__(16) float drow[WG_ZS * 64];
+    const int D = xin.D, B = xin.B;
+    const int dx = blockIdx.x / 3, dyy = blockIdx.x % 3;
+    const int ciq = threadIdx.x & 15, coq = threadIdx.x >> 4;
+    float acc[3][4][4];
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.f;
+    const int nlines = B * D * D;
+    const int nseg = (D + WG_ZS - 1) / WG_ZS;
+    for (int line = blockIdx.y; line < nlines; line += gridDim.y) {
+        const int y = line % D, x = (line / D) % D, b = line / (D * D);
+        for (int sg = 0; sg < nseg; ++sg) {
+            const int zb = sg * WG_ZS;
+            const int zl = min(WG_ZS, D - zb);
+            __syncthreads();
+            // input rows: padded coords (x+dx, y+dy, zb .. zb+zl+1)  == interior (x+dx-1, y+dy-1, zb-1 ..)
+            for (int i = threadIdx.x; i < (zl + 2) * 8; i += 256) {
+                int rz = i >> 3, c8 = (i & 7) * 8;
+                float v[8];
+                act_load8(xin.hi, xin.lo, act_off(D, b, x + dx - 1, y + dyy - 1, zb + rz - 1) + c8, v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) xrow[rz * 64 + c8 + k] = v[k];
+            }
+            for (int i = threadIdx.x; i < zl * 16; i += 256) {
+                int rz = i >> 4, c4 = (i & 15) * 4;
+                *reinterpret_cast<float4*>(drow + rz * 64 + c4) =
+                    *reinterpret_cast<const float4*>(dy + g4_off(D, b, x, y, zb + rz) + c4);
+            }
+            __syncthreads();
+            float4 a0 = *reinterpret_cast<const float4*>(xrow + 0 * 64 + ciq * 4);
+            float4 a1 = *reinterpret_cast<const float4*>(xrow + 1 * 64 + ciq * 4);
+            for (int z = 0; z < zl; ++z) {
+                float4 a2 = *reinterpret_cast<const float4*>(xrow + (z + 2) * 64 + ciq * 4);
+                float4 d = *reinterpret_cast<const float4*>(drow + z * 64 + coq * 4);
+                const float av[3][4] = {{a0.x, a0.y, a0.z, a0.w}, {a1.x, a1.y, a1.z, a1.w}, {a2.x, a2.y, a2.z, a2.w}};
+                const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[t][i][j] = fmaf(av[t][i], dv[j], acc[t][i][j]);
+                a0 = a1; a1 = a2;
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int tap = (dx * 3 + dyy) * 3 + t;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float* o = partial + ((size_t)blockIdx.y * 27 + tap) * 4096 + (ciq * 4 + i) * 64 + coq * 4;
+            *reinterpret_cast<float4*>(o) = make_float4(acc[t][i][0], acc[t][i][1], acc[t][i][2], acc[t][i][3]);
+        }
+    }
+}
+
+// ---- bias gradient: column sums of a G4 interior -----------------------------------------
+constexpr int BG_VOX_PER_BLOCK = 1024;
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ dy, int B, int D, float* __restrict__ partial) {
+    const size_t nvox = (size_t)B * D * D * D;
+    const int co = threadIdx.x & 63, sub = threadIdx.x >> 6;
+    float s = 0.f;
+    const size_t nchunks = (nvox + BG_VOX_PER_BLOCK - 1) / BG_VOX_PER_BLOCK;
+    for (size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x)
+    for (int k = sub; k < BG_VOX_PER_BLOCK; k += 4) {
+        size_t vi = chunk * BG_VOX_PER_BLOCK + k;
+        if (vi >= nvox) break;
+        int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
+        s += dy[g4_off(D, b, x, y, z) + co];
+    }
+    __shared__ float red[4][64];
+    red[sub][co] = s;
+    __syncthreads();
+    if (threadIdx.x < 64) partial[(size_t)blockIdx.x * 64 + co] = red[0][co] + red[1][co] + red[2][co] + red[3][co];
+}
+
+// ---- upsample backward: d_lr = U^T d_hr, then * act'(lr) --------------------------------
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restrict__ dhr, ActView lr, float slope,
+                                                           float* __restrict__ dlr, int B, int D, int r, UpsampleTables t) {
+    const int H = D * r;
+    const size_t n = (size_t)B * D * D * D * 16;
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    size_t vi = i >> 4;
+    const int c = (i & 15) * 4;
+    int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ix = t.ibeg[x]; ix < t.iend[x]; ++ix) {
+        float wx = (t.lo[ix] == x ? 1.f - t.lerp[ix] : 0.f) + (t.hi[ix] == x ? t.lerp[ix] : 0.f);
+        if (wx == 0.f) continue;
+        for (int iy = t.ibeg[y]; iy < t.iend[y]; ++iy) {
+            float wy = (t.lo[iy] == y ? 1.f - t.lerp[iy] : 0.f) + (t.hi[iy] == y ? t.lerp[iy] : 0.f);
+            if (wy == 0.f) continue;
+            for (int iz = t.ibeg[z]; iz < t.iend[z]; ++iz) {
+                float wz = (t.lo[iz] == z ? 1.f - t.lerp[iz] : 0.f) + (t.hi[iz] == z ? t.lerp[iz] : 0.f);
+                if (wz == 0.f) continue;
+                float wgt = wx * wy * wz;
+                float4 a = *reinterpret_cast<const float4*>(dhr + g4_off(H, b, ix, iy, iz) + c);
+                s.x = fmaf(wgt, a.x, s.x); s.y = fmaf(wgt, a.y, s.y); s.z = fmaf(wgt, a.z, s.z); s.w = fmaf(wgt, a.w, s.w);
+            }
+        }
+    }
+    float sv[4];
+    act_load4(lr.hi, lr.lo, act_off(D, b, x, y, z) + c, sv);
+    s.x *= act_grad_from_out(sv[0], slope);
+    s.y *= act_grad_from_out(sv[1], slope);
+    s.z *= act_grad_from_out(sv[2], slope);
+    s.w *= act_grad_from_out(sv[3], slope);
+    *reinterpret_cast<float4*>(dlr + g4_off(D, b, x, y, z) + c) = s;
+}
+
+// ---- 1x1 (128->64) backward ----------------------------------------------------------------
+// input gradient: d_cat[v][k] = sum_co dy[v][co] W[k][co]; 8 threads per voxel, k = kg*4 + 32q + (0..3)
+__global__ void __launch_bounds__(256) conv1x1_dgrad_kernel(const float* __restrict__ dy, ActView a, ActView bq,
+                                                            const float* __restrict__ w, float* __restrict__ da,
+                                                            float* __restrict__ db) {
+    extern __shared__ float wt[];   // [64 co][128 k]
+    for (int i = threadIdx.x; i < 128 * 64; i += 256) {
+        int k = i >> 6, co = i & 63;
+        wt[co * 128 + k] = w[i];
+    }
+    __syncthreads();
+    const int D = a.D;
+    const size_t nvox = (size_t)a.B * D * D * D;
+    size_t vi = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3);
+    if (vi >= nvox) return;
+    const int kg = threadIdx.x & 7;
+    int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
+    const float* dyp = dy + g4_off(D, b, x, y, z);
+    float acc[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[q][j] = 0.f;
+    for (int co = 0; co < 64; ++co) {
+        float d = dyp[co];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 wv = *reinterpret_cast<const float4*>(wt + co * 128 + q * 32 + kg * 4);
+            acc[q][0] = fmaf(d, wv.x, acc[q][0]); acc[q][1] = fmaf(d, wv.y, acc[q][1]);
+            acc[q][2] = fmaf(d, wv.z, acc[q][2]); acc[q][3] = fmaf(d, wv.w, acc[q][3]);
+        }
+    }
+    const size_t ao = act_off(D, b, x, y, z), go = g4_off(D, b, x, y, z);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        int k = q * 32 + kg * 4;
+        const bool second = k >= 64;
+        int kk = second ? k - 64 : k;
+        float sv[4];
+        act_load4(second ? bq.hi : a.hi, second ? bq.lo : a.lo, ao + kk, sv);
+        float4 o = make_float4(sv[0] > 0.f ? acc[q][0] : 0.f, sv[1] > 0.f ? acc[q][1] : 0.f,
+                               sv[2] > 0.f ? acc[q][2] : 0.f, sv[3] > 0.f ? acc[q][3] : 0.f);
+        *reinterpret_cast<float4*>((second ? db : da) + go + kk) = o;
+    }
+}
+// weight gradient: dW[k][co] = sum_v cat[v][k] dy[v][co]; block stages 32 voxels; thread = 4 k x 8 co
+constexpr int C1_VOX_PER_BLOCK = 256;
+__global__ void __launch_bounds__(256) conv1x1_wgrad_kernel(const float* __restrict__ dy, ActView a, ActView bq,
+                                                            float* __restrict__ partial) {
+    __shared__ __align__(16) float cs[32 * 128];
+    __shared__ __align__(16) float ds[32 * 64];
+    const int D = a.D;
+    const size_t nvox = (size_t)a.B * D * D * D;
+    const int kq = threadIdx.x & 31, coq = threadIdx.x >> 5;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const size_t nstages = (nvox + 31) / 32;
+    for (size_t st = blockIdx.x; st < nstages; st += gridDim.x) {
+        size_t v0 = st * 32;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * 16; i += 256) {   // 32 voxels x 16 groups of 8 channels
+            int vv = i >> 4, g8 = i & 15;
+            size_t vi = v0 + vv;
+            float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (vi < nvox) {
+                int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
+                size_t ao = act_off(D, b, x, y, z);
+                if (g8 < 8) act_load8(a.hi, a.lo, ao + g8 * 8, v);
+                else act_load8(bq.hi, bq.lo, ao + (g8 - 8) * 8, v);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cs[vv * 128 + g8 * 8 + k] = v[k];
+        }
+        for (int i = threadIdx.x; i < 32 * 16; i += 256) {
+            int vv = i >> 4, c4 = (i & 15) * 4;
+            size_t vi = v0 + vv;
+            float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vi < nvox) {
+                int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
+                d = *reinterpret_cast<const float4*>(dy + g4_off(D, b, x, y, z) + c4);
+            }
+            *reinterpret_cast<float4*>(ds + vv * 64 + c4) = d;
+        }
+        __syncthreads();
+        for (int vv = 0; vv < 32; ++vv) {
+            float4 cv = *reinterpret_cast<const float4*>(cs + vv * 128 + kq * 4);
+            float4 d0 = *reinterpret_cast<const float4*>(ds + vv * 64 + coq * 8);
+            float4 d1 = *reinterpret_cast<const float4*>(ds + vv * 64 + coq * 8 + 4);
+            const float c4[4] = {cv.x, cv.y, cv.z, cv.w};
+            const float d8[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(c4[i], d8[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float* o = partial + (size_t)blockIdx.x * 8192 + (kq * 4 + i) * 64 + coq * 8;
+        *reinterpret_cast<float4*>(o) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+}
+
+// ---- stem 3->64 weight gradient ------------------------------------------------------------
+constexpr int SW_VOX_PER_BLOCK = 256;
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ feat, int ch0,
+                                                         const float* __restrict__ dy, int B, int P,
+                                                         float* __restrict__ partial) {
+    const size_t nvox = (size_t)B * P * P * P;
+    const int co = threadIdx.x & 63, sub = threadIdx.x >> 6;
+    float acc[81];
+#pragma unroll
+    for (int t = 0; t < 81; ++t) acc[t] = 0.f;
+    const size_t nchunks = (nvox + SW_VOX_PER_BLOCK - 1) / SW_VOX_PER_BLOCK;
+    for (size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x)
+    for (int k = sub; k < SW_VOX_PER_BLOCK; k += 4) {
+        size_t vi = chunk * SW_VOX_PER_BLOCK + k;
+        if (vi >= nvox) break;
+        int z = vi % P, y = (vi / P) % P, x = (vi / ((size_t)P * P)) % P, b = vi / ((size_t)P * P * P);
+        float d = dy[g4_off(P, b, x, y, z) + co];
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            int xx = min(max(x + dx - 1, 0), P - 1);
+#pragma unroll
+            for (int dyy = 0; dyy < 3; ++dyy) {
+                int yy = min(max(y + dyy - 1, 0), P - 1);
+#pragma unroll
+                for (int dz = 0; dz < 3; ++dz) {
+                    int zz = min(max(z + dz - 1, 0), P - 1);
+                    const float* f = feat + ((((size_t)b * P + xx) * P + yy) * P + zz) * 6 + ch0;
+                    const int t = ((dx * 3 + dyy) * 3 + dz) * 3;
+                    acc[t] = fmaf(f[0], d, acc[t]);
+                    acc[t + 1] = fmaf(f[1], d, acc[t + 1]);
+                    acc[t + 2] = fmaf(f[2], d, acc[t + 2]);
+                }
+            }
+        }
+    }
+    __shared__ float red[4][64];
+    for (int t = 0; t < 81; ++t) {
+        __syncthreads();
+        red[sub][co] = acc[t];
+        __syncthreads();
+        if (threadIdx.x < 64)
+            partial[(size_t)blockIdx.x * 81 * 64 + t * 64 + co] = red[0][co] + red[1][co] + red[2][co] + red[3][co];
+    }
+}
+
+__global__ void g4_from_dense_kernel(const float* __restrict__ dense, float* __restrict__ g4, int B, int D) {
+    const size_t n = (size_t)B * D * D * D * 16;
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    size_t vi = i >> 4;
+    int c = (i & 15) * 4;
+    int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
+    *reinterpret_cast<float4*>(g4 + g4_off(D, b, x, y, z) + c) = *reinterpret_cast<const float4*>(dense + vi * 64 + c);
+}
+__global__ void dense_from_g4_kernel(const float* __restrict__ g4, float* __restrict__ dense, int B, int D) {
+    const size_t n = (size_t)B * D * D * D * 16;
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    size_t vi = i >> 4;
+    int c = (i & 15) * 4;
+    int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
+    *reinterpret_cast<float4*>(dense + vi * 64 + c) = *reinterpret_cast<const float4*>(g4 + g4_off(D, b, x, y, z) + c);
+}
+
+inline unsigned nblocks(size_t n, int per) { return (unsigned)((n + per - 1) / per); }
+constexpr unsigned MAX_RED_BLOCKS = 1184;   // 148 SMs x 8: bounds the split-reduction scratch
+inline unsigned red_blocks(size_t n, int per) { unsigned b = nblocks(n, per); return b < MAX_RED_BLOCKS ? b : MAX_RED_BLOCKS; }
+}  // namespace
+
+cudaError_t launch_head2_dgrad(const float* g, int c, const float* w, float* raw, int B, int H, cudaStream_t s) {
+    size_t nvox = (size_t)B * (H + 2) * (H + 2) * (H + 2);
+    head2_dgrad_kernel<<<nblocks(nvox, 64), 256, 0, s>>>(g, c, w, raw, B, H);
+    return cudaGetLastError();
+}
+cudaError_t launch_head2_wgrad(ActView h, const float* g, int c, float* dw, float* db, float* scratch,
+                               cudaStream_t s) {
+    size_t nvox = (size_t)h.B * (h.D + 2) * (h.D + 2) * (h.D + 2);
+    unsigned nb = red_blocks(nvox, H2W_VOX_PER_BLOCK);
+    float* tmp = scratch + (size_t)nb * 28 * 64;   // reduced [28][64]
+    head2_wgrad_kernel<<<nb, 256, 0, s>>>(h, g, c, scratch);
+    reduce_rows_kernel<<<(28 * 64 + 255) / 256, 256, 0, s>>>(scratch, nb, 28 * 64, tmp);
+    cudaMemcpyAsync(dw, tmp, 27 * 64 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(db, tmp + 27 * 64, sizeof(float), cudaMemcpyDeviceToDevice, s);
+    return cudaGetLastError();
+}
+cudaError_t launch_fold_act(const float* raw0, const float* raw1, const float* raw2, const float* add_g4,
+                            const __half* saved_hi, const __half* saved_lo, float slope, float* out_g4, int B,
+                            int D, cudaStream_t s) {
+    size_t n = (size_t)B * D * D * D * 16;
+    fold_act_kernel<<<nblocks(n, 256), 256, 0, s>>>(raw0, raw1, raw2, add_g4, saved_hi, saved_lo, slope, out_g4, B, D);
+    return cudaGetLastError();
+}
+cudaError_t launch_wgrad64_simt(ActView x, const float* dy_g4, float* dw, float* scratch, int nchunk,
+                                cudaStream_t s) {
+    dim3 grid(9, nchunk);
+    wgrad64_kernel<<<grid, 256, 0, s>>>(x, dy_g4, scratch);
+    reduce_rows_kernel<<<(27 * 4096 + 255) / 256, 256, 0, s>>>(scratch, nchunk, 27 * 4096, dw);
+    return cudaGetLastError();
+}
+cudaError_t launch_bias_grad(const float* dy_g4, int B, int D, float* db, float* scratch, cudaStream_t s) {
+    size_t nvox = (size_t)B * D * D * D;
+    unsigned nb = red_blocks(nvox, BG_VOX_PER_BLOCK);
+    bias_grad_kernel<<<nb, 256, 0, s>>>(dy_g4, B, D, scratch);
+    reduce_rows_kernel<<<1, 64, 0, s>>>(scratch, nb, 64, db);
+    return cudaGetLastError();
+}
+cudaError_t launch_upsample_bwd(const float* dhr_g4, ActView lr_saved, float slope, float* dlr_g4, int B, int D,
+                                int r, UpsampleTables t, cudaStream_t s) {
+    size_t n = (size_t)B * D * D * D * 16;
+    upsample_bwd_kernel<<<nblocks(n, 256), 256, 0, s>>>(dhr_g4, lr_saved, slope, dlr_g4, B, D, r, t);
+    return cudaGetLastError();
+}
+cudaError_t launch_conv1x1_bwd(const float* dy_g4, ActView a, ActView b, const float* w, float* da_g4,
+                               float* db_g4, float* dw, float* dbias, float* scratch, cudaStream_t s) {
+    size_t nvox = (size_t)a.B * a.D * a.D * a.D;
+    conv1x1_dgrad_kernel<<<nblocks(nvox, 32), 256, 128 * 64 * 4, s>>>(dy_g4, a, b, w, da_g4, db_g4);
+    unsigned nb = red_blocks(nvox, C1_VOX_PER_BLOCK);
+    conv1x1_wgrad_kernel<<<nb, 256, 0, s>>>(dy_g4, a, b, scratch);
+    reduce_rows_kernel<<<8192 / 256, 256, 0, s>>>(scratch, nb, 8192, dw);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return launch_bias_grad(dy_g4, a.B, a.D, dbias, scratch, s);
+}
+cudaError_t launch_stem_wgrad(const float* feat, int ch0, const float* dy_g4, int B, int P, float* dw,
+                              float* db, float* scratch, cudaStream_t s) {
+    size_t nvox = (size_t)B * P * P * P;
+    unsigned nb = red_blocks(nvox, SW_VOX_PER_BLOCK);
+    stem_wgrad_kernel<<<nb, 256, 0, s>>>(feat, ch0, dy_g4, B, P, scratch);
+    reduce_rows_kernel<<<(81 * 64 + 255) / 256, 256, 0, s>>>(scratch, nb, 81 * 64, dw);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return launch_bias_grad(dy_g4, B, P, db, scratch, s);
+}
+cudaError_t launch_g4_from_dense(const float* dense, float* g4, int B, int D, cudaStream_t s) {
+    size_t n = (size_t)B * D * D * D * 16;
+    g4_from_dense_kernel<<<nblocks(n, 256), 256, 0, s>>>(dense, g4, B, D);
+    return cudaGetLastError();
+}
+cudaError_t launch_dense_from_g4(const float* g4, float* dense, int B, int D, cudaStream_t s) {
+    size_t n = (size_t)B * D * D * D * 16;
+    dense_from_g4_kernel<<<nblocks(n, 256), 256, 0, s>>>(g4, dense, B, D);
+    return cudaGetLastError();
+}

@@ -1,0 +1,24 @@
+// tcgen05 (5th-gen tensor core) 64->64 3x3x3 convolution: interface used by the engine.
+#pragma once
+#include "common.cuh"
+
+struct TcWeights;   // per-layer tensor-core operand images (split fp16, swizzled), device resident
+
+struct TcConvArgs {
+    ActView in;                 // interior edge D (storage D+2, replicate halo filled)
+    ActView out;                // interior edge D
+    int layer = 0;              // index into TcWeights
+    int dgrad = 0;
+    const float* bias = nullptr;
+    const __half* res_hi = nullptr;
+    const __half* res_lo = nullptr;
+    float slope = 1.f;
+    int halo = 1;
+};
+
+bool tc_available();
+cudaError_t tc_alloc_weights(TcWeights** w, int nlayers);
+void tc_free_weights(TcWeights* w);
+// (re)build the operand image of one layer from its Keras-layout fp32 kernel [27][64][64]
+cudaError_t tc_prepare_weights(TcWeights* w, int layer, const float* kernel, cudaStream_t s);
+cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s);

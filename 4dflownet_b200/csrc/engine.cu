@@ -1,0 +1,784 @@
+// libsr4d engine: owns parameters, optimizer state and workspace; sequences the kernels
+// of the 4DFlowNet SR graph (Network/SR4DFlowNet.py:7-51) forward and backward, and
+// implements the C ABI of include/sr4d.h.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sr4d.h"
+#include "kernels.h"
+#include "conv_tc.h"
+
+namespace {
+
+struct Layer {
+    int64_t w_off = 0, b_off = -1;
+    int k = 3, cin = 64, cout = 64;
+};
+
+struct ActBuf {
+    __half* base = nullptr;   // hi plane then lo plane, sized for maxB
+    int D = 0;
+    ActView view(int B) const {
+        ActView v;
+        v.hi = base;
+        v.lo = base + act_plane_elems(B, D);   // planes packed for the CURRENT batch
+        v.B = B;
+        v.D = D;
+        return v;
+    }
+};
+
+struct UpTab {
+    int* lo = nullptr; int* hi = nullptr; float* lerp = nullptr; int* ibeg = nullptr; int* iend = nullptr;
+    UpsampleTables tables() const { return UpsampleTables{lo, hi, lerp, ibeg, iend}; }
+};
+
+}  // namespace
+
+struct sr4d_handle {
+    int P = 0, r = 1, low = 0, hi = 0, maxB = 0, training = 0, device = 0, H = 0;
+    std::vector<sr4d_tensor_desc> table;
+    std::vector<Layer> layers;
+    int64_t flat = 0, nparam = 0;
+    float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
+    unsigned char* kflag = nullptr;
+    float* feat = nullptr;
+    std::vector<ActBuf> lr, hr;        // storage slots
+    std::vector<int> lr_slot, hr_slot; // tensor index -> slot
+    int n_lr_t = 0, n_hr_t = 0;
+    UpTab up;
+    // training workspace
+    float* g4_lr[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* g4_hr[3] = {nullptr, nullptr, nullptr};
+    float* raw_lr = nullptr;
+    float* raw_hr[3] = {nullptr, nullptr, nullptr};
+    float* pred = nullptr;     // (maxB,H^3,3)
+    float* gpred = nullptr;    // (maxB,H^3,3)
+    float* scratch = nullptr;  // split-reduction partials
+    size_t scratch_floats = 0;
+    double* dpartial = nullptr;
+    float* norm = nullptr;
+    float* per_sample_int = nullptr;
+    int wgrad_chunks = 64;
+    TcWeights* tcw = nullptr;  // tensor-core operand images of the 64->64 kernels
+    bool tcw_dirty = true;
+    int conv_impl = SR4D_CONV_AUTO;
+    int save_acts = 0;
+    bool have_fwd_state = false;
+    int64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+#define CK(h, expr, nk)                                                                       \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                   \
+            return SR4D_ECUDA;                                                                \
+        }                                                                                     \
+        (h)->launches += (nk);                                                                \
+    } while (0)
+
+int fail(sr4d_t* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+void build_table(sr4d_t* h) {
+    const int C = 64;
+    struct L { int k, cin, cout; bool bias; };
+    std::vector<L> ls;
+    ls.push_back({3, 3, C, true});
+    ls.push_back({3, C, C, true});
+    ls.push_back({3, 3, C, true});
+    ls.push_back({3, C, C, true});
+    ls.push_back({1, 2 * C, C, true});
+    ls.push_back({3, C, C, true});
+    for (int i = 0; i < 2 * (h->low + h->hi); ++i) ls.push_back({3, C, C, false});
+    for (int i = 0; i < 3; ++i) {
+        ls.push_back({3, C, C, true});
+        ls.push_back({3, C, 1, true});
+    }
+    int64_t off = 0;
+    h->nparam = 0;
+    for (size_t i = 0; i < ls.size(); ++i) {
+        Layer ly;
+        ly.k = ls[i].k; ly.cin = ls[i].cin; ly.cout = ls[i].cout;
+        char lname[24];
+        if (i == 0) snprintf(lname, sizeof lname, "conv3d");
+        else snprintf(lname, sizeof lname, "conv3d_%zu", i);
+        sr4d_tensor_desc d;
+        memset(&d, 0, sizeof d);
+        snprintf(d.name, sizeof d.name, "%s/kernel", lname);
+        d.offset = off;
+        d.count = (int64_t)ly.k * ly.k * ly.k * ly.cin * ly.cout;
+        d.ndim = 5;
+        d.shape[0] = d.shape[1] = d.shape[2] = ly.k; d.shape[3] = ly.cin; d.shape[4] = ly.cout;
+        d.is_kernel = 1;
+        ly.w_off = off;
+        h->table.push_back(d);
+        h->nparam += d.count;
+        off += (d.count + 31) / 32 * 32;
+        if (ls[i].bias) {
+            sr4d_tensor_desc b;
+            memset(&b, 0, sizeof b);
+            snprintf(b.name, sizeof b.name, "%s/bias", lname);
+            b.offset = off;
+            b.count = ly.cout;
+            b.ndim = 1;
+            b.shape[0] = ly.cout;
+            b.is_kernel = 0;
+            ly.b_off = off;
+            h->table.push_back(b);
+            h->nparam += b.count;
+            off += (b.count + 31) / 32 * 32;
+        }
+        h->layers.push_back(ly);
+    }
+    h->flat = off;
+}
+
+template <typename T>
+cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
+
+int build_upsample_tables(sr4d_t* h) {
+    const int in = h->P, out = h->H;
+    std::vector<int> lo(out), hi(out), ibeg(in, out), iend(in, 0);
+    std::vector<float> lerp(out);
+    // TF1 legacy resize_bilinear(align_corners=True) scaler, fp32
+    const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    for (int i = 0; i < out; ++i) {
+        float src = (float)i * scale;
+        int l = (int)floorf(src);
+        int u = (int)ceilf(src);
+        if (u > in - 1) u = in - 1;
+        lo[i] = l; hi[i] = u; lerp[i] = src - (float)l;
+        for (int j : {l, u}) {
+            if (i < ibeg[j]) ibeg[j] = i;
+            if (i + 1 > iend[j]) iend[j] = i + 1;
+        }
+    }
+    if (dmalloc(&h->up.lo, out) || dmalloc(&h->up.hi, out) || dmalloc(&h->up.lerp, out) ||
+        dmalloc(&h->up.ibeg, in) || dmalloc(&h->up.iend, in))
+        return SR4D_ENOMEM;
+    cudaMemcpy(h->up.lo, lo.data(), out * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->up.hi, hi.data(), out * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->up.lerp, lerp.data(), out * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->up.ibeg, ibeg.data(), in * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->up.iend, iend.data(), in * sizeof(int), cudaMemcpyHostToDevice);
+    return SR4D_OK;
+}
+
+int alloc_act(ActBuf& b, int maxB, int D) {
+    b.D = D;
+    size_t n = 2 * act_plane_elems(maxB, D);
+    if (dmalloc(&b.base, n) != cudaSuccess) return SR4D_ENOMEM;
+    return SR4D_OK;
+}
+
+// tensor indices (see forward())
+inline int lr_t_of_block_t(int k) { return 6 + 2 * k; }
+inline int lr_t_of_block_x(int k) { return 7 + 2 * k; }   // output of LR block k
+inline int hr_t_of_block_t(int k) { return 1 + 2 * k; }
+inline int hr_t_of_block_x(int k) { return 2 + 2 * k; }
+
+int plan_buffers(sr4d_t* h) {
+    h->n_lr_t = 6 + 2 * h->low;
+    h->n_hr_t = 1 + 2 * h->hi + 3;
+    h->lr_slot.assign(h->n_lr_t, 0);
+    h->hr_slot.assign(h->n_hr_t, 0);
+    int n_lr_slots, n_hr_slots;
+    if (h->training) {
+        for (int i = 0; i < h->n_lr_t; ++i) h->lr_slot[i] = i;
+        for (int i = 0; i < h->n_hr_t; ++i) h->hr_slot[i] = i;
+        n_lr_slots = h->n_lr_t;
+        n_hr_slots = h->n_hr_t;
+    } else {
+        // inference: rotate; pc1->0 pc2->1 ph1->2 ph2->3 c1->0 f->2, t_k->0, x_{k+1}-> 1,2,1,2..
+        const int base[6] = {0, 1, 2, 3, 0, 2};
+        for (int i = 0; i < 6; ++i) h->lr_slot[i] = base[i];
+        for (int k = 0; k < h->low; ++k) {
+            h->lr_slot[lr_t_of_block_t(k)] = 0;
+            h->lr_slot[lr_t_of_block_x(k)] = (k % 2 == 0) ? 1 : 2;
+        }
+        n_lr_slots = 4;
+        h->hr_slot[0] = 0;
+        for (int k = 0; k < h->hi; ++k) {
+            h->hr_slot[hr_t_of_block_t(k)] = 1;
+            h->hr_slot[hr_t_of_block_x(k)] = (k % 2 == 0) ? 2 : 0;
+        }
+        // heads: slot 1 (the block scratch, free once the trunk is final) and two extra slots
+        const int head_slots[3] = {1, 3, 4};
+        for (int c = 0; c < 3; ++c) h->hr_slot[1 + 2 * h->hi + c] = head_slots[c];
+        n_hr_slots = 5;
+    }
+    h->lr.resize(n_lr_slots);
+    for (auto& b : h->lr)
+        if (alloc_act(b, h->maxB, h->P)) return SR4D_ENOMEM;
+    if (h->r == 1) {
+        // upsample is the identity (SR4DFlowNet.py:72-74): HR tensor 0 aliases the LR trunk
+        h->hr.resize(n_hr_slots);
+        for (int i = 0; i < n_hr_slots; ++i) {
+            bool is_up_slot = (i == h->hr_slot[0]);
+            if (h->training && is_up_slot) { h->hr[i].D = h->H; continue; }   // aliased at run time
+            if (alloc_act(h->hr[i], h->maxB, h->H)) return SR4D_ENOMEM;
+        }
+    } else {
+        h->hr.resize(n_hr_slots);
+        for (auto& b : h->hr)
+            if (alloc_act(b, h->maxB, h->H)) return SR4D_ENOMEM;
+    }
+    return SR4D_OK;
+}
+
+ActView lr_view(sr4d_t* h, int t, int B) { return h->lr[h->lr_slot[t]].view(B); }
+ActView hr_view(sr4d_t* h, int t, int B) {
+    if (t == 0 && h->r == 1) return lr_view(h, h->low ? lr_t_of_block_x(h->low - 1) : 5, B);
+    return h->hr[h->hr_slot[t]].view(B);
+}
+
+const float* W(sr4d_t* h, int layer) { return h->params + h->layers[layer].w_off; }
+const float* Bv(sr4d_t* h, int layer) { return h->layers[layer].b_off >= 0 ? h->params + h->layers[layer].b_off : nullptr; }
+float* GW(sr4d_t* h, int layer) { return h->grads + h->layers[layer].w_off; }
+float* GB(sr4d_t* h, int layer) { return h->grads + h->layers[layer].b_off; }
+
+bool use_tc(sr4d_t* h, int impl_override = -1) {
+    int impl = impl_override >= 0 ? impl_override : h->conv_impl;
+    if (impl == SR4D_CONV_SIMT) return false;
+    return tc_available();
+}
+
+int ensure_tc_weights(sr4d_t* h, cudaStream_t s) {
+    if (!tc_available()) return SR4D_OK;
+    if (!h->tcw_dirty) return SR4D_OK;
+    for (size_t i = 0; i < h->layers.size(); ++i) {
+        const Layer& ly = h->layers[i];
+        if (ly.k == 3 && ly.cin == 64 && ly.cout == 64) {
+            CK(h, tc_prepare_weights(h->tcw, (int)i, W(h, (int)i), s), 2);
+        }
+    }
+    h->tcw_dirty = false;
+    return SR4D_OK;
+}
+
+// one 64->64 3x3x3 conv layer, Act -> Act
+int conv64_fwd(sr4d_t* h, int layer, ActView in, ActView out, const ActView* res, float slope, cudaStream_t s) {
+    if (use_tc(h)) {
+        TcConvArgs a;
+        a.in = in; a.out = out; a.layer = layer; a.dgrad = 0;
+        a.bias = Bv(h, layer);
+        a.res_hi = res ? res->hi : nullptr; a.res_lo = res ? res->lo : nullptr;
+        a.slope = slope; a.halo = 1;
+        CK(h, tc_conv64(h->tcw, a, s), 1);
+        return SR4D_OK;
+    }
+    Conv64Args a;
+    a.in_hi = in.hi; a.in_lo = in.lo; a.B = in.B; a.Do = in.D;
+    a.w = W(h, layer);
+    a.out_hi = out.hi; a.out_lo = out.lo; a.halo = 1;
+    a.bias = Bv(h, layer);
+    if (res) { a.res_hi = res->hi; a.res_lo = res->lo; }
+    a.slope = slope;
+    CK(h, launch_conv64_simt(a, s), 1);
+    return SR4D_OK;
+}
+
+int forward_impl(sr4d_t* h, const float* u, const float* v, const float* w, const float* um, const float* vm,
+                 const float* wm, float* out, int B, cudaStream_t s) {
+    if (B < 1 || B > h->maxB) return fail(h, SR4D_EINVAL, "batch size out of range (1..max_batch)");
+    int rc = ensure_tc_weights(h, s);
+    if (rc) return rc;
+    const int P = h->P;
+    CK(h, launch_prep_features(u, v, w, um, vm, wm, h->feat, B, P, s), 1);
+    ActView pc1 = lr_view(h, 0, B), pc2 = lr_view(h, 1, B), ph1 = lr_view(h, 2, B), ph2 = lr_view(h, 3, B);
+    ActView c1 = lr_view(h, 4, B), f = lr_view(h, 5, B);
+    CK(h, launch_stem_conv(h->feat, 3, W(h, 0), Bv(h, 0), pc1, s), 1);                 // SR4DFlowNet.py:17
+    if ((rc = conv64_fwd(h, 1, pc1, pc2, nullptr, 0.f, s))) return rc;                  // :18
+    CK(h, launch_stem_conv(h->feat, 0, W(h, 2), Bv(h, 2), ph1, s), 1);                 // :20
+    if ((rc = conv64_fwd(h, 3, ph1, ph2, nullptr, 0.f, s))) return rc;                  // :21
+    CK(h, launch_conv1x1_cat(ph2, pc2, W(h, 4), Bv(h, 4), c1, s), 1);                  // :23-24
+    if ((rc = conv64_fwd(h, 5, c1, f, nullptr, 0.f, s))) return rc;                     // :25
+    int li = 6;
+    ActView x = f;
+    for (int k = 0; k < h->low; ++k) {                                                  // :28-30
+        ActView t = lr_view(h, lr_t_of_block_t(k), B), xo = lr_view(h, lr_t_of_block_x(k), B);
+        if ((rc = conv64_fwd(h, li, x, t, nullptr, 0.2f, s))) return rc;
+        if ((rc = conv64_fwd(h, li + 1, t, xo, &x, 0.2f, s))) return rc;
+        x = xo;
+        li += 2;
+    }
+    ActView xh;
+    if (h->r == 1) {
+        xh = x;                                                                          // :72-74
+    } else {
+        xh = hr_view(h, 0, B);
+        CK(h, launch_upsample(x, xh, h->r, h->up.tables(), s), 1);                      // :32
+    }
+    for (int k = 0; k < h->hi; ++k) {                                                   // :35-36
+        ActView t = hr_view(h, hr_t_of_block_t(k), B), xo = hr_view(h, hr_t_of_block_x(k), B);
+        if ((rc = conv64_fwd(h, li, xh, t, nullptr, 0.2f, s))) return rc;
+        if ((rc = conv64_fwd(h, li + 1, t, xo, &xh, 0.2f, s))) return rc;
+        xh = xo;
+        li += 2;
+    }
+    ActView hd[3];
+    for (int c = 0; c < 3; ++c) {                                                       // :39-46
+        hd[c] = hr_view(h, 1 + 2 * h->hi + c, B);
+        if ((rc = conv64_fwd(h, li + 2 * c, xh, hd[c], nullptr, 0.f, s))) return rc;
+    }
+    CK(h, launch_head_out(hd[0], hd[1], hd[2], W(h, li + 1), W(h, li + 3), W(h, li + 5), Bv(h, li + 1),
+                          Bv(h, li + 3), Bv(h, li + 5), out, s), 1);                     // :40,43,46,49
+    h->have_fwd_state = h->training != 0;
+    return SR4D_OK;
+}
+
+// dgrad of a 64->64 layer: dy (G4, edge D) -> raw (edge D+2)
+int conv64_dgrad(sr4d_t* h, int layer, const float* dy_g4, float* raw, int B, int D, cudaStream_t s) {
+    Conv64Args a;
+    a.in_f32 = dy_g4; a.B = B; a.Do = D + 2;
+    a.w = W(h, layer); a.dgrad = 1;
+    a.out_raw = raw;
+    CK(h, launch_conv64_simt(a, s), 1);
+    return SR4D_OK;
+}
+int conv64_wgrad(sr4d_t* h, int layer, ActView x, const float* dy_g4, bool bias, cudaStream_t s) {
+    CK(h, launch_wgrad64_simt(x, dy_g4, GW(h, layer), h->scratch, h->wgrad_chunks, s), 2);
+    if (bias) CK(h, launch_bias_grad(dy_g4, x.B, x.D, GB(h, layer), h->scratch, s), 2);
+    return SR4D_OK;
+}
+
+// backward through `nblk` resnet blocks whose first conv is layer `l0`; S holds the gradient wrt the
+// pre-activation of the last block output on entry and wrt the pre-activation (if slope_in >= 0) of the
+// first block input on exit.  bufs = {S, T, S'} G4 buffers; returns the index of the buffer holding the result.
+int blocks_bwd(sr4d_t* h, int nblk, int l0, bool hr, float* bufs[3], float* raw, int B, int D,
+               float slope_in, cudaStream_t s, int* result_idx) {
+    int si = 0;
+    int rc;
+    for (int k = nblk - 1; k >= 0; --k) {
+        const int la = l0 + 2 * k, lb = la + 1;
+        ActView t = hr ? hr_view(h, hr_t_of_block_t(k), B) : lr_view(h, lr_t_of_block_t(k), B);
+        ActView xin;
+        if (hr) xin = k == 0 ? hr_view(h, 0, B) : hr_view(h, hr_t_of_block_x(k - 1), B);
+        else xin = k == 0 ? lr_view(h, 5, B) : lr_view(h, lr_t_of_block_x(k - 1), B);
+        float* S = bufs[si];
+        float* T = bufs[(si + 1) % 3];
+        float* S2 = bufs[(si + 2) % 3];
+        if ((rc = conv64_wgrad(h, lb, t, S, false, s))) return rc;
+        if ((rc = conv64_dgrad(h, lb, S, raw, B, D, s))) return rc;
+        CK(h, launch_fold_act(raw, nullptr, nullptr, nullptr, t.hi, t.lo, 0.2f, T, B, D, s), 1);
+        if ((rc = conv64_wgrad(h, la, xin, T, false, s))) return rc;
+        if ((rc = conv64_dgrad(h, la, T, raw, B, D, s))) return rc;
+        // gradient wrt x_k (post-activation) = fold + skip path; multiply by its producer's act'
+        float slope = k > 0 ? 0.2f : slope_in;
+        if (slope >= 0.f)
+            CK(h, launch_fold_act(raw, nullptr, nullptr, S, xin.hi, xin.lo, slope, S2, B, D, s), 1);
+        else
+            CK(h, launch_fold_act(raw, nullptr, nullptr, S, nullptr, nullptr, 1.f, S2, B, D, s), 1);
+        si = (si + 2) % 3;
+    }
+    *result_idx = si;
+    return SR4D_OK;
+}
+
+int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, const float* mask, int B,
+                  float* per_sample, float* l2_out, cudaStream_t s) {
+    if (!h->training) return fail(h, SR4D_ESTATE, "handle was not created for training");
+    const int P = h->P, H = h->H;
+    const int nvoxH = H * H * H;
+    int rc;
+    CK(h, launch_loss_stats(h->pred, hu, hv, hw, mask, B, nvoxH, h->dpartial, 64, per_sample, h->norm, s), 2);
+    CK(h, launch_loss_grad(h->pred, hu, hv, hw, mask, B, nvoxH, h->norm, h->gpred, s), 1);
+    if (l2_out)
+        CK(h, launch_sumsq(h->params, h->kflag, h->flat, h->dpartial + 64 * 5 * h->maxB, 256, 5e-7f, l2_out, s), 2);
+
+    const int l_hr0 = 6 + 2 * h->low;          // first HR block layer
+    const int l_head = l_hr0 + 2 * h->hi;      // first head layer
+    ActView trunk = h->hi > 0 ? hr_view(h, hr_t_of_block_x(h->hi - 1), B) : hr_view(h, 0, B);
+    float* A = h->g4_hr[0];
+    for (int c = 0; c < 3; ++c) {
+        ActView hd = hr_view(h, 1 + 2 * h->hi + c, B);
+        const int l1 = l_head + 2 * c, l2 = l1 + 1;
+        CK(h, launch_head2_wgrad(hd, h->gpred, c, GW(h, l2), GB(h, l2), h->scratch, s), 4);
+        CK(h, launch_head2_dgrad(h->gpred, c, W(h, l2), h->raw_hr[c], B, H, s), 1);
+        CK(h, launch_fold_act(h->raw_hr[c], nullptr, nullptr, nullptr, hd.hi, hd.lo, 0.f, A, B, H, s), 1);
+        if ((rc = conv64_wgrad(h, l1, trunk, A, true, s))) return rc;
+        if ((rc = conv64_dgrad(h, l1, A, h->raw_hr[c], B, H, s))) return rc;
+    }
+    // trunk gradient: sum of the three heads' input gradients; trunk producer: LeakyReLU block if hi>0,
+    // the (linear) upsample if hi==0 and r>1, else the LR trunk tensor itself (r==1 aliases it).
+    float* hb[3] = {h->g4_hr[1], h->g4_hr[2], h->g4_hr[0]};
+    float slope_lr_trunk = h->low > 0 ? 0.2f : 0.f;    // producer activation of the LR trunk tensor
+    float* S;
+    if (h->hi > 0) {
+        CK(h, launch_fold_act(h->raw_hr[0], h->raw_hr[1], h->raw_hr[2], nullptr, trunk.hi, trunk.lo, 0.2f, hb[0], B, H, s), 1);
+        int ri = 0;
+        float slope_in = h->r == 1 ? slope_lr_trunk : -1.f;
+        if ((rc = blocks_bwd(h, h->hi, l_hr0, true, hb, h->raw_hr[0], B, H, slope_in, s, &ri))) return rc;
+        S = hb[ri];
+    } else {
+        if (h->r == 1)
+            CK(h, launch_fold_act(h->raw_hr[0], h->raw_hr[1], h->raw_hr[2], nullptr, trunk.hi, trunk.lo, slope_lr_trunk, hb[0], B, H, s), 1);
+        else
+            CK(h, launch_fold_act(h->raw_hr[0], h->raw_hr[1], h->raw_hr[2], nullptr, nullptr, nullptr, 1.f, hb[0], B, H, s), 1);
+        S = hb[0];
+    }
+    // through the upsample
+    float* lb[3] = {h->g4_lr[0], h->g4_lr[1], h->g4_lr[2]};
+    ActView lr_trunk = h->low > 0 ? lr_view(h, lr_t_of_block_x(h->low - 1), B) : lr_view(h, 5, B);
+    if (h->r == 1) {
+        // same grid (H == P): S is already multiplied by the LR trunk's act'; keep rotating the HR buffers
+        int si = 0;
+        for (int i = 0; i < 3; ++i) if (hb[i] == S) si = i;
+        lb[0] = hb[si]; lb[1] = hb[(si + 1) % 3]; lb[2] = hb[(si + 2) % 3];
+    } else {
+        CK(h, launch_upsample_bwd(S, lr_trunk, slope_lr_trunk, lb[0], B, P, h->r, h->up.tables(), s), 1);
+    }
+    int ri = 0;
+    if (h->low > 0) {
+        if ((rc = blocks_bwd(h, h->low, 6, false, lb, h->raw_lr, B, P, 0.f, s, &ri))) return rc;
+    }
+    float* S5 = lb[ri];                 // d pre-activation of conv3d_5 (fuse 3x3)
+    float* T = lb[(ri + 1) % 3];
+    float* dA = lb[(ri + 2) % 3];
+    float* dB = h->g4_lr[3];
+    ActView pc1 = lr_view(h, 0, B), pc2 = lr_view(h, 1, B), ph1 = lr_view(h, 2, B), ph2 = lr_view(h, 3, B);
+    ActView c1 = lr_view(h, 4, B);
+    if ((rc = conv64_wgrad(h, 5, c1, S5, true, s))) return rc;
+    if ((rc = conv64_dgrad(h, 5, S5, h->raw_lr, B, P, s))) return rc;
+    CK(h, launch_fold_act(h->raw_lr, nullptr, nullptr, nullptr, c1.hi, c1.lo, 0.f, T, B, P, s), 1);
+    CK(h, launch_conv1x1_bwd(T, ph2, pc2, W(h, 4), dA, dB, GW(h, 4), GB(h, 4), h->scratch, s), 5);
+    // phase branch
+    if ((rc = conv64_wgrad(h, 3, ph1, dA, true, s))) return rc;
+    if ((rc = conv64_dgrad(h, 3, dA, h->raw_lr, B, P, s))) return rc;
+    CK(h, launch_fold_act(h->raw_lr, nullptr, nullptr, nullptr, ph1.hi, ph1.lo, 0.f, T, B, P, s), 1);
+    CK(h, launch_stem_wgrad(h->feat, 0, T, B, P, GW(h, 2), GB(h, 2), h->scratch, s), 4);
+    // pc branch
+    if ((rc = conv64_wgrad(h, 1, pc1, dB, true, s))) return rc;
+    if ((rc = conv64_dgrad(h, 1, dB, h->raw_lr, B, P, s))) return rc;
+    CK(h, launch_fold_act(h->raw_lr, nullptr, nullptr, nullptr, pc1.hi, pc1.lo, 0.f, T, B, P, s), 1);
+    CK(h, launch_stem_wgrad(h->feat, 3, T, B, P, GW(h, 0), GB(h, 0), h->scratch, s), 4);
+    return SR4D_OK;
+}
+
+void free_all(sr4d_t* h) {
+    cudaFree(h->params); cudaFree(h->grads); cudaFree(h->m); cudaFree(h->v); cudaFree(h->kflag);
+    cudaFree(h->feat);
+    for (auto& b : h->lr) cudaFree(b.base);
+    for (auto& b : h->hr) cudaFree(b.base);
+    cudaFree(h->up.lo); cudaFree(h->up.hi); cudaFree(h->up.lerp); cudaFree(h->up.ibeg); cudaFree(h->up.iend);
+    for (auto p : h->g4_lr) cudaFree(p);
+    for (auto p : h->g4_hr) cudaFree(p);
+    cudaFree(h->raw_lr);
+    for (auto p : h->raw_hr) cudaFree(p);
+    cudaFree(h->pred); cudaFree(h->gpred); cudaFree(h->scratch); cudaFree(h->dpartial); cudaFree(h->norm);
+    cudaFree(h->per_sample_int);
+    if (h->tcw) tc_free_weights(h->tcw);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sr4d_version(void) { return "sr4d 0.1 (sm_100a)"; }
+
+int sr4d_create(sr4d_t** out, int patch_size, int res_increase, int low_resblock, int hi_resblock, int max_batch,
+                int training, int device) {
+    if (!out) return SR4D_EINVAL;
+    *out = nullptr;
+    if (patch_size < 4 || patch_size > 128 || res_increase < 1 || res_increase > 8 || low_resblock < 0 ||
+        hi_resblock < 0 || max_batch < 1)
+        return SR4D_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return SR4D_ENODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SR4D_ENODEVICE;
+    if (prop.major != 10) return SR4D_ENODEVICE;   // sm_100a only: no fallback paths
+    if (cudaSetDevice(device) != cudaSuccess) return SR4D_ENODEVICE;
+
+    sr4d_t* h = new sr4d_handle();
+    h->P = patch_size; h->r = res_increase; h->low = low_resblock; h->hi = hi_resblock;
+    h->maxB = max_batch; h->training = training; h->device = device; h->H = patch_size * res_increase;
+    h->save_acts = training;
+    build_table(h);
+    int rc = SR4D_OK;
+    const size_t nvoxP = (size_t)h->P * h->P * h->P, nvoxH = (size_t)h->H * h->H * h->H;
+    do {
+        if (dmalloc(&h->params, h->flat) || dmalloc(&h->kflag, h->flat / 32) ||
+            dmalloc(&h->feat, (size_t)h->maxB * nvoxP * 6)) { rc = SR4D_ENOMEM; break; }
+        cudaMemset(h->params, 0, h->flat * sizeof(float));
+        std::vector<unsigned char> kf(h->flat / 32, 0);
+        for (auto& d : h->table)
+            if (d.is_kernel)
+                for (int64_t i = d.offset / 32; i < (d.offset + d.count + 31) / 32; ++i) kf[i] = 1;
+        cudaMemcpy(h->kflag, kf.data(), kf.size(), cudaMemcpyHostToDevice);
+        if ((rc = plan_buffers(h))) break;
+        if ((rc = build_upsample_tables(h))) break;
+        // zero-initialise activations once so halos of never-written regions are defined
+        for (auto& b : h->lr) if (b.base) cudaMemset(b.base, 0, 2 * act_plane_elems(h->maxB, b.D) * sizeof(__half));
+        for (auto& b : h->hr) if (b.base) cudaMemset(b.base, 0, 2 * act_plane_elems(h->maxB, b.D) * sizeof(__half));
+        if (dmalloc(&h->dpartial, (size_t)64 * 5 * h->maxB + 256) || dmalloc(&h->norm, (size_t)2 * h->maxB) ||
+            dmalloc(&h->per_sample_int, (size_t)4 * h->maxB)) { rc = SR4D_ENOMEM; break; }
+        if (tc_available()) {
+            if (tc_alloc_weights(&h->tcw, (int)h->layers.size()) != cudaSuccess) { rc = SR4D_ENOMEM; break; }
+        }
+        if (training) {
+            if (dmalloc(&h->grads, h->flat) || dmalloc(&h->m, h->flat) || dmalloc(&h->v, h->flat)) { rc = SR4D_ENOMEM; break; }
+            cudaMemset(h->grads, 0, h->flat * sizeof(float));
+            cudaMemset(h->m, 0, h->flat * sizeof(float));
+            cudaMemset(h->v, 0, h->flat * sizeof(float));
+            const size_t g4l = (size_t)h->maxB * (h->P + 4) * (h->P + 4) * (h->P + 4) * 64;
+            const size_t g4h = (size_t)h->maxB * (h->H + 4) * (h->H + 4) * (h->H + 4) * 64;
+            const size_t rwl = (size_t)h->maxB * (h->P + 2) * (h->P + 2) * (h->P + 2) * 64;
+            const size_t rwh = (size_t)h->maxB * (h->H + 2) * (h->H + 2) * (h->H + 2) * 64;
+            bool bad = false;
+            for (auto& p : h->g4_lr) { bad |= dmalloc(&p, g4l) != cudaSuccess; if (!bad) cudaMemset(p, 0, g4l * 4); }
+            for (auto& p : h->g4_hr) { bad |= dmalloc(&p, g4h) != cudaSuccess; if (!bad) cudaMemset(p, 0, g4h * 4); }
+            bad |= dmalloc(&h->raw_lr, rwl) != cudaSuccess;
+            for (auto& p : h->raw_hr) bad |= dmalloc(&p, rwh) != cudaSuccess;
+            bad |= dmalloc(&h->pred, (size_t)h->maxB * nvoxH * 3) != cudaSuccess;
+            bad |= dmalloc(&h->gpred, (size_t)h->maxB * nvoxH * 3) != cudaSuccess;
+            h->scratch_floats = (size_t)h->wgrad_chunks * 27 * 4096;
+            size_t need2 = (size_t)1184 * 8192 + 8192;
+            if (need2 > h->scratch_floats) h->scratch_floats = need2;
+            bad |= dmalloc(&h->scratch, h->scratch_floats) != cudaSuccess;
+            if (bad) { rc = SR4D_ENOMEM; break; }
+        }
+        if (cudaDeviceSynchronize() != cudaSuccess) { rc = SR4D_ECUDA; break; }
+    } while (0);
+    if (rc != SR4D_OK) {
+        free_all(h);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return SR4D_OK;
+}
+
+void sr4d_destroy(sr4d_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    free_all(h);
+    delete h;
+}
+
+const char* sr4d_last_error(const sr4d_t* h) { return h ? h->err.c_str() : "null handle"; }
+
+int sr4d_set_option(sr4d_t* h, int option, int value) {
+    if (!h) return SR4D_EINVAL;
+    switch (option) {
+        case SR4D_OPT_CONV_IMPL:
+            if (value < 0 || value > 2) return fail(h, SR4D_EINVAL, "bad conv impl");
+            if (value == SR4D_CONV_TCGEN05 && !tc_available()) return fail(h, SR4D_EINVAL, "tcgen05 conv not built");
+            h->conv_impl = value;
+            return SR4D_OK;
+        case SR4D_OPT_SAVE_ACTS:
+            h->save_acts = value != 0;
+            return SR4D_OK;
+    }
+    return fail(h, SR4D_EINVAL, "unknown option");
+}
+int sr4d_get_option(const sr4d_t* h, int option, int* value) {
+    if (!h || !value) return SR4D_EINVAL;
+    if (option == SR4D_OPT_CONV_IMPL) { *value = h->conv_impl; return SR4D_OK; }
+    if (option == SR4D_OPT_SAVE_ACTS) { *value = h->save_acts; return SR4D_OK; }
+    return SR4D_EINVAL;
+}
+
+int64_t sr4d_param_count(const sr4d_t* h) { return h ? h->nparam : 0; }
+int64_t sr4d_flat_size(const sr4d_t* h) { return h ? h->flat : 0; }
+int sr4d_num_tensors(const sr4d_t* h) { return h ? (int)h->table.size() : 0; }
+int sr4d_param_table(const sr4d_t* h, sr4d_tensor_desc* out, int capacity) {
+    if (!h || !out) return SR4D_EINVAL;
+    int n = (int)h->table.size();
+    if (capacity < n) return SR4D_EINVAL;
+    memcpy(out, h->table.data(), n * sizeof(sr4d_tensor_desc));
+    return n;
+}
+float* sr4d_params(sr4d_t* h) { return h ? h->params : nullptr; }
+float* sr4d_grads(sr4d_t* h) { return h ? h->grads : nullptr; }
+float* sr4d_adam_m(sr4d_t* h) { return h ? h->m : nullptr; }
+float* sr4d_adam_v(sr4d_t* h) { return h ? h->v : nullptr; }
+int sr4d_params_changed(sr4d_t* h, void* stream) {
+    if (!h) return SR4D_EINVAL;
+    h->tcw_dirty = true;
+    return ensure_tc_weights(h, (cudaStream_t)stream);
+}
+
+int sr4d_forward(sr4d_t* h, const float* u, const float* v, const float* w, const float* um, const float* vm,
+                 const float* wm, float* out, int B, void* stream) {
+    if (!h || !u || !v || !w || !um || !vm || !wm || !out) return fail(h, SR4D_EINVAL, "null argument");
+    cudaSetDevice(h->device);
+    return forward_impl(h, u, v, w, um, vm, wm, out, B, (cudaStream_t)stream);
+}
+
+int sr4d_loss_metrics(sr4d_t* h, const float* pred, const float* hu, const float* hv, const float* hw,
+                      const float* mask, int B, float* per_sample, void* stream) {
+    if (!h || !pred || !hu || !hv || !hw || !mask || !per_sample) return fail(h, SR4D_EINVAL, "null argument");
+    if (B < 1 || B > h->maxB) return fail(h, SR4D_EINVAL, "batch size out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    CK(h, launch_loss_stats(pred, hu, hv, hw, mask, B, h->H * h->H * h->H, h->dpartial, 64, per_sample, h->norm, s), 2);
+    return SR4D_OK;
+}
+
+int sr4d_train_fwd_bwd(sr4d_t* h, const float* u, const float* v, const float* w, const float* um, const float* vm,
+                       const float* wm, const float* hu, const float* hv, const float* hw, const float* mask, int B,
+                       float* per_sample, float* l2_out, float* pred_out, void* stream) {
+    if (!h || !u || !v || !w || !um || !vm || !wm || !hu || !hv || !hw || !mask || !per_sample)
+        return fail(h, SR4D_EINVAL, "null argument");
+    if (!h->training) return fail(h, SR4D_ESTATE, "handle was not created for training");
+    cudaSetDevice(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = forward_impl(h, u, v, w, um, vm, wm, h->pred, B, s);
+    if (rc) return rc;
+    if (pred_out)
+        CK(h, cudaMemcpyAsync(pred_out, h->pred, (size_t)B * h->H * h->H * h->H * 3 * sizeof(float),
+                              cudaMemcpyDeviceToDevice, s), 0);
+    return backward_impl(h, hu, hv, hw, mask, B, per_sample, l2_out, s);
+}
+
+int sr4d_adam_step(sr4d_t* h, float lr, float beta1, float beta2, float eps, int64_t t, float l2_grad_scale,
+                   void* stream) {
+    if (!h) return SR4D_EINVAL;
+    if (!h->training) return fail(h, SR4D_ESTATE, "handle was not created for training");
+    if (t < 1) return fail(h, SR4D_EINVAL, "t must be >= 1 (iterations + 1)");
+    cudaSetDevice(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const double alpha = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)t)) /
+                         (1.0 - std::pow((double)beta1, (double)t));
+    CK(h, launch_adam(h->params, h->grads, h->m, h->v, h->kflag, h->flat, (float)alpha, beta1, beta2, eps,
+                      l2_grad_scale, s), 1);
+    h->tcw_dirty = true;
+    return ensure_tc_weights(h, s);
+}
+
+int sr4d_stitch(sr4d_t* h, const float* pred, int nx, int ny, int nz, int side_pad_hr, int VX, int VY, int VZ,
+                float venc, int round_small, float* vol_out, void* stream) {
+    if (!h || !pred || !vol_out) return fail(h, SR4D_EINVAL, "null argument");
+    const int core = h->H - 2 * side_pad_hr;
+    if (core <= 0 || VX > nx * core || VY > ny * core || VZ > nz * core || VX < 1 || VY < 1 || VZ < 1)
+        return fail(h, SR4D_EINVAL, "stitch geometry inconsistent");
+    CK(h, launch_stitch(pred, nx, ny, nz, h->H, side_pad_hr, VX, VY, VZ, venc, round_small, vol_out,
+                        (cudaStream_t)stream), 1);
+    return SR4D_OK;
+}
+
+// ---- single-layer entry points ----------------------------------------------------------
+int sr4d_conv64_layer(sr4d_t* h, const float* x, const float* kernel, const float* bias, const float* residual,
+                      float act_slope, float* y, int B, int D, int impl, void* stream) {
+    if (!h || !x || !kernel || !y || B < 1 || D < 2) return fail(h, SR4D_EINVAL, "bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    ActBuf bi, bo, br;
+    int rc = SR4D_OK;
+    if (alloc_act(bi, B, D) || alloc_act(bo, B, D) || (residual && alloc_act(br, B, D))) rc = SR4D_ENOMEM;
+    TcWeights* tw = nullptr;
+    if (!rc) {
+        do {
+            ActView vi = bi.view(B), vo = bo.view(B), vr = br.view(B);
+            cudaError_t e = launch_pack_act(x, vi, s);
+            if (!e && residual) e = launch_pack_act(residual, vr, s);
+            if (e) { rc = SR4D_ECUDA; h->err = cudaGetErrorString(e); break; }
+            h->launches += residual ? 2 : 1;
+            if (impl == SR4D_CONV_TCGEN05) {
+                if (!tc_available()) { rc = fail(h, SR4D_EINVAL, "tcgen05 conv not built"); break; }
+                if (tc_alloc_weights(&tw, 1) != cudaSuccess) { rc = SR4D_ENOMEM; break; }
+                e = tc_prepare_weights(tw, 0, kernel, s);
+                TcConvArgs a;
+                a.in = vi; a.out = vo; a.layer = 0; a.dgrad = 0; a.bias = bias;
+                a.res_hi = residual ? vr.hi : nullptr; a.res_lo = residual ? vr.lo : nullptr;
+                a.slope = act_slope; a.halo = 1;
+                if (!e) e = tc_conv64(tw, a, s);
+                h->launches += 3;
+            } else {
+                Conv64Args a;
+                a.in_hi = vi.hi; a.in_lo = vi.lo; a.B = B; a.Do = D; a.w = kernel;
+                a.out_hi = vo.hi; a.out_lo = vo.lo; a.halo = 1; a.bias = bias;
+                if (residual) { a.res_hi = vr.hi; a.res_lo = vr.lo; }
+                a.slope = act_slope;
+                e = launch_conv64_simt(a, s);
+                h->launches += 1;
+            }
+            if (!e) e = launch_unpack_act(vo, y, s);
+            h->launches += 1;
+            if (!e) e = cudaStreamSynchronize(s);
+            if (e) { rc = SR4D_ECUDA; h->err = cudaGetErrorString(e); }
+        } while (0);
+    }
+    cudaFree(bi.base); cudaFree(bo.base); cudaFree(br.base);
+    if (tw) tc_free_weights(tw);
+    return rc;
+}
+
+int sr4d_upsample_layer(sr4d_t* h, const float* x, float* y, int B, int D, int r, void* stream) {
+    if (!h || !x || !y || B < 1) return fail(h, SR4D_EINVAL, "bad argument");
+    if (D != h->P || r != h->r || r == 1) return fail(h, SR4D_EINVAL, "upsample layer uses the handle's patch_size/res_increase (>1)");
+    cudaStream_t s = (cudaStream_t)stream;
+    ActBuf bi, bo;
+    int rc = SR4D_OK;
+    if (alloc_act(bi, B, D) || alloc_act(bo, B, D * r)) rc = SR4D_ENOMEM;
+    if (!rc) {
+        ActView vi = bi.view(B), vo = bo.view(B);
+        cudaError_t e = launch_pack_act(x, vi, s);
+        if (!e) e = launch_upsample(vi, vo, r, h->up.tables(), s);
+        if (!e) e = launch_unpack_act(vo, y, s);
+        if (!e) e = cudaStreamSynchronize(s);
+        h->launches += 3;
+        if (e) { rc = SR4D_ECUDA; h->err = cudaGetErrorString(e); }
+    }
+    cudaFree(bi.base); cudaFree(bo.base);
+    return rc;
+}
+
+int sr4d_conv64_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const float* dy, float* dx,
+                          float* dkernel, float* dbias, int B, int D, int impl, void* stream) {
+    if (!h || !x || !kernel || !dy || B < 1 || D < 2) return fail(h, SR4D_EINVAL, "bad argument");
+    (void)impl;
+    cudaStream_t s = (cudaStream_t)stream;
+    ActBuf bi;
+    float *g4 = nullptr, *raw = nullptr, *g4o = nullptr, *scr = nullptr, *dwb = nullptr;
+    const size_t n4 = (size_t)B * (D + 4) * (D + 4) * (D + 4) * 64, n2 = (size_t)B * (D + 2) * (D + 2) * (D + 2) * 64;
+    const int nchunk = 16;
+    int rc = SR4D_OK;
+    if (alloc_act(bi, B, D) || dmalloc(&g4, n4) || dmalloc(&raw, n2) || dmalloc(&g4o, n4) ||
+        dmalloc(&scr, (size_t)nchunk * 27 * 4096 + 1184 * 64) || dmalloc(&dwb, 27 * 4096 + 64))
+        rc = SR4D_ENOMEM;
+    if (!rc) {
+        cudaMemsetAsync(g4, 0, n4 * 4, s);
+        cudaMemsetAsync(g4o, 0, n4 * 4, s);
+        ActView vi = bi.view(B);
+        cudaError_t e = launch_pack_act(x, vi, s);
+        if (!e) e = launch_g4_from_dense(dy, g4, B, D, s);
+        if (!e && dx) {
+            Conv64Args a;
+            a.in_f32 = g4; a.B = B; a.Do = D + 2; a.w = kernel; a.dgrad = 1; a.out_raw = raw;
+            e = launch_conv64_simt(a, s);
+            if (!e) e = launch_fold_act(raw, nullptr, nullptr, nullptr, nullptr, nullptr, 1.f, g4o, B, D, s);
+            if (!e) e = launch_dense_from_g4(g4o, dx, B, D, s);
+            h->launches += 3;
+        }
+        if (!e && dkernel) {
+            e = launch_wgrad64_simt(vi, g4, dwb, scr, nchunk, s);
+            if (!e) e = cudaMemcpyAsync(dkernel, dwb, 27 * 4096 * 4, cudaMemcpyDeviceToDevice, s);
+            h->launches += 2;
+        }
+        if (!e && dbias) {
+            e = launch_bias_grad(g4, B, D, dwb + 27 * 4096, scr, s);
+            if (!e) e = cudaMemcpyAsync(dbias, dwb + 27 * 4096, 64 * 4, cudaMemcpyDeviceToDevice, s);
+            h->launches += 2;
+        }
+        if (!e) e = cudaStreamSynchronize(s);
+        if (e) { rc = SR4D_ECUDA; h->err = cudaGetErrorString(e); }
+    }
+    cudaFree(bi.base); cudaFree(g4); cudaFree(raw); cudaFree(g4o); cudaFree(scr); cudaFree(dwb);
+    return rc;
+}
+
+int64_t sr4d_launch_count(const sr4d_t* h) { return h ? h->launches : 0; }
+void sr4d_reset_launch_count(sr4d_t* h) { if (h) h->launches = 0; }
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+// Internal (C++) launch interface between the engine and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+struct Conv64Args {
+    // input: split-fp16 Act planes (in_hi/in_lo) or fp32 (in_f32); buffer edge = Do + 2
+    const __half* in_hi = nullptr;
+    const __half* in_lo = nullptr;
+    const float* in_f32 = nullptr;
+    int B = 0;
+    int Do = 0;                 // edge of the OUTPUT grid; in[idx + tap] feeds out[idx], tap in {0,1,2}^3
+    const float* w = nullptr;   // Keras layout [27][64 ci][64 co], fp32
+    int dgrad = 0;              // 1: use W'[tap][co][ci] = W[26-tap][ci][co]
+    // output A: Act planes with interior edge Do (storage Do+2), optional replicate halo
+    __half* out_hi = nullptr;
+    __half* out_lo = nullptr;
+    int halo = 1;
+    const float* bias = nullptr;
+    const __half* res_hi = nullptr;
+    const __half* res_lo = nullptr;
+    float slope = 1.f;
+    // output B: raw fp32 [B][Do^3][64]
+    float* out_raw = nullptr;
+};
+
+struct UpsampleTables {   // device arrays of length r*D (forward) and D (backward ranges)
+    const int* lo;
+    const int* hi;
+    const float* lerp;
+    const int* ibeg;      // for LR index j: HR indices [ibeg[j], iend[j]) may touch j
+    const int* iend;
+};
+
+cudaError_t launch_conv64_simt(const Conv64Args& a, cudaStream_t s);
+
+// ---- forward small kernels (fwd_small.cu)
+cudaError_t launch_prep_features(const float* u, const float* v, const float* w, const float* um,
+                                 const float* vm, const float* wm, float* feat, int B, int P, cudaStream_t s);
+// feat [B][P^3][6] = (u,v,w,pcmr,mag,speed); ch0 selects the 3-channel group (0: phase, 3: pc)
+cudaError_t launch_stem_conv(const float* feat, int ch0, const float* w, const float* bias, ActView out,
+                             cudaStream_t s);
+cudaError_t launch_conv1x1_cat(ActView a, ActView b, const float* w, const float* bias, ActView out, cudaStream_t s);
+cudaError_t launch_upsample(ActView in, ActView out, int r, UpsampleTables t, cudaStream_t s);
+// three 64->1 heads: in[c] -> out[b][voxel][c]
+cudaError_t launch_head_out(ActView h0, ActView h1, ActView h2, const float* w0, const float* w1,
+                            const float* w2, const float* b0, const float* b1, const float* b2, float* out,
+                            cudaStream_t s);
+// fp32 channels-last (B,D,D,D,64) <-> Act
+cudaError_t launch_pack_act(const float* x, ActView out, cudaStream_t s);
+cudaError_t launch_unpack_act(ActView in, float* y, cudaStream_t s);
+
+// ---- loss / optimizer (loss_adam.cu)
+cudaError_t launch_loss_stats(const float* pred, const float* hu, const float* hv, const float* hw,
+                              const float* mask, int B, int nvox, double* partial, int nblk, float* per_sample,
+                              float* norm, cudaStream_t s);
+cudaError_t launch_loss_grad(const float* pred, const float* hu, const float* hv, const float* hw,
+                             const float* mask, int B, int nvox, const float* norm, float* g, cudaStream_t s);
+cudaError_t launch_sumsq(const float* p, const unsigned char* kflag, int64_t n, double* partial, int nblk,
+                         float coeff, float* out, cudaStream_t s);
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, const unsigned char* kflag, int64_t n,
+                        float alpha, float beta1, float beta2, float eps, float l2_scale, cudaStream_t s);
+cudaError_t launch_stitch(const float* pred, int nx, int ny, int nz, int H, int crop, int VX, int VY, int VZ,
+                          float venc, int round_small, float* vol, cudaStream_t s);
+
+// ---- backward kernels (bwd.cu)
+// g (B,H^3,3) channel c -> raw [B][(H+2)^3][64] through the 64->1 kernel w[27][64]
+cudaError_t launch_head2_dgrad(const float* g, int c, const float* w, float* raw, int B, int H, cudaStream_t s);
+// dW[27][64] and db for the 64->1 conv: h Act (B,H), g channel c
+cudaError_t launch_head2_wgrad(ActView h, const float* g, int c, float* dw, float* db, float* scratch,
+                               cudaStream_t s);
+// out(G4 interior) = (fold(raw0+raw1+raw2) + add) * act'(saved)
+cudaError_t launch_fold_act(const float* raw0, const float* raw1, const float* raw2, const float* add_g4,
+                            const __half* saved_hi, const __half* saved_lo, float slope, float* out_g4, int B,
+                            int D, cudaStream_t s);
+// dW[27][64][64] (+= nothing; overwrite) from x Act and dy G4; scratch >= nchunk*27*64*64 floats
+cudaError_t launch_wgrad64_simt(ActView x, const float* dy_g4, float* dw, float* scratch, int nchunk,
+                                cudaStream_t s);
+cudaError_t launch_bias_grad(const float* dy_g4, int B, int D, float* db, float* scratch, cudaStream_t s);
+cudaError_t launch_upsample_bwd(const float* dhr_g4, ActView lr_saved, float slope, float* dlr_g4, int B, int D,
+                                int r, UpsampleTables t, cudaStream_t s);
+// 1x1 conv backward: dy G4 (B,D) ; a,b saved inputs (phase, pc); outputs: da,db G4 interiors already
+// multiplied by relu'(a), relu'(b); dw[128][64], dbias[64]
+cudaError_t launch_conv1x1_bwd(const float* dy_g4, ActView a, ActView b, const float* w, float* da_g4,
+                               float* db_g4, float* dw, float* dbias, float* scratch, cudaStream_t s);
+// stem 3->64 weight gradient: feat [B][P^3][6] group ch0, dy G4 -> dw[27][3][64], db[64]
+cudaError_t launch_stem_wgrad(const float* feat, int ch0, const float* dy_g4, int B, int P, float* dw,
+                              float* db, float* scratch, cudaStream_t s);
+cudaError_t launch_g4_from_dense(const float* dense, float* g4, int B, int D, cudaStream_t s);
+cudaError_t launch_dense_from_g4(const float* g4, float* dense, int B, int D, cudaStream_t s);

@@ -1,0 +1,77 @@
+"""Entry point mirroring the reference's src/predictor.py: `prepare_network` keeps the
+signature (patch_size, res_increase, low_resblock, hi_resblock) (predictor.py:11) and the
+`__main__` flow (predictor.py:31-116): load volume -> patchify -> batched predict -> stitch
+-> denormalise -> zero small values -> save."""
+import os
+import time
+
+import numpy as np
+
+from .Network.PatchGenerator import PatchGenerator
+from .Network.SR4DFlowNet import SR4DFlowModel
+
+
+def prepare_network(patch_size, res_increase, low_resblock, hi_resblock, max_batch=8, device=None):
+    return SR4DFlowModel(patch_size, res_increase, low_resblock, hi_resblock, max_batch=max_batch, training=False,
+                         device=device)
+
+
+def predict_volume(network, pgen, dataset, batch_size=8, round_small_values=True, gpu_stitch=True):
+    """Body of the reference's per-row loop (predictor.py:74-107).  Returns (3,X,Y,Z) fp32."""
+    velocities, magnitudes = pgen.patchify(dataset)
+    n = len(velocities[0])
+    eng = network.engine
+    H = eng.H
+    import torch
+    results = torch.empty((n, H, H, H, 3), device=eng.device, dtype=torch.float32)
+    for i in range(0, n, batch_size):
+        sl = slice(i, i + batch_size)
+        eng.forward([velocities[0][sl], velocities[1][sl], velocities[2][sl],
+                     magnitudes[0][sl], magnitudes[1][sl], magnitudes[2][sl]], out=results[sl])
+    venc = float(dataset.venc)
+    if gpu_stitch:
+        side_hr = (pgen.patch_size - pgen.effective_patch_size) // 2 * pgen.res_increase
+        vol = eng.stitch(results, (pgen.nr_x, pgen.nr_y, pgen.nr_z), pgen.stitched_shape(), side_hr, venc,
+                         round_small_values)
+        return vol.cpu().numpy()
+    res = results.cpu().numpy()
+    out = []
+    for c in range(3):
+        v = pgen._patchup_with_overlap(res[..., c], pgen.nr_x, pgen.nr_y, pgen.nr_z) * np.float32(venc)
+        if round_small_values:
+            v[np.abs(v) < dataset.velocity_per_px] = 0
+        out.append(v)
+    return np.stack(out)
+
+
+def main(data_dir="../data", filename="example_data.h5", output_dir="../result", output_filename="example_result.h5",
+         model_path="../models/4DFlowNet/4DFlowNet.h5", patch_size=24, res_increase=2, batch_size=8,
+         round_small_values=True, low_resblock=8, hi_resblock=4):
+    from .utils.ImageDataset import ImageDataset
+    from .utils import prediction_utils
+    input_filepath = f"{data_dir}/{filename}"
+    pgen = PatchGenerator(patch_size, res_increase)
+    dataset = ImageDataset()
+    nr_rows = dataset.get_dataset_len(input_filepath)
+    print(f"Number of rows in dataset: {nr_rows}")
+    print(f"Loading 4DFlowNet: {res_increase}x upsample")
+    network = prepare_network(patch_size, res_increase, low_resblock, hi_resblock, max_batch=batch_size)
+    network.load_weights(model_path)
+    os.makedirs(output_dir, exist_ok=True)
+    for nrow in range(nr_rows):
+        print(f"\nProcessed ({nrow + 1}/{nr_rows}) - {time.ctime()}")
+        dataset.load_vectorfield(input_filepath, nrow)
+        t0 = time.time()
+        vol = predict_volume(network, pgen, dataset, batch_size, round_small_values)
+        print(f"Predicted {vol.shape[1:]} in {time.time() - t0:.2f} secs.")
+        for i in range(3):
+            prediction_utils.save_to_h5(f"{output_dir}/{output_filename}", dataset.velocity_colnames[i],
+                                        vol[i][None], compression="gzip")
+        if dataset.dx is not None:
+            prediction_utils.save_to_h5(f"{output_dir}/{output_filename}", dataset.dx_colname,
+                                        np.expand_dims(dataset.dx / res_increase, 0), compression="gzip")
+    print("Done!")
+
+
+if __name__ == "__main__":
+    main()
