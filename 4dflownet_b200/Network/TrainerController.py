@@ -1,0 +1,327 @@
+"""Drop-in mirror of the reference's Network/TrainerController.py.
+
+Same constructor signature (TrainerController.py:18), same public methods
+(`init_model_dir` :158, `train_step` :210, `test_step` :228, `train_network` :263,
+`save_best_model` :347, `restore_model` :365, `quicksave` :415) and the same nine running
+metrics (:52-63).  What changed is underneath: the Keras graph, `tf.GradientTape` and the
+Keras Adam are one libsr4d engine (forward + loss/metric + backward kernels, one fused Adam
+kernel over the flat parameter buffer), and when `torch.distributed` is initialised the
+batch shard's summed gradients are all-reduced (SUM) once per step on the flat buffer
+before Adam — the data-parallel scheme of the north star.
+
+Step semantics reproduced exactly (TrainerController.py:209-257):
+  loss vector (B,) = fluid + non-fluid masked SSE  (+ l2 scalar broadcast onto each entry)
+  gradients       = d/dw  sum_b loss_b            (sum, not mean; hence B_global * d(l2)/dw)
+  metrics         = running means over every sample seen in the epoch.
+"""
+import datetime
+import os
+import pickle
+import shutil
+import time
+
+import numpy as np
+import torch
+
+from .SR4DFlowNet import SR4DFlowModel
+from . import utility
+
+L2_COEFF = 5e-7    # SR4DFlowNet.py:99 kernel_regularizer=l2(5e-7)
+
+
+class Mean:
+    """tf.keras.metrics.Mean: running mean over all values passed to update_state."""
+
+    def __init__(self, name=None):
+        self.name = name
+        self.total, self.count = 0.0, 0
+
+    def update_state(self, values):
+        v = np.asarray(values, dtype=np.float64).reshape(-1)
+        self.total += float(v.sum())
+        self.count += v.size
+
+    def result(self):
+        return self.total / self.count if self.count else 0.0
+
+    def reset_states(self):
+        self.total, self.count = 0.0, 0
+
+
+class _LearningRate:
+    def __init__(self, v):
+        self.v = float(v)
+
+    def numpy(self):
+        return self.v
+
+    def assign(self, v):
+        self.v = float(v)
+
+    def __float__(self):
+        return self.v
+
+
+class AdamOptimizer:
+    """The slice of tf.keras.optimizers.Adam the reference touches (TrainerController.py:73,
+    225,269,359,391): `lr`, `iterations`, `weights` = [iterations, m_0..m_n, v_0..v_n],
+    `set_weights`, and an apply step.  State lives in the engine's flat m / v buffers."""
+
+    def __init__(self, engine, lr=1e-4, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.engine = engine
+        self.lr = _LearningRate(lr)
+        self.beta_1, self.beta_2, self.epsilon = beta_1, beta_2, epsilon
+        self.iterations = 0
+
+    @property
+    def learning_rate(self):
+        return self.lr
+
+    @property
+    def weights(self):
+        m = [v.detach().cpu().numpy().copy() for _, v in self.engine.tensor_views(self.engine.adam_m)]
+        v = [v.detach().cpu().numpy().copy() for _, v in self.engine.tensor_views(self.engine.adam_v)]
+        return [np.int64(self.iterations)] + m + v
+
+    def get_weights(self):
+        return self.weights
+
+    def set_weights(self, weights):
+        n = len(self.engine.table)
+        if len(weights) != 1 + 2 * n:
+            raise ValueError(f"expected {1 + 2 * n} optimizer tensors, got {len(weights)}")
+        self.iterations = int(weights[0])
+        for (_, view), w in zip(self.engine.tensor_views(self.engine.adam_m), weights[1:1 + n]):
+            view.copy_(torch.as_tensor(np.asarray(w, dtype=np.float32)))
+        for (_, view), w in zip(self.engine.tensor_views(self.engine.adam_v), weights[1 + n:]):
+            view.copy_(torch.as_tensor(np.asarray(w, dtype=np.float32)))
+
+    def apply(self, global_batch):
+        """apply_gradients on the engine's gradient buffer (TrainerController.py:225)."""
+        self.iterations += 1
+        self.engine.adam_step(float(self.lr), self.iterations, global_batch * 2.0 * L2_COEFF,
+                              self.beta_1, self.beta_2, self.epsilon)
+
+
+def _squeeze_last(a):
+    return a[..., 0] if a.shape[-1] == 1 and a.ndim == 5 else a
+
+
+class TrainerController:
+    def __init__(self, patch_size, res_increase, initial_learning_rate=1e-4, quicksave_enable=True,
+                 network_name='4DFlowNet', low_resblock=8, hi_resblock=4, max_batch=8, device=None, seed=None):
+        self.div_weight = 0          # divergence loss is disabled in the reference (:23,:121)
+        self.non_fluid_weight = 1
+        self.res_increase = res_increase
+        self.patch_size = patch_size
+        self.QUICKSAVE_ENABLED = quicksave_enable
+        self.network_name = network_name
+
+        self.model = SR4DFlowModel(patch_size, res_increase, low_resblock, hi_resblock, max_batch=max_batch,
+                                   training=True, device=device, seed=seed)
+        self.engine = self.model.engine
+
+        self.loss_metrics = dict((k, Mean(name=k)) for k in (
+            'train_loss', 'val_loss', 'train_accuracy', 'val_accuracy', 'train_mse', 'val_mse',
+            'train_div', 'val_div', 'l2_reg_loss'))
+        self.accuracy_metric = 'val_loss'
+        print(f"Divergence loss2 * {self.div_weight}")
+        print(f"Accuracy metric: {self.accuracy_metric}")
+
+        self.learning_rate = initial_learning_rate
+        self.optimizer = AdamOptimizer(self.engine, lr=self.learning_rate)
+        self._last = None    # device tensors of the most recent step (per_sample, l2)
+
+    # ---- distributed helpers ---------------------------------------------------------------
+    @staticmethod
+    def _world():
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            return torch.distributed.get_world_size()
+        return 1
+
+    # ---- loss / metric entry points with the reference's names -------------------------------
+    def loss_function(self, y_true, y_pred, mask):
+        """(total_loss[B], mse[B], 0) — TrainerController.py:84-127."""
+        per = self.engine.loss_metrics(y_pred, y_true[..., 0], y_true[..., 1], y_true[..., 2], mask)
+        per = per.cpu().numpy()
+        return per[:, 0], per[:, 1], 0
+
+    def accuracy_function(self, y_true, y_pred, mask):
+        """relative speed error in % per sample — TrainerController.py:143-150."""
+        per = self.engine.loss_metrics(y_pred, y_true[..., 0], y_true[..., 1], y_true[..., 2], mask)
+        return per[:, 2].cpu().numpy()
+
+    def calculate_regularizer_loss(self):
+        """5e-7 * sum over the conv kernels of sum(w^2) — TrainerController.py:129-141."""
+        tot = 0.0
+        for (name, view) in self.engine.tensor_views():
+            if name.endswith("kernel"):
+                tot += float((view.double() ** 2).sum())
+        return L2_COEFF * tot
+
+    # ---- steps --------------------------------------------------------------------------------
+    def train_step_async(self, data_pairs):
+        """Enqueue forward + loss + backward (+ all-reduce) + Adam; returns device tensors
+        (per_sample (B,4), l2 (1,)) without synchronising."""
+        u, v, w, u_mag, v_mag, w_mag, u_hr, v_hr, w_hr, venc, mask = data_pairs
+        per, l2, _ = self.engine.train_fwd_bwd([u, v, w, u_mag, v_mag, w_mag],
+                                                [_squeeze_last(a) for a in (u_hr, v_hr, w_hr)], mask)
+        world = self._world()
+        B = per.shape[0]
+        if world > 1:
+            torch.distributed.all_reduce(self.engine.grads, op=torch.distributed.ReduceOp.SUM)
+        self.optimizer.apply(B * world)
+        self._last = (per, l2)
+        return per, l2
+
+    def train_step(self, data_pairs):
+        per, l2 = self.train_step_async(data_pairs)
+        self._update_metrics(per.cpu().numpy(), float(l2.item()), 'train')
+
+    def test_step(self, data_pairs):
+        u, v, w, u_mag, v_mag, w_mag, u_hr, v_hr, w_hr, venc, mask = data_pairs
+        predictions = self.model([u, v, w, u_mag, v_mag, w_mag], training=False)
+        per = self.engine.loss_metrics(predictions, *[_squeeze_last(a) for a in (u_hr, v_hr, w_hr)], mask)
+        self._update_metrics(per.cpu().numpy(), None, 'val')
+        return predictions
+
+    def _update_metrics(self, per, l2, metric_set):
+        """calculate_and_update_metrics (:241-257): l2 is added to every entry of the loss
+        vector for the train set only."""
+        loss = per[:, 0].astype(np.float64)
+        if metric_set == 'train':
+            self.loss_metrics['l2_reg_loss'].update_state(l2)
+            loss = loss + l2
+        self.loss_metrics[f'{metric_set}_loss'].update_state(loss)
+        self.loss_metrics[f'{metric_set}_mse'].update_state(per[:, 1])
+        self.loss_metrics[f'{metric_set}_div'].update_state(0.0)
+        self.loss_metrics[f'{metric_set}_accuracy'].update_state(per[:, 2])
+        return loss
+
+    def reset_metrics(self):
+        for m in self.loss_metrics.values():
+            m.reset_states()
+
+    # ---- model directory, logging ---------------------------------------------------------------
+    def init_model_dir(self, root="../models"):
+        timestamp = datetime.datetime.now().strftime("%Y%m%d-%H%M")
+        self.unique_model_name = f'{self.network_name}_{timestamp}'
+        self.model_dir = f"{root}/{self.unique_model_name}"
+        self.model_path = f"{self.model_dir}/{self.network_name}"
+        os.makedirs(self.model_dir, exist_ok=True)
+        self._prepare_logfile_and_summary()
+
+    def _prepare_logfile_and_summary(self):
+        self.train_writer = self.val_writer = None
+        try:    # TensorBoard scalars when the writer is available (tensorboard package)
+            from torch.utils.tensorboard import SummaryWriter
+            self.train_writer = SummaryWriter(self.model_dir + '/tensorboard/train')
+            self.val_writer = SummaryWriter(self.model_dir + '/tensorboard/validate')
+        except Exception:
+            pass
+        self.logfile = self.model_dir + '/loss.csv'
+        utility.log_to_file(self.logfile, f'Network: {self.network_name}\n')
+        utility.log_to_file(self.logfile, f'Initial learning rate: {self.learning_rate}\n')
+        utility.log_to_file(self.logfile, f'Accuracy metric: {self.accuracy_metric}\n')
+        utility.log_to_file(self.logfile, f'Divergence weight: {self.div_weight}\n')
+        stat_names = ','.join(self.loss_metrics.keys())
+        utility.log_to_file(self.logfile, f'epoch, {stat_names}, learning rate, elapsed (sec), best_model, '
+                                          'benchmark_err, benchmark_rel_err, benchmark_mse, benchmark_divloss\n')
+
+    def _update_summary_logging(self, epoch):
+        if self.train_writer is None:
+            return
+        self.train_writer.add_scalar(f"{self.network_name}/learning_rate", float(self.optimizer.lr), epoch)
+        for k, m in self.loss_metrics.items():
+            if k.startswith('train_'):
+                self.train_writer.add_scalar(f"{self.network_name}/{k[6:]}", m.result(), epoch)
+            elif k.startswith('val_'):
+                self.val_writer.add_scalar(f"{self.network_name}/{k[4:]}", m.result(), epoch)
+
+    # ---- main loop (TrainerController.py:263-343) -------------------------------------------------
+    def train_network(self, trainset, valset, n_epoch, testset=None):
+        print("==================== TRAINING =================")
+        print(f'Learning rate {self.optimizer.lr.numpy():.7f}')
+        print(f"Start training at {time.ctime()} - {self.unique_model_name}\n")
+        start_time = time.time()
+        previous_loss = np.inf
+        total_batch_train = len(trainset) if hasattr(trainset, "__len__") else -1
+        total_batch_val = len(valset) if hasattr(valset, "__len__") else -1
+        for epoch in range(n_epoch):
+            self.reset_metrics()
+            start_loop = time.time()
+            for i, data_pairs in enumerate(trainset):
+                self.train_step(data_pairs)
+                print(f"\rEpoch {epoch+1} Train batch {i+1}/{total_batch_train} | loss: "
+                      f"{self.loss_metrics['train_loss'].result():.5f} ({self.loss_metrics['train_accuracy'].result():.1f} %)"
+                      f" - {time.time()-start_loop:.1f} secs", end='')
+            for i, data_pairs in enumerate(valset):
+                self.test_step(data_pairs)
+                print(f"\rEpoch {epoch+1} Validation batch {i+1}/{total_batch_val} | loss: "
+                      f"{self.loss_metrics['val_loss'].result():.5f} ({self.loss_metrics['val_accuracy'].result():.1f} %)"
+                      f" - {time.time()-start_loop:.1f} secs", end='')
+            message = (f"\rEpoch {epoch+1} Train loss: {self.loss_metrics['train_loss'].result():.5f} "
+                       f"({self.loss_metrics['train_accuracy'].result():.1f} %), Val loss: "
+                       f"{self.loss_metrics['val_loss'].result():.5f} ({self.loss_metrics['val_accuracy'].result():.1f} %)"
+                       f" - {time.time()-start_loop:.1f} secs")
+            loss_str = ','.join(f'{m.result():.5f}' for m in self.loss_metrics.values())
+            log_line = f"{epoch+1},{loss_str},{self.optimizer.lr.numpy():.6f},{time.time()-start_loop:.1f}"
+            self._update_summary_logging(epoch)
+            if self.loss_metrics[self.accuracy_metric].result() < previous_loss:
+                self.save_best_model()
+                previous_loss = self.loss_metrics[self.accuracy_metric].result()
+                message += ' **'
+                log_line += ',**'
+                if self.QUICKSAVE_ENABLED and testset is not None:
+                    q = [float(np.mean(x)) for x in self.quicksave(testset, epoch + 1)]
+                    message += f' Benchmark loss: {q[0]:.5f} ({q[1]:.1f} %)'
+                    log_line += f', {q[0]:.7f}, {q[1]:.2f}%, {q[2]:.7f}, {q[3]:.7f}'
+            print(message)
+            utility.log_to_file(self.logfile, log_line + "\n")
+        hrs, mins, secs = utility.calculate_time_elapsed(start_time)
+        message = (f"\nTraining {self.network_name} completed! - name: {self.unique_model_name}"
+                   f"\nTotal training time: {hrs} hrs {mins} mins {secs} secs."
+                   f"\nFinished at {time.ctime()}\n==================== END TRAINING =================")
+        utility.log_to_file(self.logfile, message)
+        print(message)
+
+    # ---- checkpoints (TrainerController.py:347-394) -------------------------------------------------
+    def save_latest_model(self, epoch):
+        if epoch > 0 and epoch % 10 == 0:
+            self.model.save(f'{self.model_path}-latest.h5')
+            print(f'Saving current model - {time.ctime()}\n')
+
+    def save_best_model(self):
+        self.model.save(f'{self.model_path}-best.h5')
+        with open(f'{self.model_dir}/optimizer.pkl', 'wb') as f:
+            pickle.dump(self.optimizer.weights, f)
+
+    def restore_model(self, old_model_dir, old_model_file):
+        with open(f"{old_model_dir}/optimizer.pkl", 'rb') as f:
+            opt_weights = pickle.load(f)
+        self.optimizer.set_weights(opt_weights)
+        self.model.load_weights(f"{old_model_dir}/{old_model_file}")
+
+    def quicksave(self, testset, epoch_nr):
+        """First batch of the benchmark set -> quicksave_<network_name>.h5 (:415-454)."""
+        from . import h5util
+        for data_pairs in testset:
+            u, v, w, u_mag, v_mag, w_mag, u_hr, v_hr, w_hr, venc, mask = data_pairs
+            preds_dev = self.model([u, v, w, u_mag, v_mag, w_mag])
+            per = self.engine.loss_metrics(preds_dev, *[_squeeze_last(a) for a in (u_hr, v_hr, w_hr)], mask)
+            per = per.cpu().numpy()
+            preds = preds_dev.cpu().numpy()
+            break
+        fn = f"quicksave_{self.network_name}.h5"
+        h5util.save_predictions(self.model_dir, fn, "epoch", np.asarray([epoch_nr]), compression='gzip')
+        p = np.expand_dims(preds, 0)
+        for i, c in enumerate("uvw"):
+            h5util.save_predictions(self.model_dir, fn, c, p[..., i], compression='gzip')
+        if epoch_nr == 1:
+            for name, a in (("lr_u", u), ("lr_v", v), ("lr_w", w)):
+                h5util.save_predictions(self.model_dir, fn, name, np.asarray(a), compression='gzip')
+            for name, a in (("hr_u", u_hr), ("hr_v", v_hr), ("hr_w", w_hr)):
+                h5util.save_predictions(self.model_dir, fn, name, np.squeeze(np.asarray(a), -1), compression='gzip')
+            h5util.save_predictions(self.model_dir, fn, "venc", np.asarray(venc), compression='gzip')
+            h5util.save_predictions(self.model_dir, fn, "mask", np.asarray(mask), compression='gzip')
+        return per[:, 0], per[:, 2], per[:, 1], np.zeros_like(per[:, 0])

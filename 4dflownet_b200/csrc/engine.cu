@@ -69,6 +69,11 @@ struct sr4d_handle {
     int save_acts = 0;
     bool have_fwd_state = false;
     int64_t launches = 0;
+    // per-kernel-class device timing (SR4D_OPT_PROFILE): event pairs on the launch stream
+    int profile = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::vector<int> ev_class;        // class of pair i (events 2i, 2i+1)
     std::string err;
 };
 
@@ -88,6 +93,23 @@ int fail(sr4d_t* h, int code, const std::string& msg) {
     if (h) h->err = msg;
     return code;
 }
+
+struct ProfScope {
+    sr4d_t* h; cudaStream_t s; bool on;
+    ProfScope(sr4d_t* h_, int cls, cudaStream_t s_) : h(h_), s(s_), on(h_->profile != 0) {
+        if (!on) return;
+        if (h->ev_used + 2 > h->ev_pool.size()) {
+            for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
+        }
+        h->ev_class.push_back(cls);
+        cudaEventRecord(h->ev_pool[h->ev_used], s);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(h->ev_pool[h->ev_used + 1], s);
+        h->ev_used += 2;
+    }
+};
 
 void build_table(sr4d_t* h) {
     const int C = 64;
@@ -268,6 +290,7 @@ int ensure_tc_weights(sr4d_t* h, cudaStream_t s) {
 
 // one 64->64 3x3x3 conv layer, Act -> Act
 int conv64_fwd(sr4d_t* h, int layer, ActView in, ActView out, const ActView* res, float slope, cudaStream_t s) {
+    ProfScope prof(h, in.D == h->P ? SR4D_PROF_CONV64_FWD_LR : SR4D_PROF_CONV64_FWD_HR, s);
     if (use_tc(h)) {
         TcConvArgs a;
         a.in = in; a.out = out; a.layer = layer; a.dgrad = 0;
@@ -339,6 +362,7 @@ int forward_impl(sr4d_t* h, const float* u, const float* v, const float* w, cons
 
 // dgrad of a 64->64 layer: dy (G4, edge D) -> raw (edge D+2)
 int conv64_dgrad(sr4d_t* h, int layer, const float* dy_g4, float* raw, int B, int D, cudaStream_t s) {
+    ProfScope prof(h, D == h->P ? SR4D_PROF_CONV64_DGRAD_LR : SR4D_PROF_CONV64_DGRAD_HR, s);
     Conv64Args a;
     a.in_f32 = dy_g4; a.B = B; a.Do = D + 2;
     a.w = W(h, layer); a.dgrad = 1;
@@ -347,6 +371,7 @@ int conv64_dgrad(sr4d_t* h, int layer, const float* dy_g4, float* raw, int B, in
     return SR4D_OK;
 }
 int conv64_wgrad(sr4d_t* h, int layer, ActView x, const float* dy_g4, bool bias, cudaStream_t s) {
+    ProfScope prof(h, x.D == h->P ? SR4D_PROF_CONV64_WGRAD_LR : SR4D_PROF_CONV64_WGRAD_HR, s);
     CK(h, launch_wgrad64_simt(x, dy_g4, GW(h, layer), h->scratch, h->wgrad_chunks, s), 2);
     if (bias) CK(h, launch_bias_grad(dy_g4, x.B, x.D, GB(h, layer), h->scratch, s), 2);
     return SR4D_OK;
@@ -478,6 +503,7 @@ void free_all(sr4d_t* h) {
     cudaFree(h->pred); cudaFree(h->gpred); cudaFree(h->scratch); cudaFree(h->dpartial); cudaFree(h->norm);
     cudaFree(h->per_sample_int);
     if (h->tcw) tc_free_weights(h->tcw);
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
 }
 
 }  // namespace
@@ -580,6 +606,11 @@ int sr4d_set_option(sr4d_t* h, int option, int value) {
         case SR4D_OPT_SAVE_ACTS:
             h->save_acts = value != 0;
             return SR4D_OK;
+        case SR4D_OPT_PROFILE:
+            h->profile = value != 0;
+            h->ev_used = 0;
+            h->ev_class.clear();
+            return SR4D_OK;
     }
     return fail(h, SR4D_EINVAL, "unknown option");
 }
@@ -587,6 +618,7 @@ int sr4d_get_option(const sr4d_t* h, int option, int* value) {
     if (!h || !value) return SR4D_EINVAL;
     if (option == SR4D_OPT_CONV_IMPL) { *value = h->conv_impl; return SR4D_OK; }
     if (option == SR4D_OPT_SAVE_ACTS) { *value = h->save_acts; return SR4D_OK; }
+    if (option == SR4D_OPT_PROFILE) { *value = h->profile; return SR4D_OK; }
     return SR4D_EINVAL;
 }
 
@@ -776,6 +808,24 @@ int sr4d_conv64_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const 
     }
     cudaFree(bi.base); cudaFree(g4); cudaFree(raw); cudaFree(g4o); cudaFree(scr); cudaFree(dwb);
     return rc;
+}
+
+int sr4d_profile_read(sr4d_t* h, double* ms, int64_t* launches, int nclasses) {
+    if (!h || !ms || !launches || nclasses < SR4D_PROF_NCLASSES) return fail(h, SR4D_EINVAL, "bad argument");
+    for (int i = 0; i < nclasses; ++i) { ms[i] = 0.0; launches[i] = 0; }
+    if (h->ev_used) {
+        cudaError_t e = cudaEventSynchronize(h->ev_pool[h->ev_used - 1]);
+        if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return SR4D_ECUDA; }
+    }
+    for (size_t i = 0; i < h->ev_class.size(); ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]) != cudaSuccess) continue;
+        ms[h->ev_class[i]] += t;
+        launches[h->ev_class[i]] += 1;
+    }
+    h->ev_used = 0;
+    h->ev_class.clear();
+    return SR4D_OK;
 }
 
 int64_t sr4d_launch_count(const sr4d_t* h) { return h ? h->launches : 0; }

@@ -88,6 +88,16 @@ class Engine:
     def set_option(self, opt, value):
         self._check(self.lib.sr4d_set_option(self._h, opt, value), "sr4d_set_option")
 
+    def profile(self, on=True):
+        self.set_option(_lib.OPT_PROFILE, int(bool(on)))
+
+    def profile_read(self):
+        """{class name: (device ms, launches)} since the last read (OPT_PROFILE must be on)."""
+        n = len(_lib.PROF_CLASSES)
+        ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+        self._check(self.lib.sr4d_profile_read(self._h, ms, cnt, n), "sr4d_profile_read")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(_lib.PROF_CLASSES)}
+
     def launch_count(self):
         return int(self.lib.sr4d_launch_count(self._h))
 

@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the patch-based SR hot path (BASELINE.json metric: 24^3->48^3 SR patches/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's B200 engine
+    python bench.py --impl reference --gpus N --steps K ...   # the reference graph on the host CPU
+
+Workload (BASELINE.json configs[1]): one trainer.py step -- forward + masked-MSE loss/metric +
+backward + Adam -- at patch_size=24, res_increase=2, 8 low / 4 hi resblocks, batch 8 PER GPU
+(weak scaling; N=8 is configs[3], global batch 64, one NCCL all-reduce of the flat gradient
+buffer per step).  A forward-only leg (the predictor.py path, same geometry) is timed in the
+same run and reported under "forward" because the metric also asks for the forward roofline.
+
+One JSON line on stdout (rank 0).  `value` = patches/s with the batch already resident in HBM;
+`e2e` = the same step through TrainerController.train_step from pinned HOST buffers, including
+the host->device copies of the 11-tuple and the device->host read of the per-sample metrics.
+The CPU oracle (oracle/) is used here only as the timed `cpu_baseline` / `--impl reference` arm.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+P, R, LOW, HI = 24, 2, 8, 4
+FLOPS_FWD_PER_PATCH = 328.83e9        # SURVEY 8d, sum over layers of 2*k^3*Ci*Co*D^3 (r=2)
+BYTES_FWD_PER_PATCH = 1037.4e6        # SURVEY 8d, layer-wise algorithmic HBM bytes at B=8
+FLOPS_CONV64 = {"lr": 2 * 27 * 64 * 64 * P ** 3, "hr": 2 * 27 * 64 * 64 * (P * R) ** 3}   # per patch per launch
+METRIC = "24^3->48^3 SR patches/sec"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            return {"hbm_gbs": float(d["hbm_gbs"]), "tflops_burst": float(d["bf16_tflops"]),
+                    "tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    "source": "measured (MEASURED_PEAKS.json)"}
+        except Exception:
+            pass
+    # B200_PROFILING.md fallback: 6.65 TB/s copy, 1.59 PF cuBLAS bf16 burst (~1.4 PF sustained)
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.thr = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thr = threading.Thread(target=lambda: self.rows.extend(self.proc.stdout), daemon=True)
+        self.thr.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thr.join(timeout=2)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w": statistics.median(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle's restatement of the reference graph on host cores
+# --------------------------------------------------------------------------------------------
+def cpu_train_steps(n_steps, warmup, batch=1):
+    """Times `n_steps` full train steps (fwd + loss + autograd bwd + Adam) of the torch-CPU fp32
+    restatement (oracle/sr4d_oracle.py) on all host cores, `batch` patches per step."""
+    import numpy as np
+    import torch
+    oracle = importlib.import_module("oracle.sr4d_oracle")
+    params = {k: torch.tensor(v, requires_grad=True) for k, v in oracle.glorot_params(LOW, HI, seed=1234).items()}
+    m = {k: np.zeros(v.shape, np.float32) for k, v in params.items()}
+    v2 = {k: np.zeros(v.shape, np.float32) for k, v in params.items()}
+    bt = [torch.tensor(np.asarray(b)) for b in oracle.synthetic_batch(batch, P, R, seed=0)]
+    times = []
+    for it in range(warmup + n_steps):
+        t0 = time.perf_counter()
+        for p in params.values():
+            p.grad = None
+        obj, _ = oracle.train_objective(params, bt, R, LOW, HI)
+        obj.backward()
+        with torch.no_grad():
+            for k, p in params.items():
+                pn, m[k], v2[k] = oracle.adam_step(p.numpy(), p.grad.numpy(), m[k], v2[k], it + 1, 1e-4)
+                p.copy_(torch.from_numpy(np.asarray(pn, dtype=np.float32)))
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times, cores = cpu_train_steps(args.steps, args.warmup, batch=1)
+    total = sum(times)
+    val = len(times) * 1 / total
+    sample = "1 patch per step (full train step: fwd+loss+bwd+Adam) of the same P=24,r=2,8/4 network"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "patches/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, 1),
+        "cpu_baseline": {"value": val, "unit": "patches/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "TensorFlow is not installable here; torch-CPU (oneDNN) restatement of the "
+                                 "reference graph stands in for the TF-CPU path"},
+        "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, batch_per_gpu):
+    return {"workload": "configs[1]: trainer.py single step (forward + masked-MSE loss/metric + backward + Adam), "
+                        "patch_size=24, res_increase=2, 8 low / 4 hi resblocks, fp32",
+            "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * n_gpus, "parallelism": f"dp{n_gpus}",
+            "l2": "no explicit flush: one step streams ~3.3 GB of saved activations per GPU (>> 126 MB L2)"}
+
+
+# --------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = importlib.import_module("4dflownet_b200")
+    tcm = importlib.import_module("4dflownet_b200.Network.TrainerController")
+    oracle_data = importlib.import_module("oracle.sr4d_oracle").synthetic_batch   # data generator only
+    B, K, W = args.batch, args.steps, args.warmup
+    dev = torch.device("cuda", local)
+
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        ctl = tcm.TrainerController(P, R, 1e-4, False, "4DFlowNet", LOW, HI, max_batch=B, device=local, seed=1234)
+    eng = ctl.engine
+    host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in oracle_data(B, P, R, seed=rank)]
+    devb = [h.to(dev) for h in host]
+    h2d = sum(h.numel() * 4 for i, h in enumerate(host) if i != 9)     # venc is not an input of the step
+    per_host = torch.empty((B, 4), dtype=torch.float32).pin_memory()
+    l2_host = torch.empty((1,), dtype=torch.float32).pin_memory()
+    d2h = per_host.numel() * 4 + 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_dev():
+        ctl.train_step_async(devb)
+
+    def step_e2e():
+        db = [h.to(dev, non_blocking=True) for h in host]
+        per, l2 = ctl.train_step_async(db)
+        per_host.copy_(per, non_blocking=True)
+        l2_host.copy_(l2, non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the caller reads the metrics every step
+        ctl._update_metrics(per_host.numpy(), float(l2_host[0]), 'train')
+
+    # ---- headline: device-resident train step --------------------------------------------------
+    clocks = ClockSampler(local)
+    eng.reset_launch_count()
+    for _ in range(W):
+        step_dev()
+    barrier()
+    eng.reset_launch_count()
+    clocks.start()
+    ms_total = timed(step_dev, K, 0)
+    clk = clocks.stop()
+    launches = eng.launch_count()
+    ms_step = ms_total / K
+    value = B * world / (ms_step * 1e-3)
+
+    # ---- e2e from pinned host buffers -------------------------------------------------------------
+    ms_e2e = timed(step_e2e, K, max(1, W // 2)) / K
+    e2e_val = B * world / (ms_e2e * 1e-3)
+
+    # ---- per-kernel-class device time (CUDA events on the launch stream), same steps -------------
+    eng.profile(True)
+    for _ in range(K):
+        step_dev()
+    prof = eng.profile_read()
+    eng.profile(False)
+    prof_step = {k: (ms / K, n // K) for k, (ms, n) in prof.items()}
+
+    # ---- forward-only leg (predictor path), device resident + e2e through model.predict ----------
+    out = torch.empty((B, P * R, P * R, P * R, 3), device=dev)
+
+    def fwd_dev():
+        eng.forward(devb[:6], out=out)
+    ms_fwd = timed(fwd_dev, K, W) / K
+    eng.profile(True)
+    for _ in range(K):
+        fwd_dev()
+    fprof = eng.profile_read()
+    eng.profile(False)
+    host_np = [h.numpy() for h in host[:6]]
+
+    def fwd_e2e():
+        ctl.model.predict(host_np, batch_size=B)
+    ms_fwd_e2e = timed(fwd_e2e, max(1, K // 2), 1) / max(1, K // 2)
+
+    peaks = measured_peaks()
+    if rank == 0:
+        # dominant kernel class of the train step
+        dom = max(prof_step, key=lambda k: prof_step[k][0])
+        dom_ms, dom_n = prof_step[dom]
+        grid = "hr" if dom.endswith("hr") else "lr"
+        flops_launch = FLOPS_CONV64[grid] * B
+        ach = flops_launch / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12 if dom_n else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as f:
+                    traffic = json.load(f).get(dom)
+            except Exception:
+                traffic = None
+        peak = peaks["tflops_sustained"]
+        f_hr_ms, f_hr_n = fprof["conv64_fwd_hr"]
+        f_lr_ms, f_lr_n = fprof["conv64_fwd_lr"]
+        fwd = {
+            "value": B * world / (ms_fwd * 1e-3), "unit": "patches/s", "ms_per_step": ms_fwd,
+            "e2e": {"value": B * world / (ms_fwd_e2e * 1e-3), "unit": "patches/s",
+                    "h2d_bytes_per_step": 6 * B * P ** 3 * 4, "d2h_bytes_per_step": B * (P * R) ** 3 * 3 * 4},
+            "hbm_gbs_algorithmic": BYTES_FWD_PER_PATCH * B / (ms_fwd * 1e-3) / 1e9,
+            "hbm_frac": BYTES_FWD_PER_PATCH * B / (ms_fwd * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "tflops_fp32_equiv": FLOPS_FWD_PER_PATCH * B / (ms_fwd * 1e-3) / 1e12,
+            "conv64_fwd_hr": {"ms_per_launch": f_hr_ms / max(f_hr_n, 1), "launches_per_step": f_hr_n // K,
+                              "tflops_fp32_equiv": FLOPS_CONV64["hr"] * B / (f_hr_ms / max(f_hr_n, 1) * 1e-3) / 1e12
+                              if f_hr_n else None},
+            "conv64_share_of_step": (f_hr_ms + f_lr_ms) / K / ms_fwd,
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world, B),
+            "clocks": clk,
+            "e2e": {"value": e2e_val, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                         "frac": ach / peak, "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16",
+                         "ms_per_launch": dom_ms / max(dom_n, 1), "launches_per_step": dom_n,
+                         "share_of_step": dom_ms / ms_step,
+                         "note": "achieved = algorithmic fp32 FLOPs (2*27*64*64*B*D^3) / event time; the "
+                                 "split-fp16 tensor-core path executes 4 fp16 MMA products per fp32 MAC"},
+            "kernel_classes_ms_per_step": {k: round(v[0], 4) for k, v in prof_step.items()},
+            "forward": fwd,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            times, cores = cpu_train_steps(2, 1, batch=1)
+            line["cpu_baseline"] = {"value": len(times) / sum(times), "unit": "patches/s", "cores": cores,
+                                    "kind": "port", "sample": "2 timed train steps of 1 patch (after 1 warm-up) on the "
+                                    "torch-CPU restatement of the reference graph (TF not installable)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8, help="patches per GPU per step (configs[1]: 8)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,18 @@ extern "C" {
 #define SR4D_CONV_SIMT       1   /* fp32 CUDA-core kernels everywhere (correctness anchor) */
 #define SR4D_CONV_TCGEN05    2   /* force the tcgen05 split-fp16 kernel for every 64->64 conv */
 #define SR4D_OPT_SAVE_ACTS   2   /* 1: forward keeps every activation (needed before backward) */
+#define SR4D_OPT_PROFILE     3   /* 1: bracket every 64->64 conv launch with CUDA events on its stream */
+
+/* kernel classes timed under SR4D_OPT_PROFILE (index into sr4d_profile_read's arrays):
+ * the 64->64 3x3x3 convolution forward / input-gradient / weight-gradient, on the LR
+ * (patch_size^3) and HR ((patch_size*res_increase)^3) grids */
+#define SR4D_PROF_CONV64_FWD_LR    0
+#define SR4D_PROF_CONV64_FWD_HR    1
+#define SR4D_PROF_CONV64_DGRAD_LR  2
+#define SR4D_PROF_CONV64_DGRAD_HR  3
+#define SR4D_PROF_CONV64_WGRAD_LR  4
+#define SR4D_PROF_CONV64_WGRAD_HR  5
+#define SR4D_PROF_NCLASSES         6
 
 typedef struct sr4d_handle sr4d_t;
 
@@ -141,6 +153,10 @@ int  sr4d_upsample_layer(sr4d_t* h, const float* x, float* y, int B, int D, int 
 int  sr4d_conv64_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const float* dy,
                            float* dx, float* dkernel, float* dbias, int B, int D, int impl,
                            void* stream);
+
+/* device time (ms, CUDA events on the launch stream) and launch count per kernel class since
+ * the last read; synchronises with the last recorded event.  Used by bench.py's roofline. */
+int  sr4d_profile_read(sr4d_t* h, double* ms, int64_t* launches, int nclasses);
 
 /* counters for bench.py: number of kernels this library launched since the last reset */
 int64_t sr4d_launch_count(const sr4d_t* h);

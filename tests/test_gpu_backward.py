@@ -60,6 +60,10 @@ def test_train_step_gradients_vs_oracle(pkg, oracle, P, r, low, hi, B):
     eng.set_weights(params)
     per, l2, pred = eng.train_fwd_bwd(batch[:6], [b[..., 0] for b in batch[6:9]], batch[10], want_pred=True)
     gref, met = oracle.gradients({k: v.astype(np.float64) for k, v in params.items()}, batch, r, low, hi)
+    # fp32 autograd of the same graph (what the reference's TF fp32 path amounts to): its distance from
+    # the fp64 truth calibrates the gradient tolerance -- through this depth fp32 itself is off by up to
+    # ~5e-4 on the stem kernels (tools/diag_grads.py), so the bar is max(1e-4, 2x the fp32 error).
+    g32, _ = oracle.gradients(params, batch, r, low, hi, dtype=torch.float32)
     l2c = oracle.L2_COEFF
     assert abs(float(l2) - float(met["l2"])) <= 1e-5 * float(met["l2"])
     np.testing.assert_allclose(per[:, 0].cpu().numpy() + float(l2), met["loss"], rtol=1e-4)
@@ -68,7 +72,8 @@ def test_train_step_gradients_vs_oracle(pkg, oracle, P, r, low, hi, B):
     for name, view in eng.tensor_views(eng.grads):
         got = view.cpu().numpy()
         want = gref[name] - (B * 2 * l2c * params[name] if name.endswith("kernel") else 0.0)
-        assert rel_l2(got, want) < 1e-4, (name, rel_l2(got, want))
+        tol = max(1e-4, 2.0 * rel_l2(g32[name], gref[name]))
+        assert rel_l2(got, want) < tol, (name, rel_l2(got, want), tol)
     # one Adam step (Keras semantics, L2 gradient folded in) vs the oracle's numpy Adam
     lr = 1e-3
     before = dict(zip([n for n, *_ in eng.table], eng.get_weights()))
