@@ -1,30 +1,32 @@
 // tcgen05 (5th-gen tensor core) 64->64 3x3x3 convolution for sm_100a, split-fp16 "fp32-accurate".
 //
 // Reference op: conv3d() of Network/SR4DFlowNet.py:93-108 / resnet_block :111-120 (30 of the
-// 36 layers, 99.5 % of the FLOPs).
+// 36 layers, 99.5 % of the FLOPs); with the dgrad weight image the same kernel evaluates
+// Conv3DBackpropInput on the padded grid.
 //
-// Formulation (implicit GEMM, transposed so the voxel dimension is the flexible MMA N):
-//     D[128 x N] += A_tap[128 x 64] * B_tap[N x 64]^T        for the 27 taps
+// Formulation (implicit GEMM, weights as the M operand so the voxel dimension is the flexible N):
+//     D[128 x N] += A_tap[128 x 64] * B_tap[N x 64]^T        for the 27 taps, K = 64 channels
 //   A_tap rows  = the layer's weights for that tap, split in fp16: W = Whi + Wlo/2048.
 //                 Row 32q+l holds Whi[co=16q+l] for l<16 and Wlo[co=16q+l-16] for l>=16, so
 //                 the hi and lo partial sums of one output channel sit in lanes l and l^16 of
 //                 the same epilogue warp (one shuffle combines them).
-//   B_tap rows  = N = TY*TZ voxels of one (y,z) tile at a fixed x: their 64 input channels,
-//                 taken from the activation's fp16 hi plane (accumulator D1) and lo plane (D2).
+//   B_tap rows  = the N = 8*TY voxels of a (TY y-lines x 8 z) tile at a fixed x: their 64 input
+//                 channels, from the activation's fp16 hi plane (accumulator D1) and lo plane (D2).
 //   out[co][v]  = D1[hi] + (D1[lo] + D2[hi]) / 2048 + D2[lo] / 2048^2     (fp32 in TMEM)
 //
-// Data movement: one TMA box per (dx,dz) loads the (TY+2) x TZ x 64ch plane (hi and lo) into
-// shared memory in the canonical K-major SWIZZLE_128B layout; the three dy taps are then
-// 1024B-aligned row offsets into that plane, so every activation byte is fetched 9x (not 27x)
-// from L2.  Weights stream per tap as pre-swizzled 16 KB images (cp.async.bulk).
-// Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue
-// (TMEM -> registers -> bias / residual / activation / fp16 split -> global, replicate halo).
+// Data movement: ONE TMA box per dx loads the (TY+2) x 10 voxel halo plane (hi and lo) into
+// shared memory as dense 128-byte rows (SWIZZLE_128B).  All nine (dy,dz) taps of that plane are
+// then plain descriptor start-address shifts of (dy*10+dz) rows with an 8-row-group stride of
+// 1280 B: the tensor core applies the 128B swizzle on absolute shared-memory address bits, so
+// shifted starts and a non-1024 group stride read the TMA-written rows correctly (verified on
+// B200 by tools/probe/mma_probe.cu).  Every activation byte is fetched 3x from L2 per layer
+// (plus y/z halo), weights stream per tap as pre-swizzled 16 KB images (cp.async.bulk).
+// Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue:
+// TMEM -> registers -> (hi/lo row combine, bias) -> fp32 shared-memory transpose -> coalesced
+// 16-byte residual loads / activation / fp16 split / stores with the replicate halo.
 #include <cuda.h>
 
 #include <cstdio>
-#include <map>
-#include <mutex>
-#include <tuple>
 #include <vector>
 
 #include "conv_tc.h"
@@ -34,46 +36,59 @@ namespace {
 
 constexpr int W_TAP_BYTES = 128 * 64 * 2;   // 16 KB: [Whi;Wlo] x 64 ci, fp16, swizzled
 constexpr int NUM_THREADS = 192;
+constexpr int TZ = 8;                       // voxels per 8-row group (one z run)
+constexpr int ZP = TZ + 2;                  // plane row pitch in voxels
+constexpr int STAGE_FLOATS = 64 * 64;       // epilogue transpose buffer: 64 voxels x 64 channels
 
-template <int TY, int TZ>
+template <int TY>
 struct Cfg {
-    static constexpr int N = TY * TZ;                       // voxels per tile = MMA N
-    static constexpr int ROWS = (TY + 2) * TZ;              // rows of one staged plane
-    static constexpr int PLANE_BYTES = ROWS * 128;          // one of hi / lo
-    static constexpr int XSTAGE_BYTES = 2 * PLANE_BYTES;
+    static constexpr int N = TY * TZ;                                  // voxels per tile = MMA N
+    static constexpr int ROWS = (TY + 2) * ZP;                         // rows of one staged plane part
+    static constexpr int PART_BYTES = (ROWS * 128 + 1023) / 1024 * 1024;
+    static constexpr int XSTAGE_BYTES = 2 * PART_BYTES;                // hi part | lo part
     static constexpr int NXS = 2;
-    static constexpr int NWS = (200 * 1024 - NXS * XSTAGE_BYTES) / W_TAP_BYTES >= 6
-                                   ? 6 : (200 * 1024 - NXS * XSTAGE_BYTES) / W_TAP_BYTES;
-    static constexpr int SMEM_BYTES = 1024 + NXS * XSTAGE_BYTES + NWS * W_TAP_BYTES + 256;
+    static constexpr int NWS = 4;
+    static constexpr int SMEM_BYTES = 1024 + NXS * XSTAGE_BYTES + NWS * W_TAP_BYTES + STAGE_FLOATS * 4 + 256;
     static constexpr int TMEM_COLS = 2 * N <= 32 ? 32 : 2 * N <= 64 ? 64 : 2 * N <= 128 ? 128 : 2 * N <= 256 ? 256 : 512;
-    static_assert(TZ % 8 == 0, "plane rows must stay 1024B aligned under dy shifts");
-    static_assert(N % 16 == 0 && N >= 16 && N <= 256, "UMMA N constraint for M=128");
-    static_assert(NWS >= 3, "need at least one plane worth of weight taps in flight");
-    static_assert(TY + 2 <= 256 && TZ <= 256, "TMA box limits");
+    static constexpr int NCHUNK = TY / 8;                              // epilogue chunks of 64 voxels
+    static_assert(TY % 8 == 0 && N % 16 == 0 && N >= 16 && N <= 256, "UMMA N constraint for M=128");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 struct KParams {
-    const __half* w_img;     // [27][128][64] fp16 pre-swizzled, tap order = (dx*3+dz)*3+dy
+    const __half* w_img;     // [27][128][64] fp16 pre-swizzled, tap order = Keras (dx*3+dy)*3+dz
     __half* out_hi;
     __half* out_lo;
     const __half* res_hi;
     const __half* res_lo;
     const float* bias;
     float* out_raw;          // optional fp32 [B][Do^3][64] output instead of Act
+    unsigned int* absmax;    // optional: atomicMax of |out_raw| bit patterns
     float slope;
     int B, Do, halo;
     int nyt, nzt, ntiles;
 };
 
-template <int TY, int TZ>
+__device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <int TY>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
-    using C = Cfg<TY, TZ>;
+    using C = Cfg<TY>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* xs = smem;                                   // NXS x [hi plane | lo plane]
+    uint8_t* xs = smem;                                   // NXS x [hi part | lo part]
     uint8_t* wsm = smem + C::NXS * C::XSTAGE_BYTES;       // NWS x 16 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + C::NWS * W_TAP_BYTES);
+    float* stage = reinterpret_cast<float*>(wsm + C::NWS * W_TAP_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage) + STAGE_FLOATS * 4);
     uint64_t* x_full = bars;                 // [NXS]
     uint64_t* x_empty = bars + C::NXS;       // [NXS]
     uint64_t* w_full = bars + 2 * C::NXS;    // [NWS]
@@ -90,7 +105,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
         mbar_init(t_full, 1);
         mbar_init(t_empty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+        prefetch_tmap(&xmap);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -103,7 +118,8 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int tiles_per_b = p.Do * p.nyt * p.nzt;
+    const int tiles_per_x = p.nyt * p.nzt;
+    const int tiles_per_b = p.Do * tiles_per_x;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -112,24 +128,23 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
                 const int b = t / tiles_per_b;
                 int rem = t % tiles_per_b;
-                const int x = rem / (p.nyt * p.nzt);
-                rem %= p.nyt * p.nzt;
+                const int x = rem / tiles_per_x;
+                rem %= tiles_per_x;
                 const int y0 = (rem / p.nzt) * TY, z0 = (rem % p.nzt) * TZ;
-                for (int pl = 0; pl < 9; ++pl) {
-                    const int dx = pl / 3, dz = pl % 3;
+                for (int dx = 0; dx < 3; ++dx) {
                     const uint32_t s = xi % C::NXS, ph = (xi / C::NXS) & 1;
                     mbar_wait(&x_empty[s], ph ^ 1);
-                    mbar_expect_tx(&x_full[s], C::XSTAGE_BYTES);
+                    mbar_expect_tx(&x_full[s], 2 * C::ROWS * 128);
                     uint8_t* dst = xs + s * C::XSTAGE_BYTES;
-                    tma_load_5d(dst, &xmap, &x_full[s], 0, z0 + dz, y0, x + dx, b);
-                    tma_load_5d(dst + C::PLANE_BYTES, &xmap, &x_full[s], 0, z0 + dz, y0, x + dx, p.B + b);
+                    tma_load_5d(dst, &xmap, &x_full[s], 0, z0, y0, x + dx, b);
+                    tma_load_5d(dst + C::PART_BYTES, &xmap, &x_full[s], 0, z0, y0, x + dx, p.B + b);
                     ++xi;
-                    for (int dy = 0; dy < 3; ++dy) {
+                    for (int tp = 0; tp < 9; ++tp) {
                         const uint32_t ws = wi % C::NWS, wph = (wi / C::NWS) & 1;
                         mbar_wait(&w_empty[ws], wph ^ 1);
                         mbar_expect_tx(&w_full[ws], W_TAP_BYTES);
                         bulk_load(wsm + ws * W_TAP_BYTES,
-                                  reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)(pl * 3 + dy) * W_TAP_BYTES,
+                                  reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)(dx * 9 + tp) * W_TAP_BYTES,
                                   W_TAP_BYTES, &w_full[ws]);
                         ++wi;
                     }
@@ -146,24 +161,25 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
                 mbar_wait(t_empty, (ti & 1) ^ 1);
                 tc_fence_after();
-                for (int pl = 0; pl < 9; ++pl) {
+                for (int dx = 0; dx < 3; ++dx) {
                     const uint32_t s = xi % C::NXS, ph = (xi / C::NXS) & 1;
                     mbar_wait(&x_full[s], ph);
                     tc_fence_after();
                     const uint32_t xhi = smem_u32(xs + s * C::XSTAGE_BYTES);
-                    const uint32_t xlo = xhi + C::PLANE_BYTES;
-                    for (int dy = 0; dy < 3; ++dy) {
+                    const uint32_t xlo = xhi + C::PART_BYTES;
+#pragma unroll 1
+                    for (int tp = 0; tp < 9; ++tp) {
                         const uint32_t ws = wi % C::NWS, wph = (wi / C::NWS) & 1;
                         mbar_wait(&w_full[ws], wph);
                         tc_fence_after();
                         const uint32_t wa = smem_u32(wsm + ws * W_TAP_BYTES);
-                        const uint32_t boff = dy * TZ * 128;
+                        const uint32_t boff = ((tp / 3) * ZP + (tp % 3)) * 128;     // (dy, dz) row shift
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint64_t ad = make_desc(wa + k * 32);
-                            const uint32_t acc = (pl | dy | k) != 0;
-                            tc_mma_f16(d1, ad, make_desc(xhi + boff + k * 32), idesc, acc);
-                            tc_mma_f16(d2, ad, make_desc(xlo + boff + k * 32), idesc, acc);
+                            const uint64_t ad = make_desc_sbo(wa + k * 32, 1024);
+                            const uint32_t acc = (dx | tp | k) != 0;
+                            tc_mma_f16(d1, ad, make_desc_sbo(xhi + boff + k * 32, ZP * 128), idesc, acc);
+                            tc_mma_f16(d2, ad, make_desc_sbo(xlo + boff + k * 32, ZP * 128), idesc, acc);
                         }
                         tc_commit(&w_empty[ws]);
                         ++wi;
@@ -175,53 +191,105 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
             }
         }
     } else {
-        // ================= epilogue (warps 2..5) =================
+        // ================= epilogue (warps 2..5, 128 threads) =================
         const int e = warp & 3;                      // TMEM lane quarter this warp may access
+        const int et = threadIdx.x - 64;             // 0..127
         const int co = 16 * e + (lane & 15);
         const bool is_lo = lane >= 16;
         const float bias = p.bias ? p.bias[co] : 0.f;
+        const float s1 = is_lo ? SR4D_LO_INV : 1.f;
         const int Do = p.Do;
+        const int g8 = et & 7;                       // 8-channel group handled in the store phase
+        float amax = 0.f;
         uint32_t ti = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
             const int b = t / tiles_per_b;
             int rem = t % tiles_per_b;
-            const int x = rem / (p.nyt * p.nzt);
-            rem %= p.nyt * p.nzt;
+            const int x = rem / tiles_per_x;
+            rem %= tiles_per_x;
             const int y0 = (rem / p.nzt) * TY, z0 = (rem % p.nzt) * TZ;
             mbar_wait(t_full, ti & 1);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(32 * e) << 16);
 #pragma unroll 1
-            for (int c0 = 0; c0 < C::N; c0 += 16) {
-                float a[16], d[16];
-                tc_ld16(trow + c0, a);
-                tc_ld16(trow + C::N + c0, d);
-                tc_ld_wait();
-                const float s1 = is_lo ? SR4D_LO_INV : 1.f;
+            for (int ch = 0; ch < C::NCHUNK; ++ch) {
+                // residual prefetch for the 4 (voxel, channel-group) items this thread stores
+                uint4 rh[4], rl[4];
+                if (p.res_hi) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float v = fmaf(d[j], SR4D_LO_INV, a[j]) * s1;
-                    a[j] = v + __shfl_xor_sync(0xffffffffu, v, 16);
+                    for (int r = 0; r < 4; ++r) {
+                        const int v = (et >> 3) + 16 * r;
+                        const int y = y0 + ch * 8 + (v >> 3), z = z0 + (v & 7);
+                        if (y < Do && z < Do) {
+                            const size_t o = act_off(Do, b, x, y, z) + g8 * 8;
+                            rh[r] = *reinterpret_cast<const uint4*>(p.res_hi + o);
+                            rl[r] = *reinterpret_cast<const uint4*>(p.res_lo + o);
+                        }
+                    }
                 }
+                // ---- phase A: TMEM -> registers -> fp32 transpose buffer [voxel][channel] ----
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float v0 = is_lo ? a[8 + j] : a[j];
-                    const int n = c0 + (is_lo ? 8 : 0) + j;
-                    const int y = y0 + n / TZ, z = z0 + n % TZ;
+                for (int q = 0; q < 4; ++q) {
+                    const int c0 = ch * 64 + q * 16;
+                    float a[16], d[16];
+                    tc_ld16(trow + c0, a);
+                    tc_ld16(trow + C::N + c0, d);
+                    tc_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float v = fmaf(d[j], SR4D_LO_INV, a[j]) * s1;
+                        a[j] = v + __shfl_xor_sync(0xffffffffu, v, 16);
+                    }
+                    // lanes 0..15 keep columns 0..7 (y-line 2q), lanes 16..31 columns 8..15 (y-line 2q+1)
+                    const int vb = q * 16 + (is_lo ? 8 : 0);
+                    const int sw = co ^ (is_lo ? 16 : 0);      // bank swizzle: ((v >> 3) & 1) << 4
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) stage[(vb + j) * 64 + sw] = (is_lo ? a[8 + j] : a[j]) + bias;
+                }
+                if (ch == C::NCHUNK - 1) {
+                    // all TMEM reads of this tile are done: let the MMA warp start the next tile
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty);
+                }
+                named_bar(1, 128);
+                // ---- phase B: coalesced residual / activation / split / store ----
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int v = (et >> 3) + 16 * r;
+                    const int y = y0 + ch * 8 + (v >> 3), z = z0 + (v & 7);
                     if (y >= Do || z >= Do) continue;
-                    float v = v0 + bias;
+                    const float* sp = stage + v * 64 + ((g8 * 8) ^ (((v >> 3) & 1) << 4));
+                    float4 f0 = *reinterpret_cast<const float4*>(sp);
+                    float4 f1 = *reinterpret_cast<const float4*>(sp + 4);
+                    float val[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
                     if (p.out_raw) {
-                        p.out_raw[((((size_t)b * Do + x) * Do + y) * Do + z) * 64 + co] = v;
+                        float* o = p.out_raw + ((((size_t)b * Do + x) * Do + y) * Do + z) * 64 + g8 * 8;
+                        *reinterpret_cast<float4*>(o) = f0;
+                        *reinterpret_cast<float4*>(o + 4) = f1;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(val[k]));
                         continue;
                     }
-                    const size_t o = act_off(Do, b, x, y, z) + co;
-                    if (p.res_hi) v += join_f16(p.res_hi[o], p.res_lo[o]);
-                    v = act_fn(v, p.slope);
-                    __half h, l;
-                    split_f16(v, h, l);
+                    if (p.res_hi) {
+                        const __half2* hh = reinterpret_cast<const __half2*>(&rh[r]);
+                        const __half2* ll = reinterpret_cast<const __half2*>(&rl[r]);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float2 ha = __half22float2(hh[k]), la = __half22float2(ll[k]);
+                            val[2 * k] += fmaf(la.x, SR4D_LO_INV, ha.x);
+                            val[2 * k + 1] += fmaf(la.y, SR4D_LO_INV, ha.y);
+                        }
+                    }
+                    __align__(16) __half hv[8];
+                    __align__(16) __half lv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) split_f16(act_fn(val[k], p.slope), hv[k], lv[k]);
+                    const uint4 H = *reinterpret_cast<const uint4*>(hv), L = *reinterpret_cast<const uint4*>(lv);
                     if (!p.halo) {
-                        p.out_hi[o] = h;
-                        p.out_lo[o] = l;
+                        const size_t o = act_off(Do, b, x, y, z) + g8 * 8;
+                        *reinterpret_cast<uint4*>(p.out_hi + o) = H;
+                        *reinterpret_cast<uint4*>(p.out_lo + o) = L;
                     } else {
                         for (int ddx = -1; ddx <= 1; ++ddx) {
                             if ((ddx == -1 && x != 0) || (ddx == 1 && x != Do - 1)) continue;
@@ -229,18 +297,21 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                                 if ((ddy == -1 && y != 0) || (ddy == 1 && y != Do - 1)) continue;
                                 for (int ddz = -1; ddz <= 1; ++ddz) {
                                     if ((ddz == -1 && z != 0) || (ddz == 1 && z != Do - 1)) continue;
-                                    const size_t oo = act_off(Do, b, x + ddx, y + ddy, z + ddz) + co;
-                                    p.out_hi[oo] = h;
-                                    p.out_lo[oo] = l;
+                                    const size_t oo = act_off(Do, b, x + ddx, y + ddy, z + ddz) + g8 * 8;
+                                    *reinterpret_cast<uint4*>(p.out_hi + oo) = H;
+                                    *reinterpret_cast<uint4*>(p.out_lo + oo) = L;
                                 }
                             }
                         }
                     }
                 }
+                named_bar(1, 128);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(t_empty);
+        }
+        if (p.absmax) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+            if (lane == 0) atomicMax(p.absmax, __float_as_uint(amax));
         }
     }
 
@@ -253,15 +324,13 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// weight image: fp32 Keras [27][ci][co] -> fp16 split, row-permuted, swizzled, tap-reordered
+// weight image: fp32 Keras [27][ci][co] -> fp16 split, row-permuted, swizzled
 // ------------------------------------------------------------------------------------------
 __global__ void prep_weights_kernel(const float* __restrict__ w, __half* __restrict__ img, int dgrad) {
-    // one thread per (tap_img, row, k)
+    // one thread per (tap, row, k)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 27 * 128 * 64) return;
-    const int k = i & 63, row = (i >> 6) & 127, ti = i >> 13;
-    const int pl = ti / 3, dy = ti % 3, dx = pl / 3, dz = pl % 3;
-    const int tap = (dx * 3 + dy) * 3 + dz;
+    const int k = i & 63, row = (i >> 6) & 127, tap = i >> 13;
     const int q = row >> 5, l = row & 31;
     const int n = 16 * q + (l & 15);
     const bool is_lo = l >= 16;
@@ -270,7 +339,7 @@ __global__ void prep_weights_kernel(const float* __restrict__ w, __half* __restr
     __half h, lo;
     split_f16(v, h, lo);
     const int grp = row >> 3, rr = row & 7;
-    const size_t off = (size_t)ti * (128 * 64) + grp * 512 + rr * 64 + (((k >> 3) ^ rr) << 3) + (k & 7);
+    const size_t off = (size_t)tap * (128 * 64) + grp * 512 + rr * 64 + (((k >> 3) ^ rr) << 3) + (k & 7);
     img[off] = is_lo ? lo : h;
 }
 
@@ -296,12 +365,12 @@ EncodeTiledFn get_encode() {
 }
 
 // 5-D map over the packed [2B][Dp][Dp][Dp][64] fp16 planes of an Act (hi planes then lo planes)
-bool make_xmap(CUtensorMap* map, const __half* base, int B, int Dp, int ty2, int tz) {
+bool make_xmap(CUtensorMap* map, const __half* base, int B, int Dp, int ty2, int tz2) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[5] = {64, (cuuint64_t)Dp, (cuuint64_t)Dp, (cuuint64_t)Dp, (cuuint64_t)(2 * B)};
     cuuint64_t strides[4] = {128, (cuuint64_t)128 * Dp, (cuuint64_t)128 * Dp * Dp, (cuuint64_t)128 * Dp * Dp * Dp};
-    cuuint32_t box[5] = {64, (cuuint32_t)tz, (cuuint32_t)ty2, 1, 1};
+    cuuint32_t box[5] = {64, (cuuint32_t)tz2, (cuuint32_t)ty2, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -319,12 +388,12 @@ int num_sms() {
     return n;
 }
 
-template <int TY, int TZ>
+template <int TY>
 cudaError_t launch_cfg(const CUtensorMap& map, KParams p, cudaStream_t s) {
-    using C = Cfg<TY, TZ>;
+    using C = Cfg<TY>;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv64_tc_kernel<TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(conv64_tc_kernel<TY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              C::SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr = true;
@@ -333,7 +402,7 @@ cudaError_t launch_cfg(const CUtensorMap& map, KParams p, cudaStream_t s) {
     p.nzt = (p.Do + TZ - 1) / TZ;
     p.ntiles = p.B * p.Do * p.nyt * p.nzt;
     int grid = p.ntiles < num_sms() ? p.ntiles : num_sms();
-    conv64_tc_kernel<TY, TZ><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(map, p);
+    conv64_tc_kernel<TY><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(map, p);
     return cudaGetLastError();
 }
 
@@ -368,29 +437,21 @@ cudaError_t tc_prepare_weights(TcWeights* w, int layer, const float* kernel, cud
 }
 
 cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
-    const int Do = a.out.D, B = a.in.B, Dp = a.in.D + 2;
-    if (a.in.D != Do) return cudaErrorInvalidValue;
+    const int Do = a.in.D, B = a.in.B, Dp = a.in.D + 2;
+    if (!a.out_raw && a.out.D != Do) return cudaErrorInvalidValue;
     KParams p;
     p.w_img = w->img + ((size_t)a.layer * 2 + (a.dgrad ? 1 : 0)) * 27 * 128 * 64;
     p.out_hi = a.out.hi; p.out_lo = a.out.lo;
     p.res_hi = a.res_hi; p.res_lo = a.res_lo;
-    p.bias = a.bias; p.out_raw = nullptr;
+    p.bias = a.bias; p.out_raw = a.out_raw; p.absmax = a.absmax;
     p.slope = a.slope; p.B = B; p.Do = Do; p.halo = a.halo;
-    // tile shape by grid edge: full-z lines, N = TY*TZ <= 256
-    int ty, tz;
-    if (Do <= 8) { ty = 8; tz = 8; }
-    else if (Do <= 16) { ty = 8; tz = 16; }
-    else if (Do <= 24) { ty = 8; tz = 24; }
-    else if (Do <= 32) { ty = 6; tz = 32; }
-    else { ty = 4; tz = 48; }            // larger grids are tiled along z as well
+    const int ty = Do <= 8 ? 8 : Do <= 16 ? 16 : 24;
     CUtensorMap map;
-    if (!make_xmap(&map, a.in.hi, B, Dp, ty + 2, tz)) return cudaErrorUnknown;
+    if (!make_xmap(&map, a.in.hi, B, Dp, ty + 2, ZP)) return cudaErrorUnknown;
     if (a.in.lo != a.in.hi + act_plane_elems(B, a.in.D)) return cudaErrorInvalidValue;   // planes must be packed
-    switch (tz) {
-        case 8: return launch_cfg<8, 8>(map, p, s);
-        case 16: return launch_cfg<8, 16>(map, p, s);
-        case 24: return launch_cfg<8, 24>(map, p, s);
-        case 32: return launch_cfg<6, 32>(map, p, s);
-        default: return launch_cfg<4, 48>(map, p, s);
+    switch (ty) {
+        case 8: return launch_cfg<8>(map, p, s);
+        case 16: return launch_cfg<16>(map, p, s);
+        default: return launch_cfg<24>(map, p, s);
     }
 }

@@ -14,6 +14,8 @@ struct TcConvArgs {
     const __half* res_lo = nullptr;
     float slope = 1.f;
     int halo = 1;
+    float* out_raw = nullptr;          // fp32 [B][D^3][64] output (no bias/activation/halo) instead of `out`
+    unsigned int* absmax = nullptr;    // with out_raw: atomicMax of the |value| bit patterns written
 };
 
 bool tc_available();

@@ -20,9 +20,12 @@ def eng_small(pkg):
     return pkg.Engine(8, 2, 1, 1, max_batch=3, training=False, device=0)
 
 
-@pytest.mark.parametrize("D,B", [(8, 2), (5, 1), (24, 1), (26, 1)])
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+@pytest.mark.parametrize("D,B", [(8, 2), (5, 1), (24, 1), (26, 1), (12, 2), (48, 1)])
 @pytest.mark.parametrize("variant", ["linear", "bias_relu", "res_lrelu"])
-def test_conv64_simt_layer(pkg, oracle, eng_small, D, B, variant):
+def test_conv64_layer(pkg, oracle, eng_small, D, B, variant, impl):
+    if impl == "simt" and D == 48:
+        pytest.skip("covered by the tensor-core case")
     g = np.random.default_rng(D * 10 + B)
     x = g.standard_normal((B, D, D, D, 64)).astype(np.float32)
     k = (g.standard_normal((3, 3, 3, 64, 64)) * 0.04).astype(np.float32)
@@ -34,7 +37,8 @@ def test_conv64_simt_layer(pkg, oracle, eng_small, D, B, variant):
     if variant == "res_lrelu":
         res = g.standard_normal((B, D, D, D, 64)).astype(np.float32)
         slope = 0.2
-    y = eng_small.conv64_layer(x, k, bias, res, slope, impl=pkg._lib.CONV_SIMT).cpu().numpy()
+    impl_id = pkg._lib.CONV_SIMT if impl == "simt" else pkg._lib.CONV_TCGEN05
+    y = eng_small.conv64_layer(x, k, bias, res, slope, impl=impl_id).cpu().numpy()
     t = oracle.conv3d(torch.tensor(x, dtype=torch.float64), torch.tensor(k, dtype=torch.float64),
                       None if bias is None else torch.tensor(bias, dtype=torch.float64))
     if res is not None:
