@@ -111,14 +111,35 @@ __global__ void __launch_bounds__(256) head2_wgrad_kernel(ActView h, const float
     }
 }
 
+// block-wide max of |v| folded into *p with at most one atomic per block (all threads must call)
+__device__ __forceinline__ void absmax_commit(float m, unsigned int* p) {
+    __shared__ float wm[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int w = 1; w < nw; ++w) m = fmaxf(m, wm[w]);
+        const unsigned int bits = __float_as_uint(m);
+        if (bits > *reinterpret_cast<volatile unsigned int*>(p)) atomicMax(p, bits);
+    }
+}
+__device__ __forceinline__ float exp2_scale(const int* e, int sign) { return e ? exp2f((float)(sign * *e)) : 1.f; }
+
 // ---- halo fold (MirrorPadGrad) + add + activation gradient -------------------------------
+// raw_i carry the power-of-two scale 2^(*e_i) of the split-fp16 gradient they were computed from
 __global__ void __launch_bounds__(256) fold_act_kernel(const float* __restrict__ r0, const float* __restrict__ r1,
-                                                       const float* __restrict__ r2, const float* __restrict__ add,
+                                                       const float* __restrict__ r2, const int* e0, const int* e1,
+                                                       const int* e2, const float* __restrict__ add,
                                                        const __half* __restrict__ shi, const __half* __restrict__ slo,
-                                                       float slope, float* __restrict__ out, int B, int D) {
+                                                       float slope, float* __restrict__ out, unsigned int* amax,
+                                                       int B, int D) {
     const size_t n = (size_t)B * D * D * D * 16;
     size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
+    float m = 0.f;
+    if (i < n) {
+    const float k0 = exp2_scale(e0, -1), k1 = exp2_scale(e1, -1), k2 = exp2_scale(e2, -1);
     size_t vi = i >> 4;
     const int c = (i & 15) * 4;
     int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
@@ -137,9 +158,9 @@ __global__ void __launch_bounds__(256) fold_act_kernel(const float* __restrict__
                 if (dz == 1 && z != D - 1) continue;
                 size_t o = raw_off(D, b, x + 1 + dx, y + 1 + dy, z + 1 + dz) + c;
                 float4 a = *reinterpret_cast<const float4*>(r0 + o);
-                s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-                if (r1) { a = *reinterpret_cast<const float4*>(r1 + o); s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w; }
-                if (r2) { a = *reinterpret_cast<const float4*>(r2 + o); s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w; }
+                s.x = fmaf(a.x, k0, s.x); s.y = fmaf(a.y, k0, s.y); s.z = fmaf(a.z, k0, s.z); s.w = fmaf(a.w, k0, s.w);
+                if (r1) { a = *reinterpret_cast<const float4*>(r1 + o); s.x = fmaf(a.x, k1, s.x); s.y = fmaf(a.y, k1, s.y); s.z = fmaf(a.z, k1, s.z); s.w = fmaf(a.w, k1, s.w); }
+                if (r2) { a = *reinterpret_cast<const float4*>(r2 + o); s.x = fmaf(a.x, k2, s.x); s.y = fmaf(a.y, k2, s.y); s.z = fmaf(a.z, k2, s.z); s.w = fmaf(a.w, k2, s.w); }
             }
         }
     }
@@ -157,6 +178,35 @@ __global__ void __launch_bounds__(256) fold_act_kernel(const float* __restrict__
         s.w *= act_grad_from_out(sv[3], slope);
     }
     *reinterpret_cast<float4*>(out + go) = s;
+    m = fmaxf(fmaxf(fabsf(s.x), fabsf(s.y)), fmaxf(fabsf(s.z), fabsf(s.w)));
+    }
+    if (amax) absmax_commit(m, amax);
+}
+
+// ---- fp32 G4 interior -> split-fp16 copy scaled by 2^e, e chosen from the tensor's |max| so the
+// largest element lands in [2^13, 2^14) (the tensor-core dgrad / wgrad operands) -----------------
+__global__ void __launch_bounds__(256) g4_split_kernel(const float* __restrict__ src, const unsigned int* amax,
+                                                       __half* __restrict__ hi, __half* __restrict__ lo,
+                                                       int* exp_out, int B, int D) {
+    const size_t n = (size_t)B * D * D * D * 16;
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const float mx = __uint_as_float(*amax);
+    int e = 0;
+    if (mx > 0.f && mx < 3.0e38f) e = 13 - ilogbf(mx);
+    e = max(-120, min(120, e));
+    if (i == 0) *exp_out = e;
+    if (i >= n) return;
+    const float k = exp2f((float)e);
+    size_t vi = i >> 4;
+    const int c = (i & 15) * 4;
+    int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
+    const size_t go = g4_off(D, b, x, y, z) + c;
+    const float4 v = *reinterpret_cast<const float4*>(src + go);
+    const float vv[4] = {v.x * k, v.y * k, v.z * k, v.w * k};
+    uint2 h, l;
+    act_pack4(vv, h, l);
+    *reinterpret_cast<uint2*>(hi + go) = h;
+    *reinterpret_cast<uint2*>(lo + go) = l;
 }
 
 // ---- 64->64 3x3x3 weight gradient: dW[t][ci][co] = sum_{b,v} Xp[b,v+t][ci] dY[b,v][co] ------
@@ -247,11 +297,13 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
 
 // ---- upsample backward: d_lr = U^T d_hr, then * act'(lr) --------------------------------
 __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restrict__ dhr, ActView lr, float slope,
-                                                           float* __restrict__ dlr, int B, int D, int r, UpsampleTables t) {
+                                                           float* __restrict__ dlr, unsigned int* amax, int B, int D,
+                                                           int r, UpsampleTables t) {
     const int H = D * r;
     const size_t n = (size_t)B * D * D * D * 16;
     size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
+    float m = 0.f;
+    if (i < n) {
     size_t vi = i >> 4;
     const int c = (i & 15) * 4;
     int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
@@ -278,13 +330,17 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restri
     s.z *= act_grad_from_out(sv[2], slope);
     s.w *= act_grad_from_out(sv[3], slope);
     *reinterpret_cast<float4*>(dlr + g4_off(D, b, x, y, z) + c) = s;
+    m = fmaxf(fmaxf(fabsf(s.x), fabsf(s.y)), fmaxf(fabsf(s.z), fabsf(s.w)));
+    }
+    if (amax) absmax_commit(m, amax);
 }
 
 // ---- 1x1 (128->64) backward ----------------------------------------------------------------
 // input gradient: d_cat[v][k] = sum_co dy[v][co] W[k][co]; 8 threads per voxel, k = kg*4 + 32q + (0..3)
 __global__ void __launch_bounds__(256) conv1x1_dgrad_kernel(const float* __restrict__ dy, ActView a, ActView bq,
                                                             const float* __restrict__ w, float* __restrict__ da,
-                                                            float* __restrict__ db) {
+                                                            float* __restrict__ db, unsigned int* amax_a,
+                                                            unsigned int* amax_b) {
     extern __shared__ float wt[];   // [64 co][128 k]
     for (int i = threadIdx.x; i < 128 * 64; i += 256) {
         int k = i >> 6, co = i & 63;
@@ -294,7 +350,8 @@ __global__ void __launch_bounds__(256) conv1x1_dgrad_kernel(const float* __restr
     const int D = a.D;
     const size_t nvox = (size_t)a.B * D * D * D;
     size_t vi = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3);
-    if (vi >= nvox) return;
+    float ma = 0.f, mb = 0.f;
+    if (vi < nvox) {
     const int kg = threadIdx.x & 7;
     int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
     const float* dyp = dy + g4_off(D, b, x, y, z);
@@ -323,7 +380,11 @@ __global__ void __launch_bounds__(256) conv1x1_dgrad_kernel(const float* __restr
         float4 o = make_float4(sv[0] > 0.f ? acc[q][0] : 0.f, sv[1] > 0.f ? acc[q][1] : 0.f,
                                sv[2] > 0.f ? acc[q][2] : 0.f, sv[3] > 0.f ? acc[q][3] : 0.f);
         *reinterpret_cast<float4*>((second ? db : da) + go + kk) = o;
+        const float mo = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w)));
+        if (second) mb = fmaxf(mb, mo); else ma = fmaxf(ma, mo);
     }
+    }
+    if (amax_a) { absmax_commit(ma, amax_a); __syncthreads(); absmax_commit(mb, amax_b); }
 }
 // weight gradient: dW[k][co] = sum_v cat[v][k] dy[v][co]; block stages 32 voxels; thread = 4 k x 8 co
 constexpr int C1_VOX_PER_BLOCK = 256;
@@ -432,14 +493,20 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
     }
 }
 
-__global__ void g4_from_dense_kernel(const float* __restrict__ dense, float* __restrict__ g4, int B, int D) {
+__global__ void g4_from_dense_kernel(const float* __restrict__ dense, float* __restrict__ g4, unsigned int* amax,
+                                     int B, int D) {
     const size_t n = (size_t)B * D * D * D * 16;
     size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    size_t vi = i >> 4;
-    int c = (i & 15) * 4;
-    int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
-    *reinterpret_cast<float4*>(g4 + g4_off(D, b, x, y, z) + c) = *reinterpret_cast<const float4*>(dense + vi * 64 + c);
+    float m = 0.f;
+    if (i < n) {
+        size_t vi = i >> 4;
+        int c = (i & 15) * 4;
+        int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
+        const float4 v = *reinterpret_cast<const float4*>(dense + vi * 64 + c);
+        *reinterpret_cast<float4*>(g4 + g4_off(D, b, x, y, z) + c) = v;
+        m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    if (amax) absmax_commit(m, amax);
 }
 __global__ void dense_from_g4_kernel(const float* __restrict__ g4, float* __restrict__ dense, int B, int D) {
     const size_t n = (size_t)B * D * D * D * 16;
@@ -472,11 +539,19 @@ cudaError_t launch_head2_wgrad(ActView h, const float* g, int c, float* dw, floa
     cudaMemcpyAsync(db, tmp + 27 * 64, sizeof(float), cudaMemcpyDeviceToDevice, s);
     return cudaGetLastError();
 }
-cudaError_t launch_fold_act(const float* raw0, const float* raw1, const float* raw2, const float* add_g4,
-                            const __half* saved_hi, const __half* saved_lo, float slope, float* out_g4, int B,
-                            int D, cudaStream_t s) {
+cudaError_t launch_fold_act(const float* raw0, const float* raw1, const float* raw2, const int* e0, const int* e1,
+                            const int* e2, const float* add_g4, const __half* saved_hi, const __half* saved_lo,
+                            float slope, float* out_g4, unsigned int* amax, int B, int D, cudaStream_t s) {
     size_t n = (size_t)B * D * D * D * 16;
-    fold_act_kernel<<<nblocks(n, 256), 256, 0, s>>>(raw0, raw1, raw2, add_g4, saved_hi, saved_lo, slope, out_g4, B, D);
+    fold_act_kernel<<<nblocks(n, 256), 256, 0, s>>>(raw0, raw1, raw2, e0, e1, e2, add_g4, saved_hi, saved_lo, slope,
+                                                    out_g4, amax, B, D);
+    return cudaGetLastError();
+}
+cudaError_t launch_g4_split(const float* g4, const unsigned int* amax, __half* split, int* exp_out, int B, int D,
+                            cudaStream_t s) {
+    size_t n = (size_t)B * D * D * D * 16;
+    const size_t plane = (size_t)B * (D + 4) * (D + 4) * (D + 4) * 64;
+    g4_split_kernel<<<nblocks(n, 256), 256, 0, s>>>(g4, amax, split, split + plane, exp_out, B, D);
     return cudaGetLastError();
 }
 cudaError_t launch_wgrad64_simt(ActView x, const float* dy_g4, float* dw, float* scratch, int nchunk,
@@ -493,16 +568,17 @@ cudaError_t launch_bias_grad(const float* dy_g4, int B, int D, float* db, float*
     reduce_rows_kernel<<<1, 64, 0, s>>>(scratch, nb, 64, db);
     return cudaGetLastError();
 }
-cudaError_t launch_upsample_bwd(const float* dhr_g4, ActView lr_saved, float slope, float* dlr_g4, int B, int D,
-                                int r, UpsampleTables t, cudaStream_t s) {
+cudaError_t launch_upsample_bwd(const float* dhr_g4, ActView lr_saved, float slope, float* dlr_g4,
+                                unsigned int* amax, int B, int D, int r, UpsampleTables t, cudaStream_t s) {
     size_t n = (size_t)B * D * D * D * 16;
-    upsample_bwd_kernel<<<nblocks(n, 256), 256, 0, s>>>(dhr_g4, lr_saved, slope, dlr_g4, B, D, r, t);
+    upsample_bwd_kernel<<<nblocks(n, 256), 256, 0, s>>>(dhr_g4, lr_saved, slope, dlr_g4, amax, B, D, r, t);
     return cudaGetLastError();
 }
 cudaError_t launch_conv1x1_bwd(const float* dy_g4, ActView a, ActView b, const float* w, float* da_g4,
-                               float* db_g4, float* dw, float* dbias, float* scratch, cudaStream_t s) {
+                               float* db_g4, unsigned int* amax_a, unsigned int* amax_b, float* dw, float* dbias,
+                               float* scratch, cudaStream_t s) {
     size_t nvox = (size_t)a.B * a.D * a.D * a.D;
-    conv1x1_dgrad_kernel<<<nblocks(nvox, 32), 256, 128 * 64 * 4, s>>>(dy_g4, a, b, w, da_g4, db_g4);
+    conv1x1_dgrad_kernel<<<nblocks(nvox, 32), 256, 128 * 64 * 4, s>>>(dy_g4, a, b, w, da_g4, db_g4, amax_a, amax_b);
     unsigned nb = red_blocks(nvox, C1_VOX_PER_BLOCK);
     conv1x1_wgrad_kernel<<<nb, 256, 0, s>>>(dy_g4, a, b, scratch);
     reduce_rows_kernel<<<8192 / 256, 256, 0, s>>>(scratch, nb, 8192, dw);
@@ -520,9 +596,9 @@ cudaError_t launch_stem_wgrad(const float* feat, int ch0, const float* dy_g4, in
     if (e != cudaSuccess) return e;
     return launch_bias_grad(dy_g4, B, P, db, scratch, s);
 }
-cudaError_t launch_g4_from_dense(const float* dense, float* g4, int B, int D, cudaStream_t s) {
+cudaError_t launch_g4_from_dense(const float* dense, float* g4, unsigned int* amax, int B, int D, cudaStream_t s) {
     size_t n = (size_t)B * D * D * D * 16;
-    g4_from_dense_kernel<<<nblocks(n, 256), 256, 0, s>>>(dense, g4, B, D);
+    g4_from_dense_kernel<<<nblocks(n, 256), 256, 0, s>>>(dense, g4, amax, B, D);
     return cudaGetLastError();
 }
 cudaError_t launch_dense_from_g4(const float* g4, float* dense, int B, int D, cudaStream_t s) {

@@ -21,12 +21,13 @@
 // shifted starts and a non-1024 group stride read the TMA-written rows correctly (verified on
 // B200 by tools/probe/mma_probe.cu).  Every activation byte is fetched 3x from L2 per layer
 // (plus y/z halo), weights stream per tap as pre-swizzled 16 KB images (cp.async.bulk).
-// Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue:
+// Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue:
 // TMEM -> registers -> (hi/lo row combine, bias) -> fp32 shared-memory transpose -> coalesced
 // 16-byte residual loads / activation / fp16 split / stores with the replicate halo.
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "conv_tc.h"
@@ -35,7 +36,9 @@
 namespace {
 
 constexpr int W_TAP_BYTES = 128 * 64 * 2;   // 16 KB: [Whi;Wlo] x 64 ci, fp16, swizzled
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI = NUM_EPI_WARPS * 32;   // epilogue threads
+constexpr int NUM_THREADS = 64 + NUM_EPI;
 constexpr int TZ = 8;                       // voxels per 8-row group (one z run)
 constexpr int ZP = TZ + 2;                  // plane row pitch in voxels
 constexpr int STAGE_FLOATS = 64 * 64;       // epilogue transpose buffer: 64 voxels x 64 channels
@@ -67,6 +70,7 @@ struct KParams {
     float slope;
     int B, Do, halo;
     int nyt, nzt, ntiles;
+    long long* dbg;          // SR4D_TC_DEBUG=1: per-CTA cycles the MMA warp spent waiting {t_empty, x_full, w_full, total}
 };
 
 __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo) {
@@ -103,7 +107,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
         for (int i = 0; i < C::NXS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
         for (int i = 0; i < C::NWS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         mbar_init(t_full, 1);
-        mbar_init(t_empty, 4);
+        mbar_init(t_empty, NUM_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&xmap);
     }
@@ -158,19 +162,26 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
             const uint32_t idesc = (1u << 4) | ((uint32_t)(C::N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t d1 = tmem_base, d2 = tmem_base + C::N;
             uint32_t xi = 0, wi = 0, ti = 0;
+            long long wt = 0, wx = 0, ww = 0, c0 = 0, tbeg = p.dbg ? clock64() : 0;
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
+                if (p.dbg) c0 = clock64();
                 mbar_wait(t_empty, (ti & 1) ^ 1);
+                if (p.dbg) wt += clock64() - c0;
                 tc_fence_after();
                 for (int dx = 0; dx < 3; ++dx) {
                     const uint32_t s = xi % C::NXS, ph = (xi / C::NXS) & 1;
+                    if (p.dbg) c0 = clock64();
                     mbar_wait(&x_full[s], ph);
+                    if (p.dbg) wx += clock64() - c0;
                     tc_fence_after();
                     const uint32_t xhi = smem_u32(xs + s * C::XSTAGE_BYTES);
                     const uint32_t xlo = xhi + C::PART_BYTES;
 #pragma unroll 1
                     for (int tp = 0; tp < 9; ++tp) {
                         const uint32_t ws = wi % C::NWS, wph = (wi / C::NWS) & 1;
+                        if (p.dbg) c0 = clock64();
                         mbar_wait(&w_full[ws], wph);
+                        if (p.dbg) ww += clock64() - c0;
                         tc_fence_after();
                         const uint32_t wa = smem_u32(wsm + ws * W_TAP_BYTES);
                         const uint32_t boff = ((tp / 3) * ZP + (tp % 3)) * 128;     // (dy, dz) row shift
@@ -189,11 +200,17 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                 }
                 tc_commit(t_full);
             }
+            if (p.dbg) {
+                p.dbg[blockIdx.x * 4 + 0] = wt; p.dbg[blockIdx.x * 4 + 1] = wx;
+                p.dbg[blockIdx.x * 4 + 2] = ww; p.dbg[blockIdx.x * 4 + 3] = clock64() - tbeg;
+            }
         }
     } else {
-        // ================= epilogue (warps 2..5, 128 threads) =================
-        const int e = warp & 3;                      // TMEM lane quarter this warp may access
-        const int et = threadIdx.x - 64;             // 0..127
+        // ================= epilogue (warps 2..9, 256 threads) =================
+        // warp w may only read TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter split the columns
+        const int e = warp & 3;
+        const int half = (warp - 2) >> 2;            // which 32 of a chunk's 64 columns this warp converts
+        const int et = threadIdx.x - 64;             // 0..255
         const int co = 16 * e + (lane & 15);
         const bool is_lo = lane >= 16;
         const float bias = p.bias ? p.bias[co] : 0.f;
@@ -208,17 +225,18 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
             const int x = rem / tiles_per_x;
             rem %= tiles_per_x;
             const int y0 = (rem / p.nzt) * TY, z0 = (rem % p.nzt) * TZ;
+            const bool x_edge = p.halo && (x == 0 || x == Do - 1);
             mbar_wait(t_full, ti & 1);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(32 * e) << 16);
 #pragma unroll 1
             for (int ch = 0; ch < C::NCHUNK; ++ch) {
-                // residual prefetch for the 4 (voxel, channel-group) items this thread stores
-                uint4 rh[4], rl[4];
+                // residual prefetch for the 2 (voxel, channel-group) items this thread stores
+                uint4 rh[2], rl[2];
                 if (p.res_hi) {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const int v = (et >> 3) + 16 * r;
+                    for (int r = 0; r < 2; ++r) {
+                        const int v = (et >> 3) + 32 * r;
                         const int y = y0 + ch * 8 + (v >> 3), z = z0 + (v & 7);
                         if (y < Do && z < Do) {
                             const size_t o = act_off(Do, b, x, y, z) + g8 * 8;
@@ -229,7 +247,8 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                 }
                 // ---- phase A: TMEM -> registers -> fp32 transpose buffer [voxel][channel] ----
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int qq = 0; qq < 2; ++qq) {
+                    const int q = half * 2 + qq;
                     const int c0 = ch * 64 + q * 16;
                     float a[16], d[16];
                     tc_ld16(trow + c0, a);
@@ -252,11 +271,11 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(t_empty);
                 }
-                named_bar(1, 128);
+                named_bar(1, NUM_EPI);
                 // ---- phase B: coalesced residual / activation / split / store ----
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int v = (et >> 3) + 16 * r;
+                for (int r = 0; r < 2; ++r) {
+                    const int v = (et >> 3) + 32 * r;
                     const int y = y0 + ch * 8 + (v >> 3), z = z0 + (v & 7);
                     if (y >= Do || z >= Do) continue;
                     const float* sp = stage + v * 64 + ((g8 * 8) ^ (((v >> 3) & 1) << 4));
@@ -286,17 +305,19 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) split_f16(act_fn(val[k], p.slope), hv[k], lv[k]);
                     const uint4 H = *reinterpret_cast<const uint4*>(hv), L = *reinterpret_cast<const uint4*>(lv);
-                    if (!p.halo) {
-                        const size_t o = act_off(Do, b, x, y, z) + g8 * 8;
-                        *reinterpret_cast<uint4*>(p.out_hi + o) = H;
-                        *reinterpret_cast<uint4*>(p.out_lo + o) = L;
-                    } else {
+                    const size_t o = act_off(Do, b, x, y, z) + g8 * 8;
+                    *reinterpret_cast<uint4*>(p.out_hi + o) = H;
+                    *reinterpret_cast<uint4*>(p.out_lo + o) = L;
+                    const bool edge = p.halo && (x_edge || y == 0 || y == Do - 1 || z == 0 || z == Do - 1);
+                    if (edge) {
+                        // replicate into the halo positions this voxel is the clamp image of
                         for (int ddx = -1; ddx <= 1; ++ddx) {
                             if ((ddx == -1 && x != 0) || (ddx == 1 && x != Do - 1)) continue;
                             for (int ddy = -1; ddy <= 1; ++ddy) {
                                 if ((ddy == -1 && y != 0) || (ddy == 1 && y != Do - 1)) continue;
                                 for (int ddz = -1; ddz <= 1; ++ddz) {
                                     if ((ddz == -1 && z != 0) || (ddz == 1 && z != Do - 1)) continue;
+                                    if ((ddx | ddy | ddz) == 0) continue;
                                     const size_t oo = act_off(Do, b, x + ddx, y + ddy, z + ddz) + g8 * 8;
                                     *reinterpret_cast<uint4*>(p.out_hi + oo) = H;
                                     *reinterpret_cast<uint4*>(p.out_lo + oo) = L;
@@ -305,7 +326,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                         }
                     }
                 }
-                named_bar(1, 128);
+                named_bar(1, NUM_EPI);
             }
         }
         if (p.absmax) {
@@ -445,13 +466,32 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
     p.res_hi = a.res_hi; p.res_lo = a.res_lo;
     p.bias = a.bias; p.out_raw = a.out_raw; p.absmax = a.absmax;
     p.slope = a.slope; p.B = B; p.Do = Do; p.halo = a.halo;
+    p.dbg = nullptr;
+    static const bool debug = getenv("SR4D_TC_DEBUG") != nullptr;
+    static long long* dbg_buf = nullptr;
+    if (debug) {
+        if (!dbg_buf) cudaMalloc((void**)&dbg_buf, 148 * 4 * sizeof(long long));
+        cudaMemsetAsync(dbg_buf, 0, 148 * 4 * sizeof(long long), s);
+        p.dbg = dbg_buf;
+    }
     const int ty = Do <= 8 ? 8 : Do <= 16 ? 16 : 24;
     CUtensorMap map;
     if (!make_xmap(&map, a.in.hi, B, Dp, ty + 2, ZP)) return cudaErrorUnknown;
     if (a.in.lo != a.in.hi + act_plane_elems(B, a.in.D)) return cudaErrorInvalidValue;   // planes must be packed
+    cudaError_t e;
     switch (ty) {
-        case 8: return launch_cfg<8>(map, p, s);
-        case 16: return launch_cfg<16>(map, p, s);
-        default: return launch_cfg<24>(map, p, s);
+        case 8: e = launch_cfg<8>(map, p, s); break;
+        case 16: e = launch_cfg<16>(map, p, s); break;
+        default: e = launch_cfg<24>(map, p, s); break;
     }
+    if (debug && e == cudaSuccess) {
+        long long h[148 * 4];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h, dbg_buf, sizeof h, cudaMemcpyDeviceToHost);
+        double a4[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 148; ++i) for (int k = 0; k < 4; ++k) a4[k] += (double)h[i * 4 + k] / 148;
+        fprintf(stderr, "[tc dbg] Do=%d B=%d tiles=%d: MMA-warp wait cycles avg/CTA: t_empty %.0f  x_full %.0f  w_full %.0f  of total %.0f\n",
+                Do, B, B * Do * ((Do + ty - 1) / ty) * ((Do + TZ - 1) / TZ), a4[0], a4[1], a4[2], a4[3]);
+    }
+    return e;
 }

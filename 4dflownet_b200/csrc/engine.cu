@@ -31,6 +31,17 @@ struct ActBuf {
     }
 };
 
+struct GBuf {
+    float* f = nullptr;            // fp32 [B][D+4]^3[64], zero halo
+    __half* s = nullptr;           // split-fp16 copy scaled by 2^(*exp): [2B][D+4]^3[64]
+    unsigned int* amax = nullptr;  // device: max |f| (bit pattern)
+    int* exp = nullptr;            // device: exponent of the split copy
+};
+struct RawBuf {
+    float* p = nullptr;            // fp32 [B][D+2]^3[64]
+    const int* exp = nullptr;      // device exponent the values are scaled by (NULL: unscaled)
+};
+
 struct UpTab {
     int* lo = nullptr; int* hi = nullptr; float* lerp = nullptr; int* ibeg = nullptr; int* iend = nullptr;
     UpsampleTables tables() const { return UpsampleTables{lo, hi, lerp, ibeg, iend}; }
@@ -50,11 +61,14 @@ struct sr4d_handle {
     std::vector<int> lr_slot, hr_slot; // tensor index -> slot
     int n_lr_t = 0, n_hr_t = 0;
     UpTab up;
-    // training workspace
-    float* g4_lr[4] = {nullptr, nullptr, nullptr, nullptr};
-    float* g4_hr[3] = {nullptr, nullptr, nullptr};
-    float* raw_lr = nullptr;
-    float* raw_hr[3] = {nullptr, nullptr, nullptr};
+    // training workspace: gradient tensors (fp32 G4 + scaled split-fp16 copy for the tensor cores) and
+    // dgrad outputs on the padded grid (raw, carrying the scale exponent of the gradient they came from)
+    GBuf g4_lr[4];
+    GBuf g4_hr[3];
+    RawBuf raw_lr;
+    RawBuf raw_hr[3];
+    int* gmeta = nullptr;      // device: {absmax bits, exponent} per GBuf, then head_exp[2]
+    int* head_exp = nullptr;
     float* pred = nullptr;     // (maxB,H^3,3)
     float* gpred = nullptr;    // (maxB,H^3,3)
     float* scratch = nullptr;  // split-reduction partials
@@ -360,27 +374,54 @@ int forward_impl(sr4d_t* h, const float* u, const float* v, const float* w, cons
     return SR4D_OK;
 }
 
-// dgrad of a 64->64 layer: dy (G4, edge D) -> raw (edge D+2)
-int conv64_dgrad(sr4d_t* h, int layer, const float* dy_g4, float* raw, int B, int D, cudaStream_t s) {
-    ProfScope prof(h, D == h->P ? SR4D_PROF_CONV64_DGRAD_LR : SR4D_PROF_CONV64_DGRAD_HR, s);
-    Conv64Args a;
-    a.in_f32 = dy_g4; a.B = B; a.Do = D + 2;
-    a.w = W(h, layer); a.dgrad = 1;
-    a.out_raw = raw;
-    CK(h, launch_conv64_simt(a, s), 1);
-    return SR4D_OK;
-}
-int conv64_wgrad(sr4d_t* h, int layer, ActView x, const float* dy_g4, bool bias, cudaStream_t s) {
-    ProfScope prof(h, x.D == h->P ? SR4D_PROF_CONV64_WGRAD_LR : SR4D_PROF_CONV64_WGRAD_HR, s);
-    CK(h, launch_wgrad64_simt(x, dy_g4, GW(h, layer), h->scratch, h->wgrad_chunks, s), 2);
-    if (bias) CK(h, launch_bias_grad(dy_g4, x.B, x.D, GB(h, layer), h->scratch, s), 2);
+// A gradient tensor has just been written to g.f (and its |max| to g.amax): make the scaled
+// split-fp16 copy the tensor-core dgrad / wgrad kernels consume.
+int grad_ready(sr4d_t* h, GBuf& g, int B, int D, cudaStream_t s) {
+    if (!use_tc(h)) return SR4D_OK;
+    CK(h, launch_g4_split(g.f, g.amax, g.s, g.exp, B, D, s), 1);
     return SR4D_OK;
 }
 
-// backward through `nblk` resnet blocks whose first conv is layer `l0`; S holds the gradient wrt the
-// pre-activation of the last block output on entry and wrt the pre-activation (if slope_in >= 0) of the
-// first block input on exit.  bufs = {S, T, S'} G4 buffers; returns the index of the buffer holding the result.
-int blocks_bwd(sr4d_t* h, int nblk, int l0, bool hr, float* bufs[3], float* raw, int B, int D,
+// dgrad of a 64->64 layer: dy (G4, edge D) -> raw (edge D+2)
+int conv64_dgrad(sr4d_t* h, int layer, const GBuf& dy, RawBuf& raw, int B, int D, cudaStream_t s) {
+    ProfScope prof(h, D == h->P ? SR4D_PROF_CONV64_DGRAD_LR : SR4D_PROF_CONV64_DGRAD_HR, s);
+    if (use_tc(h)) {
+        TcConvArgs a;
+        a.in.hi = dy.s; a.in.lo = dy.s + act_plane_elems(B, D + 2); a.in.B = B; a.in.D = D + 2;
+        a.layer = layer; a.dgrad = 1;
+        a.out_raw = raw.p;
+        raw.exp = dy.exp;
+        CK(h, tc_conv64(h->tcw, a, s), 1);
+        return SR4D_OK;
+    }
+    Conv64Args a;
+    a.in_f32 = dy.f; a.B = B; a.Do = D + 2;
+    a.w = W(h, layer); a.dgrad = 1;
+    a.out_raw = raw.p;
+    raw.exp = nullptr;
+    CK(h, launch_conv64_simt(a, s), 1);
+    return SR4D_OK;
+}
+int conv64_wgrad(sr4d_t* h, int layer, ActView x, const GBuf& dy, bool bias, cudaStream_t s) {
+    ProfScope prof(h, x.D == h->P ? SR4D_PROF_CONV64_WGRAD_LR : SR4D_PROF_CONV64_WGRAD_HR, s);
+    CK(h, launch_wgrad64_simt(x, dy.f, GW(h, layer), h->scratch, h->wgrad_chunks, s), 2);
+    if (bias) CK(h, launch_bias_grad(dy.f, x.B, x.D, GB(h, layer), h->scratch, s), 2);
+    return SR4D_OK;
+}
+// out = (fold(raw0 [+raw1 +raw2]) + add) * act'(saved); then the split copy
+int fold_act(sr4d_t* h, const RawBuf* r0, const RawBuf* r1, const RawBuf* r2, const GBuf* add, const ActView* saved,
+             float slope, GBuf& out, int B, int D, cudaStream_t s) {
+    CK(h, cudaMemsetAsync(out.amax, 0, sizeof(int), s), 0);
+    CK(h, launch_fold_act(r0->p, r1 ? r1->p : nullptr, r2 ? r2->p : nullptr, r0->exp, r1 ? r1->exp : nullptr,
+                          r2 ? r2->exp : nullptr, add ? add->f : nullptr, saved ? saved->hi : nullptr,
+                          saved ? saved->lo : nullptr, slope, out.f, out.amax, B, D, s), 1);
+    return grad_ready(h, out, B, D, s);
+}
+
+// backward through `nblk` resnet blocks whose first conv is layer `l0`; bufs[0] holds the gradient wrt the
+// pre-activation of the last block output on entry; on exit bufs[*result_idx] holds the gradient wrt the
+// pre-activation (if slope_in >= 0, else the value) of the first block input.
+int blocks_bwd(sr4d_t* h, int nblk, int l0, bool hr, GBuf* bufs[3], RawBuf& raw, int B, int D,
                float slope_in, cudaStream_t s, int* result_idx) {
     int si = 0;
     int rc;
@@ -390,20 +431,19 @@ int blocks_bwd(sr4d_t* h, int nblk, int l0, bool hr, float* bufs[3], float* raw,
         ActView xin;
         if (hr) xin = k == 0 ? hr_view(h, 0, B) : hr_view(h, hr_t_of_block_x(k - 1), B);
         else xin = k == 0 ? lr_view(h, 5, B) : lr_view(h, lr_t_of_block_x(k - 1), B);
-        float* S = bufs[si];
-        float* T = bufs[(si + 1) % 3];
-        float* S2 = bufs[(si + 2) % 3];
+        GBuf& S = *bufs[si];
+        GBuf& T = *bufs[(si + 1) % 3];
+        GBuf& S2 = *bufs[(si + 2) % 3];
         if ((rc = conv64_wgrad(h, lb, t, S, false, s))) return rc;
         if ((rc = conv64_dgrad(h, lb, S, raw, B, D, s))) return rc;
-        CK(h, launch_fold_act(raw, nullptr, nullptr, nullptr, t.hi, t.lo, 0.2f, T, B, D, s), 1);
+        if ((rc = fold_act(h, &raw, nullptr, nullptr, nullptr, &t, 0.2f, T, B, D, s))) return rc;
         if ((rc = conv64_wgrad(h, la, xin, T, false, s))) return rc;
         if ((rc = conv64_dgrad(h, la, T, raw, B, D, s))) return rc;
         // gradient wrt x_k (post-activation) = fold + skip path; multiply by its producer's act'
         float slope = k > 0 ? 0.2f : slope_in;
-        if (slope >= 0.f)
-            CK(h, launch_fold_act(raw, nullptr, nullptr, S, xin.hi, xin.lo, slope, S2, B, D, s), 1);
-        else
-            CK(h, launch_fold_act(raw, nullptr, nullptr, S, nullptr, nullptr, 1.f, S2, B, D, s), 1);
+        if (slope >= 0.f) rc = fold_act(h, &raw, nullptr, nullptr, &S, &xin, slope, S2, B, D, s);
+        else rc = fold_act(h, &raw, nullptr, nullptr, &S, nullptr, 1.f, S2, B, D, s);
+        if (rc) return rc;
         si = (si + 2) % 3;
     }
     *result_idx = si;
@@ -424,36 +464,41 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
     const int l_hr0 = 6 + 2 * h->low;          // first HR block layer
     const int l_head = l_hr0 + 2 * h->hi;      // first head layer
     ActView trunk = h->hi > 0 ? hr_view(h, hr_t_of_block_x(h->hi - 1), B) : hr_view(h, 0, B);
-    float* A = h->g4_hr[0];
+    GBuf& A = h->g4_hr[0];
     for (int c = 0; c < 3; ++c) {
         ActView hd = hr_view(h, 1 + 2 * h->hi + c, B);
         const int l1 = l_head + 2 * c, l2 = l1 + 1;
         CK(h, launch_head2_wgrad(hd, h->gpred, c, GW(h, l2), GB(h, l2), h->scratch, s), 4);
-        CK(h, launch_head2_dgrad(h->gpred, c, W(h, l2), h->raw_hr[c], B, H, s), 1);
-        CK(h, launch_fold_act(h->raw_hr[c], nullptr, nullptr, nullptr, hd.hi, hd.lo, 0.f, A, B, H, s), 1);
+        CK(h, launch_head2_dgrad(h->gpred, c, W(h, l2), h->raw_hr[c].p, B, H, s), 1);
+        h->raw_hr[c].exp = nullptr;
+        if ((rc = fold_act(h, &h->raw_hr[c], nullptr, nullptr, nullptr, &hd, 0.f, A, B, H, s))) return rc;
         if ((rc = conv64_wgrad(h, l1, trunk, A, true, s))) return rc;
         if ((rc = conv64_dgrad(h, l1, A, h->raw_hr[c], B, H, s))) return rc;
+        if (use_tc(h) && c < 2) {
+            // raw_hr[c] stays scaled by A's exponent, which the next head overwrites: keep a private copy
+            CK(h, cudaMemcpyAsync(h->head_exp + c, A.exp, sizeof(int), cudaMemcpyDeviceToDevice, s), 0);
+            h->raw_hr[c].exp = h->head_exp + c;
+        }
     }
     // trunk gradient: sum of the three heads' input gradients; trunk producer: LeakyReLU block if hi>0,
     // the (linear) upsample if hi==0 and r>1, else the LR trunk tensor itself (r==1 aliases it).
-    float* hb[3] = {h->g4_hr[1], h->g4_hr[2], h->g4_hr[0]};
+    GBuf* hb[3] = {&h->g4_hr[1], &h->g4_hr[2], &h->g4_hr[0]};
     float slope_lr_trunk = h->low > 0 ? 0.2f : 0.f;    // producer activation of the LR trunk tensor
-    float* S;
+    GBuf* S;
     if (h->hi > 0) {
-        CK(h, launch_fold_act(h->raw_hr[0], h->raw_hr[1], h->raw_hr[2], nullptr, trunk.hi, trunk.lo, 0.2f, hb[0], B, H, s), 1);
+        if ((rc = fold_act(h, &h->raw_hr[0], &h->raw_hr[1], &h->raw_hr[2], nullptr, &trunk, 0.2f, *hb[0], B, H, s))) return rc;
         int ri = 0;
         float slope_in = h->r == 1 ? slope_lr_trunk : -1.f;
         if ((rc = blocks_bwd(h, h->hi, l_hr0, true, hb, h->raw_hr[0], B, H, slope_in, s, &ri))) return rc;
         S = hb[ri];
     } else {
-        if (h->r == 1)
-            CK(h, launch_fold_act(h->raw_hr[0], h->raw_hr[1], h->raw_hr[2], nullptr, trunk.hi, trunk.lo, slope_lr_trunk, hb[0], B, H, s), 1);
-        else
-            CK(h, launch_fold_act(h->raw_hr[0], h->raw_hr[1], h->raw_hr[2], nullptr, nullptr, nullptr, 1.f, hb[0], B, H, s), 1);
+        if (h->r == 1) rc = fold_act(h, &h->raw_hr[0], &h->raw_hr[1], &h->raw_hr[2], nullptr, &trunk, slope_lr_trunk, *hb[0], B, H, s);
+        else rc = fold_act(h, &h->raw_hr[0], &h->raw_hr[1], &h->raw_hr[2], nullptr, nullptr, 1.f, *hb[0], B, H, s);
+        if (rc) return rc;
         S = hb[0];
     }
     // through the upsample
-    float* lb[3] = {h->g4_lr[0], h->g4_lr[1], h->g4_lr[2]};
+    GBuf* lb[3] = {&h->g4_lr[0], &h->g4_lr[1], &h->g4_lr[2]};
     ActView lr_trunk = h->low > 0 ? lr_view(h, lr_t_of_block_x(h->low - 1), B) : lr_view(h, 5, B);
     if (h->r == 1) {
         // same grid (H == P): S is already multiplied by the LR trunk's act'; keep rotating the HR buffers
@@ -461,32 +506,38 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
         for (int i = 0; i < 3; ++i) if (hb[i] == S) si = i;
         lb[0] = hb[si]; lb[1] = hb[(si + 1) % 3]; lb[2] = hb[(si + 2) % 3];
     } else {
-        CK(h, launch_upsample_bwd(S, lr_trunk, slope_lr_trunk, lb[0], B, P, h->r, h->up.tables(), s), 1);
+        CK(h, cudaMemsetAsync(lb[0]->amax, 0, sizeof(int), s), 0);
+        CK(h, launch_upsample_bwd(S->f, lr_trunk, slope_lr_trunk, lb[0]->f, lb[0]->amax, B, P, h->r, h->up.tables(), s), 1);
+        if ((rc = grad_ready(h, *lb[0], B, P, s))) return rc;
     }
     int ri = 0;
     if (h->low > 0) {
         if ((rc = blocks_bwd(h, h->low, 6, false, lb, h->raw_lr, B, P, 0.f, s, &ri))) return rc;
     }
-    float* S5 = lb[ri];                 // d pre-activation of conv3d_5 (fuse 3x3)
-    float* T = lb[(ri + 1) % 3];
-    float* dA = lb[(ri + 2) % 3];
-    float* dB = h->g4_lr[3];
+    GBuf& S5 = *lb[ri];                 // d pre-activation of conv3d_5 (fuse 3x3)
+    GBuf& T = *lb[(ri + 1) % 3];
+    GBuf& dA = *lb[(ri + 2) % 3];
+    GBuf& dB = h->g4_lr[3];
     ActView pc1 = lr_view(h, 0, B), pc2 = lr_view(h, 1, B), ph1 = lr_view(h, 2, B), ph2 = lr_view(h, 3, B);
     ActView c1 = lr_view(h, 4, B);
     if ((rc = conv64_wgrad(h, 5, c1, S5, true, s))) return rc;
     if ((rc = conv64_dgrad(h, 5, S5, h->raw_lr, B, P, s))) return rc;
-    CK(h, launch_fold_act(h->raw_lr, nullptr, nullptr, nullptr, c1.hi, c1.lo, 0.f, T, B, P, s), 1);
-    CK(h, launch_conv1x1_bwd(T, ph2, pc2, W(h, 4), dA, dB, GW(h, 4), GB(h, 4), h->scratch, s), 5);
+    if ((rc = fold_act(h, &h->raw_lr, nullptr, nullptr, nullptr, &c1, 0.f, T, B, P, s))) return rc;
+    CK(h, cudaMemsetAsync(dA.amax, 0, sizeof(int), s), 0);
+    CK(h, cudaMemsetAsync(dB.amax, 0, sizeof(int), s), 0);
+    CK(h, launch_conv1x1_bwd(T.f, ph2, pc2, W(h, 4), dA.f, dB.f, dA.amax, dB.amax, GW(h, 4), GB(h, 4), h->scratch, s), 5);
+    if ((rc = grad_ready(h, dA, B, P, s))) return rc;
+    if ((rc = grad_ready(h, dB, B, P, s))) return rc;
     // phase branch
     if ((rc = conv64_wgrad(h, 3, ph1, dA, true, s))) return rc;
     if ((rc = conv64_dgrad(h, 3, dA, h->raw_lr, B, P, s))) return rc;
-    CK(h, launch_fold_act(h->raw_lr, nullptr, nullptr, nullptr, ph1.hi, ph1.lo, 0.f, T, B, P, s), 1);
-    CK(h, launch_stem_wgrad(h->feat, 0, T, B, P, GW(h, 2), GB(h, 2), h->scratch, s), 4);
+    if ((rc = fold_act(h, &h->raw_lr, nullptr, nullptr, nullptr, &ph1, 0.f, T, B, P, s))) return rc;
+    CK(h, launch_stem_wgrad(h->feat, 0, T.f, B, P, GW(h, 2), GB(h, 2), h->scratch, s), 4);
     // pc branch
     if ((rc = conv64_wgrad(h, 1, pc1, dB, true, s))) return rc;
     if ((rc = conv64_dgrad(h, 1, dB, h->raw_lr, B, P, s))) return rc;
-    CK(h, launch_fold_act(h->raw_lr, nullptr, nullptr, nullptr, pc1.hi, pc1.lo, 0.f, T, B, P, s), 1);
-    CK(h, launch_stem_wgrad(h->feat, 3, T, B, P, GW(h, 0), GB(h, 0), h->scratch, s), 4);
+    if ((rc = fold_act(h, &h->raw_lr, nullptr, nullptr, nullptr, &pc1, 0.f, T, B, P, s))) return rc;
+    CK(h, launch_stem_wgrad(h->feat, 3, T.f, B, P, GW(h, 0), GB(h, 0), h->scratch, s), 4);
     return SR4D_OK;
 }
 
@@ -496,10 +547,11 @@ void free_all(sr4d_t* h) {
     for (auto& b : h->lr) cudaFree(b.base);
     for (auto& b : h->hr) cudaFree(b.base);
     cudaFree(h->up.lo); cudaFree(h->up.hi); cudaFree(h->up.lerp); cudaFree(h->up.ibeg); cudaFree(h->up.iend);
-    for (auto p : h->g4_lr) cudaFree(p);
-    for (auto p : h->g4_hr) cudaFree(p);
-    cudaFree(h->raw_lr);
-    for (auto p : h->raw_hr) cudaFree(p);
+    for (auto& g : h->g4_lr) { cudaFree(g.f); cudaFree(g.s); }
+    for (auto& g : h->g4_hr) { cudaFree(g.f); cudaFree(g.s); }
+    cudaFree(h->raw_lr.p);
+    for (auto& r : h->raw_hr) cudaFree(r.p);
+    cudaFree(h->gmeta);
     cudaFree(h->pred); cudaFree(h->gpred); cudaFree(h->scratch); cudaFree(h->dpartial); cudaFree(h->norm);
     cudaFree(h->per_sample_int);
     if (h->tcw) tc_free_weights(h->tcw);
@@ -562,10 +614,24 @@ int sr4d_create(sr4d_t** out, int patch_size, int res_increase, int low_resblock
             const size_t rwl = (size_t)h->maxB * (h->P + 2) * (h->P + 2) * (h->P + 2) * 64;
             const size_t rwh = (size_t)h->maxB * (h->H + 2) * (h->H + 2) * (h->H + 2) * 64;
             bool bad = false;
-            for (auto& p : h->g4_lr) { bad |= dmalloc(&p, g4l) != cudaSuccess; if (!bad) cudaMemset(p, 0, g4l * 4); }
-            for (auto& p : h->g4_hr) { bad |= dmalloc(&p, g4h) != cudaSuccess; if (!bad) cudaMemset(p, 0, g4h * 4); }
-            bad |= dmalloc(&h->raw_lr, rwl) != cudaSuccess;
-            for (auto& p : h->raw_hr) bad |= dmalloc(&p, rwh) != cudaSuccess;
+            bad |= dmalloc(&h->gmeta, 16) != cudaSuccess;
+            if (!bad) cudaMemset(h->gmeta, 0, 16 * sizeof(int));
+            h->head_exp = h->gmeta + 14;
+            int gi = 0;
+            auto alloc_g = [&](GBuf& g, size_t n) {
+                // fp32 tensor and its split-fp16 copy (2 planes of n halves); halos are zeroed once and never written
+                bad |= dmalloc(&g.f, n) != cudaSuccess;
+                if (!bad) cudaMemset(g.f, 0, n * 4);
+                bad |= dmalloc(&g.s, 2 * n) != cudaSuccess;
+                if (!bad) cudaMemset(g.s, 0, 2 * n * sizeof(__half));
+                g.amax = reinterpret_cast<unsigned int*>(h->gmeta + 2 * gi);
+                g.exp = h->gmeta + 2 * gi + 1;
+                ++gi;
+            };
+            for (auto& g : h->g4_lr) alloc_g(g, g4l);
+            for (auto& g : h->g4_hr) alloc_g(g, g4h);
+            bad |= dmalloc(&h->raw_lr.p, rwl) != cudaSuccess;
+            for (auto& r : h->raw_hr) bad |= dmalloc(&r.p, rwh) != cudaSuccess;
             bad |= dmalloc(&h->pred, (size_t)h->maxB * nvoxH * 3) != cudaSuccess;
             bad |= dmalloc(&h->gpred, (size_t)h->maxB * nvoxH * 3) != cudaSuccess;
             h->scratch_floats = (size_t)h->wgrad_chunks * 27 * 4096;
@@ -769,27 +835,47 @@ int sr4d_upsample_layer(sr4d_t* h, const float* x, float* y, int B, int D, int r
 int sr4d_conv64_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const float* dy, float* dx,
                           float* dkernel, float* dbias, int B, int D, int impl, void* stream) {
     if (!h || !x || !kernel || !dy || B < 1 || D < 2) return fail(h, SR4D_EINVAL, "bad argument");
-    (void)impl;
+    const bool tc = impl == SR4D_CONV_TCGEN05;
+    if (tc && !tc_available()) return fail(h, SR4D_EINVAL, "tcgen05 conv not built");
     cudaStream_t s = (cudaStream_t)stream;
     ActBuf bi;
     float *g4 = nullptr, *raw = nullptr, *g4o = nullptr, *scr = nullptr, *dwb = nullptr;
+    __half* g4s = nullptr;
+    int* meta = nullptr;
+    TcWeights* tw = nullptr;
     const size_t n4 = (size_t)B * (D + 4) * (D + 4) * (D + 4) * 64, n2 = (size_t)B * (D + 2) * (D + 2) * (D + 2) * 64;
     const int nchunk = 16;
     int rc = SR4D_OK;
     if (alloc_act(bi, B, D) || dmalloc(&g4, n4) || dmalloc(&raw, n2) || dmalloc(&g4o, n4) ||
-        dmalloc(&scr, (size_t)nchunk * 27 * 4096 + 1184 * 64) || dmalloc(&dwb, 27 * 4096 + 64))
+        dmalloc(&scr, (size_t)nchunk * 27 * 4096 + 1184 * 64) || dmalloc(&dwb, 27 * 4096 + 64) || dmalloc(&meta, 2) ||
+        (tc && (dmalloc(&g4s, 2 * n4) || tc_alloc_weights(&tw, 1) != cudaSuccess)))
         rc = SR4D_ENOMEM;
     if (!rc) {
         cudaMemsetAsync(g4, 0, n4 * 4, s);
         cudaMemsetAsync(g4o, 0, n4 * 4, s);
+        cudaMemsetAsync(meta, 0, 2 * sizeof(int), s);
+        if (tc) cudaMemsetAsync(g4s, 0, 2 * n4 * sizeof(__half), s);
         ActView vi = bi.view(B);
         cudaError_t e = launch_pack_act(x, vi, s);
-        if (!e) e = launch_g4_from_dense(dy, g4, B, D, s);
+        if (!e) e = launch_g4_from_dense(dy, g4, reinterpret_cast<unsigned int*>(meta), B, D, s);
         if (!e && dx) {
-            Conv64Args a;
-            a.in_f32 = g4; a.B = B; a.Do = D + 2; a.w = kernel; a.dgrad = 1; a.out_raw = raw;
-            e = launch_conv64_simt(a, s);
-            if (!e) e = launch_fold_act(raw, nullptr, nullptr, nullptr, nullptr, nullptr, 1.f, g4o, B, D, s);
+            const int* rexp = nullptr;
+            if (tc) {
+                e = launch_g4_split(g4, reinterpret_cast<unsigned int*>(meta), g4s, meta + 1, B, D, s);
+                if (!e) e = tc_prepare_weights(tw, 0, kernel, s);
+                TcConvArgs a;
+                a.in.hi = g4s; a.in.lo = g4s + act_plane_elems(B, D + 2); a.in.B = B; a.in.D = D + 2;
+                a.layer = 0; a.dgrad = 1; a.out_raw = raw;
+                if (!e) e = tc_conv64(tw, a, s);
+                rexp = meta + 1;
+                h->launches += 3;
+            } else {
+                Conv64Args a;
+                a.in_f32 = g4; a.B = B; a.Do = D + 2; a.w = kernel; a.dgrad = 1; a.out_raw = raw;
+                e = launch_conv64_simt(a, s);
+            }
+            if (!e) e = launch_fold_act(raw, nullptr, nullptr, rexp, nullptr, nullptr, nullptr, nullptr, nullptr, 1.f,
+                                        g4o, nullptr, B, D, s);
             if (!e) e = launch_dense_from_g4(g4o, dx, B, D, s);
             h->launches += 3;
         }
@@ -806,7 +892,9 @@ int sr4d_conv64_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const 
         if (!e) e = cudaStreamSynchronize(s);
         if (e) { rc = SR4D_ECUDA; h->err = cudaGetErrorString(e); }
     }
-    cudaFree(bi.base); cudaFree(g4); cudaFree(raw); cudaFree(g4o); cudaFree(scr); cudaFree(dwb);
+    cudaFree(bi.base); cudaFree(g4); cudaFree(raw); cudaFree(g4o); cudaFree(scr); cudaFree(dwb); cudaFree(g4s);
+    cudaFree(meta);
+    if (tw) tc_free_weights(tw);
     return rc;
 }
 

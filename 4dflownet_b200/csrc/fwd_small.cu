@@ -135,41 +135,83 @@ __global__ void __launch_bounds__(256) upsample_kernel(ActView in, ActView out, 
     act_store4_halo(out.hi, out.lo, H, b, x, y, z, c + 4, o + 4, true);
 }
 
-// ---- 64->1 head conv, linear (+bias), writes channel c of (B,H^3,3): SR4DFlowNet.py:40,43,46,49
-// 8 threads per voxel (8 input channels each) + 3 shuffle steps.
+// ---- 64->1 head conv, linear (+bias), writes (B,H^3,3): SR4DFlowNet.py:40,43,46,49 -------
+// A CTA owns an 8x8x8 output brick.  Phase 1: every voxel of the 10x10x10 halo brick (the
+// replicate halo is already materialised in the Act) is read ONCE and reduced against the 27
+// tap vectors (27 dot products of length 64) into shared memory; phase 2: each output voxel
+// gathers its 27 partial sums.  HBM/L2 traffic ~2x the input instead of 27x.
 struct HeadArgs {
     const __half* hi[3];
     const __half* lo[3];
     const float* w[3];
     const float* b[3];
 };
-__global__ void __launch_bounds__(256) head_out_kernel(HeadArgs a, float* __restrict__ out, int B, int H) {
-    __shared__ float ws[27 * 64];
-    const int c = blockIdx.y;
-    for (int i = threadIdx.x; i < 27 * 64; i += 256) ws[i] = a.w[c][i];
-    __syncthreads();
-    const size_t nvox = (size_t)B * H * H * H;
-    size_t vi = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3);
-    const bool valid = vi < nvox;
-    if (!valid) vi = nvox - 1;
-    const int k8 = (threadIdx.x & 7) * 8;
-    int z = vi % H, y = (vi / H) % H, x = (vi / ((size_t)H * H)) % H, b = vi / ((size_t)H * H * H);
-    const __half* hi = a.hi[c];
-    const __half* lo = a.lo[c];
-    float acc = 0.f;
-    for (int dx = -1; dx <= 1; ++dx)
-        for (int dy = -1; dy <= 1; ++dy)
-            for (int dz = -1; dz <= 1; ++dz) {
-                float xv[8];
-                act_load8(hi, lo, act_off(H, b, x + dx, y + dy, z + dz) + k8, xv);   // halo makes clamp implicit
-                const float* wp = ws + (((dx + 1) * 3 + (dy + 1)) * 3 + (dz + 1)) * 64 + k8;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc = fmaf(xv[k], wp[k], acc);
+constexpr int HB = 8, HBP = HB + 2, HB_HALO = HBP * HBP * HBP;            // 1000 halo voxels
+constexpr int HEAD_SMEM = (HB_HALO * 27 + 27 * 64) * 4;
+__global__ void __launch_bounds__(512) head_out_kernel(HeadArgs a, float* __restrict__ out, int B, int H) {
+    extern __shared__ float hsm[];
+    float* t = hsm;                      // [1000][27]
+    float* ws = hsm + HB_HALO * 27;      // [27][64]
+    const int nb = (H + HB - 1) / HB;
+    int bi = blockIdx.x;
+    const int bz = bi % nb; bi /= nb;
+    const int by = bi % nb; bi /= nb;
+    const int bx = bi % nb;
+    const int b = bi / nb;
+    const int x0 = bx * HB, y0 = by * HB, z0 = bz * HB;
+    const int Hp = H + 2;
+    const int tid = threadIdx.x;
+    const int ox = tid >> 6, oy = (tid >> 3) & 7, oz = tid & 7;
+    float res[3] = {0.f, 0.f, 0.f};
+    for (int c = 0; c < 3; ++c) {
+        __syncthreads();                 // previous head's gather is done with t / ws
+        for (int i = tid; i < 27 * 64; i += 512) ws[i] = a.w[c][i];
+        __syncthreads();
+        const __half* hi = a.hi[c];
+        const __half* lo = a.lo[c];
+        for (int hv = tid; hv < HB_HALO; hv += 512) {
+            const int hx = hv / (HBP * HBP), hy = (hv / HBP) % HBP, hz = hv % HBP;
+            const int px = x0 + hx, py = y0 + hy, pz = z0 + hz;      // padded coordinates
+            float* tp = t + hv * 27;
+            if (px >= Hp || py >= Hp || pz >= Hp) {
+                for (int k = 0; k < 27; ++k) tp[k] = 0.f;
+                continue;
             }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    if (valid && (threadIdx.x & 7) == 0) out[vi * 3 + c] = acc + a.b[c][0];
+            const size_t off = ((((size_t)b * Hp + px) * Hp + py) * Hp + pz) * 64;
+            float xv[64];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) act_load8(hi, lo, off + k * 8, xv + k * 8);
+#pragma unroll 1
+            for (int tap = 0; tap < 27; ++tap) {
+                const float4* wp = reinterpret_cast<const float4*>(ws + tap * 64);
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float4 wv = wp[k];
+                    s0 = fmaf(xv[4 * k], wv.x, s0);
+                    s1 = fmaf(xv[4 * k + 1], wv.y, s1);
+                    s2 = fmaf(xv[4 * k + 2], wv.z, s2);
+                    s3 = fmaf(xv[4 * k + 3], wv.w, s3);
+                }
+                tp[tap] = (s0 + s1) + (s2 + s3);
+            }
+        }
+        __syncthreads();
+        float acc = a.b[c][0];
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dz = 0; dz < 3; ++dz)
+                    acc += t[(((ox + dx) * HBP + (oy + dy)) * HBP + (oz + dz)) * 27 + (dx * 3 + dy) * 3 + dz];
+        res[c] = acc;
+    }
+    const int x = x0 + ox, y = y0 + oy, z = z0 + oz;
+    if (x < H && y < H && z < H) {
+        float* o = out + ((((size_t)b * H + x) * H + y) * H + z) * 3;
+        o[0] = res[0]; o[1] = res[1]; o[2] = res[2];
+    }
 }
 
 __global__ void pack_act_kernel(const float* __restrict__ x, ActView out) {
@@ -229,9 +271,14 @@ cudaError_t launch_head_out(ActView h0, ActView h1, ActView h2, const float* w0,
     a.lo[0] = h0.lo; a.lo[1] = h1.lo; a.lo[2] = h2.lo;
     a.w[0] = w0; a.w[1] = w1; a.w[2] = w2;
     a.b[0] = b0; a.b[1] = b1; a.b[2] = b2;
-    size_t nvox = (size_t)h0.B * h0.D * h0.D * h0.D;
-    dim3 grid((unsigned)((nvox + 31) / 32), 3);
-    head_out_kernel<<<grid, 256, 0, s>>>(a, out, h0.B, h0.D);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(head_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    const int nb = (h0.D + HB - 1) / HB;
+    head_out_kernel<<<(unsigned)(h0.B * nb * nb * nb), 512, HEAD_SMEM, s>>>(a, out, h0.B, h0.D);
     return cudaGetLastError();
 }
 cudaError_t launch_pack_act(const float* x, ActView out, cudaStream_t s) {

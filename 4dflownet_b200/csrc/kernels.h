@@ -68,22 +68,29 @@ cudaError_t launch_head2_dgrad(const float* g, int c, const float* w, float* raw
 // dW[27][64] and db for the 64->1 conv: h Act (B,H), g channel c
 cudaError_t launch_head2_wgrad(ActView h, const float* g, int c, float* dw, float* db, float* scratch,
                                cudaStream_t s);
-// out(G4 interior) = (fold(raw0+raw1+raw2) + add) * act'(saved)
-cudaError_t launch_fold_act(const float* raw0, const float* raw1, const float* raw2, const float* add_g4,
-                            const __half* saved_hi, const __half* saved_lo, float slope, float* out_g4, int B,
-                            int D, cudaStream_t s);
+// out(G4 interior) = (fold(raw0*2^-e0 + raw1*2^-e1 + raw2*2^-e2) + add) * act'(saved); e_i are device
+// exponents (NULL = 0) of the scaled split-fp16 gradients the raws were computed from; amax (optional)
+// receives atomicMax of |out|
+cudaError_t launch_fold_act(const float* raw0, const float* raw1, const float* raw2, const int* e0, const int* e1,
+                            const int* e2, const float* add_g4, const __half* saved_hi, const __half* saved_lo,
+                            float slope, float* out_g4, unsigned int* amax, int B, int D, cudaStream_t s);
+// split-fp16 copy [2B][D+4]^3[64] (hi planes then lo planes, zero halo kept) of a fp32 G4 tensor, scaled by
+// 2^e with e derived from *amax so max|x|*2^e is in [2^13, 2^14); *exp_out = e
+cudaError_t launch_g4_split(const float* g4, const unsigned int* amax, __half* split, int* exp_out, int B, int D,
+                            cudaStream_t s);
 // dW[27][64][64] (+= nothing; overwrite) from x Act and dy G4; scratch >= nchunk*27*64*64 floats
 cudaError_t launch_wgrad64_simt(ActView x, const float* dy_g4, float* dw, float* scratch, int nchunk,
                                 cudaStream_t s);
 cudaError_t launch_bias_grad(const float* dy_g4, int B, int D, float* db, float* scratch, cudaStream_t s);
-cudaError_t launch_upsample_bwd(const float* dhr_g4, ActView lr_saved, float slope, float* dlr_g4, int B, int D,
-                                int r, UpsampleTables t, cudaStream_t s);
+cudaError_t launch_upsample_bwd(const float* dhr_g4, ActView lr_saved, float slope, float* dlr_g4,
+                                unsigned int* amax, int B, int D, int r, UpsampleTables t, cudaStream_t s);
 // 1x1 conv backward: dy G4 (B,D) ; a,b saved inputs (phase, pc); outputs: da,db G4 interiors already
 // multiplied by relu'(a), relu'(b); dw[128][64], dbias[64]
 cudaError_t launch_conv1x1_bwd(const float* dy_g4, ActView a, ActView b, const float* w, float* da_g4,
-                               float* db_g4, float* dw, float* dbias, float* scratch, cudaStream_t s);
+                               float* db_g4, unsigned int* amax_a, unsigned int* amax_b, float* dw, float* dbias,
+                               float* scratch, cudaStream_t s);
 // stem 3->64 weight gradient: feat [B][P^3][6] group ch0, dy G4 -> dw[27][3][64], db[64]
 cudaError_t launch_stem_wgrad(const float* feat, int ch0, const float* dy_g4, int B, int P, float* dw,
                               float* db, float* scratch, cudaStream_t s);
-cudaError_t launch_g4_from_dense(const float* dense, float* g4, int B, int D, cudaStream_t s);
+cudaError_t launch_g4_from_dense(const float* dense, float* g4, unsigned int* amax, int B, int D, cudaStream_t s);
 cudaError_t launch_dense_from_g4(const float* g4, float* dense, int B, int D, cudaStream_t s);

@@ -12,14 +12,17 @@ def rel_l2(a, b):
     return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
 
 
-@pytest.mark.parametrize("D,B", [(6, 2), (9, 1)])
-def test_conv64_layer_bwd(pkg, D, B):
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+@pytest.mark.parametrize("D,B,dy_scale", [(6, 2, 1.0), (9, 1, 1.0), (24, 1, 3e-7), (26, 1, 1e3)])
+def test_conv64_layer_bwd(pkg, D, B, dy_scale, impl):
+    """dy_scale exercises the power-of-two rescaling of the split-fp16 gradient operand: loss gradients
+    of this network are ~1e-6, far below the fp16 normal range."""
     eng = pkg.Engine(8, 2, 0, 0, max_batch=2, training=False, device=0)
     g = np.random.default_rng(D)
     x = g.standard_normal((B, D, D, D, 64)).astype(np.float32)
     k = (g.standard_normal((3, 3, 3, 64, 64)) * 0.05).astype(np.float32)
-    dy = g.standard_normal((B, D, D, D, 64)).astype(np.float32)
-    dx, dk, db = eng.conv64_layer_bwd(x, k, dy)
+    dy = (g.standard_normal((B, D, D, D, 64)) * dy_scale).astype(np.float32)
+    dx, dk, db = eng.conv64_layer_bwd(x, k, dy, impl=pkg._lib.CONV_SIMT if impl == "simt" else pkg._lib.CONV_TCGEN05)
     import importlib
     oracle = importlib.import_module("oracle.sr4d_oracle")
     xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
@@ -51,12 +54,14 @@ def test_loss_metrics(pkg, oracle):
     eng.close()
 
 
-@pytest.mark.parametrize("P,r,low,hi,B", [(8, 2, 1, 1, 2), (6, 1, 1, 1, 2), (6, 2, 0, 1, 1), (6, 2, 2, 0, 2), (6, 1, 0, 0, 1)])
-def test_train_step_gradients_vs_oracle(pkg, oracle, P, r, low, hi, B):
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+@pytest.mark.parametrize("P,r,low,hi,B", [(8, 2, 1, 1, 2), (6, 1, 1, 1, 2), (6, 2, 0, 1, 1), (6, 2, 2, 0, 2), (6, 1, 0, 0, 1),
+                                          (12, 2, 2, 2, 1)])
+def test_train_step_gradients_vs_oracle(pkg, oracle, P, r, low, hi, B, impl):
     params = oracle.glorot_params(low, hi, seed=P + r, bias_scale=0.05)
     batch = oracle.synthetic_batch(B, P, r, seed=4)
     eng = pkg.Engine(P, r, low, hi, max_batch=B, training=True, device=0)
-    eng.set_option(pkg._lib.OPT_CONV_IMPL, pkg._lib.CONV_SIMT)
+    eng.set_option(pkg._lib.OPT_CONV_IMPL, pkg._lib.CONV_SIMT if impl == "simt" else pkg._lib.CONV_AUTO)
     eng.set_weights(params)
     per, l2, pred = eng.train_fwd_bwd(batch[:6], [b[..., 0] for b in batch[6:9]], batch[10], want_pred=True)
     gref, met = oracle.gradients({k: v.astype(np.float64) for k, v in params.items()}, batch, r, low, hi)
@@ -73,7 +78,9 @@ def test_train_step_gradients_vs_oracle(pkg, oracle, P, r, low, hi, B):
     for name, view in eng.tensor_views(eng.grads):
         got = view.cpu().numpy()
         want = gref[name] - (B * 2 * l2c * params[name] if name.endswith("kernel") else 0.0)
-        tol = max(2e-4, 2.0 * rel_l2(g32[name], gref[name]))
+        # tensor-core path: the tcgen05 fp32 accumulator is not IEEE round-to-nearest (~2e-6 per layer relative to
+        # the tensor max, tools/tc_probe.py), which the ill-conditioned stem-kernel gradients amplify to <1e-3
+        tol = max(2e-4 if impl == "simt" else 1e-3, 2.0 * rel_l2(g32[name], gref[name]))
         assert rel_l2(got, want) < tol, (name, rel_l2(got, want), tol)
     # the flat gradient the optimizer consumes: 1e-4 relative
     flat_got = np.concatenate([v.cpu().numpy().ravel() for _, v in eng.tensor_views(eng.grads)])
