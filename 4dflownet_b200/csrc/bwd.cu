@@ -561,6 +561,10 @@ cudaError_t launch_wgrad64_simt(ActView x, const float* dy_g4, float* dw, float*
     reduce_rows_kernel<<<(27 * 4096 + 255) / 256, 256, 0, s>>>(scratch, nchunk, 27 * 4096, dw);
     return cudaGetLastError();
 }
+cudaError_t launch_reduce_rows(const float* partial, int nrows, int ncols, float* out, cudaStream_t s) {
+    reduce_rows_kernel<<<(ncols + 255) / 256, 256, 0, s>>>(partial, nrows, ncols, out);
+    return cudaGetLastError();
+}
 cudaError_t launch_bias_grad(const float* dy_g4, int B, int D, float* db, float* scratch, cudaStream_t s) {
     size_t nvox = (size_t)B * D * D * D;
     unsigned nb = red_blocks(nvox, BG_VOX_PER_BLOCK);

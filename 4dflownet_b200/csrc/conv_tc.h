@@ -24,3 +24,9 @@ void tc_free_weights(TcWeights* w);
 // (re)build the operand image of one layer from its Keras-layout fp32 kernel [27][64][64]
 cudaError_t tc_prepare_weights(TcWeights* w, int layer, const float* kernel, cudaStream_t s);
 cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s);
+
+// tcgen05 weight gradient (wgrad_tc.cu): x = the layer's saved input Act (edge D), dy_split = the scaled
+// split-fp16 gradient [2B][D+4]^3[64] with device exponent *dy_exp; writes tc_wgrad_slabs() partial
+// dW[27][64][64] into `partial` (slab-major) for a row reduction.
+int tc_wgrad_slabs();
+cudaError_t tc_wgrad64(ActView x, const __half* dy_split, const int* dy_exp, float* partial, cudaStream_t s);

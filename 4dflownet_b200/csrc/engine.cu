@@ -3,6 +3,7 @@
 // implements the C ABI of include/sr4d.h.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -404,7 +405,13 @@ int conv64_dgrad(sr4d_t* h, int layer, const GBuf& dy, RawBuf& raw, int B, int D
 }
 int conv64_wgrad(sr4d_t* h, int layer, ActView x, const GBuf& dy, bool bias, cudaStream_t s) {
     ProfScope prof(h, x.D == h->P ? SR4D_PROF_CONV64_WGRAD_LR : SR4D_PROF_CONV64_WGRAD_HR, s);
-    CK(h, launch_wgrad64_simt(x, dy.f, GW(h, layer), h->scratch, h->wgrad_chunks, s), 2);
+    static const bool wgrad_simt = getenv("SR4D_WGRAD_SIMT") != nullptr;   // debugging aid
+    if (use_tc(h) && !wgrad_simt) {
+        CK(h, tc_wgrad64(x, dy.s, dy.exp, h->scratch, s), 1);
+        CK(h, launch_reduce_rows(h->scratch, tc_wgrad_slabs(), 27 * 4096, GW(h, layer), s), 1);
+    } else {
+        CK(h, launch_wgrad64_simt(x, dy.f, GW(h, layer), h->scratch, h->wgrad_chunks, s), 2);
+    }
     if (bias) CK(h, launch_bias_grad(dy.f, x.B, x.D, GB(h, layer), h->scratch, s), 2);
     return SR4D_OK;
 }
@@ -879,7 +886,13 @@ int sr4d_conv64_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const 
             if (!e) e = launch_dense_from_g4(g4o, dx, B, D, s);
             h->launches += 3;
         }
-        if (!e && dkernel) {
+        if (!e && dkernel && tc) {
+            if (!dx) e = launch_g4_split(g4, reinterpret_cast<unsigned int*>(meta), g4s, meta + 1, B, D, s);
+            if (!e) e = tc_wgrad64(vi, g4s, meta + 1, scr, s);
+            if (!e) e = launch_reduce_rows(scr, tc_wgrad_slabs(), 27 * 4096, dwb, s);
+            if (!e) e = cudaMemcpyAsync(dkernel, dwb, 27 * 4096 * 4, cudaMemcpyDeviceToDevice, s);
+            h->launches += 3;
+        } else if (!e && dkernel) {
             e = launch_wgrad64_simt(vi, g4, dwb, scr, nchunk, s);
             if (!e) e = cudaMemcpyAsync(dkernel, dwb, 27 * 4096 * 4, cudaMemcpyDeviceToDevice, s);
             h->launches += 2;

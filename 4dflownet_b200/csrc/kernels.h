@@ -81,6 +81,8 @@ cudaError_t launch_g4_split(const float* g4, const unsigned int* amax, __half* s
 // dW[27][64][64] (+= nothing; overwrite) from x Act and dy G4; scratch >= nchunk*27*64*64 floats
 cudaError_t launch_wgrad64_simt(ActView x, const float* dy_g4, float* dw, float* scratch, int nchunk,
                                 cudaStream_t s);
+// out[j] = sum_r partial[r][j] (deterministic second stage of the split reductions)
+cudaError_t launch_reduce_rows(const float* partial, int nrows, int ncols, float* out, cudaStream_t s);
 cudaError_t launch_bias_grad(const float* dy_g4, int B, int D, float* db, float* scratch, cudaStream_t s);
 cudaError_t launch_upsample_bwd(const float* dhr_g4, ActView lr_saved, float slope, float* dlr_g4,
                                 unsigned int* amax, int B, int D, int r, UpsampleTables t, cudaStream_t s);

@@ -78,15 +78,18 @@ def test_train_step_gradients_vs_oracle(pkg, oracle, P, r, low, hi, B, impl):
     for name, view in eng.tensor_views(eng.grads):
         got = view.cpu().numpy()
         want = gref[name] - (B * 2 * l2c * params[name] if name.endswith("kernel") else 0.0)
-        # tensor-core path: the tcgen05 fp32 accumulator is not IEEE round-to-nearest (~2e-6 per layer relative to
-        # the tensor max, tools/tc_probe.py), which the ill-conditioned stem-kernel gradients amplify to <1e-3
-        tol = max(2e-4 if impl == "simt" else 1e-3, 2.0 * rel_l2(g32[name], gref[name]))
+        # ReLU / LeakyReLU gates make the gradient discontinuous in the forward activations: a forward
+        # perturbation of relative size eps flips ~eps of the gates and moves a random-sign gradient sum by
+        # ~sqrt(eps).  fp32 autograd (eps ~1e-7) is therefore 1e-4..5e-4 from fp64 on some tensors, and the
+        # tensor-core forward (eps ~3e-6: the tcgen05 fp32 accumulator truncates) 1e-3..3e-3 (tools/diag_grads.py).
+        # The backward KERNELS are held to 1e-5 given identical inputs in test_conv64_layer_bwd.
+        tol = max(2e-4 if impl == "simt" else 5e-3, 2.0 * rel_l2(g32[name], gref[name]))
         assert rel_l2(got, want) < tol, (name, rel_l2(got, want), tol)
     # the flat gradient the optimizer consumes: 1e-4 relative
     flat_got = np.concatenate([v.cpu().numpy().ravel() for _, v in eng.tensor_views(eng.grads)])
     flat_want = np.concatenate([(gref[n] - (B * 2 * l2c * params[n] if n.endswith("kernel") else 0.0)).ravel()
                                 for n, *_ in eng.table])
-    assert rel_l2(flat_got, flat_want) < 1e-4
+    assert rel_l2(flat_got, flat_want) < (1e-4 if impl == "simt" else 3e-3)
     # one Adam step (Keras semantics, L2 gradient folded in) vs the oracle's numpy Adam
     lr = 1e-3
     before = dict(zip([n for n, *_ in eng.table], eng.get_weights()))
@@ -99,5 +102,5 @@ def test_train_step_gradients_vs_oracle(pkg, oracle, P, r, low, hi, B, impl):
         upd_ref = p1 - before[name]
         upd = after[name].astype(np.float64) - before[name]
         big = np.abs(g_tot) > 1e-3 * np.abs(g_tot).max()
-        assert np.abs(upd[big] - upd_ref[big]).max() < 2e-2 * lr, name
+        assert np.abs(upd[big] - upd_ref[big]).max() < (2e-2 if impl == "simt" else 5e-2) * lr, name
     eng.close()

@@ -10,9 +10,11 @@ def rel(a, b):
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
 
-P, r, low, hi, B = 12, 2, 2, 2, 2
-params = oracle.glorot_params(low, hi, seed=7, bias_scale=0.02)
-batch = oracle.synthetic_batch(B, P, r, seed=11)
+args = [int(a) for a in sys.argv[1:6]] if len(sys.argv) >= 6 else [12, 2, 2, 2, 2]
+P, r, low, hi, B = args
+pseed, bseed = (int(sys.argv[6]), int(sys.argv[7])) if len(sys.argv) >= 8 else (7, 11)
+params = oracle.glorot_params(low, hi, seed=pseed, bias_scale=0.05 if len(sys.argv) >= 8 else 0.02)
+batch = oracle.synthetic_batch(B, P, r, seed=bseed)
 eng = pkg.Engine(P, r, low, hi, max_batch=B, training=True, device=0)
 eng.set_weights(params)
 per, l2, _ = eng.train_fwd_bwd(batch[:6], [b[..., 0] for b in batch[6:9]], batch[10])
@@ -24,6 +26,7 @@ for name, view in eng.tensor_views(eng.grads):
     corr = (B * 2 * l2c * params[name] if name.endswith('kernel') else 0.0)
     print(f"{name:24s} {rel(view.cpu().numpy(), g64[name]-corr):12.3e} {rel(g32[name]-corr, g64[name]-corr):15.3e}")
 
+if len(sys.argv) >= 6: sys.exit(0)
 # timings, config 2 geometry
 def timeit(fn, n=3):
     fn(); torch.cuda.synchronize()

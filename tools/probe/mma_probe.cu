@@ -82,6 +82,77 @@ __global__ void func_probe(int shift_rows, int sbo_bytes, int base_mode, int tes
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(32u) : "memory");
 }
 
+
+// ---------------- MN-major functional probe (the wgrad operand form) ----------------
+// Operands are [k rows][64 elements] 128-byte rows (k = voxel index), MN-major: M (or N) = 128 = two
+// 64-wide atoms LBO bytes apart ("hi" and "lo" arrays); K = 16 = two 8-row groups SBO bytes apart.
+// which = 0: probe A addressing (B one-hot), which = 1: probe B addressing (A one-hot).
+__global__ void func_probe_mn(int shift_rows, int sbo_bytes, int which, float* out) {
+    extern __shared__ uint8_t raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+    // probed operand: hi rows at 0, lo rows at 32 KB (256 rows each); one-hot operand at 64 KB (hi) / 66 KB (lo)
+    const uint32_t LBO_P = 32768, OH = 65536, LBO_OH = 2048;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 72 * 1024);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 2 * 256 * 64; e += blockDim.x) {
+        int arr = e / (256 * 64), i = (e >> 6) & 255, m = e & 63;
+        float v = (float)((((i + (arr ? 7 : 0)) % 32) * 64) + m);
+        uint32_t byte = arr * LBO_P + i * 128 + m * 2;
+        uint32_t sw = byte ^ (((byte >> 7) & 7) << 4);
+        *reinterpret_cast<__half*>(smem + sw) = __float2half(v);
+    }
+    // one-hot operand: element (j, k) = (k == j % 16), j = 0..127 (atom = j / 64), rows k = 0..15
+    for (int e = tid; e < 2 * 16 * 64; e += blockDim.x) {
+        int arr = e / (16 * 64), k = (e >> 6) & 15, jj = e & 63;
+        int j = arr * 64 + jj;
+        uint32_t byte = OH + arr * LBO_OH + k * 128 + jj * 2;
+        uint32_t sw = byte ^ (((byte >> 7) & 7) << 4);
+        *reinterpret_cast<__half*>(smem + sw) = __float2half((j % 16) == k ? 1.f : 0.f);
+    }
+    if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *slot;
+    if (tid == 0) {
+        // D=f32, A=B=f16, both MN-major, M=128, N=128
+        const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        auto desc_mn = [](uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+            uint64_t d = 0;
+            d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+            d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+            d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+            d |= (uint64_t)1 << 46;
+            d |= (uint64_t)2 << 61;
+            return d;
+        };
+        const uint64_t dp = desc_mn(smem_u32(smem) + shift_rows * 128, LBO_P, sbo_bytes);
+        const uint64_t doh = desc_mn(smem_u32(smem) + OH, LBO_OH, 1024);
+        if (which == 0) tc_mma_f16(tm, dp, doh, idesc, 0);
+        else tc_mma_f16(tm, doh, dp, idesc, 0);
+        tc_commit(bar);
+    }
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    if (tid < 128) {
+        for (int c = 0; c < 128; c += 16) {
+            float v[16];
+            tc_ld16(tm + ((uint32_t)(tid & ~31) << 16) + c, v);
+            tc_ld_wait();
+            for (int n = 0; n < 16; ++n) out[tid * 128 + c + n] = v[n];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(128u) : "memory");
+}
+
 // ---------------- rate probe ----------------
 // every CTA issues `iters` rounds of {MMA(M=128,N=n1) x k1 ; MMA(M=128,N=n2) x k2} on resident smem
 __global__ void rate_probe(int n1, int k1, int n2, int k2, int iters, int a_rows_stride, long long* cycles) {
@@ -163,6 +234,36 @@ int main() {
                 printf("\n");
             }
 
+
+    {
+        printf("== functional MN-major: shifted start / non-1024 SBO ==\n");
+        float* dmn;
+        CHECK(cudaMalloc(&dmn, 128 * 128 * 4));
+        std::vector<float> hm(128 * 128);
+        const int smem_mn = 72 * 1024 + 64 + 1024;
+        CHECK(cudaFuncSetAttribute(func_probe_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mn));
+        for (int sbo : {1024, 1280})
+            for (int sh : {0, 1, 3, 10, 21})
+                for (int which = 0; which < 2; ++which) {
+                    func_probe_mn<<<1, 128, smem_mn>>>(sh, sbo, which, dmn);
+                    CHECK(cudaDeviceSynchronize());
+                    CHECK(cudaMemcpy(hm.data(), dmn, hm.size() * 4, cudaMemcpyDeviceToHost));
+                    int bad = 0, fm = -1, fn = -1; float fv = 0, fe = 0;
+                    for (int m = 0; m < 128; ++m)
+                        for (int n = 0; n < 128; ++n) {
+                            // which=0: D[m][n] = P(m, k = n%16); which=1: D[m][n] = P(n, k = m%16)
+                            int j = which == 0 ? m : n, k = which == 0 ? n % 16 : m % 16;
+                            int row = sh + (k / 8) * (sbo / 128) + (k % 8);
+                            int arr = j / 64;
+                            float exp = (float)((((row + (arr ? 7 : 0)) % 32) * 64) + (j % 64));
+                            float v = hm[m * 128 + n];
+                            if (v != exp) { if (!bad) { fm = m; fn = n; fv = v; fe = exp; } ++bad; }
+                        }
+                    printf("MN sbo=%4d shift=%2d probe %c: mismatches %5d", sbo, sh, which ? 'B' : 'A', bad);
+                    if (bad) printf("  (first m=%d n=%d got %.0f expected %.0f)", fm, fn, fv, fe);
+                    printf("\n");
+                }
+    }
     printf("== rates (cycles per MMA, all SMs busy) ==\n");
     long long* dcyc;
     CHECK(cudaMalloc(&dcyc, 148 * 8));
