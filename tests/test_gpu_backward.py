@@ -90,17 +90,27 @@ def test_train_step_gradients_vs_oracle(pkg, oracle, P, r, low, hi, B, impl):
     flat_want = np.concatenate([(gref[n] - (B * 2 * l2c * params[n] if n.endswith("kernel") else 0.0)).ravel()
                                 for n, *_ in eng.table])
     assert rel_l2(flat_got, flat_want) < (1e-4 if impl == "simt" else 3e-3)
-    # one Adam step (Keras semantics, L2 gradient folded in) vs the oracle's numpy Adam
+    # one Adam step (Keras semantics, L2 gradient folded in) vs the oracle's numpy Adam, fed the gradient the
+    # engine itself produced: the first step moves a weight by lr*g/(|g|+3.2e-6), so near g ~ 1e-6 the update
+    # amplifies gradient noise that the checks above already bound; this isolates the Adam kernel.
     lr = 1e-3
-    before = dict(zip([n for n, *_ in eng.table], eng.get_weights()))
+    names = [n for n, *_ in eng.table]
+    before = dict(zip(names, eng.get_weights()))
+    g_eng = {n: v.cpu().numpy().astype(np.float64) for n, v in eng.tensor_views(eng.grads)}
     eng.adam_step(lr, 1, B * 2 * l2c)
-    after = dict(zip([n for n, *_ in eng.table], eng.get_weights()))
+    after = dict(zip(names, eng.get_weights()))
+    m_after = {n: v.cpu().numpy() for n, v in eng.tensor_views(eng.adam_m)}
     for name in before:
-        g_tot = gref[name]
-        p1, _, _ = oracle.adam_step(before[name].astype(np.float64), g_tot, 0.0, 0.0, 1, lr)
-        # first Adam step moves every weight by ~lr*sign(g): compare the update, not the weight
-        upd_ref = p1 - before[name]
-        upd = after[name].astype(np.float64) - before[name]
-        big = np.abs(g_tot) > 1e-3 * np.abs(g_tot).max()
-        assert np.abs(upd[big] - upd_ref[big]).max() < (2e-2 if impl == "simt" else 5e-2) * lr, name
+        w0 = before[name].astype(np.float64)
+        g_tot = g_eng[name] + (B * 2 * l2c * w0 if name.endswith("kernel") else 0.0)
+        p1, m1, _ = oracle.adam_step(w0, g_tot, 0.0, 0.0, 1, lr)
+        upd_ref = p1 - w0
+        upd = after[name].astype(np.float64) - w0
+        assert np.abs(upd - upd_ref).max() < 2e-3 * lr, name     # fp32 rounding of w - update
+        np.testing.assert_allclose(m_after[name], m1, rtol=1e-5, atol=1e-12)
+        # and the update implied by the fp64 reference gradient agrees wherever the gradient is well above eps
+        p_ref, _, _ = oracle.adam_step(w0, gref[name], 0.0, 0.0, 1, lr)
+        big = np.abs(gref[name]) > 1e-2 * np.abs(gref[name]).max()
+        if np.abs(gref[name]).max() > 1e-3:
+            assert np.percentile(np.abs(upd[big] - (p_ref - w0)[big]), 99) < 0.2 * lr, name
     eng.close()
