@@ -25,92 +25,6 @@ __global__ void reduce_rows_kernel(const float* __restrict__ partial, int nrows,
     out[j] = s;
 }
 
-// ---- 64->1 head conv, input gradient on the padded grid --------------------------------
-__global__ void __launch_bounds__(256) head2_dgrad_kernel(const float* __restrict__ g, int c,
-                                                          const float* __restrict__ w, float* __restrict__ raw,
-                                                          int B, int H) {
-    __shared__ float ws[27 * 64];
-    for (int i = threadIdx.x; i < 27 * 64; i += 256) ws[i] = w[i];
-    __syncthreads();
-    const int Hp = H + 2;
-    const size_t nvox = (size_t)B * Hp * Hp * Hp;
-    size_t vi = (size_t)blockIdx.x * 64 + (threadIdx.x >> 2);
-    if (vi >= nvox) return;
-    const int cq = (threadIdx.x & 3) * 16;
-    int pz = vi % Hp, py = (vi / Hp) % Hp, px = (vi / ((size_t)Hp * Hp)) % Hp, b = vi / ((size_t)Hp * Hp * Hp);
-    float acc[16];
-#pragma unroll
-    for (int n = 0; n < 16; ++n) acc[n] = 0.f;
-    for (int tx = 0; tx < 3; ++tx) {
-        int x = px - tx;
-        if (x < 0 || x >= H) continue;
-        for (int ty = 0; ty < 3; ++ty) {
-            int y = py - ty;
-            if (y < 0 || y >= H) continue;
-            for (int tz = 0; tz < 3; ++tz) {
-                int z = pz - tz;
-                if (z < 0 || z >= H) continue;
-                float gv = g[((((size_t)b * H + x) * H + y) * H + z) * 3 + c];
-                const float* wp = ws + ((tx * 3 + ty) * 3 + tz) * 64 + cq;
-#pragma unroll
-                for (int n = 0; n < 16; ++n) acc[n] = fmaf(gv, wp[n], acc[n]);
-            }
-        }
-    }
-    float* o = raw + vi * 64 + cq;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<float4*>(o + q * 4) = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
-}
-
-// ---- 64->1 head conv, weight gradient: dw[t][ci] = sum_p hp[p][ci] * g[p - t] ------------
-// partial[blk][28][64]: rows 0..26 = dw taps, row 27 = (all 64 entries) sum of g (bias grad)
-constexpr int H2W_VOX_PER_BLOCK = 512;
-__global__ void __launch_bounds__(256) head2_wgrad_kernel(ActView h, const float* __restrict__ g, int c,
-                                                          float* __restrict__ partial) {
-    const int H = h.D, Hp = H + 2;
-    const size_t nvox = (size_t)h.B * Hp * Hp * Hp;
-    const int ci = threadIdx.x & 63, sub = threadIdx.x >> 6;
-    float acc[28];
-#pragma unroll
-    for (int t = 0; t < 28; ++t) acc[t] = 0.f;
-    const size_t nchunks = (nvox + H2W_VOX_PER_BLOCK - 1) / H2W_VOX_PER_BLOCK;
-    for (size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x)
-    for (int k = sub; k < H2W_VOX_PER_BLOCK; k += 4) {
-        size_t vi = chunk * H2W_VOX_PER_BLOCK + k;
-        if (vi >= nvox) break;
-        int pz = vi % Hp, py = (vi / Hp) % Hp, px = (vi / ((size_t)Hp * Hp)) % Hp, b = vi / ((size_t)Hp * Hp * Hp);
-        float hv = join_f16(h.hi[vi * 64 + ci], h.lo[vi * 64 + ci]);
-#pragma unroll
-        for (int tx = 0; tx < 3; ++tx) {
-            int x = px - tx;
-#pragma unroll
-            for (int ty = 0; ty < 3; ++ty) {
-                int y = py - ty;
-#pragma unroll
-                for (int tz = 0; tz < 3; ++tz) {
-                    int z = pz - tz;
-                    float gv = 0.f;
-                    if (x >= 0 && x < H && y >= 0 && y < H && z >= 0 && z < H)
-                        gv = g[((((size_t)b * H + x) * H + y) * H + z) * 3 + c];
-                    acc[(tx * 3 + ty) * 3 + tz] = fmaf(hv, gv, acc[(tx * 3 + ty) * 3 + tz]);
-                }
-            }
-        }
-        // bias gradient: count g once per interior voxel (padded coords 1..H)
-        if (px >= 1 && px <= H && py >= 1 && py <= H && pz >= 1 && pz <= H)
-            acc[27] += g[((((size_t)b * H + px - 1) * H + py - 1) * H + pz - 1) * 3 + c];
-    }
-    __shared__ float red[4][28][64];
-#pragma unroll
-    for (int t = 0; t < 28; ++t) red[sub][t][ci] = acc[t];
-    __syncthreads();
-    for (int i = threadIdx.x; i < 28 * 64; i += 256) {
-        int t = i >> 6, cc = i & 63;
-        partial[(size_t)blockIdx.x * 28 * 64 + i] = red[0][t][cc] + red[1][t][cc] + red[2][t][cc] + red[3][t][cc];
-    }
-}
-
 // block-wide max of |v| folded into *p with at most one atomic per block (all threads must call)
 __device__ __forceinline__ void absmax_commit(float m, unsigned int* p) {
     __shared__ float wm[32];
@@ -125,6 +39,100 @@ __device__ __forceinline__ void absmax_commit(float m, unsigned int* p) {
         if (bits > *reinterpret_cast<volatile unsigned int*>(p)) atomicMax(p, bits);
     }
 }
+// ---- 64->1 head conv (SR4DFlowNet.py:40,43,46), whole backward in one pass ------------------
+// With the clamp padding folded in, both gradients of out[i] = b + sum_t w[t] . hpad[i+t] share one
+// channel-independent quantity, G(j,t) = sum of g[i] over the output voxels i whose tap t reads
+// (clamped) input voxel j:
+//     dh[j][ci] = relu'(h[j][ci]) * sum_t w[t][ci] * G(j,t)          (dgrad + MirrorPadGrad + ReluGrad)
+//     dw[t][ci] = sum_j h[j][ci] * G(j,t)                            (Conv3DBackpropFilter)
+//     db        = sum_i g[i]
+// Per axis the set {i : clamp(i + t - 1) = j} is {j - t + 1} plus {j} again when (j==0,t==0) or
+// (j==D-1,t==2).  A block walks (b,x,y) z-lines: it stages the 3x3 neighbouring g lines, builds
+// G[z][27] in shared memory, then 64 channels x 4 z-phases of threads stream h once, write dh (fp32 G4
+// interior) and keep dw in registers across lines.  partial[blk][28][64]: rows 0..26 = dw, row 27 = db.
+__global__ void __launch_bounds__(256) head2_bwd_kernel(ActView h, const float* __restrict__ g, int c,
+                                                        const float* __restrict__ w, float* __restrict__ out_g4,
+                                                        unsigned int* amax, float* __restrict__ partial) {
+    extern __shared__ __align__(16) float h2sm[];
+    const int H = h.D, Hz = H + 2;
+    float* gl = h2sm;                              // [3][3][H+2]
+    float* Gs = h2sm + (9 * Hz + 3) / 4 * 4;       // [H][28], 16-byte aligned rows
+    const int ci = threadIdx.x & 63, q = threadIdx.x >> 6;
+    float wr[27], dw[28];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) { wr[t] = w[t * 64 + ci]; dw[t] = 0.f; }
+    dw[27] = 0.f;
+    float m = 0.f;
+    const int nlines = h.B * H * H;
+    for (int line = blockIdx.x; line < nlines; line += gridDim.x) {
+        const int y = line % H, x = (line / H) % H, b = line / (H * H);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 9 * Hz; i += 256) {
+            const int r = i / Hz, zz = i % Hz - 1;
+            const int ix = x + r / 3 - 1, iy = y + r % 3 - 1;
+            float v = 0.f;
+            if (ix >= 0 && ix < H && iy >= 0 && iy < H && zz >= 0 && zz < H)
+                v = g[((((size_t)b * H + ix) * H + iy) * H + zz) * 3 + c];
+            gl[i] = v;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < H * 28; i += 256) {
+            const int z = i / 28, t = i % 28;
+            float s = 0.f;
+            if (t == 27) {
+                s = gl[4 * Hz + z + 1];                      // g at the voxel itself (bias gradient)
+            } else {
+                const int tx = t / 9, ty = (t / 3) % 3, tz = t % 3;
+                // offsets o = i - j contributing along each axis: 1 - t always (zero if out of range), plus 0
+                // again at the clamped ends
+                const int ex = (x == 0 && tx == 0) || (x == H - 1 && tx == 2);
+                const int ey = (y == 0 && ty == 0) || (y == H - 1 && ty == 2);
+                const int ez = (z == 0 && tz == 0) || (z == H - 1 && tz == 2);
+                for (int ax = 0; ax <= ex; ++ax) {
+                    const int rx = ax ? 1 : 2 - tx;              // row index = o + 1
+                    for (int ay = 0; ay <= ey; ++ay) {
+                        const int ry = ay ? 1 : 2 - ty;
+                        const float* gp = gl + (rx * 3 + ry) * Hz + z + 1;
+                        s += gp[1 - tz];
+                        if (ez) s += gp[0];
+                    }
+                }
+            }
+            Gs[i] = s;
+        }
+        __syncthreads();
+        for (int z = q; z < H; z += 4) {
+            const size_t ao = act_off(H, b, x, y, z) + ci;
+            const float hv = join_f16(h.hi[ao], h.lo[ao]);
+            const float4* G4p = reinterpret_cast<const float4*>(Gs + z * 28);
+            float Gt[28];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const float4 v = G4p[k];
+                Gt[4 * k] = v.x; Gt[4 * k + 1] = v.y; Gt[4 * k + 2] = v.z; Gt[4 * k + 3] = v.w;
+            }
+            float sacc = 0.f;
+#pragma unroll
+            for (int t = 0; t < 27; ++t) {
+                sacc = fmaf(wr[t], Gt[t], sacc);
+                dw[t] = fmaf(hv, Gt[t], dw[t]);
+            }
+            dw[27] += Gt[27];
+            const float d = hv > 0.f ? sacc : 0.f;
+            out_g4[g4_off(H, b, x, y, z) + ci] = d;
+            m = fmaxf(m, fabsf(d));
+        }
+    }
+    __syncthreads();
+    float* red = h2sm;                             // [4][28][64] (aliases gl / Gs)
+#pragma unroll
+    for (int t = 0; t < 28; ++t) red[(q * 28 + t) * 64 + ci] = dw[t];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 28 * 64; i += 256)
+        partial[(size_t)blockIdx.x * 28 * 64 + i] = red[i] + red[28 * 64 + i] + red[2 * 28 * 64 + i] + red[3 * 28 * 64 + i];
+    if (amax) absmax_commit(m, amax);
+}
+
 __device__ __forceinline__ float exp2_scale(const int* e, int sign) { return e ? exp2f((float)(sign * *e)) : 1.f; }
 
 // ---- halo fold (MirrorPadGrad) + add + activation gradient -------------------------------
@@ -275,24 +283,45 @@ __global__ void __launch_bounds__(256) wgrad64_kernel(ActView xin, const float* 
     }
 }
 
-// ---- bias gradient: column sums of a G4 interior -----------------------------------------
-constexpr int BG_VOX_PER_BLOCK = 1024;
+// ---- bias gradient (BiasAddGrad): column sums of a G4 interior ---------------------------
+// 16 threads x float4 cover one voxel's 64 channels; 16 voxels per pass, grid-stride over voxels.
 __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ dy, int B, int D, float* __restrict__ partial) {
     const size_t nvox = (size_t)B * D * D * D;
-    const int co = threadIdx.x & 63, sub = threadIdx.x >> 6;
-    float s = 0.f;
-    const size_t nchunks = (nvox + BG_VOX_PER_BLOCK - 1) / BG_VOX_PER_BLOCK;
-    for (size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x)
-    for (int k = sub; k < BG_VOX_PER_BLOCK; k += 4) {
-        size_t vi = chunk * BG_VOX_PER_BLOCK + k;
-        if (vi >= nvox) break;
+    const int c4 = (threadIdx.x & 15) * 4, sub = threadIdx.x >> 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t vi = (size_t)blockIdx.x * 16 + sub; vi < nvox; vi += (size_t)gridDim.x * 16) {
         int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
-        s += dy[g4_off(D, b, x, y, z) + co];
+        const float4 v = *reinterpret_cast<const float4*>(dy + g4_off(D, b, x, y, z) + c4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-    __shared__ float red[4][64];
-    red[sub][co] = s;
+    __shared__ float4 red[16][16];
+    red[sub][threadIdx.x & 15] = s;
     __syncthreads();
-    if (threadIdx.x < 64) partial[(size_t)blockIdx.x * 64 + co] = red[0][co] + red[1][co] + red[2][co] + red[3][co];
+    if (threadIdx.x < 16) {
+        float4 t = red[0][threadIdx.x];
+        for (int k = 1; k < 16; ++k) {
+            const float4 v = red[k][threadIdx.x];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        *reinterpret_cast<float4*>(partial + (size_t)blockIdx.x * 64 + c4) = t;
+    }
+}
+
+// out[j] = sum_r partial[r][j] for a few (<= 256) columns: 256/ncols row phases per block, fixed order
+__global__ void __launch_bounds__(256) reduce_rows_small_kernel(const float* __restrict__ partial, int nrows, int ncols,
+                                                                float* __restrict__ out) {
+    __shared__ float red[256];
+    const int nph = 256 / ncols;
+    const int j = threadIdx.x % ncols, ph = threadIdx.x / ncols;
+    float s = 0.f;
+    if (ph < nph)
+        for (int r = ph; r < nrows; r += nph) s += partial[(size_t)r * ncols + j];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < ncols) {
+        for (int k = 1; k < nph; ++k) s += red[k * ncols + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
 }
 
 // ---- upsample backward: d_lr = U^T d_hr, then * act'(lr) --------------------------------
@@ -523,17 +552,21 @@ constexpr unsigned MAX_RED_BLOCKS = 1184;   // 148 SMs x 8: bounds the split-red
 inline unsigned red_blocks(size_t n, int per) { unsigned b = nblocks(n, per); return b < MAX_RED_BLOCKS ? b : MAX_RED_BLOCKS; }
 }  // namespace
 
-cudaError_t launch_head2_dgrad(const float* g, int c, const float* w, float* raw, int B, int H, cudaStream_t s) {
-    size_t nvox = (size_t)B * (H + 2) * (H + 2) * (H + 2);
-    head2_dgrad_kernel<<<nblocks(nvox, 64), 256, 0, s>>>(g, c, w, raw, B, H);
-    return cudaGetLastError();
-}
-cudaError_t launch_head2_wgrad(ActView h, const float* g, int c, float* dw, float* db, float* scratch,
-                               cudaStream_t s) {
-    size_t nvox = (size_t)h.B * (h.D + 2) * (h.D + 2) * (h.D + 2);
-    unsigned nb = red_blocks(nvox, H2W_VOX_PER_BLOCK);
+cudaError_t launch_head2_bwd(ActView h, const float* g, int c, const float* w, float* out_g4, unsigned int* amax,
+                             float* dw, float* db, float* scratch, cudaStream_t s) {
+    const int H = h.D;
+    const int nlines = h.B * H * H;
+    const unsigned nb = nlines < 592 ? nlines : 592;           // 148 SMs x 4 resident blocks
+    size_t smem = (size_t)((9 * (H + 2) + 3) / 4 * 4 + H * 28) * sizeof(float);
+    if (smem < 4 * 28 * 64 * sizeof(float)) smem = 4 * 28 * 64 * sizeof(float);
+    static size_t attr_smem = 0;
+    if (smem > 48 * 1024 && smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(head2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_smem = smem;
+    }
     float* tmp = scratch + (size_t)nb * 28 * 64;   // reduced [28][64]
-    head2_wgrad_kernel<<<nb, 256, 0, s>>>(h, g, c, scratch);
+    head2_bwd_kernel<<<nb, 256, smem, s>>>(h, g, c, w, out_g4, amax, scratch);
     reduce_rows_kernel<<<(28 * 64 + 255) / 256, 256, 0, s>>>(scratch, nb, 28 * 64, tmp);
     cudaMemcpyAsync(dw, tmp, 27 * 64 * sizeof(float), cudaMemcpyDeviceToDevice, s);
     cudaMemcpyAsync(db, tmp + 27 * 64, sizeof(float), cudaMemcpyDeviceToDevice, s);
@@ -567,9 +600,9 @@ cudaError_t launch_reduce_rows(const float* partial, int nrows, int ncols, float
 }
 cudaError_t launch_bias_grad(const float* dy_g4, int B, int D, float* db, float* scratch, cudaStream_t s) {
     size_t nvox = (size_t)B * D * D * D;
-    unsigned nb = red_blocks(nvox, BG_VOX_PER_BLOCK);
+    unsigned nb = red_blocks(nvox, 64);
     bias_grad_kernel<<<nb, 256, 0, s>>>(dy_g4, B, D, scratch);
-    reduce_rows_kernel<<<1, 64, 0, s>>>(scratch, nb, 64, db);
+    reduce_rows_small_kernel<<<1, 256, 0, s>>>(scratch, nb, 64, db);
     return cudaGetLastError();
 }
 cudaError_t launch_upsample_bwd(const float* dhr_g4, ActView lr_saved, float slope, float* dlr_g4,

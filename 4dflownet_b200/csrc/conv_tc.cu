@@ -6,13 +6,18 @@
 //
 // Formulation (implicit GEMM, weights as the M operand so the voxel dimension is the flexible N):
 //     D[128 x N] += A_tap[128 x 64] * B_tap[N x 64]^T        for the 27 taps, K = 64 channels
-//   A_tap rows  = the layer's weights for that tap, split in fp16: W = Whi + Wlo/2048.
-//                 Row 32q+l holds Whi[co=16q+l] for l<16 and Wlo[co=16q+l-16] for l>=16, so
-//                 the hi and lo partial sums of one output channel sit in lanes l and l^16 of
-//                 the same epilogue warp (one shuffle combines them).
-//   B_tap rows  = the N = 8*TY voxels of a (TY y-lines x 8 z) tile at a fixed x: their 64 input
-//                 channels, from the activation's fp16 hi plane (accumulator D1) and lo plane (D2).
-//   out[co][v]  = D1[hi] + (D1[lo] + D2[hi]) / 2048 + D2[lo] / 2048^2     (fp32 in TMEM)
+//   Operands are split in fp16: W = Whi + Wlo/2048, X = Xhi + Xlo/2048.  ONE accumulator per tile:
+//     TMEM lanes 0..63   ("L", lane = co)      accumulate  Wlo*Xhi + Whi*Xlo   (both scaled by 2048)
+//     TMEM lanes 64..127 ("H", lane = 64 + co) accumulate  Whi*Xhi
+//   through two MMAs per K-step that share one 16 KB weight image [Wlo rows ; Whi rows] followed by an
+//   8 KB block of zeros in shared memory:
+//     MMA_a: A = image            = [Wlo ; Whi],  B = the activation's hi plane
+//     MMA_b: A = image + 8 KB     = [Whi ; 0  ],  B = the activation's lo plane
+//   out[co][v] = D[H] + D[L]/2048 (the Wlo*Xlo term, 2^-22 relative, is dropped).  With a single
+//   accumulator of N <= 208 columns the 512 TMEM columns hold TWO tiles, so the epilogue of tile i
+//   overlaps the MMAs of tile i+1 (the previous two-accumulator version stalled the tensor pipe for
+//   ~30 % of every tile while the epilogue drained TMEM).
+//   B_tap rows = the N = 8*TY voxels of a (TY y-lines x 8 z) tile at a fixed x, 64 channels each.
 //
 // Data movement: ONE TMA box per dx loads the (TY+2) x 10 voxel halo plane (hi and lo) into
 // shared memory as dense 128-byte rows (SWIZZLE_128B).  All nine (dy,dz) taps of that plane are
@@ -22,7 +27,7 @@
 // B200 by tools/probe/mma_probe.cu).  Every activation byte is fetched 3x from L2 per layer
 // (plus y/z halo), weights stream per tap as pre-swizzled 16 KB images (cp.async.bulk).
 // Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue:
-// TMEM -> registers -> (hi/lo row combine, bias) -> fp32 shared-memory transpose -> coalesced
+// TMEM -> registers -> fp32 shared-memory staging (H part + bias, L part / 2048) -> coalesced
 // 16-byte residual loads / activation / fp16 split / stores with the replicate halo.
 #include <cuda.h>
 
@@ -35,13 +40,16 @@
 
 namespace {
 
-constexpr int W_TAP_BYTES = 128 * 64 * 2;   // 16 KB: [Whi;Wlo] x 64 ci, fp16, swizzled
+constexpr int W_TAP_BYTES = 128 * 64 * 2;            // 16 KB: [Wlo ; Whi] x 64 ci, fp16, swizzled
+constexpr int W_ZERO_BYTES = 64 * 64 * 2;            // 8 KB of zeros behind every staged image
+constexpr int W_STAGE_BYTES = W_TAP_BYTES + W_ZERO_BYTES;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_EPI = NUM_EPI_WARPS * 32;   // epilogue threads
 constexpr int NUM_THREADS = 64 + NUM_EPI;
 constexpr int TZ = 8;                       // voxels per 8-row group (one z run)
 constexpr int ZP = TZ + 2;                  // plane row pitch in voxels
-constexpr int STAGE_FLOATS = 64 * 64;       // epilogue transpose buffer: 64 voxels x 64 channels
+constexpr int TMEM_COLS = 512;              // two accumulators of up to 256 columns
+constexpr int ACC_STRIDE = 256;             // column offset of the second accumulator
 
 template <int TY>
 struct Cfg {
@@ -50,11 +58,14 @@ struct Cfg {
     static constexpr int PART_BYTES = (ROWS * 128 + 1023) / 1024 * 1024;
     static constexpr int XSTAGE_BYTES = 2 * PART_BYTES;                // hi part | lo part
     static constexpr int NXS = 2;
-    static constexpr int NWS = 4;
-    static constexpr int SMEM_BYTES = 1024 + NXS * XSTAGE_BYTES + NWS * W_TAP_BYTES + STAGE_FLOATS * 4 + 256;
-    static constexpr int TMEM_COLS = 2 * N <= 32 ? 32 : 2 * N <= 64 ? 64 : 2 * N <= 128 ? 128 : 2 * N <= 256 ? 256 : 512;
-    static constexpr int NCHUNK = TY / 8;                              // epilogue chunks of 64 voxels
-    static_assert(TY % 8 == 0 && N % 16 == 0 && N >= 16 && N <= 256, "UMMA N constraint for M=128");
+    static constexpr int NWS = 3;
+    static constexpr int LPC = (TY % 4 == 0) ? 4 : 3;                  // y-lines per epilogue chunk
+    static constexpr int CV = LPC * TZ;                                // voxels (TMEM columns) per chunk
+    static constexpr int NCHUNK = (TY + LPC - 1) / LPC;
+    static constexpr int STAGE_FLOATS = 2 * CV * 64;                   // [H | L][voxel][channel]
+    static constexpr int SMEM_BYTES = 1024 + NXS * XSTAGE_BYTES + NWS * W_STAGE_BYTES + STAGE_FLOATS * 4 + 256;
+    static_assert(N % 16 == 0 && N >= 16 && N <= 256, "UMMA N constraint for M=128");
+    static_assert(CV == 32 || CV == 24, "epilogue chunk shapes");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -70,7 +81,6 @@ struct KParams {
     float slope;
     int B, Do, halo;
     int nyt, nzt, ntiles;
-    long long* dbg;          // SR4D_TC_DEBUG=1: per-CTA cycles the MMA warp spent waiting {t_empty, x_full, w_full, total}
 };
 
 __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo) {
@@ -90,30 +100,35 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* xs = smem;                                   // NXS x [hi part | lo part]
-    uint8_t* wsm = smem + C::NXS * C::XSTAGE_BYTES;       // NWS x 16 KB
-    float* stage = reinterpret_cast<float*>(wsm + C::NWS * W_TAP_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage) + STAGE_FLOATS * 4);
+    uint8_t* wsm = smem + C::NXS * C::XSTAGE_BYTES;       // NWS x (16 KB image + 8 KB zeros)
+    float* stage = reinterpret_cast<float*>(wsm + C::NWS * W_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage) + C::STAGE_FLOATS * 4);
     uint64_t* x_full = bars;                 // [NXS]
     uint64_t* x_empty = bars + C::NXS;       // [NXS]
     uint64_t* w_full = bars + 2 * C::NXS;    // [NWS]
     uint64_t* w_empty = w_full + C::NWS;     // [NWS]
-    uint64_t* t_full = w_empty + C::NWS;     // [1]
-    uint64_t* t_empty = t_full + 1;          // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 1);
+    uint64_t* t_full = w_empty + C::NWS;     // [2]
+    uint64_t* t_empty = t_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    // the zero blocks are written once (generic proxy) and only ever read by the tensor core
+    for (int i = threadIdx.x; i < C::NWS * (W_ZERO_BYTES / 16); i += NUM_THREADS) {
+        const int st = i / (W_ZERO_BYTES / 16), o = i % (W_ZERO_BYTES / 16);
+        *reinterpret_cast<uint4*>(wsm + st * W_STAGE_BYTES + W_TAP_BYTES + o * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NXS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
         for (int i = 0; i < C::NWS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        mbar_init(t_full, 1);
-        mbar_init(t_empty, NUM_EPI_WARPS);
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&xmap);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)C::TMEM_COLS)
+                     "r"((uint32_t)TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -147,7 +162,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                         const uint32_t ws = wi % C::NWS, wph = (wi / C::NWS) & 1;
                         mbar_wait(&w_empty[ws], wph ^ 1);
                         mbar_expect_tx(&w_full[ws], W_TAP_BYTES);
-                        bulk_load(wsm + ws * W_TAP_BYTES,
+                        bulk_load(wsm + ws * W_STAGE_BYTES,
                                   reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)(dx * 9 + tp) * W_TAP_BYTES,
                                   W_TAP_BYTES, &w_full[ws]);
                         ++wi;
@@ -160,37 +175,33 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N
             const uint32_t idesc = (1u << 4) | ((uint32_t)(C::N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t d1 = tmem_base, d2 = tmem_base + C::N;
             uint32_t xi = 0, wi = 0, ti = 0;
-            long long wt = 0, wx = 0, ww = 0, c0 = 0, tbeg = p.dbg ? clock64() : 0;
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
-                if (p.dbg) c0 = clock64();
-                mbar_wait(t_empty, (ti & 1) ^ 1);
-                if (p.dbg) wt += clock64() - c0;
+                const uint32_t buf = ti & 1;
+                const uint32_t dacc = tmem_base + buf * ACC_STRIDE;
+                mbar_wait(&t_empty[buf], ((ti >> 1) & 1) ^ 1);
                 tc_fence_after();
                 for (int dx = 0; dx < 3; ++dx) {
                     const uint32_t s = xi % C::NXS, ph = (xi / C::NXS) & 1;
-                    if (p.dbg) c0 = clock64();
                     mbar_wait(&x_full[s], ph);
-                    if (p.dbg) wx += clock64() - c0;
                     tc_fence_after();
                     const uint32_t xhi = smem_u32(xs + s * C::XSTAGE_BYTES);
                     const uint32_t xlo = xhi + C::PART_BYTES;
 #pragma unroll 1
                     for (int tp = 0; tp < 9; ++tp) {
                         const uint32_t ws = wi % C::NWS, wph = (wi / C::NWS) & 1;
-                        if (p.dbg) c0 = clock64();
                         mbar_wait(&w_full[ws], wph);
-                        if (p.dbg) ww += clock64() - c0;
                         tc_fence_after();
-                        const uint32_t wa = smem_u32(wsm + ws * W_TAP_BYTES);
+                        const uint32_t wa = smem_u32(wsm + ws * W_STAGE_BYTES);
                         const uint32_t boff = ((tp / 3) * ZP + (tp % 3)) * 128;     // (dy, dz) row shift
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint64_t ad = make_desc_sbo(wa + k * 32, 1024);
                             const uint32_t acc = (dx | tp | k) != 0;
-                            tc_mma_f16(d1, ad, make_desc_sbo(xhi + boff + k * 32, ZP * 128), idesc, acc);
-                            tc_mma_f16(d2, ad, make_desc_sbo(xlo + boff + k * 32, ZP * 128), idesc, acc);
+                            // [Wlo ; Whi] x Xhi, then [Whi ; 0] x Xlo into the same accumulator
+                            tc_mma_f16(dacc, make_desc_sbo(wa + k * 32, 1024),
+                                       make_desc_sbo(xhi + boff + k * 32, ZP * 128), idesc, acc);
+                            tc_mma_f16(dacc, make_desc_sbo(wa + W_ZERO_BYTES + k * 32, 1024),
+                                       make_desc_sbo(xlo + boff + k * 32, ZP * 128), idesc, 1u);
                         }
                         tc_commit(&w_empty[ws]);
                         ++wi;
@@ -198,25 +209,24 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                     tc_commit(&x_empty[s]);
                     ++xi;
                 }
-                tc_commit(t_full);
-            }
-            if (p.dbg) {
-                p.dbg[blockIdx.x * 4 + 0] = wt; p.dbg[blockIdx.x * 4 + 1] = wx;
-                p.dbg[blockIdx.x * 4 + 2] = ww; p.dbg[blockIdx.x * 4 + 3] = clock64() - tbeg;
+                tc_commit(&t_full[buf]);
             }
         }
     } else {
         // ================= epilogue (warps 2..9, 256 threads) =================
-        // warp w may only read TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter split the columns
+        // warp w may only read TMEM lanes 32*(w%4)..+31: quadrants 0,1 hold the L rows (co = 32e + lane),
+        // quadrants 2,3 the H rows; the two warps of a quadrant split a chunk's columns
         const int e = warp & 3;
-        const int half = (warp - 2) >> 2;            // which 32 of a chunk's 64 columns this warp converts
+        const int half = (warp - 2) >> 2;
         const int et = threadIdx.x - 64;             // 0..255
-        const int co = 16 * e + (lane & 15);
-        const bool is_lo = lane >= 16;
-        const float bias = p.bias ? p.bias[co] : 0.f;
-        const float s1 = is_lo ? SR4D_LO_INV : 1.f;
+        const bool is_h = e >= 2;
+        const int co = 32 * (e & 1) + lane;
+        const float bias = (is_h && p.bias) ? p.bias[co] : 0.f;
+        const float s1 = is_h ? 1.f : SR4D_LO_INV;
         const int Do = p.Do;
         const int g8 = et & 7;                       // 8-channel group handled in the store phase
+        const int vq = et >> 3;                      // voxel of the chunk handled in the store phase
+        float* my_stage = stage + (is_h ? 0 : C::CV * 64) + co;
         float amax = 0.f;
         uint32_t ti = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
@@ -226,101 +236,101 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
             rem %= tiles_per_x;
             const int y0 = (rem / p.nzt) * TY, z0 = (rem % p.nzt) * TZ;
             const bool x_edge = p.halo && (x == 0 || x == Do - 1);
-            mbar_wait(t_full, ti & 1);
+            const uint32_t buf = ti & 1;
+            mbar_wait(&t_full[buf], (ti >> 1) & 1);
             tc_fence_after();
-            const uint32_t trow = tmem_base + ((uint32_t)(32 * e) << 16);
+            const uint32_t trow = tmem_base + buf * ACC_STRIDE + ((uint32_t)(32 * e) << 16);
 #pragma unroll 1
             for (int ch = 0; ch < C::NCHUNK; ++ch) {
-                // residual prefetch for the 2 (voxel, channel-group) items this thread stores
-                uint4 rh[2], rl[2];
-                if (p.res_hi) {
-#pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        const int v = (et >> 3) + 32 * r;
-                        const int y = y0 + ch * 8 + (v >> 3), z = z0 + (v & 7);
-                        if (y < Do && z < Do) {
-                            const size_t o = act_off(Do, b, x, y, z) + g8 * 8;
-                            rh[r] = *reinterpret_cast<const uint4*>(p.res_hi + o);
-                            rl[r] = *reinterpret_cast<const uint4*>(p.res_lo + o);
-                        }
-                    }
+                const int line = ch * C::LPC + (vq >> 3);
+                const int y = y0 + line, z = z0 + (vq & 7);
+                const bool active = vq < C::CV && line < TY && y < Do && z < Do;
+                // residual prefetch for the (voxel, channel-group) item this thread stores
+                uint4 rh, rl;
+                if (p.res_hi && active) {
+                    const size_t o = act_off(Do, b, x, y, z) + g8 * 8;
+                    rh = *reinterpret_cast<const uint4*>(p.res_hi + o);
+                    rl = *reinterpret_cast<const uint4*>(p.res_lo + o);
                 }
-                // ---- phase A: TMEM -> registers -> fp32 transpose buffer [voxel][channel] ----
-#pragma unroll
-                for (int qq = 0; qq < 2; ++qq) {
-                    const int q = half * 2 + qq;
-                    const int c0 = ch * 64 + q * 16;
-                    float a[16], d[16];
+                // ---- phase A: TMEM -> registers -> fp32 staging [part][voxel][channel] ----
+                const int c0 = ch * C::CV;
+                const int ncols = (C::N - c0) < C::CV ? (C::N - c0) : C::CV;
+                if (half == 0) {
+                    float a[16];
                     tc_ld16(trow + c0, a);
-                    tc_ld16(trow + C::N + c0, d);
                     tc_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float v = fmaf(d[j], SR4D_LO_INV, a[j]) * s1;
-                        a[j] = v + __shfl_xor_sync(0xffffffffu, v, 16);
-                    }
-                    // lanes 0..15 keep columns 0..7 (y-line 2q), lanes 16..31 columns 8..15 (y-line 2q+1)
-                    const int vb = q * 16 + (is_lo ? 8 : 0);
-                    const int sw = co ^ (is_lo ? 16 : 0);      // bank swizzle: ((v >> 3) & 1) << 4
+                    for (int j = 0; j < 16; ++j) my_stage[j * 64] = fmaf(a[j], s1, bias);
+                } else if (ncols > 16) {
+                    if (C::CV == 32) {
+                        float a[16];
+                        tc_ld16(trow + c0 + 16, a);
+                        tc_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) stage[(vb + j) * 64 + sw] = (is_lo ? a[8 + j] : a[j]) + bias;
+                        for (int j = 0; j < 16; ++j) my_stage[(16 + j) * 64] = fmaf(a[j], s1, bias);
+                    } else {
+                        float a[8];
+                        tc_ld8(trow + c0 + 16, a);
+                        tc_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) my_stage[(16 + j) * 64] = fmaf(a[j], s1, bias);
+                    }
                 }
                 if (ch == C::NCHUNK - 1) {
-                    // all TMEM reads of this tile are done: let the MMA warp start the next tile
+                    // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(t_empty);
+                    if (lane == 0) mbar_arrive(&t_empty[buf]);
                 }
                 named_bar(1, NUM_EPI);
                 // ---- phase B: coalesced residual / activation / split / store ----
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int v = (et >> 3) + 32 * r;
-                    const int y = y0 + ch * 8 + (v >> 3), z = z0 + (v & 7);
-                    if (y >= Do || z >= Do) continue;
-                    const float* sp = stage + v * 64 + ((g8 * 8) ^ (((v >> 3) & 1) << 4));
-                    float4 f0 = *reinterpret_cast<const float4*>(sp);
-                    float4 f1 = *reinterpret_cast<const float4*>(sp + 4);
-                    float val[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                if (active) {
+                    const float* sp = stage + vq * 64 + g8 * 8;
+                    const float4 h0 = *reinterpret_cast<const float4*>(sp);
+                    const float4 h1 = *reinterpret_cast<const float4*>(sp + 4);
+                    const float4 l0 = *reinterpret_cast<const float4*>(sp + C::CV * 64);
+                    const float4 l1 = *reinterpret_cast<const float4*>(sp + C::CV * 64 + 4);
+                    float val[8] = {h0.x + l0.x, h0.y + l0.y, h0.z + l0.z, h0.w + l0.w,
+                                    h1.x + l1.x, h1.y + l1.y, h1.z + l1.z, h1.w + l1.w};
                     if (p.out_raw) {
                         float* o = p.out_raw + ((((size_t)b * Do + x) * Do + y) * Do + z) * 64 + g8 * 8;
-                        *reinterpret_cast<float4*>(o) = f0;
-                        *reinterpret_cast<float4*>(o + 4) = f1;
+                        *reinterpret_cast<float4*>(o) = make_float4(val[0], val[1], val[2], val[3]);
+                        *reinterpret_cast<float4*>(o + 4) = make_float4(val[4], val[5], val[6], val[7]);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(val[k]));
-                        continue;
-                    }
-                    if (p.res_hi) {
-                        const __half2* hh = reinterpret_cast<const __half2*>(&rh[r]);
-                        const __half2* ll = reinterpret_cast<const __half2*>(&rl[r]);
+                    } else {
+                        if (p.res_hi) {
+                            const __half2* hh = reinterpret_cast<const __half2*>(&rh);
+                            const __half2* ll = reinterpret_cast<const __half2*>(&rl);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            float2 ha = __half22float2(hh[k]), la = __half22float2(ll[k]);
-                            val[2 * k] += fmaf(la.x, SR4D_LO_INV, ha.x);
-                            val[2 * k + 1] += fmaf(la.y, SR4D_LO_INV, ha.y);
+                            for (int k = 0; k < 4; ++k) {
+                                float2 ha = __half22float2(hh[k]), la = __half22float2(ll[k]);
+                                val[2 * k] += fmaf(la.x, SR4D_LO_INV, ha.x);
+                                val[2 * k + 1] += fmaf(la.y, SR4D_LO_INV, ha.y);
+                            }
                         }
-                    }
-                    __align__(16) __half hv[8];
-                    __align__(16) __half lv[8];
+                        __align__(16) __half hv[8];
+                        __align__(16) __half lv[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) split_f16(act_fn(val[k], p.slope), hv[k], lv[k]);
-                    const uint4 H = *reinterpret_cast<const uint4*>(hv), L = *reinterpret_cast<const uint4*>(lv);
-                    const size_t o = act_off(Do, b, x, y, z) + g8 * 8;
-                    *reinterpret_cast<uint4*>(p.out_hi + o) = H;
-                    *reinterpret_cast<uint4*>(p.out_lo + o) = L;
-                    const bool edge = p.halo && (x_edge || y == 0 || y == Do - 1 || z == 0 || z == Do - 1);
-                    if (edge) {
-                        // replicate into the halo positions this voxel is the clamp image of
-                        for (int ddx = -1; ddx <= 1; ++ddx) {
-                            if ((ddx == -1 && x != 0) || (ddx == 1 && x != Do - 1)) continue;
-                            for (int ddy = -1; ddy <= 1; ++ddy) {
-                                if ((ddy == -1 && y != 0) || (ddy == 1 && y != Do - 1)) continue;
-                                for (int ddz = -1; ddz <= 1; ++ddz) {
-                                    if ((ddz == -1 && z != 0) || (ddz == 1 && z != Do - 1)) continue;
-                                    if ((ddx | ddy | ddz) == 0) continue;
-                                    const size_t oo = act_off(Do, b, x + ddx, y + ddy, z + ddz) + g8 * 8;
-                                    *reinterpret_cast<uint4*>(p.out_hi + oo) = H;
-                                    *reinterpret_cast<uint4*>(p.out_lo + oo) = L;
+                        for (int k = 0; k < 8; ++k) split_f16(act_fn(val[k], p.slope), hv[k], lv[k]);
+                        const uint4 H = *reinterpret_cast<const uint4*>(hv), L = *reinterpret_cast<const uint4*>(lv);
+                        const size_t o = act_off(Do, b, x, y, z) + g8 * 8;
+                        *reinterpret_cast<uint4*>(p.out_hi + o) = H;
+                        *reinterpret_cast<uint4*>(p.out_lo + o) = L;
+                        const bool edge = p.halo && (x_edge || y == 0 || y == Do - 1 || z == 0 || z == Do - 1);
+                        if (edge) {
+                            // replicate into the halo positions this voxel is the clamp image of
+                            for (int ddx = -1; ddx <= 1; ++ddx) {
+                                if ((ddx == -1 && x != 0) || (ddx == 1 && x != Do - 1)) continue;
+                                for (int ddy = -1; ddy <= 1; ++ddy) {
+                                    if ((ddy == -1 && y != 0) || (ddy == 1 && y != Do - 1)) continue;
+                                    for (int ddz = -1; ddz <= 1; ++ddz) {
+                                        if ((ddz == -1 && z != 0) || (ddz == 1 && z != Do - 1)) continue;
+                                        if ((ddx | ddy | ddz) == 0) continue;
+                                        const size_t oo = act_off(Do, b, x + ddx, y + ddy, z + ddz) + g8 * 8;
+                                        *reinterpret_cast<uint4*>(p.out_hi + oo) = H;
+                                        *reinterpret_cast<uint4*>(p.out_lo + oo) = L;
+                                    }
                                 }
                             }
                         }
@@ -339,22 +349,29 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                      : "memory");
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// weight image: fp32 Keras [27][ci][co] -> fp16 split, row-permuted, swizzled
+// weight image: fp32 Keras [27][ci][co] -> fp16 split, rows [Wlo(co 0..63) ; Whi(co 0..63)], swizzled
 // ------------------------------------------------------------------------------------------
-__global__ void prep_weights_kernel(const float* __restrict__ w, __half* __restrict__ img, int dgrad) {
-    // one thread per (tap, row, k)
+struct PrepList {
+    int n;
+    int layer[64];           // image slot of entry i
+    long long off[64];       // float offset of its Keras kernel in the flat parameter buffer
+};
+// grid (27*128*64/256, n entries, 2 images): one thread per (tap, row, k) element
+__global__ void prep_weights_kernel(const float* __restrict__ params, PrepList l, __half* __restrict__ images) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 27 * 128 * 64) return;
+    const float* w = params + l.off[blockIdx.y];
+    const int dgrad = blockIdx.z;
+    __half* img = images + ((size_t)l.layer[blockIdx.y] * 2 + dgrad) * (27 * 128 * 64);
     const int k = i & 63, row = (i >> 6) & 127, tap = i >> 13;
-    const int q = row >> 5, l = row & 31;
-    const int n = 16 * q + (l & 15);
-    const bool is_lo = l >= 16;
+    const int n = row & 63;
+    const bool is_lo = row < 64;
     // forward: A[n=co][k=ci] = W[tap][ci][co];  dgrad: A[n=ci][k=co] = W[26-tap][ci][co]
     const float v = dgrad ? w[((size_t)(26 - tap) * 64 + n) * 64 + k] : w[((size_t)tap * 64 + k) * 64 + n];
     __half h, lo;
@@ -449,11 +466,15 @@ void tc_free_weights(TcWeights* w) {
     cudaFree(w->img);
     delete w;
 }
-cudaError_t tc_prepare_weights(TcWeights* w, int layer, const float* kernel, cudaStream_t s) {
-    const int n = 27 * 128 * 64;
-    __half* base = w->img + (size_t)layer * 2 * n;
-    prep_weights_kernel<<<(n + 255) / 256, 256, 0, s>>>(kernel, base, 0);
-    prep_weights_kernel<<<(n + 255) / 256, 256, 0, s>>>(kernel, base + n, 1);
+cudaError_t tc_prepare_weights(TcWeights* w, const float* params, const int* layers, const long long* offsets, int n,
+                               cudaStream_t s) {
+    for (int i0 = 0; i0 < n; i0 += 64) {
+        PrepList l;
+        l.n = n - i0 < 64 ? n - i0 : 64;
+        for (int i = 0; i < l.n; ++i) { l.layer[i] = layers[i0 + i]; l.off[i] = offsets[i0 + i]; }
+        dim3 grid((27 * 128 * 64 + 255) / 256, l.n, 2);
+        prep_weights_kernel<<<grid, 256, 0, s>>>(params, l, w->img);
+    }
     return cudaGetLastError();
 }
 
@@ -466,15 +487,17 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
     p.res_hi = a.res_hi; p.res_lo = a.res_lo;
     p.bias = a.bias; p.out_raw = a.out_raw; p.absmax = a.absmax;
     p.slope = a.slope; p.B = B; p.Do = Do; p.halo = a.halo;
-    p.dbg = nullptr;
-    static const bool debug = getenv("SR4D_TC_DEBUG") != nullptr;
-    static long long* dbg_buf = nullptr;
-    if (debug) {
-        if (!dbg_buf) cudaMalloc((void**)&dbg_buf, 148 * 4 * sizeof(long long));
-        cudaMemsetAsync(dbg_buf, 0, 148 * 4 * sizeof(long long), s);
-        p.dbg = dbg_buf;
+    // y-tile height: the candidate that wastes the fewest MMA columns on this grid (26 serves the
+    // padded dgrad grids 26^3 / 50^3, 24 the forward grids 24^3 / 48^3)
+    int ty = 8;
+    if (Do > 8) {
+        const int cand[3] = {16, 24, 26};
+        long best = -1;
+        for (int c : cand) {
+            const long cost = (long)((Do + c - 1) / c) * c;
+            if (best < 0 || cost < best || (cost == best && c > ty)) { best = cost; ty = c; }
+        }
     }
-    const int ty = Do <= 8 ? 8 : Do <= 16 ? 16 : 24;
     CUtensorMap map;
     if (!make_xmap(&map, a.in.hi, B, Dp, ty + 2, ZP)) return cudaErrorUnknown;
     if (a.in.lo != a.in.hi + act_plane_elems(B, a.in.D)) return cudaErrorInvalidValue;   // planes must be packed
@@ -482,16 +505,8 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
     switch (ty) {
         case 8: e = launch_cfg<8>(map, p, s); break;
         case 16: e = launch_cfg<16>(map, p, s); break;
-        default: e = launch_cfg<24>(map, p, s); break;
-    }
-    if (debug && e == cudaSuccess) {
-        long long h[148 * 4];
-        cudaStreamSynchronize(s);
-        cudaMemcpy(h, dbg_buf, sizeof h, cudaMemcpyDeviceToHost);
-        double a4[4] = {0, 0, 0, 0};
-        for (int i = 0; i < 148; ++i) for (int k = 0; k < 4; ++k) a4[k] += (double)h[i * 4 + k] / 148;
-        fprintf(stderr, "[tc dbg] Do=%d B=%d tiles=%d: MMA-warp wait cycles avg/CTA: t_empty %.0f  x_full %.0f  w_full %.0f  of total %.0f\n",
-                Do, B, B * Do * ((Do + ty - 1) / ty) * ((Do + TZ - 1) / TZ), a4[0], a4[1], a4[2], a4[3]);
+        case 24: e = launch_cfg<24>(map, p, s); break;
+        default: e = launch_cfg<26>(map, p, s); break;
     }
     return e;
 }

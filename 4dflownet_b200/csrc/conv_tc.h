@@ -21,8 +21,10 @@ struct TcConvArgs {
 bool tc_available();
 cudaError_t tc_alloc_weights(TcWeights** w, int nlayers);
 void tc_free_weights(TcWeights* w);
-// (re)build the operand image of one layer from its Keras-layout fp32 kernel [27][64][64]
-cudaError_t tc_prepare_weights(TcWeights* w, int layer, const float* kernel, cudaStream_t s);
+// (re)build the operand images (forward + dgrad) of n layers in one launch: entry i is image slot layers[i],
+// built from the Keras-layout fp32 kernel [27][64][64] at params + offsets[i]
+cudaError_t tc_prepare_weights(TcWeights* w, const float* params, const int* layers, const long long* offsets, int n,
+                               cudaStream_t s);
 cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s);
 
 // tcgen05 weight gradient (wgrad_tc.cu): x = the layer's saved input Act (edge D), dy_split = the scaled

@@ -293,12 +293,13 @@ bool use_tc(sr4d_t* h, int impl_override = -1) {
 int ensure_tc_weights(sr4d_t* h, cudaStream_t s) {
     if (!tc_available()) return SR4D_OK;
     if (!h->tcw_dirty) return SR4D_OK;
+    std::vector<int> idx;
+    std::vector<long long> off;
     for (size_t i = 0; i < h->layers.size(); ++i) {
         const Layer& ly = h->layers[i];
-        if (ly.k == 3 && ly.cin == 64 && ly.cout == 64) {
-            CK(h, tc_prepare_weights(h->tcw, (int)i, W(h, (int)i), s), 2);
-        }
+        if (ly.k == 3 && ly.cin == 64 && ly.cout == 64) { idx.push_back((int)i); off.push_back(ly.w_off); }
     }
+    if (!idx.empty()) CK(h, tc_prepare_weights(h->tcw, h->params, idx.data(), off.data(), (int)idx.size(), s), 1);
     h->tcw_dirty = false;
     return SR4D_OK;
 }
@@ -475,10 +476,9 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
     for (int c = 0; c < 3; ++c) {
         ActView hd = hr_view(h, 1 + 2 * h->hi + c, B);
         const int l1 = l_head + 2 * c, l2 = l1 + 1;
-        CK(h, launch_head2_wgrad(hd, h->gpred, c, GW(h, l2), GB(h, l2), h->scratch, s), 4);
-        CK(h, launch_head2_dgrad(h->gpred, c, W(h, l2), h->raw_hr[c].p, B, H, s), 1);
-        h->raw_hr[c].exp = nullptr;
-        if ((rc = fold_act(h, &h->raw_hr[c], nullptr, nullptr, nullptr, &hd, 0.f, A, B, H, s))) return rc;
+        CK(h, cudaMemsetAsync(A.amax, 0, sizeof(int), s), 0);
+        CK(h, launch_head2_bwd(hd, h->gpred, c, W(h, l2), A.f, A.amax, GW(h, l2), GB(h, l2), h->scratch, s), 4);
+        if ((rc = grad_ready(h, A, B, H, s))) return rc;
         if ((rc = conv64_wgrad(h, l1, trunk, A, true, s))) return rc;
         if ((rc = conv64_dgrad(h, l1, A, h->raw_hr[c], B, H, s))) return rc;
         if (use_tc(h) && c < 2) {
@@ -792,7 +792,7 @@ int sr4d_conv64_layer(sr4d_t* h, const float* x, const float* kernel, const floa
             if (impl == SR4D_CONV_TCGEN05) {
                 if (!tc_available()) { rc = fail(h, SR4D_EINVAL, "tcgen05 conv not built"); break; }
                 if (tc_alloc_weights(&tw, 1) != cudaSuccess) { rc = SR4D_ENOMEM; break; }
-                e = tc_prepare_weights(tw, 0, kernel, s);
+                { const int l0 = 0; const long long o0 = 0; e = tc_prepare_weights(tw, kernel, &l0, &o0, 1, s); }
                 TcConvArgs a;
                 a.in = vi; a.out = vo; a.layer = 0; a.dgrad = 0; a.bias = bias;
                 a.res_hi = residual ? vr.hi : nullptr; a.res_lo = residual ? vr.lo : nullptr;
@@ -869,7 +869,7 @@ int sr4d_conv64_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const 
             const int* rexp = nullptr;
             if (tc) {
                 e = launch_g4_split(g4, reinterpret_cast<unsigned int*>(meta), g4s, meta + 1, B, D, s);
-                if (!e) e = tc_prepare_weights(tw, 0, kernel, s);
+                if (!e) { const int l0 = 0; const long long o0 = 0; e = tc_prepare_weights(tw, kernel, &l0, &o0, 1, s); }
                 TcConvArgs a;
                 a.in.hi = g4s; a.in.lo = g4s + act_plane_elems(B, D + 2); a.in.B = B; a.in.D = D + 2;
                 a.layer = 0; a.dgrad = 1; a.out_raw = raw;

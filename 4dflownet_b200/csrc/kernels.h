@@ -63,11 +63,11 @@ cudaError_t launch_stitch(const float* pred, int nx, int ny, int nz, int H, int 
                           float venc, int round_small, float* vol, cudaStream_t s);
 
 // ---- backward kernels (bwd.cu)
-// g (B,H^3,3) channel c -> raw [B][(H+2)^3][64] through the 64->1 kernel w[27][64]
-cudaError_t launch_head2_dgrad(const float* g, int c, const float* w, float* raw, int B, int H, cudaStream_t s);
-// dW[27][64] and db for the 64->1 conv: h Act (B,H), g channel c
-cudaError_t launch_head2_wgrad(ActView h, const float* g, int c, float* dw, float* db, float* scratch,
-                               cudaStream_t s);
+// whole backward of a 64->1 head conv: h = its saved input Act (B,H), g (B,H^3,3) channel c, w[27][64];
+// writes d(pre-activation of h) = relu'(h) * dgrad (clamp padding folded in) into the G4 interior with |max|,
+// dw[27][64] and db; scratch >= (592 + 1) * 28 * 64 floats
+cudaError_t launch_head2_bwd(ActView h, const float* g, int c, const float* w, float* out_g4, unsigned int* amax,
+                             float* dw, float* db, float* scratch, cudaStream_t s);
 // out(G4 interior) = (fold(raw0*2^-e0 + raw1*2^-e1 + raw2*2^-e2) + add) * act'(saved); e_i are device
 // exponents (NULL = 0) of the scaled split-fp16 gradients the raws were computed from; amax (optional)
 // receives atomicMax of |out|
