@@ -81,6 +81,7 @@ struct KParams {
     float slope;
     int B, Do, halo;
     int nyt, nzt, ntiles;
+    long long* dbg;          // SR4D_TC_DEBUG=1: per-CTA cycles the MMA warp waited on {t_empty, x_full, w_full} and its total
 };
 
 __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo) {
@@ -98,7 +99,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
     using C = Cfg<TY>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // align by OFFSET (not by pointer cast) so the compiler keeps the shared address space (STS/LDS, not generic)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* xs = smem;                                   // NXS x [hi part | lo part]
     uint8_t* wsm = smem + C::NXS * C::XSTAGE_BYTES;       // NWS x (16 KB image + 8 KB zeros)
     float* stage = reinterpret_cast<float*>(wsm + C::NWS * W_STAGE_BYTES);
@@ -176,21 +178,29 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
             // instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N
             const uint32_t idesc = (1u << 4) | ((uint32_t)(C::N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             uint32_t xi = 0, wi = 0, ti = 0;
+            long long wt = 0, wx = 0, ww = 0, c0 = 0;
+            const long long tbeg = p.dbg ? clock64() : 0;
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
                 const uint32_t buf = ti & 1;
                 const uint32_t dacc = tmem_base + buf * ACC_STRIDE;
+                if (p.dbg) c0 = clock64();
                 mbar_wait(&t_empty[buf], ((ti >> 1) & 1) ^ 1);
+                if (p.dbg) wt += clock64() - c0;
                 tc_fence_after();
                 for (int dx = 0; dx < 3; ++dx) {
                     const uint32_t s = xi % C::NXS, ph = (xi / C::NXS) & 1;
+                    if (p.dbg) c0 = clock64();
                     mbar_wait(&x_full[s], ph);
+                    if (p.dbg) wx += clock64() - c0;
                     tc_fence_after();
                     const uint32_t xhi = smem_u32(xs + s * C::XSTAGE_BYTES);
                     const uint32_t xlo = xhi + C::PART_BYTES;
 #pragma unroll 1
                     for (int tp = 0; tp < 9; ++tp) {
                         const uint32_t ws = wi % C::NWS, wph = (wi / C::NWS) & 1;
+                        if (p.dbg) c0 = clock64();
                         mbar_wait(&w_full[ws], wph);
+                        if (p.dbg) ww += clock64() - c0;
                         tc_fence_after();
                         const uint32_t wa = smem_u32(wsm + ws * W_STAGE_BYTES);
                         const uint32_t boff = ((tp / 3) * ZP + (tp % 3)) * 128;     // (dy, dz) row shift
@@ -210,6 +220,10 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                     ++xi;
                 }
                 tc_commit(&t_full[buf]);
+            }
+            if (p.dbg) {
+                p.dbg[blockIdx.x * 4 + 0] = wt; p.dbg[blockIdx.x * 4 + 1] = wx;
+                p.dbg[blockIdx.x * 4 + 2] = ww; p.dbg[blockIdx.x * 4 + 3] = clock64() - tbeg;
             }
         }
     } else {
@@ -487,6 +501,14 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
     p.res_hi = a.res_hi; p.res_lo = a.res_lo;
     p.bias = a.bias; p.out_raw = a.out_raw; p.absmax = a.absmax;
     p.slope = a.slope; p.B = B; p.Do = Do; p.halo = a.halo;
+    p.dbg = nullptr;
+    static const bool debug = getenv("SR4D_TC_DEBUG") != nullptr;
+    static long long* dbg_buf = nullptr;
+    if (debug) {
+        if (!dbg_buf) cudaMalloc((void**)&dbg_buf, 148 * 4 * sizeof(long long));
+        cudaMemsetAsync(dbg_buf, 0, 148 * 4 * sizeof(long long), s);
+        p.dbg = dbg_buf;
+    }
     // y-tile height: the candidate that wastes the fewest MMA columns on this grid (26 serves the
     // padded dgrad grids 26^3 / 50^3, 24 the forward grids 24^3 / 48^3)
     int ty = 8;
@@ -507,6 +529,15 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
         case 16: e = launch_cfg<16>(map, p, s); break;
         case 24: e = launch_cfg<24>(map, p, s); break;
         default: e = launch_cfg<26>(map, p, s); break;
+    }
+    if (debug && e == cudaSuccess) {
+        long long hb[148 * 4];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(hb, dbg_buf, sizeof hb, cudaMemcpyDeviceToHost);
+        double a4[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 148; ++i) for (int k = 0; k < 4; ++k) a4[k] += (double)hb[i * 4 + k] / 148;
+        fprintf(stderr, "[tc dbg] Do=%d B=%d ty=%d dgrad=%d: MMA-warp wait cycles avg/CTA: t_empty %.0f  x_full %.0f  w_full %.0f  of total %.0f\n",
+                Do, B, ty, a.dgrad, a4[0], a4[1], a4[2], a4[3]);
     }
     return e;
 }

@@ -41,11 +41,15 @@ def raw(path):
             if any(k == x or (k.startswith(x) and k[len(x):] in ('', '.per_second')) for x in KEYS):
                 print(f"   {k:75s} {d[k]:>16s} {units[hdr.index(k)]}")
 
-def stalls(path, n=30):
+def stalls(path, n=30, which=0):
     out = subprocess.run(['ncu', '-i', path, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr = rows[1]; idx = {k: i for i, k in enumerate(hdr)}
-    sec = [r for r in rows[2:] if len(r) >= len(hdr)]
+    # one section per profiled launch: a "Kernel Name" row, a header row, then one row per SASS instruction
+    starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name'] + [len(rows)]
+    lo, hi = starts[which], starts[which + 1]
+    print('kernel:', rows[lo][1][:100])
+    hdr = rows[lo + 1]; idx = {k: i for i, k in enumerate(hdr)}
+    sec = [r for r in rows[lo + 2:hi] if len(r) >= len(hdr)]
     tot = sum(int(r[idx['# Samples']] or 0) for r in sec)
     print('total samples', tot)
     names = [k for k in hdr if k.startswith('stall_') and 'Not Issued' not in k]
@@ -56,7 +60,7 @@ def stalls(path, n=30):
     for r in sorted(sec, key=lambda r: -int(r[idx['# Samples']] or 0))[:n]:
         st = {k: int(r[idx[k]] or 0) for k in names}
         main = sorted(((k, v) for k, v in st.items() if v), key=lambda kv: -kv[1])[:2]
-        print(r[idx['# Samples']].rjust(7), r[idx['Instructions Executed']].rjust(9), r[idx['Source']][:80].ljust(80), main)
+        print(r[idx['# Samples']].rjust(7), r[idx['Instructions Executed']].rjust(9), r[idx['Address']][-5:], r[idx['Source']][:80].ljust(80), main)
 
 if __name__ == '__main__':
     cmd = sys.argv[1]
