@@ -50,6 +50,8 @@ __device__ __forceinline__ void absmax_commit(float m, unsigned int* p) {
 // (j==D-1,t==2).  A block walks (b,x,y) z-lines: it stages the 3x3 neighbouring g lines, builds
 // G[z][27] in shared memory, then 64 channels x 4 z-phases of threads stream h once, write dh (fp32 G4
 // interior) and keep dw in registers across lines.  partial[blk][28][64]: rows 0..26 = dw, row 27 = db.
+// HZ_MAX = z-voxels per thread (4 z-phases): 12 serves H <= 48, 32 serves H <= 128
+template <int HZ_MAX>
 __global__ void __launch_bounds__(256) head2_bwd_kernel(ActView h, const float* __restrict__ g, int c,
                                                         const float* __restrict__ w, float* __restrict__ out_g4,
                                                         unsigned int* amax, float* __restrict__ partial) {
@@ -66,6 +68,17 @@ __global__ void __launch_bounds__(256) head2_bwd_kernel(ActView h, const float* 
     const int nlines = h.B * H * H;
     for (int line = blockIdx.x; line < nlines; line += gridDim.x) {
         const int y = line % H, x = (line / H) % H, b = line / (H * H);
+        // this thread's voxels z = q, q+4, ...: issue the (2-byte, latency-bound) loads before building G
+        float hvp[HZ_MAX];
+#pragma unroll
+        for (int u = 0; u < HZ_MAX; ++u) {
+            const int z = q + 4 * u;
+            hvp[u] = 0.f;
+            if (z < H) {
+                const size_t ao = act_off(H, b, x, y, z) + ci;
+                hvp[u] = join_f16(h.hi[ao], h.lo[ao]);
+            }
+        }
         __syncthreads();
         for (int i = threadIdx.x; i < 9 * Hz; i += 256) {
             const int r = i / Hz, zz = i % Hz - 1;
@@ -101,26 +114,29 @@ __global__ void __launch_bounds__(256) head2_bwd_kernel(ActView h, const float* 
             Gs[i] = s;
         }
         __syncthreads();
-        for (int z = q; z < H; z += 4) {
-            const size_t ao = act_off(H, b, x, y, z) + ci;
-            const float hv = join_f16(h.hi[ao], h.lo[ao]);
-            const float4* G4p = reinterpret_cast<const float4*>(Gs + z * 28);
-            float Gt[28];
 #pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const float4 v = G4p[k];
-                Gt[4 * k] = v.x; Gt[4 * k + 1] = v.y; Gt[4 * k + 2] = v.z; Gt[4 * k + 3] = v.w;
-            }
-            float sacc = 0.f;
+        for (int u = 0; u < HZ_MAX; ++u) {
+            const int z = q + 4 * u;
+            if (z < H) {
+                const float4* G4p = reinterpret_cast<const float4*>(Gs + z * 28);
+                float Gt[28];
 #pragma unroll
-            for (int t = 0; t < 27; ++t) {
-                sacc = fmaf(wr[t], Gt[t], sacc);
-                dw[t] = fmaf(hv, Gt[t], dw[t]);
+                for (int k = 0; k < 7; ++k) {
+                    const float4 v = G4p[k];
+                    Gt[4 * k] = v.x; Gt[4 * k + 1] = v.y; Gt[4 * k + 2] = v.z; Gt[4 * k + 3] = v.w;
+                }
+                const float hv = hvp[u];
+                float sa = 0.f;
+#pragma unroll
+                for (int t = 0; t < 27; ++t) {
+                    sa = fmaf(wr[t], Gt[t], sa);
+                    dw[t] = fmaf(hv, Gt[t], dw[t]);
+                }
+                dw[27] += Gt[27];
+                const float d = hv > 0.f ? sa : 0.f;
+                out_g4[g4_off(H, b, x, y, z) + ci] = d;
+                m = fmaxf(m, fabsf(d));
             }
-            dw[27] += Gt[27];
-            const float d = hv > 0.f ? sacc : 0.f;
-            out_g4[g4_off(H, b, x, y, z) + ci] = d;
-            m = fmaxf(m, fabsf(d));
         }
     }
     __syncthreads();
@@ -307,11 +323,11 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
     }
 }
 
-// out[j] = sum_r partial[r][j] for a few (<= 256) columns: 256/ncols row phases per block, fixed order
-__global__ void __launch_bounds__(256) reduce_rows_small_kernel(const float* __restrict__ partial, int nrows, int ncols,
-                                                                float* __restrict__ out) {
-    __shared__ float red[256];
-    const int nph = 256 / ncols;
+// out[j] = sum_r partial[r][j] for a few (<= 256) columns: 1024/ncols row phases in one block, fixed order
+__global__ void __launch_bounds__(1024) reduce_rows_small_kernel(const float* __restrict__ partial, int nrows, int ncols,
+                                                                 float* __restrict__ out) {
+    __shared__ float red[1024];
+    const int nph = 1024 / ncols;
     const int j = threadIdx.x % ncols, ph = threadIdx.x / ncols;
     float s = 0.f;
     if (ph < nph)
@@ -477,45 +493,50 @@ __global__ void __launch_bounds__(256) conv1x1_wgrad_kernel(const float* __restr
     }
 }
 
-// ---- stem 3->64 weight gradient ------------------------------------------------------------
-constexpr int SW_VOX_PER_BLOCK = 256;
+// ---- stem 3->64 weight gradient: dW[t][c][co] = sum_v feat[clamp(v+t)][c] * dY[v][co] ------------
+// A block walks (b,x,y) z-lines: the 3x3 clamped neighbour lines of the 3-channel features are staged in
+// shared memory (float4 per voxel), 64 output channels x 4 z-phases of threads keep dW in registers.
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ feat, int ch0,
                                                          const float* __restrict__ dy, int B, int P,
                                                          float* __restrict__ partial) {
-    const size_t nvox = (size_t)B * P * P * P;
-    const int co = threadIdx.x & 63, sub = threadIdx.x >> 6;
+    extern __shared__ __align__(16) float swsm[];      // [9][P+2] float4
+    float4* fl = reinterpret_cast<float4*>(swsm);
+    const int Pz = P + 2;
+    const int co = threadIdx.x & 63, q = threadIdx.x >> 6;
     float acc[81];
 #pragma unroll
     for (int t = 0; t < 81; ++t) acc[t] = 0.f;
-    const size_t nchunks = (nvox + SW_VOX_PER_BLOCK - 1) / SW_VOX_PER_BLOCK;
-    for (size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x)
-    for (int k = sub; k < SW_VOX_PER_BLOCK; k += 4) {
-        size_t vi = chunk * SW_VOX_PER_BLOCK + k;
-        if (vi >= nvox) break;
-        int z = vi % P, y = (vi / P) % P, x = (vi / ((size_t)P * P)) % P, b = vi / ((size_t)P * P * P);
-        float d = dy[g4_off(P, b, x, y, z) + co];
+    const int nlines = B * P * P;
+    for (int line = blockIdx.x; line < nlines; line += gridDim.x) {
+        const int y = line % P, x = (line / P) % P, b = line / (P * P);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 9 * Pz; i += 256) {
+            const int r = i / Pz;
+            const int zz = min(max(i % Pz - 1, 0), P - 1);
+            const int xx = min(max(x + r / 3 - 1, 0), P - 1), yy = min(max(y + r % 3 - 1, 0), P - 1);
+            const float* f = feat + ((((size_t)b * P + xx) * P + yy) * P + zz) * 6 + ch0;
+            fl[i] = make_float4(f[0], f[1], f[2], 0.f);
+        }
+        __syncthreads();
+        for (int z = q; z < P; z += 4) {
+            const float d = dy[g4_off(P, b, x, y, z) + co];
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-            int xx = min(max(x + dx - 1, 0), P - 1);
-#pragma unroll
-            for (int dyy = 0; dyy < 3; ++dyy) {
-                int yy = min(max(y + dyy - 1, 0), P - 1);
+            for (int r = 0; r < 9; ++r)
 #pragma unroll
                 for (int dz = 0; dz < 3; ++dz) {
-                    int zz = min(max(z + dz - 1, 0), P - 1);
-                    const float* f = feat + ((((size_t)b * P + xx) * P + yy) * P + zz) * 6 + ch0;
-                    const int t = ((dx * 3 + dyy) * 3 + dz) * 3;
-                    acc[t] = fmaf(f[0], d, acc[t]);
-                    acc[t + 1] = fmaf(f[1], d, acc[t + 1]);
-                    acc[t + 2] = fmaf(f[2], d, acc[t + 2]);
+                    const float4 f = fl[r * Pz + z + dz];
+                    const int t = (r * 3 + dz) * 3;
+                    acc[t] = fmaf(f.x, d, acc[t]);
+                    acc[t + 1] = fmaf(f.y, d, acc[t + 1]);
+                    acc[t + 2] = fmaf(f.z, d, acc[t + 2]);
                 }
-            }
         }
     }
     __shared__ float red[4][64];
+#pragma unroll
     for (int t = 0; t < 81; ++t) {
         __syncthreads();
-        red[sub][co] = acc[t];
+        red[q][co] = acc[t];
         __syncthreads();
         if (threadIdx.x < 64)
             partial[(size_t)blockIdx.x * 81 * 64 + t * 64 + co] = red[0][co] + red[1][co] + red[2][co] + red[3][co];
@@ -559,14 +580,10 @@ cudaError_t launch_head2_bwd(ActView h, const float* g, int c, const float* w, f
     const unsigned nb = nlines < 592 ? nlines : 592;           // 148 SMs x 4 resident blocks
     size_t smem = (size_t)((9 * (H + 2) + 3) / 4 * 4 + H * 28) * sizeof(float);
     if (smem < 4 * 28 * 64 * sizeof(float)) smem = 4 * 28 * 64 * sizeof(float);
-    static size_t attr_smem = 0;
-    if (smem > 48 * 1024 && smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(head2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_smem = smem;
-    }
+    if (H > 128) return cudaErrorInvalidValue;
     float* tmp = scratch + (size_t)nb * 28 * 64;   // reduced [28][64]
-    head2_bwd_kernel<<<nb, 256, smem, s>>>(h, g, c, w, out_g4, amax, scratch);
+    if (H <= 48) head2_bwd_kernel<12><<<nb, 256, smem, s>>>(h, g, c, w, out_g4, amax, scratch);
+    else head2_bwd_kernel<32><<<nb, 256, smem, s>>>(h, g, c, w, out_g4, amax, scratch);
     reduce_rows_kernel<<<(28 * 64 + 255) / 256, 256, 0, s>>>(scratch, nb, 28 * 64, tmp);
     cudaMemcpyAsync(dw, tmp, 27 * 64 * sizeof(float), cudaMemcpyDeviceToDevice, s);
     cudaMemcpyAsync(db, tmp + 27 * 64, sizeof(float), cudaMemcpyDeviceToDevice, s);
@@ -602,7 +619,7 @@ cudaError_t launch_bias_grad(const float* dy_g4, int B, int D, float* db, float*
     size_t nvox = (size_t)B * D * D * D;
     unsigned nb = red_blocks(nvox, 64);
     bias_grad_kernel<<<nb, 256, 0, s>>>(dy_g4, B, D, scratch);
-    reduce_rows_small_kernel<<<1, 256, 0, s>>>(scratch, nb, 64, db);
+    reduce_rows_small_kernel<<<1, 1024, 0, s>>>(scratch, nb, 64, db);
     return cudaGetLastError();
 }
 cudaError_t launch_upsample_bwd(const float* dhr_g4, ActView lr_saved, float slope, float* dlr_g4,
@@ -625,9 +642,9 @@ cudaError_t launch_conv1x1_bwd(const float* dy_g4, ActView a, ActView b, const f
 }
 cudaError_t launch_stem_wgrad(const float* feat, int ch0, const float* dy_g4, int B, int P, float* dw,
                               float* db, float* scratch, cudaStream_t s) {
-    size_t nvox = (size_t)B * P * P * P;
-    unsigned nb = red_blocks(nvox, SW_VOX_PER_BLOCK);
-    stem_wgrad_kernel<<<nb, 256, 0, s>>>(feat, ch0, dy_g4, B, P, scratch);
+    const int nlines = B * P * P;
+    const unsigned nb = nlines < 592 ? nlines : 592;
+    stem_wgrad_kernel<<<nb, 256, (size_t)9 * (P + 2) * sizeof(float4), s>>>(feat, ch0, dy_g4, B, P, scratch);
     reduce_rows_kernel<<<(81 * 64 + 255) / 256, 256, 0, s>>>(scratch, nb, 81 * 64, dw);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
