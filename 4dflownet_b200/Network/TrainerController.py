@@ -25,6 +25,7 @@ import torch
 
 from .SR4DFlowNet import SR4DFlowModel
 from . import utility
+from .. import parallel
 
 L2_COEFF = 5e-7    # SR4DFlowNet.py:99 kernel_regularizer=l2(5e-7)
 
@@ -132,13 +133,6 @@ class TrainerController:
         self.optimizer = AdamOptimizer(self.engine, lr=self.learning_rate)
         self._last = None    # device tensors of the most recent step (per_sample, l2)
 
-    # ---- distributed helpers ---------------------------------------------------------------
-    @staticmethod
-    def _world():
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            return torch.distributed.get_world_size()
-        return 1
-
     # ---- loss / metric entry points with the reference's names -------------------------------
     def loss_function(self, y_true, y_pred, mask):
         """(total_loss[B], mse[B], 0) — TrainerController.py:84-127."""
@@ -166,23 +160,23 @@ class TrainerController:
         u, v, w, u_mag, v_mag, w_mag, u_hr, v_hr, w_hr, venc, mask = data_pairs
         per, l2, _ = self.engine.train_fwd_bwd([u, v, w, u_mag, v_mag, w_mag],
                                                 [_squeeze_last(a) for a in (u_hr, v_hr, w_hr)], mask)
-        world = self._world()
-        B = per.shape[0]
-        if world > 1:
-            torch.distributed.all_reduce(self.engine.grads, op=torch.distributed.ReduceOp.SUM)
-        self.optimizer.apply(B * world)
+        # data parallel: every rank holds an equal shard of the global batch; ONE all-reduce (SUM) of
+        # the flat gradient buffer, then the same Adam step everywhere with the L2 gradient of the GLOBAL batch
+        parallel.allreduce_gradients(self.engine.grads)
+        self.optimizer.apply(per.shape[0] * parallel.world_size())
         self._last = (per, l2)
         return per, l2
 
     def train_step(self, data_pairs):
         per, l2 = self.train_step_async(data_pairs)
+        per = parallel.gather_metrics(per)          # running means cover every sample of the global batch
         self._update_metrics(per.cpu().numpy(), float(l2.item()), 'train')
 
     def test_step(self, data_pairs):
         u, v, w, u_mag, v_mag, w_mag, u_hr, v_hr, w_hr, venc, mask = data_pairs
         predictions = self.model([u, v, w, u_mag, v_mag, w_mag], training=False)
         per = self.engine.loss_metrics(predictions, *[_squeeze_last(a) for a in (u_hr, v_hr, w_hr)], mask)
-        self._update_metrics(per.cpu().numpy(), None, 'val')
+        self._update_metrics(parallel.gather_metrics(per).cpu().numpy(), None, 'val')
         return predictions
 
     def _update_metrics(self, per, l2, metric_set):

@@ -1,0 +1,99 @@
+"""Host-side data-parallel plumbing: one process per GPU, `torch.distributed`.
+
+The path shards on the patch / batch axis and nothing else:
+  * training  -- rank k takes a contiguous shard of the global batch, leaves the SUM over its samples of the
+    per-sample loss gradients in the engine's flat gradient buffer, ONE all-reduce(SUM) of that buffer per step,
+    then every rank applies the identical fused Adam step with the L2 term scaled by the GLOBAL batch
+    (TrainerController.py:223,249: tape.gradient of the (B,) loss vector sums over samples and the scalar l2 is
+    added to each entry);
+  * inference -- the patch list of a volume is cut into contiguous chunks per rank (predictor.py:82-94 is
+    embarrassingly parallel), results are gathered for the unchanged stitcher.
+Everything here works on CPU tensors with the gloo backend too (tests/test_parallel_gloo.py).
+"""
+import torch
+import torch.distributed as dist
+
+
+def initialized():
+    return dist.is_available() and dist.is_initialized()
+
+
+def world_size():
+    return dist.get_world_size() if initialized() else 1
+
+
+def rank():
+    return dist.get_rank() if initialized() else 0
+
+
+def shard_bounds(n, rank_=None, world=None):
+    """[lo, hi) of the contiguous chunk of `n` items owned by `rank_`; sizes differ by at most one and the
+    larger chunks come first."""
+    r = rank() if rank_ is None else int(rank_)
+    w = world_size() if world is None else int(world)
+    base, extra = divmod(int(n), w)
+    lo = r * base + min(r, extra)
+    return lo, lo + base + (1 if r < extra else 0)
+
+
+def shard_batch(data_pairs, rank_=None, world=None):
+    """This rank's slice of a global-batch 11-tuple (PatchHandler3D.py:78-81), along axis 0."""
+    n = len(data_pairs[0])
+    lo, hi = shard_bounds(n, rank_, world)
+    return tuple(a[lo:hi] for a in data_pairs)
+
+
+def allreduce_gradients(flat_grads):
+    """The one collective of a training step: SUM of the flat gradient buffer over ranks, in place."""
+    if world_size() > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
+    return flat_grads
+
+
+def l2_grad_scale(local_batch, l2_coeff=5e-7):
+    """d/dw of the regulariser as the reference differentiates it: 2*l2*w added once per sample of the
+    GLOBAL batch (every rank must apply the same scale after the all-reduce)."""
+    return float(global_count(local_batch)) * 2.0 * l2_coeff
+
+
+def global_count(local_count):
+    """Sum of an integer over ranks (global batch size when shards are ragged)."""
+    if world_size() == 1:
+        return int(local_count)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([int(local_count)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return int(t.item())
+
+
+def gather_rows(local, n_total):
+    """All-gather of row-sharded tensors whose shard sizes follow `shard_bounds(n_total)`; returns the
+    (n_total, ...) tensor on every rank."""
+    w = world_size()
+    if w == 1:
+        return local
+    chunk = -(-int(n_total) // w)
+    pad = torch.zeros((chunk,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = torch.empty((w * chunk,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad)
+    parts = []
+    for r in range(w):
+        lo, hi = shard_bounds(n_total, r, w)
+        parts.append(out[r * chunk:r * chunk + (hi - lo)])
+    return torch.cat(parts, dim=0)
+
+
+def gather_metrics(per_sample):
+    """(B_local,4) per-sample metrics -> (B_global,4) on every rank: the reference's running means
+    (TrainerController.py:52-63,241-257) average over every sample of the global batch."""
+    w = world_size()
+    if w == 1:
+        return per_sample
+    n = global_count(per_sample.shape[0])
+    counts = [shard_bounds(n, r, w) for r in range(w)]
+    if all(hi - lo == per_sample.shape[0] for lo, hi in counts[:1]) and n == w * per_sample.shape[0]:
+        out = torch.empty((n,) + tuple(per_sample.shape[1:]), dtype=per_sample.dtype, device=per_sample.device)
+        dist.all_gather_into_tensor(out, per_sample.contiguous())
+        return out
+    return gather_rows(per_sample, n)

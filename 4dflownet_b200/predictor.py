@@ -17,17 +17,22 @@ def prepare_network(patch_size, res_increase, low_resblock, hi_resblock, max_bat
 
 
 def predict_volume(network, pgen, dataset, batch_size=8, round_small_values=True, gpu_stitch=True):
-    """Body of the reference's per-row loop (predictor.py:74-107).  Returns (3,X,Y,Z) fp32."""
+    """Body of the reference's per-row loop (predictor.py:74-107).  Returns (3,X,Y,Z) fp32.
+    Under torch.distributed the patch list is cut into contiguous per-rank chunks (no collective on the
+    compute path) and the predictions are gathered for the stitcher; every rank returns the full volume."""
+    import torch
+    from . import parallel
     velocities, magnitudes = pgen.patchify(dataset)
     n = len(velocities[0])
     eng = network.engine
     H = eng.H
-    import torch
-    results = torch.empty((n, H, H, H, 3), device=eng.device, dtype=torch.float32)
-    for i in range(0, n, batch_size):
-        sl = slice(i, i + batch_size)
+    lo, hi = parallel.shard_bounds(n)
+    local = torch.empty((hi - lo, H, H, H, 3), device=eng.device, dtype=torch.float32)
+    for i in range(lo, hi, batch_size):
+        sl = slice(i, min(i + batch_size, hi))
         eng.forward([velocities[0][sl], velocities[1][sl], velocities[2][sl],
-                     magnitudes[0][sl], magnitudes[1][sl], magnitudes[2][sl]], out=results[sl])
+                     magnitudes[0][sl], magnitudes[1][sl], magnitudes[2][sl]], out=local[i - lo:sl.stop - lo])
+    results = parallel.gather_rows(local, n)
     venc = float(dataset.venc)
     if gpu_stitch:
         side_hr = (pgen.patch_size - pgen.effective_patch_size) // 2 * pgen.res_increase

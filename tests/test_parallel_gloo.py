@@ -1,0 +1,110 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: shard arithmetic, the single gradient
+all-reduce reproducing the reference's summed-gradient + global-batch L2 semantics, row gathers.
+The oracle stands in for the engine's gradient computation here (tests may use it; the product never does)."""
+import importlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run(fn, world=2):
+    port = _free_port()
+    mp.spawn(_entry, args=(world, port, fn), nprocs=world, join=True)
+
+
+def _entry(rank, world, port, fn):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        globals()[fn](rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def _par():
+    return importlib.import_module("4dflownet_b200.parallel")
+
+
+def test_shard_bounds_cover_exactly():
+    par = _par()
+    for n in (0, 1, 7, 12, 256, 1176):
+        for w in (1, 2, 3, 8):
+            got = [par.shard_bounds(n, r, w) for r in range(w)]
+            assert got[0][0] == 0 and got[-1][1] == n
+            assert all(got[i][1] == got[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in got]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    assert par.shard_bounds(256, 3, 8) == (96, 128)      # config 5: 256 patches over 8 ranks
+
+
+def _dp_gradient_identity(rank, world):
+    par = _par()
+    oracle = importlib.import_module("oracle.sr4d_oracle")
+    P, r, low, hi, Bg = 6, 2, 1, 1, 4
+    params = {k: v.astype(np.float64) for k, v in oracle.glorot_params(low, hi, seed=3, bias_scale=0.05).items()}
+    batch = oracle.synthetic_batch(Bg, P, r, seed=9)
+    names = [n for n, _ in oracle.param_table(low, hi)]
+    # reference semantics on the full batch: d/dw [ sum_b loss_b + Bg * l2 ]
+    g_full, met_full = oracle.gradients(params, batch, r, low, hi)
+    # this rank: summed gradient of its shard WITHOUT the regulariser (what sr4d_train_fwd_bwd leaves in grads)
+    shard = par.shard_batch(batch)
+    Bl = len(shard[0])
+    assert Bl == Bg // world
+    g_loc, met_loc = oracle.gradients(params, shard, r, low, hi)
+    flat = torch.cat([torch.from_numpy(np.ascontiguousarray(
+        g_loc[n] - (Bl * 2 * oracle.L2_COEFF * params[n] if n.endswith("kernel") else 0.0))).reshape(-1) for n in names])
+    par.allreduce_gradients(flat)                                   # the one collective
+    scale = par.l2_grad_scale(Bl)
+    assert abs(scale - Bg * 2 * oracle.L2_COEFF) < 1e-18
+    off = 0
+    for n in names:
+        cnt = params[n].size
+        g = flat[off:off + cnt].numpy().reshape(params[n].shape)
+        off += cnt
+        if n.endswith("kernel"):
+            g = g + scale * params[n]
+        np.testing.assert_allclose(g, g_full[n], rtol=1e-9, atol=1e-14, err_msg=n)
+    # metrics: gathering the per-sample rows reproduces the full-batch vector
+    per = torch.from_numpy(np.stack([met_loc["loss"], met_loc["mse"], met_loc["rel_err"], np.zeros(Bl)], 1))
+    allm = par.gather_metrics(per)
+    np.testing.assert_allclose(allm[:, 0].numpy() , met_full["loss"], rtol=1e-12)
+    np.testing.assert_allclose(allm[:, 2].numpy(), met_full["rel_err"], rtol=1e-12)
+
+
+def _ragged_gather(rank, world):
+    par = _par()
+    n = 7                                                           # ragged: 4 + 3
+    lo, hi = par.shard_bounds(n)
+    full = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3)
+    out = par.gather_rows(full[lo:hi].clone(), n)
+    assert torch.equal(out, full)
+    assert par.global_count(hi - lo) == n
+    per = par.gather_metrics(full[lo:hi].clone())
+    assert torch.equal(per, full)
+
+
+def test_dp_allreduce_reproduces_full_batch_gradient():
+    _run("_dp_gradient_identity")
+
+
+def test_ragged_row_gather():
+    _run("_ragged_gather")
