@@ -81,8 +81,25 @@ struct KParams {
     float slope;
     int B, Do, halo;
     int nyt, nzt, ntiles;
+    int nx;                  // x planes that get tiles (Do, or the interior edge in fused-dgrad mode)
+    // fused dgrad: the padded-grid result is folded onto the interior voxels inside the kernel
+    // (x by re-indexing the boundary planes' (input plane, weight slice) pairs, y/z in the epilogue staging), then
+    // out = (fold * 2^-e + add_pre) * act'(saved) + add_post goes to the interior of an fp32 G4 tensor
+    int fused, Dint;
+    const int* dy_exp;
+    const float* add_pre;
+    const float* add_post;
+    const __half* sav_hi;
+    const __half* sav_lo;
+    float* out_g4;
     long long* dbg;          // SR4D_TC_DEBUG=1: per-CTA cycles the MMA warp waited on {t_empty, x_full, w_full} and its total
 };
+
+// element offset of channel 0 of interior voxel (x,y,z) of an fp32 G4 tensor [B][D+4]^3[64]
+__device__ __forceinline__ size_t g4_off(int D, int b, int x, int y, int z) {
+    const int dp = D + 4;
+    return ((((size_t)b * dp + (x + 2)) * dp + (y + 2)) * dp + (z + 2)) * 64;
+}
 
 __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo) {
     uint64_t d = 0;
@@ -140,7 +157,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
     const uint32_t tmem_base = *tmem_slot;
 
     const int tiles_per_x = p.nyt * p.nzt;
-    const int tiles_per_b = p.Do * tiles_per_x;
+    const int tiles_per_b = p.nx * tiles_per_x;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -157,15 +174,23 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                     mbar_wait(&x_empty[s], ph ^ 1);
                     mbar_expect_tx(&x_full[s], 2 * C::ROWS * 128);
                     uint8_t* dst = xs + s * C::XSTAGE_BYTES;
-                    tma_load_5d(dst, &xmap, &x_full[s], 0, z0, y0, x + dx, b);
-                    tma_load_5d(dst + C::PART_BYTES, &xmap, &x_full[s], 0, z0, y0, x + dx, p.B + b);
+                    int plane = x + dx, wsel = dx;
+                    if (p.fused) {
+                        // interior plane x of dX: storage planes x+1..x+3 of the zero-haloed dY; at the two boundary
+                        // planes the all-zero halo pass is replaced by the pass that the folded halo plane would add
+                        plane = x + 1 + dx;
+                        if (dx == 0 && x == 0) { plane = 2; wsel = 2; }
+                        if (dx == 2 && x == p.Dint - 1) { plane = p.Dint + 1; wsel = 0; }
+                    }
+                    tma_load_5d(dst, &xmap, &x_full[s], 0, z0, y0, plane, b);
+                    tma_load_5d(dst + C::PART_BYTES, &xmap, &x_full[s], 0, z0, y0, plane, p.B + b);
                     ++xi;
                     for (int tp = 0; tp < 9; ++tp) {
                         const uint32_t ws = wi % C::NWS, wph = (wi / C::NWS) & 1;
                         mbar_wait(&w_empty[ws], wph ^ 1);
                         mbar_expect_tx(&w_full[ws], W_TAP_BYTES);
                         bulk_load(wsm + ws * W_STAGE_BYTES,
-                                  reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)(dx * 9 + tp) * W_TAP_BYTES,
+                                  reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)(wsel * 9 + tp) * W_TAP_BYTES,
                                   W_TAP_BYTES, &w_full[ws]);
                         ++wi;
                     }
@@ -258,10 +283,31 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
             for (int ch = 0; ch < C::NCHUNK; ++ch) {
                 const int line = ch * C::LPC + (vq >> 3);
                 const int y = y0 + line, z = z0 + (vq & 7);
-                const bool active = vq < C::CV && line < TY && y < Do && z < Do;
+                bool active = vq < C::CV && line < TY && y < Do && z < Do;
+                // fused dgrad: (y, z) are padded-grid coordinates; only interior voxels produce output
+                const int Di = p.Dint;
+                if (p.fused) active = active && y >= 1 && y <= Di && z >= 1 && z <= Di;
+                float4 ap0, ap1, aq0, aq1;
                 // residual prefetch for the (voxel, channel-group) item this thread stores
                 uint4 rh, rl;
-                if (p.res_hi && active) {
+                if (p.fused) {
+                    if (active) {
+                        const size_t go = g4_off(Di, b, x, y - 1, z - 1) + g8 * 8;
+                        if (p.add_pre) {
+                            ap0 = *reinterpret_cast<const float4*>(p.add_pre + go);
+                            ap1 = *reinterpret_cast<const float4*>(p.add_pre + go + 4);
+                        }
+                        if (p.add_post) {
+                            aq0 = *reinterpret_cast<const float4*>(p.add_post + go);
+                            aq1 = *reinterpret_cast<const float4*>(p.add_post + go + 4);
+                        }
+                        if (p.sav_hi) {
+                            const size_t o = act_off(Di, b, x, y - 1, z - 1) + g8 * 8;
+                            rh = *reinterpret_cast<const uint4*>(p.sav_hi + o);
+                            rl = *reinterpret_cast<const uint4*>(p.sav_lo + o);
+                        }
+                    }
+                } else if (p.res_hi && active) {
                     const size_t o = act_off(Do, b, x, y, z) + g8 * 8;
                     rh = *reinterpret_cast<const uint4*>(p.res_hi + o);
                     rl = *reinterpret_cast<const uint4*>(p.res_lo + o);
@@ -306,7 +352,49 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                     const float4 l1 = *reinterpret_cast<const float4*>(sp + C::CV * 64 + 4);
                     float val[8] = {h0.x + l0.x, h0.y + l0.y, h0.z + l0.z, h0.w + l0.w,
                                     h1.x + l1.x, h1.y + l1.y, h1.z + l1.z, h1.w + l1.w};
-                    if (p.out_raw) {
+                    if (p.fused) {
+                        // MirrorPadGrad inside the chunk: halo lines / columns fold onto their clamped neighbour
+                        auto fold = [&](int dv) {
+                            const float* q = sp + dv * 64;
+                            const float4 a0 = *reinterpret_cast<const float4*>(q);
+                            const float4 a1 = *reinterpret_cast<const float4*>(q + 4);
+                            const float4 b0 = *reinterpret_cast<const float4*>(q + C::CV * 64);
+                            const float4 b1 = *reinterpret_cast<const float4*>(q + C::CV * 64 + 4);
+                            val[0] += a0.x + b0.x; val[1] += a0.y + b0.y; val[2] += a0.z + b0.z; val[3] += a0.w + b0.w;
+                            val[4] += a1.x + b1.x; val[5] += a1.y + b1.y; val[6] += a1.z + b1.z; val[7] += a1.w + b1.w;
+                        };
+                        const bool ylo = y == 1, yhi = y == Di, zlo = z == 1, zhi = z == Di;
+                        if (ylo) fold(-8);
+                        if (yhi) fold(8);
+                        if (zlo) { fold(-1); if (ylo) fold(-9); if (yhi) fold(7); }
+                        if (zhi) { fold(1); if (ylo) fold(-7); if (yhi) fold(9); }
+                        const float ks = p.dy_exp ? exp2f((float)(-*p.dy_exp)) : 1.f;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) val[k] *= ks;
+                        if (p.add_pre) {
+                            val[0] += ap0.x; val[1] += ap0.y; val[2] += ap0.z; val[3] += ap0.w;
+                            val[4] += ap1.x; val[5] += ap1.y; val[6] += ap1.z; val[7] += ap1.w;
+                        }
+                        if (p.sav_hi) {
+                            const __half2* hh = reinterpret_cast<const __half2*>(&rh);
+                            const __half2* ll = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float2 ha = __half22float2(hh[k]), la = __half22float2(ll[k]);
+                                val[2 * k] *= act_grad_from_out(fmaf(la.x, SR4D_LO_INV, ha.x), p.slope);
+                                val[2 * k + 1] *= act_grad_from_out(fmaf(la.y, SR4D_LO_INV, ha.y), p.slope);
+                            }
+                        }
+                        if (p.add_post) {
+                            val[0] += aq0.x; val[1] += aq0.y; val[2] += aq0.z; val[3] += aq0.w;
+                            val[4] += aq1.x; val[5] += aq1.y; val[6] += aq1.z; val[7] += aq1.w;
+                        }
+                        float* o = p.out_g4 + g4_off(Di, b, x, y - 1, z - 1) + g8 * 8;
+                        *reinterpret_cast<float4*>(o) = make_float4(val[0], val[1], val[2], val[3]);
+                        *reinterpret_cast<float4*>(o + 4) = make_float4(val[4], val[5], val[6], val[7]);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(val[k]));
+                    } else if (p.out_raw) {
                         float* o = p.out_raw + ((((size_t)b * Do + x) * Do + y) * Do + z) * 64 + g8 * 8;
                         *reinterpret_cast<float4*>(o) = make_float4(val[0], val[1], val[2], val[3]);
                         *reinterpret_cast<float4*>(o + 4) = make_float4(val[4], val[5], val[6], val[7]);
@@ -452,7 +540,7 @@ cudaError_t launch_cfg(const CUtensorMap& map, KParams p, cudaStream_t s) {
     }
     p.nyt = (p.Do + TY - 1) / TY;
     p.nzt = (p.Do + TZ - 1) / TZ;
-    p.ntiles = p.B * p.Do * p.nyt * p.nzt;
+    p.ntiles = p.B * p.nx * p.nyt * p.nzt;
     int grid = p.ntiles < num_sms() ? p.ntiles : num_sms();
     conv64_tc_kernel<TY><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(map, p);
     return cudaGetLastError();
@@ -492,23 +580,8 @@ cudaError_t tc_prepare_weights(TcWeights* w, const float* params, const int* lay
     return cudaGetLastError();
 }
 
-cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
-    const int Do = a.in.D, B = a.in.B, Dp = a.in.D + 2;
-    if (!a.out_raw && a.out.D != Do) return cudaErrorInvalidValue;
-    KParams p;
-    p.w_img = w->img + ((size_t)a.layer * 2 + (a.dgrad ? 1 : 0)) * 27 * 128 * 64;
-    p.out_hi = a.out.hi; p.out_lo = a.out.lo;
-    p.res_hi = a.res_hi; p.res_lo = a.res_lo;
-    p.bias = a.bias; p.out_raw = a.out_raw; p.absmax = a.absmax;
-    p.slope = a.slope; p.B = B; p.Do = Do; p.halo = a.halo;
-    p.dbg = nullptr;
-    static const bool debug = getenv("SR4D_TC_DEBUG") != nullptr;
-    static long long* dbg_buf = nullptr;
-    if (debug) {
-        if (!dbg_buf) cudaMalloc((void**)&dbg_buf, 148 * 4 * sizeof(long long));
-        cudaMemsetAsync(dbg_buf, 0, 148 * 4 * sizeof(long long), s);
-        p.dbg = dbg_buf;
-    }
+namespace {
+int pick_ty(int Do) {
     // y-tile height: the candidate that wastes the fewest MMA columns on this grid (26 serves the
     // padded dgrad grids 26^3 / 50^3, 24 the forward grids 24^3 / 48^3)
     int ty = 8;
@@ -520,6 +593,41 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
             if (best < 0 || cost < best || (cost == best && c > ty)) { best = cost; ty = c; }
         }
     }
+    return ty;
+}
+}  // namespace
+
+bool tc_dgrad_fusable(int D) {
+    if (D < 2) return false;
+    const int ty = pick_ty(D + 2);
+    const int lpc = ty % 4 == 0 ? 4 : 3;
+    auto chunk = [&](int line) { return (line / ty) * 1000 + (line % ty) / lpc; };
+    return chunk(0) == chunk(1) && chunk(D) == chunk(D + 1) && D / TZ == (D + 1) / TZ;
+}
+
+cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
+    const int Do = a.in.D, B = a.in.B, Dp = a.in.D + 2;
+    if (!a.out_raw && !a.fused && a.out.D != Do) return cudaErrorInvalidValue;
+    if (a.fused && (!a.dgrad || !a.out_g4 || !tc_dgrad_fusable(Do - 2))) return cudaErrorInvalidValue;
+    KParams p;
+    p.w_img = w->img + ((size_t)a.layer * 2 + (a.dgrad ? 1 : 0)) * 27 * 128 * 64;
+    p.out_hi = a.out.hi; p.out_lo = a.out.lo;
+    p.res_hi = a.res_hi; p.res_lo = a.res_lo;
+    p.bias = a.bias; p.out_raw = a.out_raw; p.absmax = a.absmax;
+    p.slope = a.slope; p.B = B; p.Do = Do; p.halo = a.halo;
+    p.nx = a.fused ? Do - 2 : Do;
+    p.fused = a.fused; p.Dint = Do - 2;
+    p.dy_exp = a.dy_exp; p.add_pre = a.add_pre; p.add_post = a.add_post;
+    p.sav_hi = a.sav_hi; p.sav_lo = a.sav_lo; p.out_g4 = a.out_g4;
+    p.dbg = nullptr;
+    static const bool debug = getenv("SR4D_TC_DEBUG") != nullptr;
+    static long long* dbg_buf = nullptr;
+    if (debug) {
+        if (!dbg_buf) cudaMalloc((void**)&dbg_buf, 148 * 4 * sizeof(long long));
+        cudaMemsetAsync(dbg_buf, 0, 148 * 4 * sizeof(long long), s);
+        p.dbg = dbg_buf;
+    }
+    const int ty = pick_ty(Do);
     CUtensorMap map;
     if (!make_xmap(&map, a.in.hi, B, Dp, ty + 2, ZP)) return cudaErrorUnknown;
     if (a.in.lo != a.in.hi + act_plane_elems(B, a.in.D)) return cudaErrorInvalidValue;   // planes must be packed

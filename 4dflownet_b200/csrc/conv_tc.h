@@ -15,7 +15,17 @@ struct TcConvArgs {
     float slope = 1.f;
     int halo = 1;
     float* out_raw = nullptr;          // fp32 [B][D^3][64] output (no bias/activation/halo) instead of `out`
-    unsigned int* absmax = nullptr;    // with out_raw: atomicMax of the |value| bit patterns written
+    unsigned int* absmax = nullptr;    // with out_raw / fused: atomicMax of the |value| bit patterns written
+    // fused dgrad (dgrad = 1, tc_dgrad_fusable(D)): `in` is the scaled split gradient viewed with interior edge
+    // D+2; the halo fold, the skip add, the activation derivative and the accumulation happen in the epilogue:
+    //   out_g4(interior) = (fold(dgrad) * 2^-(*dy_exp) + add_pre) * act'(saved; slope) + add_post
+    int fused = 0;
+    const int* dy_exp = nullptr;
+    const float* add_pre = nullptr;    // fp32 G4 [B][D+4]^3[64] or NULL
+    const float* add_post = nullptr;   // fp32 G4 or NULL (may alias out_g4)
+    const __half* sav_hi = nullptr;    // saved activation planes (edge D) or NULL (no activation)
+    const __half* sav_lo = nullptr;
+    float* out_g4 = nullptr;
 };
 
 bool tc_available();
@@ -26,6 +36,9 @@ void tc_free_weights(TcWeights* w);
 cudaError_t tc_prepare_weights(TcWeights* w, const float* params, const int* layers, const long long* offsets, int n,
                                cudaStream_t s);
 cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s);
+// true when the fused dgrad's in-epilogue fold works for interior edge D (the halo line / column pairs
+// (0,1) and (D,D+1) of the padded grid fall into one epilogue chunk and one z tile)
+bool tc_dgrad_fusable(int D);
 
 // tcgen05 weight gradient (wgrad_tc.cu): x = the layer's saved input Act (edge D), dy_split = the scaled
 // split-fp16 gradient [2B][D+4]^3[64] with device exponent *dy_exp; writes tc_wgrad_slabs() partial

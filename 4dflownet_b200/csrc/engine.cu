@@ -82,6 +82,7 @@ struct sr4d_handle {
     bool tcw_dirty = true;
     int conv_impl = SR4D_CONV_AUTO;
     int save_acts = 0;
+    int fused_dgrad = 1;       // SR4D_OPT_FUSED_DGRAD
     bool have_fwd_state = false;
     int64_t launches = 0;
     // per-kernel-class device timing (SR4D_OPT_PROFILE): event pairs on the launch stream
@@ -426,6 +427,37 @@ int fold_act(sr4d_t* h, const RawBuf* r0, const RawBuf* r1, const RawBuf* r2, co
     return grad_ready(h, out, B, D, s);
 }
 
+// does the tensor-core dgrad fold / add / activation-gradient inside its epilogue for this grid?
+bool dgrad_fused(sr4d_t* h, int D) {
+    return use_tc(h) && h->fused_dgrad && tc_dgrad_fusable(D);
+}
+// fused dgrad of `layer`: out.f (interior) = (fold(dgrad(dy)) + add_pre) * act'(saved) + add_post; updates out.amax
+int conv64_dgrad_fused(sr4d_t* h, int layer, const GBuf& dy, const float* add_pre, const float* add_post,
+                       const ActView* saved, float slope, GBuf& out, int B, int D, cudaStream_t s) {
+    ProfScope prof(h, D == h->P ? SR4D_PROF_CONV64_DGRAD_LR : SR4D_PROF_CONV64_DGRAD_HR, s);
+    TcConvArgs a;
+    a.in.hi = dy.s; a.in.lo = dy.s + act_plane_elems(B, D + 2); a.in.B = B; a.in.D = D + 2;
+    a.layer = layer; a.dgrad = 1; a.fused = 1;
+    a.dy_exp = dy.exp; a.add_pre = add_pre; a.add_post = add_post;
+    a.sav_hi = saved ? saved->hi : nullptr; a.sav_lo = saved ? saved->lo : nullptr;
+    a.slope = slope; a.out_g4 = out.f; a.absmax = out.amax;
+    CK(h, tc_conv64(h->tcw, a, s), 1);
+    return SR4D_OK;
+}
+// gradient wrt the pre-activation of a 64->64 layer's input: out = (MirrorPadGrad(dgrad(dy)) + add) * act'(saved)
+// (saved == NULL: no activation), followed by the split copy for the tensor-core consumers
+int dgrad_fold(sr4d_t* h, int layer, const GBuf& dy, const GBuf* add, const ActView* saved, float slope, GBuf& out,
+               RawBuf& raw, int B, int D, cudaStream_t s) {
+    int rc;
+    if (dgrad_fused(h, D)) {
+        CK(h, cudaMemsetAsync(out.amax, 0, sizeof(int), s), 0);
+        if ((rc = conv64_dgrad_fused(h, layer, dy, add ? add->f : nullptr, nullptr, saved, slope, out, B, D, s))) return rc;
+        return grad_ready(h, out, B, D, s);
+    }
+    if ((rc = conv64_dgrad(h, layer, dy, raw, B, D, s))) return rc;
+    return fold_act(h, &raw, nullptr, nullptr, add, saved, slope, out, B, D, s);
+}
+
 // backward through `nblk` resnet blocks whose first conv is layer `l0`; bufs[0] holds the gradient wrt the
 // pre-activation of the last block output on entry; on exit bufs[*result_idx] holds the gradient wrt the
 // pre-activation (if slope_in >= 0, else the value) of the first block input.
@@ -443,14 +475,12 @@ int blocks_bwd(sr4d_t* h, int nblk, int l0, bool hr, GBuf* bufs[3], RawBuf& raw,
         GBuf& T = *bufs[(si + 1) % 3];
         GBuf& S2 = *bufs[(si + 2) % 3];
         if ((rc = conv64_wgrad(h, lb, t, S, false, s))) return rc;
-        if ((rc = conv64_dgrad(h, lb, S, raw, B, D, s))) return rc;
-        if ((rc = fold_act(h, &raw, nullptr, nullptr, nullptr, &t, 0.2f, T, B, D, s))) return rc;
+        if ((rc = dgrad_fold(h, lb, S, nullptr, &t, 0.2f, T, raw, B, D, s))) return rc;
         if ((rc = conv64_wgrad(h, la, xin, T, false, s))) return rc;
-        if ((rc = conv64_dgrad(h, la, T, raw, B, D, s))) return rc;
         // gradient wrt x_k (post-activation) = fold + skip path; multiply by its producer's act'
         float slope = k > 0 ? 0.2f : slope_in;
-        if (slope >= 0.f) rc = fold_act(h, &raw, nullptr, nullptr, &S, &xin, slope, S2, B, D, s);
-        else rc = fold_act(h, &raw, nullptr, nullptr, &S, nullptr, 1.f, S2, B, D, s);
+        if (slope >= 0.f) rc = dgrad_fold(h, la, T, &S, &xin, slope, S2, raw, B, D, s);
+        else rc = dgrad_fold(h, la, T, &S, nullptr, 1.f, S2, raw, B, D, s);
         if (rc) return rc;
         si = (si + 2) % 3;
     }
@@ -473,6 +503,14 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
     const int l_head = l_hr0 + 2 * h->hi;      // first head layer
     ActView trunk = h->hi > 0 ? hr_view(h, hr_t_of_block_x(h->hi - 1), B) : hr_view(h, 0, B);
     GBuf& A = h->g4_hr[0];
+    // trunk gradient: sum of the three heads' input gradients; trunk producer: LeakyReLU block if hi>0,
+    // the (linear) upsample if hi==0 and r>1, else the LR trunk tensor itself (r==1 aliases it).
+    GBuf* hb[3] = {&h->g4_hr[1], &h->g4_hr[2], &h->g4_hr[0]};
+    float slope_lr_trunk = h->low > 0 ? 0.2f : 0.f;    // producer activation of the LR trunk tensor
+    const bool trunk_act = h->hi > 0 || h->r == 1;
+    const float trunk_slope = h->hi > 0 ? 0.2f : (h->r == 1 ? slope_lr_trunk : 1.f);
+    const bool fused_heads = dgrad_fused(h, H);
+    if (fused_heads) CK(h, cudaMemsetAsync(hb[0]->amax, 0, sizeof(int), s), 0);
     for (int c = 0; c < 3; ++c) {
         ActView hd = hr_view(h, 1 + 2 * h->hi + c, B);
         const int l1 = l_head + 2 * c, l2 = l1 + 1;
@@ -480,6 +518,12 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
         CK(h, launch_head2_bwd(hd, h->gpred, c, W(h, l2), A.f, A.amax, GW(h, l2), GB(h, l2), h->scratch, s), 4);
         if ((rc = grad_ready(h, A, B, H, s))) return rc;
         if ((rc = conv64_wgrad(h, l1, trunk, A, true, s))) return rc;
+        if (fused_heads) {
+            // the three heads accumulate act'(trunk) * fold(dgrad_c) in place (the activation gradient is linear)
+            if ((rc = conv64_dgrad_fused(h, l1, A, nullptr, c ? hb[0]->f : nullptr, trunk_act ? &trunk : nullptr,
+                                         trunk_slope, *hb[0], B, H, s))) return rc;
+            continue;
+        }
         if ((rc = conv64_dgrad(h, l1, A, h->raw_hr[c], B, H, s))) return rc;
         if (use_tc(h) && c < 2) {
             // raw_hr[c] stays scaled by A's exponent, which the next head overwrites: keep a private copy
@@ -487,21 +531,19 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
             h->raw_hr[c].exp = h->head_exp + c;
         }
     }
-    // trunk gradient: sum of the three heads' input gradients; trunk producer: LeakyReLU block if hi>0,
-    // the (linear) upsample if hi==0 and r>1, else the LR trunk tensor itself (r==1 aliases it).
-    GBuf* hb[3] = {&h->g4_hr[1], &h->g4_hr[2], &h->g4_hr[0]};
-    float slope_lr_trunk = h->low > 0 ? 0.2f : 0.f;    // producer activation of the LR trunk tensor
+    if (fused_heads) {
+        if ((rc = grad_ready(h, *hb[0], B, H, s))) return rc;
+    } else {
+        if ((rc = fold_act(h, &h->raw_hr[0], &h->raw_hr[1], &h->raw_hr[2], nullptr, trunk_act ? &trunk : nullptr,
+                           trunk_slope, *hb[0], B, H, s))) return rc;
+    }
     GBuf* S;
     if (h->hi > 0) {
-        if ((rc = fold_act(h, &h->raw_hr[0], &h->raw_hr[1], &h->raw_hr[2], nullptr, &trunk, 0.2f, *hb[0], B, H, s))) return rc;
         int ri = 0;
         float slope_in = h->r == 1 ? slope_lr_trunk : -1.f;
         if ((rc = blocks_bwd(h, h->hi, l_hr0, true, hb, h->raw_hr[0], B, H, slope_in, s, &ri))) return rc;
         S = hb[ri];
     } else {
-        if (h->r == 1) rc = fold_act(h, &h->raw_hr[0], &h->raw_hr[1], &h->raw_hr[2], nullptr, &trunk, slope_lr_trunk, *hb[0], B, H, s);
-        else rc = fold_act(h, &h->raw_hr[0], &h->raw_hr[1], &h->raw_hr[2], nullptr, nullptr, 1.f, *hb[0], B, H, s);
-        if (rc) return rc;
         S = hb[0];
     }
     // through the upsample
@@ -528,8 +570,7 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
     ActView pc1 = lr_view(h, 0, B), pc2 = lr_view(h, 1, B), ph1 = lr_view(h, 2, B), ph2 = lr_view(h, 3, B);
     ActView c1 = lr_view(h, 4, B);
     if ((rc = conv64_wgrad(h, 5, c1, S5, true, s))) return rc;
-    if ((rc = conv64_dgrad(h, 5, S5, h->raw_lr, B, P, s))) return rc;
-    if ((rc = fold_act(h, &h->raw_lr, nullptr, nullptr, nullptr, &c1, 0.f, T, B, P, s))) return rc;
+    if ((rc = dgrad_fold(h, 5, S5, nullptr, &c1, 0.f, T, h->raw_lr, B, P, s))) return rc;
     CK(h, cudaMemsetAsync(dA.amax, 0, sizeof(int), s), 0);
     CK(h, cudaMemsetAsync(dB.amax, 0, sizeof(int), s), 0);
     CK(h, launch_conv1x1_bwd(T.f, ph2, pc2, W(h, 4), dA.f, dB.f, dA.amax, dB.amax, GW(h, 4), GB(h, 4), h->scratch, s), 5);
@@ -537,13 +578,11 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
     if ((rc = grad_ready(h, dB, B, P, s))) return rc;
     // phase branch
     if ((rc = conv64_wgrad(h, 3, ph1, dA, true, s))) return rc;
-    if ((rc = conv64_dgrad(h, 3, dA, h->raw_lr, B, P, s))) return rc;
-    if ((rc = fold_act(h, &h->raw_lr, nullptr, nullptr, nullptr, &ph1, 0.f, T, B, P, s))) return rc;
+    if ((rc = dgrad_fold(h, 3, dA, nullptr, &ph1, 0.f, T, h->raw_lr, B, P, s))) return rc;
     CK(h, launch_stem_wgrad(h->feat, 0, T.f, B, P, GW(h, 2), GB(h, 2), h->scratch, s), 4);
     // pc branch
     if ((rc = conv64_wgrad(h, 1, pc1, dB, true, s))) return rc;
-    if ((rc = conv64_dgrad(h, 1, dB, h->raw_lr, B, P, s))) return rc;
-    if ((rc = fold_act(h, &h->raw_lr, nullptr, nullptr, nullptr, &pc1, 0.f, T, B, P, s))) return rc;
+    if ((rc = dgrad_fold(h, 1, dB, nullptr, &pc1, 0.f, T, h->raw_lr, B, P, s))) return rc;
     CK(h, launch_stem_wgrad(h->feat, 3, T.f, B, P, GW(h, 0), GB(h, 0), h->scratch, s), 4);
     return SR4D_OK;
 }
@@ -684,6 +723,9 @@ int sr4d_set_option(sr4d_t* h, int option, int value) {
             h->ev_used = 0;
             h->ev_class.clear();
             return SR4D_OK;
+        case SR4D_OPT_FUSED_DGRAD:
+            h->fused_dgrad = value != 0;
+            return SR4D_OK;
     }
     return fail(h, SR4D_EINVAL, "unknown option");
 }
@@ -692,6 +734,7 @@ int sr4d_get_option(const sr4d_t* h, int option, int* value) {
     if (option == SR4D_OPT_CONV_IMPL) { *value = h->conv_impl; return SR4D_OK; }
     if (option == SR4D_OPT_SAVE_ACTS) { *value = h->save_acts; return SR4D_OK; }
     if (option == SR4D_OPT_PROFILE) { *value = h->profile; return SR4D_OK; }
+    if (option == SR4D_OPT_FUSED_DGRAD) { *value = h->fused_dgrad; return SR4D_OK; }
     return SR4D_EINVAL;
 }
 

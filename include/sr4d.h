@@ -45,6 +45,9 @@ extern "C" {
 #define SR4D_CONV_TCGEN05    2   /* force the tcgen05 split-fp16 kernel for every 64->64 conv */
 #define SR4D_OPT_SAVE_ACTS   2   /* 1: forward keeps every activation (needed before backward) */
 #define SR4D_OPT_PROFILE     3   /* 1: bracket every 64->64 conv launch with CUDA events on its stream */
+#define SR4D_OPT_FUSED_DGRAD 4   /* 1 (default): the tensor-core dgrad folds the clamp-padding halo, adds the skip
+                                    gradient and applies the activation derivative in its epilogue where the grid
+                                    allows; 0: separate raw dgrad + fold kernel */
 
 /* kernel classes timed under SR4D_OPT_PROFILE (index into sr4d_profile_read's arrays):
  * the 64->64 3x3x3 convolution forward / input-gradient / weight-gradient, on the LR

@@ -54,7 +54,7 @@ def test_loss_metrics(pkg, oracle):
     eng.close()
 
 
-@pytest.mark.parametrize("impl", ["simt", "auto"])
+@pytest.mark.parametrize("impl", ["simt", "auto", "auto_unfused"])
 @pytest.mark.parametrize("P,r,low,hi,B", [(8, 2, 1, 1, 2), (6, 1, 1, 1, 2), (6, 2, 0, 1, 1), (6, 2, 2, 0, 2), (6, 1, 0, 0, 1),
                                           (12, 2, 2, 2, 1)])
 def test_train_step_gradients_vs_oracle(pkg, oracle, P, r, low, hi, B, impl):
@@ -62,6 +62,9 @@ def test_train_step_gradients_vs_oracle(pkg, oracle, P, r, low, hi, B, impl):
     batch = oracle.synthetic_batch(B, P, r, seed=4)
     eng = pkg.Engine(P, r, low, hi, max_batch=B, training=True, device=0)
     eng.set_option(pkg._lib.OPT_CONV_IMPL, pkg._lib.CONV_SIMT if impl == "simt" else pkg._lib.CONV_AUTO)
+    # "auto": tensor-core kernels with the halo fold / skip add / activation gradient fused into the dgrad
+    # epilogue; "auto_unfused": the same kernels with the separate raw-dgrad + fold kernel
+    eng.set_option(pkg._lib.OPT_FUSED_DGRAD, 0 if impl == "auto_unfused" else 1)
     eng.set_weights(params)
     per, l2, pred = eng.train_fwd_bwd(batch[:6], [b[..., 0] for b in batch[6:9]], batch[10], want_pred=True)
     gref, met = oracle.gradients({k: v.astype(np.float64) for k, v in params.items()}, batch, r, low, hi)
