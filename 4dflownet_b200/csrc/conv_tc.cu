@@ -92,6 +92,14 @@ struct KParams {
     const __half* sav_hi;
     const __half* sav_lo;
     float* out_g4;
+    // optional split-fp16 copy of out_g4 written by the same epilogue, scaled by 2^e with e derived from a
+    // rigorous bound on |out|: 8 (fold multiplicity) * gain (max_ci sum_{t,co} |W|) * max|dy| + max|add_pre|
+    __half* split_hi;
+    __half* split_lo;
+    int* split_exp;
+    const float* gain;
+    const unsigned int* dy_amax;
+    const unsigned int* add_amax;
     long long* dbg;          // SR4D_TC_DEBUG=1: per-CTA cycles the MMA warp waited on {t_empty, x_full, w_full} and its total
 };
 
@@ -267,6 +275,16 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
         const int vq = et >> 3;                      // voxel of the chunk handled in the store phase
         float* my_stage = stage + (is_h ? 0 : C::CV * 64) + co;
         float amax = 0.f;
+        float ksplit = 0.f;
+        if (p.fused && p.split_hi) {
+            float bound = 8.f * *p.gain * __uint_as_float(*p.dy_amax);
+            if (p.add_amax) bound += __uint_as_float(*p.add_amax);
+            int e = 0;
+            if (bound > 0.f && bound < 3.0e38f) e = 14 - ilogbf(bound);     // bound * 2^e < 2^15
+            e = max(-120, min(120, e));
+            ksplit = exp2f((float)e);
+            if (blockIdx.x == 0 && et == 0) *p.split_exp = e;
+        }
         uint32_t ti = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
             const int b = t / tiles_per_b;
@@ -389,9 +407,18 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                             val[0] += aq0.x; val[1] += aq0.y; val[2] += aq0.z; val[3] += aq0.w;
                             val[4] += aq1.x; val[5] += aq1.y; val[6] += aq1.z; val[7] += aq1.w;
                         }
-                        float* o = p.out_g4 + g4_off(Di, b, x, y - 1, z - 1) + g8 * 8;
+                        const size_t go = g4_off(Di, b, x, y - 1, z - 1) + g8 * 8;
+                        float* o = p.out_g4 + go;
                         *reinterpret_cast<float4*>(o) = make_float4(val[0], val[1], val[2], val[3]);
                         *reinterpret_cast<float4*>(o + 4) = make_float4(val[4], val[5], val[6], val[7]);
+                        if (p.split_hi) {
+                            __align__(16) __half hv[8];
+                            __align__(16) __half lv[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) split_f16(val[k] * ksplit, hv[k], lv[k]);
+                            *reinterpret_cast<uint4*>(p.split_hi + go) = *reinterpret_cast<const uint4*>(hv);
+                            *reinterpret_cast<uint4*>(p.split_lo + go) = *reinterpret_cast<const uint4*>(lv);
+                        }
 #pragma unroll
                         for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(val[k]));
                     } else if (p.out_raw) {
@@ -483,6 +510,23 @@ __global__ void prep_weights_kernel(const float* __restrict__ params, PrepList l
     img[off] = is_lo ? lo : h;
 }
 
+// dgrad gain of each listed layer: max over ci of sum_{tap,co} |W[tap][ci][co]| (bounds |dX| <= gain * max|dY|)
+__global__ void __launch_bounds__(64) weight_gain_kernel(const float* __restrict__ params, PrepList l, float* __restrict__ gain) {
+    const float* w = params + l.off[blockIdx.x];
+    const int ci = threadIdx.x;
+    float s = 0.f;
+    for (int t = 0; t < 27; ++t)
+        for (int co = 0; co < 64; ++co) s += fabsf(w[((size_t)t * 64 + ci) * 64 + co]);
+    __shared__ float red[64];
+    red[ci] = s;
+    __syncthreads();
+    if (ci == 0) {
+        float m = 0.f;
+        for (int i = 0; i < 64; ++i) m = fmaxf(m, red[i]);
+        gain[l.layer[blockIdx.x]] = m;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -551,6 +595,7 @@ cudaError_t launch_cfg(const CUtensorMap& map, KParams p, cudaStream_t s) {
 struct TcWeights {
     int nlayers = 0;
     __half* img = nullptr;   // [nlayers][2 (fwd, dgrad)][27*128*64]
+    float* gain = nullptr;   // [nlayers] dgrad gain bound (weight_gain_kernel)
 };
 
 bool tc_available() { return true; }
@@ -559,13 +604,15 @@ cudaError_t tc_alloc_weights(TcWeights** w, int nlayers) {
     TcWeights* t = new TcWeights();
     t->nlayers = nlayers;
     cudaError_t e = cudaMalloc((void**)&t->img, (size_t)nlayers * 2 * 27 * 128 * 64 * sizeof(__half));
-    if (e != cudaSuccess) { delete t; return e; }
+    if (e == cudaSuccess) e = cudaMalloc((void**)&t->gain, (size_t)nlayers * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(t->img); delete t; return e; }
     *w = t;
     return cudaSuccess;
 }
 void tc_free_weights(TcWeights* w) {
     if (!w) return;
     cudaFree(w->img);
+    cudaFree(w->gain);
     delete w;
 }
 cudaError_t tc_prepare_weights(TcWeights* w, const float* params, const int* layers, const long long* offsets, int n,
@@ -576,6 +623,7 @@ cudaError_t tc_prepare_weights(TcWeights* w, const float* params, const int* lay
         for (int i = 0; i < l.n; ++i) { l.layer[i] = layers[i0 + i]; l.off[i] = offsets[i0 + i]; }
         dim3 grid((27 * 128 * 64 + 255) / 256, l.n, 2);
         prep_weights_kernel<<<grid, 256, 0, s>>>(params, l, w->img);
+        weight_gain_kernel<<<l.n, 64, 0, s>>>(params, l, w->gain);
     }
     return cudaGetLastError();
 }
@@ -619,6 +667,10 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
     p.fused = a.fused; p.Dint = Do - 2;
     p.dy_exp = a.dy_exp; p.add_pre = a.add_pre; p.add_post = a.add_post;
     p.sav_hi = a.sav_hi; p.sav_lo = a.sav_lo; p.out_g4 = a.out_g4;
+    p.split_hi = a.split_out;
+    p.split_lo = a.split_out ? a.split_out + act_plane_elems(B, Do) : nullptr;   // [2B][D+4]^3[64]: hi planes then lo planes
+    p.split_exp = a.split_exp; p.gain = w->gain + a.layer; p.dy_amax = a.dy_amax; p.add_amax = a.add_amax;
+    if (a.split_out && (!a.split_exp || !a.dy_amax || !a.fused)) return cudaErrorInvalidValue;
     p.dbg = nullptr;
     static const bool debug = getenv("SR4D_TC_DEBUG") != nullptr;
     static long long* dbg_buf = nullptr;

@@ -26,6 +26,12 @@ struct TcConvArgs {
     const __half* sav_hi = nullptr;    // saved activation planes (edge D) or NULL (no activation)
     const __half* sav_lo = nullptr;
     float* out_g4 = nullptr;
+    // optional: also write the scaled split-fp16 copy [2B][D+4]^3[64] of out_g4 (what g4_split_kernel produces) with
+    // an exponent derived in-kernel from max|dy| (*dy_amax), the layer's weight gain and max|add_pre| (*add_amax)
+    __half* split_out = nullptr;
+    int* split_exp = nullptr;
+    const unsigned int* dy_amax = nullptr;
+    const unsigned int* add_amax = nullptr;
 };
 
 bool tc_available();

@@ -432,13 +432,16 @@ bool dgrad_fused(sr4d_t* h, int D) {
     return use_tc(h) && h->fused_dgrad && tc_dgrad_fusable(D);
 }
 // fused dgrad of `layer`: out.f (interior) = (fold(dgrad(dy)) + add_pre) * act'(saved) + add_post; updates out.amax
-int conv64_dgrad_fused(sr4d_t* h, int layer, const GBuf& dy, const float* add_pre, const float* add_post,
-                       const ActView* saved, float slope, GBuf& out, int B, int D, cudaStream_t s) {
+int conv64_dgrad_fused(sr4d_t* h, int layer, const GBuf& dy, const GBuf* add_pre, const float* add_post,
+                       const ActView* saved, float slope, GBuf& out, bool with_split, int B, int D, cudaStream_t s) {
     ProfScope prof(h, D == h->P ? SR4D_PROF_CONV64_DGRAD_LR : SR4D_PROF_CONV64_DGRAD_HR, s);
     TcConvArgs a;
     a.in.hi = dy.s; a.in.lo = dy.s + act_plane_elems(B, D + 2); a.in.B = B; a.in.D = D + 2;
     a.layer = layer; a.dgrad = 1; a.fused = 1;
-    a.dy_exp = dy.exp; a.add_pre = add_pre; a.add_post = add_post;
+    a.dy_exp = dy.exp; a.add_pre = add_pre ? add_pre->f : nullptr; a.add_post = add_post;
+    if (with_split) {
+        a.split_out = out.s; a.split_exp = out.exp; a.dy_amax = dy.amax; a.add_amax = add_pre ? add_pre->amax : nullptr;
+    }
     a.sav_hi = saved ? saved->hi : nullptr; a.sav_lo = saved ? saved->lo : nullptr;
     a.slope = slope; a.out_g4 = out.f; a.absmax = out.amax;
     CK(h, tc_conv64(h->tcw, a, s), 1);
@@ -451,8 +454,8 @@ int dgrad_fold(sr4d_t* h, int layer, const GBuf& dy, const GBuf* add, const ActV
     int rc;
     if (dgrad_fused(h, D)) {
         CK(h, cudaMemsetAsync(out.amax, 0, sizeof(int), s), 0);
-        if ((rc = conv64_dgrad_fused(h, layer, dy, add ? add->f : nullptr, nullptr, saved, slope, out, B, D, s))) return rc;
-        return grad_ready(h, out, B, D, s);
+        // the epilogue also writes the scaled split copy (exponent from a rigorous bound): no g4_split pass
+        return conv64_dgrad_fused(h, layer, dy, add, nullptr, saved, slope, out, true, B, D, s);
     }
     if ((rc = conv64_dgrad(h, layer, dy, raw, B, D, s))) return rc;
     return fold_act(h, &raw, nullptr, nullptr, add, saved, slope, out, B, D, s);
@@ -521,7 +524,7 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
         if (fused_heads) {
             // the three heads accumulate act'(trunk) * fold(dgrad_c) in place (the activation gradient is linear)
             if ((rc = conv64_dgrad_fused(h, l1, A, nullptr, c ? hb[0]->f : nullptr, trunk_act ? &trunk : nullptr,
-                                         trunk_slope, *hb[0], B, H, s))) return rc;
+                                         trunk_slope, *hb[0], false, B, H, s))) return rc;
             continue;
         }
         if ((rc = conv64_dgrad(h, l1, A, h->raw_hr[c], B, H, s))) return rc;
