@@ -32,21 +32,30 @@ class PatchGenerator:
         self.padding = tuple(f * self.res_increase for f in far)
         return np.pad(img, [(side, side + f) for f in far], "constant")
 
-    def _generate_overlapping_patches(self, img):
+    def _generate_overlapping_patches(self, img, lo=None, hi=None):
+        """All patches of `img` in the reference's x-major order, or only patches [lo, hi) of that list (what one
+        rank of a sharded prediction needs: the windows are views, only the selected ones are copied)."""
         side, far, nr = self._plan(img.shape)
         padded = self._pad_to_patch_size_with_overlap(img)
         P, e = self.patch_size, self.effective_patch_size
         win = np.lib.stride_tricks.sliding_window_view(padded, (P, P, P))[::e, ::e, ::e]
         win = win[:nr[0], :nr[1], :nr[2]]
-        return np.ascontiguousarray(win.reshape(-1, P, P, P)), nr[0], nr[1], nr[2]
+        if lo is None:
+            return np.ascontiguousarray(win.reshape(-1, P, P, P)), nr[0], nr[1], nr[2]
+        ix, iy, iz = np.unravel_index(np.arange(lo, hi), nr)
+        return np.ascontiguousarray(win[ix, iy, iz]), nr[0], nr[1], nr[2]
 
-    def patchify(self, dataset):
+    def patchify(self, dataset, lo=None, hi=None):
         stacks = []
         for img in (dataset.u, dataset.v, dataset.w, dataset.mag_u, dataset.mag_v, dataset.mag_w):
-            s, i, j, k = self._generate_overlapping_patches(img)
+            s, i, j, k = self._generate_overlapping_patches(img, lo, hi)
             stacks.append(s[..., None])
         self.nr_x, self.nr_y, self.nr_z = i, j, k
         return tuple(stacks[:3]), tuple(stacks[3:])
+
+    def count_patches(self, shape):
+        nr = self._plan(shape)[2]
+        return nr[0] * nr[1] * nr[2]
 
     def unpatchify(self, results):
         return tuple(self._patchup_with_overlap(results[..., c], self.nr_x, self.nr_y, self.nr_z) for c in range(3))

@@ -66,12 +66,29 @@ def global_count(local_count):
     return int(t.item())
 
 
-def gather_rows(local, n_total):
-    """All-gather of row-sharded tensors whose shard sizes follow `shard_bounds(n_total)`; returns the
-    (n_total, ...) tensor on every rank."""
+def gather_rows(local, n_total, dst=None):
+    """Gather of row-sharded tensors whose shard sizes follow `shard_bounds(n_total)`.  dst=None: all-gather, every
+    rank returns the (n_total, ...) tensor; dst=k: only rank k receives it (the others return None)."""
     w = world_size()
     if w == 1:
         return local
+    if dst is not None:
+        me = rank()
+        out = torch.empty((int(n_total),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) if me == dst else None
+        ops = []
+        if me == dst:
+            for r in range(w):
+                lo, hi = shard_bounds(n_total, r, w)
+                if r == me:
+                    out[lo:hi] = local
+                elif hi > lo:
+                    ops.append(dist.P2POp(dist.irecv, out[lo:hi], r))
+        elif local.shape[0] > 0:
+            ops.append(dist.P2POp(dist.isend, local.contiguous(), dst))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return out
     chunk = -(-int(n_total) // w)
     pad = torch.zeros((chunk,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[:local.shape[0]] = local

@@ -16,29 +16,50 @@ def prepare_network(patch_size, res_increase, low_resblock, hi_resblock, max_bat
                          device=device)
 
 
-def predict_volume(network, pgen, dataset, batch_size=8, round_small_values=True, gpu_stitch=True):
+_PINNED = {}
+
+
+def _pinned_like(t):
+    """Reusable page-locked host buffer for the stitched volume (a pageable D2H copy of ~150 MB costs tens of ms)."""
+    import torch
+    key = (tuple(t.shape), t.dtype)
+    if key not in _PINNED:
+        _PINNED.clear()
+        _PINNED[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    return _PINNED[key]
+
+
+def predict_volume(network, pgen, dataset, batch_size=8, round_small_values=True, gpu_stitch=True, all_ranks=False,
+                   reuse_host_buffer=False):
     """Body of the reference's per-row loop (predictor.py:74-107).  Returns (3,X,Y,Z) fp32.
-    Under torch.distributed the patch list is cut into contiguous per-rank chunks (no collective on the
-    compute path) and the predictions are gathered for the stitcher; every rank returns the full volume."""
+    Under torch.distributed the patch list is cut into contiguous per-rank chunks (no collective on the compute
+    path): every rank tiles and predicts only its own patches, the predictions are sent to rank 0, which stitches
+    and returns the volume (the other ranks return None unless all_ranks=True).  reuse_host_buffer=True returns
+    a view of an internal page-locked buffer that the next call overwrites (saves one ~150 MB host copy)."""
     import torch
     from . import parallel
-    velocities, magnitudes = pgen.patchify(dataset)
-    n = len(velocities[0])
     eng = network.engine
     H = eng.H
+    n = pgen.count_patches(dataset.u.shape)
     lo, hi = parallel.shard_bounds(n)
+    velocities, magnitudes = pgen.patchify(dataset, lo, hi) if parallel.world_size() > 1 else pgen.patchify(dataset)
     local = torch.empty((hi - lo, H, H, H, 3), device=eng.device, dtype=torch.float32)
-    for i in range(lo, hi, batch_size):
-        sl = slice(i, min(i + batch_size, hi))
+    for i in range(0, hi - lo, batch_size):
+        sl = slice(i, min(i + batch_size, hi - lo))
         eng.forward([velocities[0][sl], velocities[1][sl], velocities[2][sl],
-                     magnitudes[0][sl], magnitudes[1][sl], magnitudes[2][sl]], out=local[i - lo:sl.stop - lo])
-    results = parallel.gather_rows(local, n)
+                     magnitudes[0][sl], magnitudes[1][sl], magnitudes[2][sl]], out=local[sl])
+    results = parallel.gather_rows(local, n, dst=None if all_ranks else 0)
+    if results is None:
+        return None
     venc = float(dataset.venc)
     if gpu_stitch:
         side_hr = (pgen.patch_size - pgen.effective_patch_size) // 2 * pgen.res_increase
         vol = eng.stitch(results, (pgen.nr_x, pgen.nr_y, pgen.nr_z), pgen.stitched_shape(), side_hr, venc,
                          round_small_values)
-        return vol.cpu().numpy()
+        host = _pinned_like(vol)
+        host.copy_(vol, non_blocking=True)
+        torch.cuda.current_stream(eng.device).synchronize()
+        return host.numpy() if reuse_host_buffer else host.numpy().copy()
     res = results.cpu().numpy()
     out = []
     for c in range(3):
@@ -68,6 +89,8 @@ def main(data_dir="../data", filename="example_data.h5", output_dir="../result",
         dataset.load_vectorfield(input_filepath, nrow)
         t0 = time.time()
         vol = predict_volume(network, pgen, dataset, batch_size, round_small_values)
+        if vol is None:
+            continue            # not rank 0 of a sharded prediction
         print(f"Predicted {vol.shape[1:]} in {time.time() - t0:.2f} secs.")
         for i in range(3):
             prediction_utils.save_to_h5(f"{output_dir}/{output_filename}", dataset.velocity_colnames[i],

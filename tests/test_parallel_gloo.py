@@ -100,6 +100,10 @@ def _ragged_gather(rank, world):
     assert par.global_count(hi - lo) == n
     per = par.gather_metrics(full[lo:hi].clone())
     assert torch.equal(per, full)
+    only0 = par.gather_rows(full[lo:hi].clone(), n, dst=0)          # point-to-point gather to one rank
+    assert (only0 is None) == (rank != 0)
+    if rank == 0:
+        assert torch.equal(only0, full)
 
 
 def test_dp_allreduce_reproduces_full_batch_gradient():
