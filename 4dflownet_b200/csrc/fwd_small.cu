@@ -136,81 +136,144 @@ __global__ void __launch_bounds__(256) upsample_kernel(ActView in, ActView out, 
 }
 
 // ---- 64->1 head conv, linear (+bias), writes (B,H^3,3): SR4DFlowNet.py:40,43,46,49 -------
-// A CTA owns an 8x8x8 output brick.  Phase 1: every voxel of the 10x10x10 halo brick (the
-// replicate halo is already materialised in the Act) is read ONCE and reduced against the 27
-// tap vectors (27 dot products of length 64) into shared memory; phase 2: each output voxel
-// gathers its 27 partial sums.  HBM/L2 traffic ~2x the input instead of 27x.
+// out[x,y,z] = b + sum_t dot64(hpad[x+dx, y+dy, z+dz], w[t]).  A CTA owns a 12x12 (y,z) output tile of one head and
+// marches along x: for every padded plane xp it (1) stages the 14x14 halo tile of the plane (replicate halo is
+// materialised in the Act) as fp32 in shared memory, (2) computes the 27 tap dot-products of every staged voxel as
+// a register-tiled 196x28x64 GEMM (thread tile 4 voxels x 7 taps, float4 shared-memory operands), (3) scatters
+// them into three running output-plane accumulators (plane xp feeds outputs xp-2..xp); a finished plane is
+// written out.  Every activation is read once per (y,z) tile (1.36x halo amplification instead of 1.95x).
 struct HeadArgs {
     const __half* hi[3];
     const __half* lo[3];
     const float* w[3];
     const float* b[3];
 };
-constexpr int HB = 8, HBP = HB + 2, HB_HALO = HBP * HBP * HBP;            // 1000 halo voxels
-constexpr int HEAD_SMEM = (HB_HALO * 27 + 27 * 64) * 4;
-__global__ void __launch_bounds__(512) head_out_kernel(HeadArgs a, float* __restrict__ out, int B, int H) {
-    extern __shared__ float hsm[];
-    float* t = hsm;                      // [1000][27]
-    float* ws = hsm + HB_HALO * 27;      // [27][64]
-    const int nb = (H + HB - 1) / HB;
+constexpr int HO_T = 12, HO_TP = HO_T + 2, HO_NV = HO_TP * HO_TP;      // 196 staged voxels per plane
+constexpr int HO_AP = 68;                                              // activation row pitch (floats)
+constexpr int HO_THREADS = 224;                                        // 49 voxel groups x 4 tap groups (+ spare)
+constexpr int HO_SEG = 16;                                             // output planes per CTA
+constexpr int HO_LD = (HO_NV * 8 + HO_THREADS - 1) / HO_THREADS;       // staged (voxel, 8-channel) items per thread
+constexpr int HEAD_SMEM = (HO_NV * HO_AP + 64 * 32 + HO_NV * 28 + 3 * HO_T * HO_T) * 4;
+__global__ void __launch_bounds__(HO_THREADS, 2) head_out_kernel(HeadArgs a, float* __restrict__ out, int B, int H) {
+    extern __shared__ __align__(16) float hsm[];
+    float* As = hsm;                           // [196][68]
+    float* Ws = As + HO_NV * HO_AP;            // [64 k][4 tap groups][8]  (7 taps + a zero)
+    float* Ts = Ws + 64 * 32;                  // [196][28]
+    float* acc = Ts + HO_NV * 28;              // [3][144]
+    const int nt = (H + HO_T - 1) / HO_T, nseg = (H + HO_SEG - 1) / HO_SEG;
     int bi = blockIdx.x;
-    const int bz = bi % nb; bi /= nb;
-    const int by = bi % nb; bi /= nb;
-    const int bx = bi % nb;
-    const int b = bi / nb;
-    const int x0 = bx * HB, y0 = by * HB, z0 = bz * HB;
+    const int tz = bi % nt; bi /= nt;
+    const int ty = bi % nt; bi /= nt;
+    const int sg = bi % nseg; bi /= nseg;
+    const int c = bi % 3;
+    const int b = bi / 3;
+    const int y0 = ty * HO_T, z0 = tz * HO_T, xs = sg * HO_SEG, xe = min(H, xs + HO_SEG);
     const int Hp = H + 2;
     const int tid = threadIdx.x;
-    const int ox = tid >> 6, oy = (tid >> 3) & 7, oz = tid & 7;
-    float res[3] = {0.f, 0.f, 0.f};
-    for (int c = 0; c < 3; ++c) {
-        __syncthreads();                 // previous head's gather is done with t / ws
-        for (int i = tid; i < 27 * 64; i += 512) ws[i] = a.w[c][i];
-        __syncthreads();
-        const __half* hi = a.hi[c];
-        const __half* lo = a.lo[c];
-        for (int hv = tid; hv < HB_HALO; hv += 512) {
-            const int hx = hv / (HBP * HBP), hy = (hv / HBP) % HBP, hz = hv % HBP;
-            const int px = x0 + hx, py = y0 + hy, pz = z0 + hz;      // padded coordinates
-            float* tp = t + hv * 27;
-            if (px >= Hp || py >= Hp || pz >= Hp) {
-                for (int k = 0; k < 27; ++k) tp[k] = 0.f;
-                continue;
+    const __half* hi = a.hi[c];
+    const __half* lo = a.lo[c];
+    for (int i = tid; i < 64 * 32; i += HO_THREADS) {
+        const int k = i >> 5, tg = (i >> 3) & 3, j = i & 7;
+        Ws[i] = (j < 7 && tg * 7 + j < 27) ? a.w[c][(tg * 7 + j) * 64 + k] : 0.f;
+    }
+    for (int i = tid; i < 3 * HO_T * HO_T; i += HO_THREADS) acc[i] = 0.f;
+    const float bias = a.b[c][0];
+    const int tg = tid & 3, vg = tid >> 2;                 // GEMM role: taps tg*7..+6 of voxels vg + 49*i
+    // all of a thread's loads of a plane are issued back to back (the two resident CTAs of an SM overlap one CTA's
+    // load phase with the other's multiply phase)
+    uint4 rh[HO_LD], rl[HO_LD];
+    auto fetch = [&](int xp) {
+#pragma unroll
+        for (int j = 0; j < HO_LD; ++j) {
+            const int i = tid + j * HO_THREADS;
+            const int v = i >> 3, c8 = (i & 7) * 8;
+            const int yp = y0 + v / HO_TP, zp = z0 + v % HO_TP;
+            rh[j] = make_uint4(0, 0, 0, 0);
+            rl[j] = make_uint4(0, 0, 0, 0);
+            if (i < HO_NV * 8 && yp < Hp && zp < Hp) {
+                const size_t off = ((((size_t)b * Hp + xp) * Hp + yp) * Hp + zp) * 64 + c8;
+                rh[j] = *reinterpret_cast<const uint4*>(hi + off);
+                rl[j] = *reinterpret_cast<const uint4*>(lo + off);
             }
-            const size_t off = ((((size_t)b * Hp + px) * Hp + py) * Hp + pz) * 64;
-            float xv[64];
+        }
+    };
+    for (int xp = xs; xp < xe + 2; ++xp) {
+        fetch(xp);
+        __syncthreads();                                   // previous plane's gather is done with As / Ts
 #pragma unroll
-            for (int k = 0; k < 8; ++k) act_load8(hi, lo, off + k * 8, xv + k * 8);
-#pragma unroll 1
-            for (int tap = 0; tap < 27; ++tap) {
-                const float4* wp = reinterpret_cast<const float4*>(ws + tap * 64);
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (int j = 0; j < HO_LD; ++j) {
+            const int i = tid + j * HO_THREADS;
+            if (i < HO_NV * 8) {
+                const int v = i >> 3, c8 = (i & 7) * 8;
+                const __half2* hh = reinterpret_cast<const __half2*>(&rh[j]);
+                const __half2* ll = reinterpret_cast<const __half2*>(&rl[j]);
+                float xv[8];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const float4 wv = wp[k];
-                    s0 = fmaf(xv[4 * k], wv.x, s0);
-                    s1 = fmaf(xv[4 * k + 1], wv.y, s1);
-                    s2 = fmaf(xv[4 * k + 2], wv.z, s2);
-                    s3 = fmaf(xv[4 * k + 3], wv.w, s3);
+                for (int k = 0; k < 4; ++k) {
+                    const float2 x2 = __half22float2(hh[k]), y2 = __half22float2(ll[k]);
+                    xv[2 * k] = fmaf(y2.x, SR4D_LO_INV, x2.x);
+                    xv[2 * k + 1] = fmaf(y2.y, SR4D_LO_INV, x2.y);
                 }
-                tp[tap] = (s0 + s1) + (s2 + s3);
+                float4* dst = reinterpret_cast<float4*>(As + v * HO_AP + c8);
+                dst[0] = make_float4(xv[0], xv[1], xv[2], xv[3]);
+                dst[1] = make_float4(xv[4], xv[5], xv[6], xv[7]);
             }
         }
         __syncthreads();
-        float acc = a.b[c][0];
+        if (vg < 49) {
+            float t[4][8];
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx)
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[i][j] = 0.f;
+#pragma unroll 4
+            for (int k4 = 0; k4 < 16; ++k4) {
+                float4 av[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(As + (vg + 49 * i) * HO_AP + k4 * 4);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(Ws + (k4 * 4 + kk) * 32 + tg * 8);
+                    const float4 w1 = *reinterpret_cast<const float4*>(Ws + (k4 * 4 + kk) * 32 + tg * 8 + 4);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float x = kk == 0 ? av[i].x : kk == 1 ? av[i].y : kk == 2 ? av[i].z : av[i].w;
+                        t[i][0] = fmaf(x, w0.x, t[i][0]); t[i][1] = fmaf(x, w0.y, t[i][1]);
+                        t[i][2] = fmaf(x, w0.z, t[i][2]); t[i][3] = fmaf(x, w0.w, t[i][3]);
+                        t[i][4] = fmaf(x, w1.x, t[i][4]); t[i][5] = fmaf(x, w1.y, t[i][5]);
+                        t[i][6] = fmaf(x, w1.z, t[i][6]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 7; ++j)
+                    if (tg * 7 + j < 28) Ts[(vg + 49 * i) * 28 + tg * 7 + j] = t[i][j];
+        }
+        __syncthreads();
+        // plane xp feeds output plane xp - dx through the nine (dy,dz) taps of x-offset dx
+        for (int i = tid; i < 3 * HO_T * HO_T; i += HO_THREADS) {
+            const int dx = i / (HO_T * HO_T), o = i % (HO_T * HO_T);
+            const int x = xp - dx;
+            if (x < xs || x >= xe) continue;
+            const int oy = o / HO_T, oz = o % HO_T;
+            float s = 0.f;
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
                 for (int dz = 0; dz < 3; ++dz)
-                    acc += t[(((ox + dx) * HBP + (oy + dy)) * HBP + (oz + dz)) * 27 + (dx * 3 + dy) * 3 + dz];
-        res[c] = acc;
-    }
-    const int x = x0 + ox, y = y0 + oy, z = z0 + oz;
-    if (x < H && y < H && z < H) {
-        float* o = out + ((((size_t)b * H + x) * H + y) * H + z) * 3;
-        o[0] = res[0]; o[1] = res[1]; o[2] = res[2];
+                    s += Ts[((oy + dy) * HO_TP + oz + dz) * 28 + dx * 9 + dy * 3 + dz];
+            float* ap = acc + (x % 3) * (HO_T * HO_T) + o;
+            s += *ap;
+            if (dx == 2) {                                  // last contribution: emit and recycle the slot
+                const int y = y0 + oy, z = z0 + oz;
+                if (y < H && z < H) out[((((size_t)b * H + x) * H + y) * H + z) * 3 + c] = s + bias;
+                *ap = 0.f;
+            } else {
+                *ap = s;
+            }
+        }
     }
 }
 
@@ -277,8 +340,8 @@ cudaError_t launch_head_out(ActView h0, ActView h1, ActView h2, const float* w0,
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    const int nb = (h0.D + HB - 1) / HB;
-    head_out_kernel<<<(unsigned)(h0.B * nb * nb * nb), 512, HEAD_SMEM, s>>>(a, out, h0.B, h0.D);
+    const int nt = (h0.D + HO_T - 1) / HO_T, nseg = (h0.D + HO_SEG - 1) / HO_SEG;
+    head_out_kernel<<<(unsigned)(h0.B * 3 * nseg * nt * nt), HO_THREADS, HEAD_SMEM, s>>>(a, out, h0.B, h0.D);
     return cudaGetLastError();
 }
 cudaError_t launch_pack_act(const float* x, ActView out, cudaStream_t s) {
