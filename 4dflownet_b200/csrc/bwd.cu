@@ -16,13 +16,22 @@ __device__ __forceinline__ size_t raw_off(int D, int b, int px, int py, int pz) 
     return ((((size_t)b * dp + px) * dp + py) * dp + pz) * 64;
 }
 
-// deterministic second stage of every split reduction: out[j] = sum_r partial[r][j]
-__global__ void reduce_rows_kernel(const float* __restrict__ partial, int nrows, int ncols, float* __restrict__ out) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= ncols) return;
+// deterministic second stage of every split reduction: out[j] = sum_r partial[r][j].
+// block = 32 columns x 8 row phases (fixed summation order: phase-strided partial sums, then phases 0..7)
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ partial, int nrows, int ncols,
+                                                          float* __restrict__ out) {
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x & 31, ph = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + cx;
     float s = 0.f;
-    for (int r = 0; r < nrows; ++r) s += partial[(size_t)r * ncols + j];
-    out[j] = s;
+    if (j < ncols)
+        for (int r = ph; r < nrows; r += 8) s += partial[(size_t)r * ncols + j];
+    red[ph][cx] = s;
+    __syncthreads();
+    if (ph == 0 && j < ncols) {
+        for (int k = 1; k < 8; ++k) s += red[k][cx];
+        out[j] = s;
+    }
 }
 
 // block-wide max of |v| folded into *p with at most one atomic per block (all threads must call)
@@ -49,22 +58,41 @@ __device__ __forceinline__ void absmax_commit(float m, unsigned int* p) {
 // Per axis the set {i : clamp(i + t - 1) = j} is {j - t + 1} plus {j} again when (j==0,t==0) or
 // (j==D-1,t==2).  A block walks (b,x,y) z-lines: it stages the 3x3 neighbouring g lines, builds
 // G[z][27] in shared memory, then 64 channels x 4 z-phases of threads stream h once, write dh (fp32 G4
-// interior) and keep dw in registers across lines.  partial[blk][28][64]: rows 0..26 = dw, row 27 = db.
+// interior) and keep dw in registers across lines.  partial[blk][29][64]: rows 0..26 = dw, row 27 = db,
+// row 28 = per-channel sum of dh (the bias gradient of the head's first conv).
 // HZ_MAX = z-voxels per thread (4 z-phases): 12 serves H <= 48, 32 serves H <= 128
 template <int HZ_MAX>
 __global__ void __launch_bounds__(256) head2_bwd_kernel(ActView h, const float* __restrict__ g, int c,
                                                         const float* __restrict__ w, float* __restrict__ out_g4,
-                                                        unsigned int* amax, float* __restrict__ partial) {
+                                                        unsigned int* amax, float* __restrict__ partial,
+                                                        __half* __restrict__ split_hi, __half* __restrict__ split_lo,
+                                                        int* split_exp, const unsigned int* gmax) {
     extern __shared__ __align__(16) float h2sm[];
     const int H = h.D, Hz = H + 2;
     float* gl = h2sm;                              // [3][3][H+2]
     float* Gs = h2sm + (9 * Hz + 3) / 4 * 4;       // [H][28], 16-byte aligned rows
     const int ci = threadIdx.x & 63, q = threadIdx.x >> 6;
-    float wr[27], dw[28];
+    float wr[27], dw[29];
+    float wabs = 0.f;
 #pragma unroll
-    for (int t = 0; t < 27; ++t) { wr[t] = w[t * 64 + ci]; dw[t] = 0.f; }
-    dw[27] = 0.f;
+    for (int t = 0; t < 27; ++t) { wr[t] = w[t * 64 + ci]; dw[t] = 0.f; wabs += fabsf(wr[t]); }
+    dw[27] = dw[28] = 0.f;
     float m = 0.f;
+    // scale of the split copy: |dh| <= 8 (fold multiplicity of G) * max|g| * max_ci sum_t |w[t][ci]|
+    float ksplit = 0.f;
+    if (split_hi) {
+        h2sm[threadIdx.x] = wabs;
+        __syncthreads();
+        float wmax = 0.f;
+        for (int i = 0; i < 64; ++i) wmax = fmaxf(wmax, h2sm[i]);
+        const float bound = 8.f * wmax * __uint_as_float(*gmax);
+        int e = 0;
+        if (bound > 0.f && bound < 3.0e38f) e = 14 - ilogbf(bound);
+        e = max(-120, min(120, e));
+        ksplit = exp2f((float)e);
+        if (blockIdx.x == 0 && threadIdx.x == 0) *split_exp = e;
+        __syncthreads();
+    }
     const int nlines = h.B * H * H;
     for (int line = blockIdx.x; line < nlines; line += gridDim.x) {
         const int y = line % H, x = (line / H) % H, b = line / (H * H);
@@ -134,18 +162,26 @@ __global__ void __launch_bounds__(256) head2_bwd_kernel(ActView h, const float* 
                 }
                 dw[27] += Gt[27];
                 const float d = hv > 0.f ? sa : 0.f;
-                out_g4[g4_off(H, b, x, y, z) + ci] = d;
+                const size_t go = g4_off(H, b, x, y, z) + ci;
+                out_g4[go] = d;
+                if (split_hi) {
+                    __half sh, sl;
+                    split_f16(d * ksplit, sh, sl);
+                    split_hi[go] = sh;
+                    split_lo[go] = sl;
+                }
+                dw[28] += d;
                 m = fmaxf(m, fabsf(d));
             }
         }
     }
     __syncthreads();
-    float* red = h2sm;                             // [4][28][64] (aliases gl / Gs)
+    float* red = h2sm;                             // [4][29][64] (aliases gl / Gs)
 #pragma unroll
-    for (int t = 0; t < 28; ++t) red[(q * 28 + t) * 64 + ci] = dw[t];
+    for (int t = 0; t < 29; ++t) red[(q * 29 + t) * 64 + ci] = dw[t];
     __syncthreads();
-    for (int i = threadIdx.x; i < 28 * 64; i += 256)
-        partial[(size_t)blockIdx.x * 28 * 64 + i] = red[i] + red[28 * 64 + i] + red[2 * 28 * 64 + i] + red[3 * 28 * 64 + i];
+    for (int i = threadIdx.x; i < 29 * 64; i += 256)
+        partial[(size_t)blockIdx.x * 29 * 64 + i] = red[i] + red[29 * 64 + i] + red[2 * 29 * 64 + i] + red[3 * 29 * 64 + i];
     if (amax) absmax_commit(m, amax);
 }
 
@@ -574,19 +610,23 @@ inline unsigned red_blocks(size_t n, int per) { unsigned b = nblocks(n, per); re
 }  // namespace
 
 cudaError_t launch_head2_bwd(ActView h, const float* g, int c, const float* w, float* out_g4, unsigned int* amax,
-                             float* dw, float* db, float* scratch, cudaStream_t s) {
+                             float* dw, float* db, float* db1, __half* split_out, int* split_exp,
+                             const unsigned int* gmax, float* scratch, cudaStream_t s) {
     const int H = h.D;
     const int nlines = h.B * H * H;
     const unsigned nb = nlines < 592 ? nlines : 592;           // 148 SMs x 4 resident blocks
     size_t smem = (size_t)((9 * (H + 2) + 3) / 4 * 4 + H * 28) * sizeof(float);
-    if (smem < 4 * 28 * 64 * sizeof(float)) smem = 4 * 28 * 64 * sizeof(float);
-    if (H > 128) return cudaErrorInvalidValue;
-    float* tmp = scratch + (size_t)nb * 28 * 64;   // reduced [28][64]
-    if (H <= 48) head2_bwd_kernel<12><<<nb, 256, smem, s>>>(h, g, c, w, out_g4, amax, scratch);
-    else head2_bwd_kernel<32><<<nb, 256, smem, s>>>(h, g, c, w, out_g4, amax, scratch);
-    reduce_rows_kernel<<<(28 * 64 + 255) / 256, 256, 0, s>>>(scratch, nb, 28 * 64, tmp);
+    if (smem < 4 * 29 * 64 * sizeof(float)) smem = 4 * 29 * 64 * sizeof(float);
+    if (H > 128 || (split_out && (!split_exp || !gmax))) return cudaErrorInvalidValue;
+    float* tmp = scratch + (size_t)nb * 29 * 64;   // reduced [29][64]
+    __half* shi = split_out;
+    __half* slo = split_out ? split_out + (size_t)h.B * (H + 4) * (H + 4) * (H + 4) * 64 : nullptr;
+    if (H <= 48) head2_bwd_kernel<12><<<nb, 256, smem, s>>>(h, g, c, w, out_g4, amax, scratch, shi, slo, split_exp, gmax);
+    else head2_bwd_kernel<32><<<nb, 256, smem, s>>>(h, g, c, w, out_g4, amax, scratch, shi, slo, split_exp, gmax);
+    launch_reduce_rows(scratch, nb, 29 * 64, tmp, s);
     cudaMemcpyAsync(dw, tmp, 27 * 64 * sizeof(float), cudaMemcpyDeviceToDevice, s);
     cudaMemcpyAsync(db, tmp + 27 * 64, sizeof(float), cudaMemcpyDeviceToDevice, s);
+    if (db1) cudaMemcpyAsync(db1, tmp + 28 * 64, 64 * sizeof(float), cudaMemcpyDeviceToDevice, s);
     return cudaGetLastError();
 }
 cudaError_t launch_fold_act(const float* raw0, const float* raw1, const float* raw2, const int* e0, const int* e1,
@@ -608,11 +648,11 @@ cudaError_t launch_wgrad64_simt(ActView x, const float* dy_g4, float* dw, float*
                                 cudaStream_t s) {
     dim3 grid(9, nchunk);
     wgrad64_kernel<<<grid, 256, 0, s>>>(x, dy_g4, scratch);
-    reduce_rows_kernel<<<(27 * 4096 + 255) / 256, 256, 0, s>>>(scratch, nchunk, 27 * 4096, dw);
+    reduce_rows_kernel<<<(27 * 4096 + 31) / 32, 256, 0, s>>>(scratch, nchunk, 27 * 4096, dw);
     return cudaGetLastError();
 }
 cudaError_t launch_reduce_rows(const float* partial, int nrows, int ncols, float* out, cudaStream_t s) {
-    reduce_rows_kernel<<<(ncols + 255) / 256, 256, 0, s>>>(partial, nrows, ncols, out);
+    reduce_rows_kernel<<<(ncols + 31) / 32, 256, 0, s>>>(partial, nrows, ncols, out);
     return cudaGetLastError();
 }
 cudaError_t launch_bias_grad(const float* dy_g4, int B, int D, float* db, float* scratch, cudaStream_t s) {
@@ -635,7 +675,7 @@ cudaError_t launch_conv1x1_bwd(const float* dy_g4, ActView a, ActView b, const f
     conv1x1_dgrad_kernel<<<nblocks(nvox, 32), 256, 128 * 64 * 4, s>>>(dy_g4, a, b, w, da_g4, db_g4, amax_a, amax_b);
     unsigned nb = red_blocks(nvox, C1_VOX_PER_BLOCK);
     conv1x1_wgrad_kernel<<<nb, 256, 0, s>>>(dy_g4, a, b, scratch);
-    reduce_rows_kernel<<<8192 / 256, 256, 0, s>>>(scratch, nb, 8192, dw);
+    reduce_rows_kernel<<<8192 / 32, 256, 0, s>>>(scratch, nb, 8192, dw);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return launch_bias_grad(dy_g4, a.B, a.D, dbias, scratch, s);
@@ -645,7 +685,7 @@ cudaError_t launch_stem_wgrad(const float* feat, int ch0, const float* dy_g4, in
     const int nlines = B * P * P;
     const unsigned nb = nlines < 592 ? nlines : 592;
     stem_wgrad_kernel<<<nb, 256, (size_t)9 * (P + 2) * sizeof(float4), s>>>(feat, ch0, dy_g4, B, P, scratch);
-    reduce_rows_kernel<<<(81 * 64 + 255) / 256, 256, 0, s>>>(scratch, nb, 81 * 64, dw);
+    reduce_rows_kernel<<<(81 * 64 + 31) / 32, 256, 0, s>>>(scratch, nb, 81 * 64, dw);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return launch_bias_grad(dy_g4, B, P, db, scratch, s);

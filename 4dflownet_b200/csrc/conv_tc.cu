@@ -511,16 +511,27 @@ __global__ void prep_weights_kernel(const float* __restrict__ params, PrepList l
 }
 
 // dgrad gain of each listed layer: max over ci of sum_{tap,co} |W[tap][ci][co]| (bounds |dX| <= gain * max|dY|)
-__global__ void __launch_bounds__(64) weight_gain_kernel(const float* __restrict__ params, PrepList l, float* __restrict__ gain) {
+__global__ void __launch_bounds__(256) weight_gain_kernel(const float* __restrict__ params, PrepList l, float* __restrict__ gain) {
     const float* w = params + l.off[blockIdx.x];
-    const int ci = threadIdx.x;
-    float s = 0.f;
-    for (int t = 0; t < 27; ++t)
-        for (int co = 0; co < 64; ++co) s += fabsf(w[((size_t)t * 64 + ci) * 64 + co]);
+    const int co = threadIdx.x & 63, ph = threadIdx.x >> 6;     // coalesced over co; 4 phases over (tap, ci)
+    __shared__ float colsum[64][65];
     __shared__ float red[64];
-    red[ci] = s;
+    // thread (ph, co) accumulates |W[t][ci][co]| into per-ci sums: walk (t, ci) pairs phase-strided
+    for (int i = threadIdx.x; i < 64 * 65; i += 256) (&colsum[0][0])[i] = 0.f;
     __syncthreads();
-    if (ci == 0) {
+    for (int ci = ph; ci < 64; ci += 4) {
+        float s = 0.f;
+        for (int t = 0; t < 27; ++t) s += fabsf(w[((size_t)t * 64 + ci) * 64 + co]);
+        colsum[ci][co] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float s = 0.f;
+        for (int c2 = 0; c2 < 64; ++c2) s += colsum[threadIdx.x][c2];
+        red[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
         float m = 0.f;
         for (int i = 0; i < 64; ++i) m = fmaxf(m, red[i]);
         gain[l.layer[blockIdx.x]] = m;
@@ -623,7 +634,7 @@ cudaError_t tc_prepare_weights(TcWeights* w, const float* params, const int* lay
         for (int i = 0; i < l.n; ++i) { l.layer[i] = layers[i0 + i]; l.off[i] = offsets[i0 + i]; }
         dim3 grid((27 * 128 * 64 + 255) / 256, l.n, 2);
         prep_weights_kernel<<<grid, 256, 0, s>>>(params, l, w->img);
-        weight_gain_kernel<<<l.n, 64, 0, s>>>(params, l, w->gain);
+        weight_gain_kernel<<<l.n, 256, 0, s>>>(params, l, w->gain);
     }
     return cudaGetLastError();
 }

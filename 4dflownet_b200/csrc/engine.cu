@@ -70,6 +70,8 @@ struct sr4d_handle {
     RawBuf raw_hr[3];
     int* gmeta = nullptr;      // device: {absmax bits, exponent} per GBuf, then head_exp[2]
     int* head_exp = nullptr;
+    unsigned int* gmax = nullptr;       // device: max |d loss / d pred|
+    unsigned int* amax_copy = nullptr;  // device: stable copy of an accumulating tensor's |max|
     float* pred = nullptr;     // (maxB,H^3,3)
     float* gpred = nullptr;    // (maxB,H^3,3)
     float* scratch = nullptr;  // split-reduction partials
@@ -440,7 +442,10 @@ int conv64_dgrad_fused(sr4d_t* h, int layer, const GBuf& dy, const GBuf* add_pre
     a.layer = layer; a.dgrad = 1; a.fused = 1;
     a.dy_exp = dy.exp; a.add_pre = add_pre ? add_pre->f : nullptr; a.add_post = add_post;
     if (with_split) {
-        a.split_out = out.s; a.split_exp = out.exp; a.dy_amax = dy.amax; a.add_amax = add_pre ? add_pre->amax : nullptr;
+        a.split_out = out.s; a.split_exp = out.exp; a.dy_amax = dy.amax;
+        // bound on |out|: this call's contribution plus what it is added to (skip gradient, or the in-place partial sum,
+        // whose |max| the caller copied to amax_copy before this launch started updating out.amax)
+        a.add_amax = add_pre ? add_pre->amax : (add_post ? h->amax_copy : nullptr);
     }
     a.sav_hi = saved ? saved->hi : nullptr; a.sav_lo = saved ? saved->lo : nullptr;
     a.slope = slope; a.out_g4 = out.f; a.absmax = out.amax;
@@ -498,7 +503,7 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
     const int nvoxH = H * H * H;
     int rc;
     CK(h, launch_loss_stats(h->pred, hu, hv, hw, mask, B, nvoxH, h->dpartial, 64, per_sample, h->norm, s), 2);
-    CK(h, launch_loss_grad(h->pred, hu, hv, hw, mask, B, nvoxH, h->norm, h->gpred, s), 1);
+    CK(h, launch_loss_grad(h->pred, hu, hv, hw, mask, B, nvoxH, h->norm, h->gpred, h->gmax, s), 1);
     if (l2_out)
         CK(h, launch_sumsq(h->params, h->kflag, h->flat, h->dpartial + 64 * 5 * h->maxB, 256, 5e-7f, l2_out, s), 2);
 
@@ -517,14 +522,19 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
     for (int c = 0; c < 3; ++c) {
         ActView hd = hr_view(h, 1 + 2 * h->hi + c, B);
         const int l1 = l_head + 2 * c, l2 = l1 + 1;
+        // whole backward of the 64->1 conv, plus what its input gradient needs downstream: the bias gradient of
+        // the head's first conv and (tensor-core path) the scaled split copy
         CK(h, cudaMemsetAsync(A.amax, 0, sizeof(int), s), 0);
-        CK(h, launch_head2_bwd(hd, h->gpred, c, W(h, l2), A.f, A.amax, GW(h, l2), GB(h, l2), h->scratch, s), 4);
-        if ((rc = grad_ready(h, A, B, H, s))) return rc;
-        if ((rc = conv64_wgrad(h, l1, trunk, A, true, s))) return rc;
+        CK(h, launch_head2_bwd(hd, h->gpred, c, W(h, l2), A.f, A.amax, GW(h, l2), GB(h, l2), GB(h, l1),
+                               use_tc(h) ? A.s : nullptr, A.exp, h->gmax, h->scratch, s), 5);
+        if ((rc = conv64_wgrad(h, l1, trunk, A, false, s))) return rc;
         if (fused_heads) {
-            // the three heads accumulate act'(trunk) * fold(dgrad_c) in place (the activation gradient is linear)
+            // the three heads accumulate act'(trunk) * fold(dgrad_c) in place (the activation gradient is linear);
+            // the last call also writes the split copy, bounded by this head's gain plus the |max| accumulated so far
+            const bool last = c == 2;
+            if (last) CK(h, cudaMemcpyAsync(h->amax_copy, hb[0]->amax, sizeof(int), cudaMemcpyDeviceToDevice, s), 0);
             if ((rc = conv64_dgrad_fused(h, l1, A, nullptr, c ? hb[0]->f : nullptr, trunk_act ? &trunk : nullptr,
-                                         trunk_slope, *hb[0], false, B, H, s))) return rc;
+                                         trunk_slope, *hb[0], last, B, H, s))) return rc;
             continue;
         }
         if ((rc = conv64_dgrad(h, l1, A, h->raw_hr[c], B, H, s))) return rc;
@@ -534,9 +544,7 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
             h->raw_hr[c].exp = h->head_exp + c;
         }
     }
-    if (fused_heads) {
-        if ((rc = grad_ready(h, *hb[0], B, H, s))) return rc;
-    } else {
+    if (!fused_heads) {
         if ((rc = fold_act(h, &h->raw_hr[0], &h->raw_hr[1], &h->raw_hr[2], nullptr, trunk_act ? &trunk : nullptr,
                            trunk_slope, *hb[0], B, H, s))) return rc;
     }
@@ -663,9 +671,11 @@ int sr4d_create(sr4d_t** out, int patch_size, int res_increase, int low_resblock
             const size_t rwl = (size_t)h->maxB * (h->P + 2) * (h->P + 2) * (h->P + 2) * 64;
             const size_t rwh = (size_t)h->maxB * (h->H + 2) * (h->H + 2) * (h->H + 2) * 64;
             bool bad = false;
-            bad |= dmalloc(&h->gmeta, 16) != cudaSuccess;
-            if (!bad) cudaMemset(h->gmeta, 0, 16 * sizeof(int));
+            bad |= dmalloc(&h->gmeta, 20) != cudaSuccess;
+            if (!bad) cudaMemset(h->gmeta, 0, 20 * sizeof(int));
             h->head_exp = h->gmeta + 14;
+            h->gmax = reinterpret_cast<unsigned int*>(h->gmeta + 16);
+            h->amax_copy = reinterpret_cast<unsigned int*>(h->gmeta + 17);
             int gi = 0;
             auto alloc_g = [&](GBuf& g, size_t n) {
                 // fp32 tensor and its split-fp16 copy (2 planes of n halves); halos are zeroed once and never written

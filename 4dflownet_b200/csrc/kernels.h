@@ -53,8 +53,10 @@ cudaError_t launch_unpack_act(ActView in, float* y, cudaStream_t s);
 cudaError_t launch_loss_stats(const float* pred, const float* hu, const float* hv, const float* hw,
                               const float* mask, int B, int nvox, double* partial, int nblk, float* per_sample,
                               float* norm, cudaStream_t s);
+// g = d(sum_b loss_b)/d pred; *gmax (optional, device) receives the bit pattern of max |g|
 cudaError_t launch_loss_grad(const float* pred, const float* hu, const float* hv, const float* hw,
-                             const float* mask, int B, int nvox, const float* norm, float* g, cudaStream_t s);
+                             const float* mask, int B, int nvox, const float* norm, float* g, unsigned int* gmax,
+                             cudaStream_t s);
 cudaError_t launch_sumsq(const float* p, const unsigned char* kflag, int64_t n, double* partial, int nblk,
                          float coeff, float* out, cudaStream_t s);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, const unsigned char* kflag, int64_t n,
@@ -66,8 +68,11 @@ cudaError_t launch_stitch(const float* pred, int nx, int ny, int nz, int H, int 
 // whole backward of a 64->1 head conv: h = its saved input Act (B,H), g (B,H^3,3) channel c, w[27][64];
 // writes d(pre-activation of h) = relu'(h) * dgrad (clamp padding folded in) into the G4 interior with |max|,
 // dw[27][64] and db; scratch >= (592 + 1) * 28 * 64 floats
+// db1 (optional, 64 floats) = per-channel sum of the written gradient (the bias gradient of the head's first conv);
+// split_out (optional) = scaled split-fp16 copy [2B][H+4]^3[64] of out_g4 with *split_exp derived from *gmax
 cudaError_t launch_head2_bwd(ActView h, const float* g, int c, const float* w, float* out_g4, unsigned int* amax,
-                             float* dw, float* db, float* scratch, cudaStream_t s);
+                             float* dw, float* db, float* db1, __half* split_out, int* split_exp,
+                             const unsigned int* gmax, float* scratch, cudaStream_t s);
 // out(G4 interior) = (fold(raw0*2^-e0 + raw1*2^-e1 + raw2*2^-e2) + add) * act'(saved); e_i are device
 // exponents (NULL = 0) of the scaled split-fp16 gradients the raws were computed from; amax (optional)
 // receives atomicMax of |out|

@@ -68,17 +68,27 @@ __global__ void loss_final_kernel(const double* __restrict__ partial, int nblk, 
 __global__ void loss_grad_kernel(const float* __restrict__ pred, const float* __restrict__ hu,
                                  const float* __restrict__ hv, const float* __restrict__ hw,
                                  const float* __restrict__ mask, int nvox, const float* __restrict__ norm,
-                                 float* __restrict__ g, size_t total) {
+                                 float* __restrict__ g, unsigned int* gmax, size_t total) {
     size_t vi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (vi >= total) return;
+    float mx = 0.f;
+    if (vi < total) {
     int b = vi / nvox;
     float sm = norm[b * 2], snf = norm[b * 2 + 1];
     float m = mask[vi];
     float nf = m < 0.5f ? 1.f : 0.f;
     float wgt = 2.f * (m / (sm + 1.f) + nf / (snf + 1.f));
-    g[vi * 3 + 0] = (pred[vi * 3 + 0] - hu[vi]) * wgt;
-    g[vi * 3 + 1] = (pred[vi * 3 + 1] - hv[vi]) * wgt;
-    g[vi * 3 + 2] = (pred[vi * 3 + 2] - hw[vi]) * wgt;
+    const float g0 = (pred[vi * 3 + 0] - hu[vi]) * wgt, g1 = (pred[vi * 3 + 1] - hv[vi]) * wgt;
+    const float g2 = (pred[vi * 3 + 2] - hw[vi]) * wgt;
+    g[vi * 3 + 0] = g0; g[vi * 3 + 1] = g1; g[vi * 3 + 2] = g2;
+    mx = fmaxf(fabsf(g0), fmaxf(fabsf(g1), fabsf(g2)));
+    }
+    // max |g| of the whole tensor (bounds the head gradients' scale): one atomic per warp that has a larger value
+    if (gmax) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0 && __float_as_uint(mx) > *reinterpret_cast<volatile unsigned int*>(gmax))
+            atomicMax(gmax, __float_as_uint(mx));
+    }
 }
 
 // ---- regulariser value: TrainerController.py:129-141 --------------------------------
@@ -161,9 +171,11 @@ cudaError_t launch_loss_stats(const float* pred, const float* hu, const float* h
     return cudaGetLastError();
 }
 cudaError_t launch_loss_grad(const float* pred, const float* hu, const float* hv, const float* hw,
-                             const float* mask, int B, int nvox, const float* norm, float* g, cudaStream_t s) {
+                             const float* mask, int B, int nvox, const float* norm, float* g, unsigned int* gmax,
+                             cudaStream_t s) {
     size_t total = (size_t)B * nvox;
-    loss_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(pred, hu, hv, hw, mask, nvox, norm, g, total);
+    if (gmax) cudaMemsetAsync(gmax, 0, sizeof(unsigned int), s);
+    loss_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(pred, hu, hv, hw, mask, nvox, norm, g, gmax, total);
     return cudaGetLastError();
 }
 cudaError_t launch_sumsq(const float* p, const unsigned char* kflag, int64_t n, double* partial, int nblk,
