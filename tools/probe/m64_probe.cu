@@ -108,6 +108,44 @@ __global__ void rate_probe(int m1, int n1, int k1, int m2, int n2, int k2, int i
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512u) : "memory");
 }
 
+// smaller footprint variant: `issuers` warps of the CTA each issue their own MMA stream into their own accumulator;
+// launched with 1 or 2 CTAs per SM.  Tells whether the ~96-cycle floor of small-N MMAs is an issue-rate limit of
+// one thread or an execution limit of the tensor pipe.
+__global__ void rate_probe2(int n, int k, int iters, int issuers, long long* cycles) {
+    extern __shared__ uint8_t raw[];
+    uint8_t* smem = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 96 * 1024);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 4);
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 96 * 1024 / 4; e += blockDim.x) reinterpret_cast<uint32_t*>(smem)[e] = 0x3c003c00u;
+    if (tid == 0) { for (int i = 0; i < 4; ++i) mbar_init(bar + i, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = *slot;
+    const int w = tid >> 5;
+    if ((tid & 31) == 0 && w < issuers) {
+        const uint32_t id = (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t a0 = smem_u32(smem) + w * 16384, b0 = smem_u32(smem) + 48 * 1024 + w * 16384;
+        uint64_t ad[4], bd[4];
+        for (int q = 0; q < 4; ++q) { ad[q] = dsc(a0 + q * 32, 1024); bd[q] = dsc(b0 + q * 32, 1024); }
+        long long t0 = clock64();
+        for (int it = 0; it < iters; ++it)
+            for (int q = 0; q < k; ++q) tc_mma_f16(tm + w * 128, ad[q & 3], bd[q & 3], id, 1);
+        tc_commit(bar + w);
+        mbar_wait(bar + w, 0);
+        cycles[blockIdx.x * 2 + w] = clock64() - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(256u) : "memory");
+}
+
 #define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
 int main() {
@@ -155,5 +193,24 @@ int main() {
         printf("%-48s: %8.1f cyc/round = %6.1f per MMA, M=128 floor %6.1f, ratio %.2f\n", c.name, per_round,
                per_round / (c.k1 + c.k2), floor_cyc, per_round / floor_cyc);
     }
+    printf("== small-N floor: issue rate or execution? (cycles per MMA per issuer) ==\n");
+    const int smem2 = 96 * 1024 + 64 + 1024;
+    CHECK(cudaFuncSetAttribute(rate_probe2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    long long* dc2;
+    CHECK(cudaMalloc(&dc2, 296 * 2 * 8));
+    std::vector<long long> h2(296 * 2);
+    for (int n : {64, 128, 192})
+        for (int ctas : {148, 296})
+            for (int issuers : {1, 2}) {
+                if (n > 128 && issuers > 1) continue;      // two 192-column accumulators do not fit the 256 allocated columns
+                CHECK(cudaMemset(dc2, 0, 296 * 2 * 8));
+                rate_probe2<<<ctas, 64, smem2>>>(n, 8, 400, issuers, dc2);
+                CHECK(cudaDeviceSynchronize());
+                CHECK(cudaMemcpy(h2.data(), dc2, 296 * 2 * 8, cudaMemcpyDeviceToHost));
+                long long mx = 0;
+                for (auto v : h2) if (v > mx) mx = v;
+                printf("N=%3d  %d CTA/SM  %d issuer warp(s): %6.1f cycles per MMA per issuer -> %6.1f cycles per MMA per SM\n", n,
+                       ctas / 148, issuers, (double)mx / (400 * 8), (double)mx / (400 * 8) / (issuers * (ctas / 148)));
+            }
     return 0;
 }
