@@ -1,0 +1,135 @@
+"""Edge cases and size-independent properties at BASELINE.json's full sizes, through the C ABI on the GPU:
+ragged / partial batches, error behaviour, determinism, batch-permutation equivariance, tiling round trips at the
+config-5 volume size, and full-geometry parity of the r=4 forward and of one config-2 train step."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def test_partial_and_ragged_batches(pkg, oracle):
+    P, r, low, hi = 8, 2, 1, 1
+    params = oracle.glorot_params(low, hi, seed=3, bias_scale=0.05)
+    batch = oracle.synthetic_batch(5, P, r, seed=2)
+    big = pkg.Engine(P, r, low, hi, max_batch=8, training=True, device=0)
+    big.set_weights(params)
+    y5 = big.forward(batch[:6]).cpu().numpy()
+    for B in (1, 3):                                     # B < max_batch reuses the same buffers with a smaller batch
+        yB = big.forward([b[:B] for b in batch[:6]]).cpu().numpy()
+        assert np.array_equal(yB, y5[:B])                # per-sample results do not depend on the batch they ride in
+    small = pkg.Engine(P, r, low, hi, max_batch=3, training=True, device=0)
+    small.set_weights(params)
+    sub = [b[:3] for b in batch]
+    per_a, l2_a, _ = big.train_fwd_bwd(sub[:6], [b[..., 0] for b in sub[6:9]], sub[10])
+    per_b, l2_b, _ = small.train_fwd_bwd(sub[:6], [b[..., 0] for b in sub[6:9]], sub[10])
+    assert torch.equal(per_a, per_b) and torch.equal(l2_a, l2_b)
+    assert torch.equal(big.grads, small.grads)           # bit-identical gradients: deterministic reductions
+    # Keras-style predict with a ragged tail (5 samples, batch 2)
+    model = pkg.prepare_network(P, r, low, hi, max_batch=2)
+    model.set_weights([params[n] for n in model.variable_names])
+    yp = model.predict(list(batch[:6]), batch_size=2)
+    assert yp.shape == (5, 16, 16, 16, 3) and np.array_equal(yp, y5)
+    big.close(); small.close()
+
+
+def test_error_behaviour(pkg, oracle):
+    L = pkg._lib
+    with pytest.raises(pkg.Sr4dError):
+        pkg.Engine(2, 2, 1, 1, max_batch=1)              # patch_size below the supported minimum -> SR4D_EINVAL
+    with pytest.raises(pkg.Sr4dError):
+        pkg.Engine(8, 0, 1, 1, max_batch=1)
+    eng = pkg.Engine(8, 2, 1, 1, max_batch=2, training=False, device=0)
+    batch = oracle.synthetic_batch(3, 8, 2, seed=0)
+    with pytest.raises(pkg.Sr4dError, match="SR4D_EINVAL"):
+        eng.forward(batch[:6])                           # B = 3 > max_batch = 2
+    assert not hasattr(eng, "grads")                     # inference handle: no gradient / optimizer state
+    with pytest.raises(pkg.Sr4dError, match="SR4D_ESTATE"):
+        eng._check(eng.lib.sr4d_adam_step(eng._h, 1e-3, 0.9, 0.999, 1e-7, 1, 0.0, None), "sr4d_adam_step")
+    with pytest.raises(ValueError):
+        eng.set_weights([np.zeros(1, np.float32)])       # wrong number of tensors
+    with pytest.raises(pkg.Sr4dError):
+        eng.set_option(99, 1)
+    eng.close()
+    eng.close()                                          # idempotent
+
+
+def test_determinism_and_batch_permutation(pkg, oracle):
+    P, r = 24, 2
+    eng = pkg.Engine(P, r, 8, 4, max_batch=4, training=True, device=0)
+    eng.set_weights(oracle.glorot_params(8, 4, seed=1234, bias_scale=0.02))
+    batch = oracle.synthetic_batch(4, P, r, seed=5)
+    hr = [b[..., 0] for b in batch[6:9]]
+    y1 = eng.forward(batch[:6]).clone()
+    y2 = eng.forward(batch[:6])
+    assert torch.equal(y1, y2)
+    perm = [2, 0, 3, 1]
+    yp = eng.forward([b[perm] for b in batch[:6]])
+    assert torch.equal(yp, y1[perm])
+    per1, _, _ = eng.train_fwd_bwd(batch[:6], hr, batch[10])
+    g1 = eng.grads.clone()
+    per2, _, _ = eng.train_fwd_bwd(batch[:6], hr, batch[10])
+    assert torch.equal(per1, per2) and torch.equal(g1, eng.grads)      # run-to-run bit-identical gradients
+    eng.close()
+
+
+def test_tiling_round_trip_at_config5_size(pkg):
+    """patchify -> (nearest-neighbour x2 'prediction') -> GPU stitch reproduces the repeated volume bit-exactly for
+    the 160x160x64 volume of config 5 (256 patches, 320x320x128 output) and a ragged volume."""
+    eng = pkg.Engine(24, 2, 0, 0, max_batch=1, training=False, device=0)
+    for shape in ((160, 160, 64), (42, 38, 36), (25, 47, 23)):
+        g = np.random.default_rng(1)
+        vol = g.integers(-1000, 1000, size=shape).astype(np.float32)
+        pg = pkg.PatchGenerator(24, 2)
+        patches, nx, ny, nz = pg._generate_overlapping_patches(vol)
+        pg.nr_x, pg.nr_y, pg.nr_z = nx, ny, nz
+        assert len(patches) == pg.count_patches(shape)
+        hr = patches.repeat(2, 1).repeat(2, 2).repeat(2, 3)
+        pred = torch.from_numpy(np.stack([hr, -hr, 2 * hr], -1)).cuda()
+        out = eng.stitch(pred, (nx, ny, nz), pg.stitched_shape(), 4, 1.0, round_small=False).cpu().numpy()
+        want = vol.repeat(2, 0).repeat(2, 1).repeat(2, 2)
+        assert out.shape == (3,) + want.shape
+        assert np.array_equal(out[0], want) and np.array_equal(out[1], -want) and np.array_equal(out[2], 2 * want)
+        assert np.array_equal(pg._patchup_with_overlap(hr, nx, ny, nz), want)
+    eng.close()
+
+
+def test_forward_r4_full_geometry_vs_oracle(pkg, oracle):
+    """BASELINE config 3 geometry (P=24, r=4 -> 96^3), one patch, against the fp32 oracle."""
+    params = oracle.glorot_params(8, 4, seed=77, bias_scale=0.02)
+    batch = oracle.synthetic_batch(1, 24, 4, seed=3)
+    eng = pkg.Engine(24, 4, 8, 4, max_batch=1, training=False, device=0)
+    eng.set_weights(params)
+    y = eng.forward(batch[:6]).cpu().numpy()
+    p32 = {k: torch.tensor(v) for k, v in params.items()}
+    with torch.no_grad():
+        ref = oracle.forward(p32, [torch.tensor(b) for b in batch[:6]], 4, 8, 4).numpy()
+    assert y.shape == (1, 96, 96, 96, 3)
+    assert relerr(y, ref) < 1e-4
+    eng.close()
+
+
+def test_train_step_full_geometry_vs_oracle(pkg, oracle):
+    """BASELINE config 2 geometry (P=24, r=2, 8/4 blocks), one sample: loss, metric and the flat gradient against
+    fp32 autograd of the oracle (tolerances as in test_gpu_backward: ReLU gate flips bound the gradient parity)."""
+    params = oracle.glorot_params(8, 4, seed=1234, bias_scale=0.02)
+    batch = oracle.synthetic_batch(1, 24, 2, seed=9)
+    eng = pkg.Engine(24, 2, 8, 4, max_batch=1, training=True, device=0)
+    eng.set_weights(params)
+    per, l2, pred = eng.train_fwd_bwd(batch[:6], [b[..., 0] for b in batch[6:9]], batch[10], want_pred=True)
+    g32, met = oracle.gradients(params, batch, 2, 8, 4, dtype=torch.float32)
+    assert relerr(pred.cpu().numpy(), met["pred"]) < 1e-4
+    np.testing.assert_allclose(per[:, 0].cpu().numpy() + float(l2), met["loss"], rtol=1e-4)
+    np.testing.assert_allclose(per[:, 2].cpu().numpy(), met["rel_err"], rtol=1e-3, atol=1e-3)
+    l2c = oracle.L2_COEFF
+    got = np.concatenate([v.cpu().numpy().ravel() for _, v in eng.tensor_views(eng.grads)])
+    want = np.concatenate([(g32[n] - (2 * l2c * params[n] if n.endswith("kernel") else 0.0)).ravel() for n, *_ in eng.table])
+    err = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert err < 5e-3, err
+    eng.close()
