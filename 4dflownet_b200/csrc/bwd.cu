@@ -34,6 +34,15 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restric
     }
 }
 
+// the same reduction for short, wide partial matrices (few rows, e.g. the 16 wgrad slabs): one thread per column
+__global__ void reduce_rows_wide_kernel(const float* __restrict__ partial, int nrows, int ncols, float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncols) return;
+    float s = 0.f;
+    for (int r = 0; r < nrows; ++r) s += partial[(size_t)r * ncols + j];
+    out[j] = s;
+}
+
 // block-wide max of |v| folded into *p with at most one atomic per block (all threads must call)
 __device__ __forceinline__ void absmax_commit(float m, unsigned int* p) {
     __shared__ float wm[32];
@@ -652,7 +661,8 @@ cudaError_t launch_wgrad64_simt(ActView x, const float* dy_g4, float* dw, float*
     return cudaGetLastError();
 }
 cudaError_t launch_reduce_rows(const float* partial, int nrows, int ncols, float* out, cudaStream_t s) {
-    reduce_rows_kernel<<<(ncols + 31) / 32, 256, 0, s>>>(partial, nrows, ncols, out);
+    if (nrows <= 32 && ncols >= 16384) reduce_rows_wide_kernel<<<(ncols + 255) / 256, 256, 0, s>>>(partial, nrows, ncols, out);
+    else reduce_rows_kernel<<<(ncols + 31) / 32, 256, 0, s>>>(partial, nrows, ncols, out);
     return cudaGetLastError();
 }
 cudaError_t launch_bias_grad(const float* dy_g4, int B, int D, float* db, float* scratch, cudaStream_t s) {

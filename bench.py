@@ -310,10 +310,10 @@ def run_b200(args):
             "forward": fwd,
         }
         if world == 1 and not args.no_cpu_baseline:
-            times, cores = cpu_train_steps(2, 1, batch=1)
+            times, cores = cpu_train_steps(12, 1, batch=1)
             line["cpu_baseline"] = {"value": len(times) / sum(times), "unit": "patches/s", "cores": cores,
-                                    "kind": "port", "sample": "2 timed train steps of 1 patch (after 1 warm-up) on the "
-                                    "torch-CPU restatement of the reference graph (TF not installable)"}
+                                    "kind": "port", "sample": "12 timed train steps of 1 patch (after 1 warm-up, ~10 s of CPU "
+                                    "work) on the torch-CPU restatement of the reference graph (TF not installable)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
