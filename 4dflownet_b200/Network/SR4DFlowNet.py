@@ -63,15 +63,54 @@ class SR4DFlowModel:
         return self.engine.forward(inputs)
 
     def predict(self, inputs, batch_size=None):
-        """model.predict([u,v,w,u_mag,v_mag,w_mag]) (predictor.py:87-92): numpy in, numpy out."""
+        """model.predict([u,v,w,u_mag,v_mag,w_mag]) (predictor.py:87-92): numpy in, numpy out.
+        Batches are staged through two sets of page-locked buffers so the host copies of batch k+1 / k-1 overlap
+        the kernels of batch k (all device work stays on torch's current stream)."""
         n = len(inputs[0])
-        bs = self.engine.max_batch if batch_size is None else min(int(batch_size), self.engine.max_batch)
-        H = self.engine.H
+        eng = self.engine
+        bs = eng.max_batch if batch_size is None else min(int(batch_size), eng.max_batch)
+        P, H = eng.patch_size, eng.H
         out = np.empty((n, H, H, H, 3), dtype=np.float32)
-        for i in range(0, n, bs):
-            y = self.engine.forward([a[i:i + bs] for a in inputs])
-            out[i:i + bs] = y.cpu().numpy()
+        if n == 0:
+            return out
+        st = self._staging(bs)
+        stream = torch.cuda.current_stream(eng.device)
+        pending = [None, None]                       # (event, lo, hi) of the batch occupying staging set i
+
+        def drain(i):
+            if pending[i] is not None:
+                ev, lo, hi = pending[i]
+                ev.synchronize()
+                out[lo:hi] = st[i]["out_host"][:hi - lo].numpy()
+                pending[i] = None
+        for k, lo in enumerate(range(0, n, bs)):
+            i = k & 1
+            hi = min(lo + bs, n)
+            drain(i)
+            hin = st[i]["in_host"]
+            for c in range(6):
+                hin[c, :hi - lo] = torch.from_numpy(np.ascontiguousarray(inputs[c][lo:hi], dtype=np.float32).reshape(hi - lo, P, P, P))
+            st[i]["in_dev"][:, :hi - lo].copy_(hin[:, :hi - lo], non_blocking=True)
+            y = eng.forward([st[i]["in_dev"][c, :hi - lo] for c in range(6)], out=st[i]["out_dev"][:hi - lo])
+            st[i]["out_host"][:hi - lo].copy_(y, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            pending[i] = (ev, lo, hi)
+        drain(0)
+        drain(1)
         return out
+
+    def _staging(self, bs):
+        st = getattr(self, "_stage", None)
+        if st is None or st[0]["in_host"].shape[1] < bs:
+            eng = self.engine
+            P, H = eng.patch_size, eng.H
+            st = [{"in_host": torch.empty((6, bs, P, P, P), dtype=torch.float32, pin_memory=True),
+                   "in_dev": torch.empty((6, bs, P, P, P), dtype=torch.float32, device=eng.device),
+                   "out_dev": torch.empty((bs, H, H, H, 3), dtype=torch.float32, device=eng.device),
+                   "out_host": torch.empty((bs, H, H, H, 3), dtype=torch.float32, pin_memory=True)} for _ in range(2)]
+            self._stage = st
+        return st
 
     # ---- weights on disk ----
     def save_weights(self, path):
