@@ -169,7 +169,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = importlib.import_module("4dflownet_b200")
     tcm = importlib.import_module("4dflownet_b200.Network.TrainerController")
-    oracle_data = importlib.import_module("oracle.sr4d_oracle").synthetic_batch   # data generator only
+    synthetic_batch = importlib.import_module("4dflownet_b200.utils.synthetic").synthetic_batch
     B, K, W = args.batch, args.steps, args.warmup
     dev = torch.device("cuda", local)
 
@@ -178,7 +178,7 @@ def run_b200(args):
     with contextlib.redirect_stdout(io.StringIO()):
         ctl = tcm.TrainerController(P, R, 1e-4, False, "4DFlowNet", LOW, HI, max_batch=B, device=local, seed=1234)
     eng = ctl.engine
-    host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in oracle_data(B, P, R, seed=rank)]
+    host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in synthetic_batch(B, P, R, seed=rank)]
     devb = [h.to(dev) for h in host]
     h2d = sum(h.numel() * 4 for i, h in enumerate(host) if i != 9)     # venc is not an input of the step
     per_host = torch.empty((B, 4), dtype=torch.float32).pin_memory()

@@ -159,3 +159,10 @@ def test_tiling_restatement_vs_reference_golden(oracle):
         if full:
             assert np.array_equal(patches, z[f"case{ci}_patches"])
             assert np.array_equal(st, z[f"case{ci}_stitched"])
+
+
+def test_synthetic_batch_matches_product_generator(oracle):
+    import importlib
+    synth = importlib.import_module("4dflownet_b200.utils.synthetic")
+    a, b = oracle.synthetic_batch(2, 6, 2, seed=3), synth.synthetic_batch(2, 6, 2, seed=3)
+    assert len(a) == len(b) == 11 and all(np.array_equal(x, y) for x, y in zip(a, b))

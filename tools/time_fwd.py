@@ -3,7 +3,7 @@ import importlib, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("4dflownet_b200")
-oracle = importlib.import_module("oracle.sr4d_oracle")
+synth = importlib.import_module("4dflownet_b200.utils.synthetic")
 L = pkg._lib
 
 def timeit(fn, n=5, warm=2):
@@ -19,8 +19,8 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 r = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 train = (sys.argv[3] == "train") if len(sys.argv) > 3 else False
 eng = pkg.Engine(24, r, 8, 4, max_batch=B, training=train, device=0)
-eng.set_weights(oracle.glorot_params(8, 4, seed=1))
-bt = oracle.synthetic_batch(B, 24, r, seed=0)
+pkg.SR4DFlowModel.initialize(type('M', (), {'engine': eng})(), seed=1)
+bt = synth.synthetic_batch(B, 24, r, seed=0)
 dev = [torch.tensor(np.ascontiguousarray(b)).cuda() for b in bt]
 hr = [d[..., 0].contiguous() for d in dev[6:9]]
 out = torch.empty((B, 24 * r, 24 * r, 24 * r, 3), device="cuda")
