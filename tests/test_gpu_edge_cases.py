@@ -133,3 +133,26 @@ def test_train_step_full_geometry_vs_oracle(pkg, oracle):
     err = np.linalg.norm(got - want) / np.linalg.norm(want)
     assert err < 5e-3, err
     eng.close()
+
+
+def test_trainer_default_geometry_vs_oracle(pkg, oracle):
+    """trainer.py's own defaults (patch_size=16, res_increase=2, 8/4 blocks; trainer.py:28-39), two samples: exercises the
+    TY=16 forward tiles and the 18^3 / 34^3 fused-dgrad grids against fp32 autograd of the oracle."""
+    params = oracle.glorot_params(8, 4, seed=21, bias_scale=0.02)
+    batch = oracle.synthetic_batch(2, 16, 2, seed=4)
+    eng = pkg.Engine(16, 2, 8, 4, max_batch=2, training=True, device=0)
+    eng.set_weights(params)
+    per, l2, pred = eng.train_fwd_bwd(batch[:6], [b[..., 0] for b in batch[6:9]], batch[10], want_pred=True)
+    g32, met = oracle.gradients(params, batch, 2, 8, 4, dtype=torch.float32)
+    assert relerr(pred.cpu().numpy(), met["pred"]) < 1e-4
+    np.testing.assert_allclose(per[:, 0].cpu().numpy() + float(l2), met["loss"], rtol=1e-4)
+    l2c = oracle.L2_COEFF
+    got = np.concatenate([v.cpu().numpy().ravel() for _, v in eng.tensor_views(eng.grads)])
+    want = np.concatenate([(g32[n] - (2 * 2 * l2c * params[n] if n.endswith("kernel") else 0.0)).ravel() for n, *_ in eng.table])
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 5e-3
+    # the unfused path gives the same gradient up to rounding of the split copies' exponents
+    eng.set_option(pkg._lib.OPT_FUSED_DGRAD, 0)
+    eng.train_fwd_bwd(batch[:6], [b[..., 0] for b in batch[6:9]], batch[10])
+    got2 = np.concatenate([v.cpu().numpy().ravel() for _, v in eng.tensor_views(eng.grads)])
+    assert np.linalg.norm(got2 - got) / np.linalg.norm(got) < 1e-4
+    eng.close()
