@@ -398,18 +398,38 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restri
     const int c = (i & 15) * 4;
     int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    // transposed interpolation weights of the HR indices that touch this LR index, per axis (tables read once)
+    auto axis_w = [&](int i, int j) {
+        return (t.lo[i] == j ? 1.f - t.lerp[i] : 0.f) + (t.hi[i] == j ? t.lerp[i] : 0.f);
+    };
+    const int zb = t.ibeg[z], zn = t.iend[z] - zb;
+    constexpr int MAXZ = 8;                       // covers res_increase <= 4; larger factors recompute in the loop
+    float wz[MAXZ];
+#pragma unroll
+    for (int k = 0; k < MAXZ; ++k) wz[k] = (k < zn) ? axis_w(zb + k, z) : 0.f;
     for (int ix = t.ibeg[x]; ix < t.iend[x]; ++ix) {
-        float wx = (t.lo[ix] == x ? 1.f - t.lerp[ix] : 0.f) + (t.hi[ix] == x ? t.lerp[ix] : 0.f);
+        const float wx = axis_w(ix, x);
         if (wx == 0.f) continue;
         for (int iy = t.ibeg[y]; iy < t.iend[y]; ++iy) {
-            float wy = (t.lo[iy] == y ? 1.f - t.lerp[iy] : 0.f) + (t.hi[iy] == y ? t.lerp[iy] : 0.f);
-            if (wy == 0.f) continue;
-            for (int iz = t.ibeg[z]; iz < t.iend[z]; ++iz) {
-                float wz = (t.lo[iz] == z ? 1.f - t.lerp[iz] : 0.f) + (t.hi[iz] == z ? t.lerp[iz] : 0.f);
-                if (wz == 0.f) continue;
-                float wgt = wx * wy * wz;
-                float4 a = *reinterpret_cast<const float4*>(dhr + g4_off(H, b, ix, iy, iz) + c);
-                s.x = fmaf(wgt, a.x, s.x); s.y = fmaf(wgt, a.y, s.y); s.z = fmaf(wgt, a.z, s.z); s.w = fmaf(wgt, a.w, s.w);
+            const float wxy = wx * axis_w(iy, y);
+            if (wxy == 0.f) continue;
+            const float* row = dhr + g4_off(H, b, ix, iy, zb) + c;
+            if (zn <= MAXZ) {
+#pragma unroll
+                for (int k = 0; k < MAXZ; ++k) {
+                    if (k < zn && wz[k] != 0.f) {
+                        const float wgt = wxy * wz[k];
+                        const float4 a = *reinterpret_cast<const float4*>(row + (size_t)k * 64);
+                        s.x = fmaf(wgt, a.x, s.x); s.y = fmaf(wgt, a.y, s.y); s.z = fmaf(wgt, a.z, s.z); s.w = fmaf(wgt, a.w, s.w);
+                    }
+                }
+            } else {
+                for (int k = 0; k < zn; ++k) {
+                    const float wgt = wxy * axis_w(zb + k, z);
+                    if (wgt == 0.f) continue;
+                    const float4 a = *reinterpret_cast<const float4*>(row + (size_t)k * 64);
+                    s.x = fmaf(wgt, a.x, s.x); s.y = fmaf(wgt, a.y, s.y); s.z = fmaf(wgt, a.z, s.z); s.w = fmaf(wgt, a.w, s.w);
+                }
             }
         }
     }
@@ -439,10 +459,10 @@ __global__ void __launch_bounds__(256) conv1x1_dgrad_kernel(const float* __restr
     __syncthreads();
     const int D = a.D;
     const size_t nvox = (size_t)a.B * D * D * D;
-    size_t vi = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3);
     float ma = 0.f, mb = 0.f;
-    if (vi < nvox) {
     const int kg = threadIdx.x & 7;
+    // grid-stride over groups of 32 voxels: the transposed weights are staged once per CTA
+    for (size_t vi = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3); vi < nvox; vi += (size_t)gridDim.x * 32) {
     int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
     const float* dyp = dy + g4_off(D, b, x, y, z);
     float acc[4][4];
@@ -682,7 +702,8 @@ cudaError_t launch_conv1x1_bwd(const float* dy_g4, ActView a, ActView b, const f
                                float* db_g4, unsigned int* amax_a, unsigned int* amax_b, float* dw, float* dbias,
                                float* scratch, cudaStream_t s) {
     size_t nvox = (size_t)a.B * a.D * a.D * a.D;
-    conv1x1_dgrad_kernel<<<nblocks(nvox, 32), 256, 128 * 64 * 4, s>>>(dy_g4, a, b, w, da_g4, db_g4, amax_a, amax_b);
+    const unsigned ngrp = nblocks(nvox, 32);
+    conv1x1_dgrad_kernel<<<ngrp < 592 ? ngrp : 592, 256, 128 * 64 * 4, s>>>(dy_g4, a, b, w, da_g4, db_g4, amax_a, amax_b);
     unsigned nb = red_blocks(nvox, C1_VOX_PER_BLOCK);
     conv1x1_wgrad_kernel<<<nb, 256, 0, s>>>(dy_g4, a, b, scratch);
     reduce_rows_kernel<<<8192 / 32, 256, 0, s>>>(scratch, nb, 8192, dw);

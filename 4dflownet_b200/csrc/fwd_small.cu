@@ -31,9 +31,9 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
     __syncthreads();
     const int P = out.D;
     const size_t nvox = (size_t)out.B * P * P * P;
-    size_t vi = (size_t)blockIdx.x * 64 + (threadIdx.x >> 2);
-    if (vi >= nvox) return;
     const int cq = (threadIdx.x & 3) * 16;
+    // grid-stride over groups of 64 voxels: the weights are staged once per CTA
+    for (size_t vi = (size_t)blockIdx.x * 64 + (threadIdx.x >> 2); vi < nvox; vi += (size_t)gridDim.x * 64) {
     int z = vi % P, y = (vi / P) % P, x = (vi / ((size_t)P * P)) % P, b = vi / ((size_t)P * P * P);
     float acc[16];
 #pragma unroll
@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
         for (int n = 0; n < 4; ++n) vv[n] = fmaxf(acc[q * 4 + n], 0.f);
         act_store4_halo(out.hi, out.lo, P, b, x, y, z, cq + q * 4, vv, true);
     }
+    }
 }
 
 // ---- 1x1 conv over concat[a(phase), b(pc)] 128->64 (+bias, ReLU): SR4DFlowNet.py:23-24
@@ -70,9 +71,8 @@ __global__ void __launch_bounds__(256) conv1x1_cat_kernel(ActView a, ActView bq,
     __syncthreads();
     const int D = out.D;
     const size_t nvox = (size_t)out.B * D * D * D;
-    size_t vi = (size_t)blockIdx.x * 64 + (threadIdx.x >> 2);
-    if (vi >= nvox) return;
     const int cq = (threadIdx.x & 3) * 16;
+    for (size_t vi = (size_t)blockIdx.x * 64 + (threadIdx.x >> 2); vi < nvox; vi += (size_t)gridDim.x * 64) {
     int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
     size_t off = act_off(D, b, x, y, z);
     float acc[16];
@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(256) conv1x1_cat_kernel(ActView a, ActView bq,
 #pragma unroll
         for (int n = 0; n < 4; ++n) vv[n] = fmaxf(acc[q * 4 + n], 0.f);
         act_store4_halo(out.hi, out.lo, D, b, x, y, z, cq + q * 4, vv, true);
+    }
     }
 }
 
@@ -312,12 +313,14 @@ cudaError_t launch_prep_features(const float* u, const float* v, const float* w,
 cudaError_t launch_stem_conv(const float* feat, int ch0, const float* w, const float* bias, ActView out,
                              cudaStream_t s) {
     size_t nvox = (size_t)out.B * out.D * out.D * out.D;
-    stem_conv_kernel<<<(unsigned)((nvox + 63) / 64), 256, 0, s>>>(feat, ch0, w, bias, out);
+    const size_t ngrp = (nvox + 63) / 64;
+    stem_conv_kernel<<<(unsigned)(ngrp < 2368 ? ngrp : 2368), 256, 0, s>>>(feat, ch0, w, bias, out);
     return cudaGetLastError();
 }
 cudaError_t launch_conv1x1_cat(ActView a, ActView b, const float* w, const float* bias, ActView out, cudaStream_t s) {
     size_t nvox = (size_t)out.B * out.D * out.D * out.D;
-    conv1x1_cat_kernel<<<(unsigned)((nvox + 63) / 64), 256, 128 * 64 * 4, s>>>(a, b, w, bias, out);
+    const size_t ngrp = (nvox + 63) / 64;
+    conv1x1_cat_kernel<<<(unsigned)(ngrp < 2368 ? ngrp : 2368), 256, 128 * 64 * 4, s>>>(a, b, w, bias, out);
     return cudaGetLastError();
 }
 cudaError_t launch_upsample(ActView in, ActView out, int r, UpsampleTables t, cudaStream_t s) {
