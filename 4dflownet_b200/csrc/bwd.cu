@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(256) head2_bwd_kernel(ActView h, const float* 
     extern __shared__ __align__(16) float h2sm[];
     const int H = h.D, Hz = H + 2;
     float* gl = h2sm;                              // [3][3][H+2]
-    float* Gs = h2sm + (9 * Hz + 3) / 4 * 4;       // [H][28], 16-byte aligned rows
+    float* Rl = h2sm + 9 * Hz;                     // [3][3][H+2]
+    float* Gs = h2sm + (18 * Hz + 3) / 4 * 4;      // [H][28], 16-byte aligned rows
     const int ci = threadIdx.x & 63, q = threadIdx.x >> 6;
     float wr[27], dw[29];
     float wabs = 0.f;
@@ -106,14 +107,14 @@ __global__ void __launch_bounds__(256) head2_bwd_kernel(ActView h, const float* 
     for (int line = blockIdx.x; line < nlines; line += gridDim.x) {
         const int y = line % H, x = (line / H) % H, b = line / (H * H);
         // this thread's voxels z = q, q+4, ...: issue the (2-byte, latency-bound) loads before building G
-        float hvp[HZ_MAX];
+        __half hph[HZ_MAX], hpl[HZ_MAX];           // raw planes: converting here would wait for the loads
+        const size_t lineo = act_off(H, b, x, y, 0) + ci;
 #pragma unroll
         for (int u = 0; u < HZ_MAX; ++u) {
             const int z = q + 4 * u;
-            hvp[u] = 0.f;
             if (z < H) {
-                const size_t ao = act_off(H, b, x, y, z) + ci;
-                hvp[u] = join_f16(h.hi[ao], h.lo[ao]);
+                hph[u] = h.hi[lineo + (size_t)z * 64];
+                hpl[u] = h.lo[lineo + (size_t)z * 64];
             }
         }
         __syncthreads();
@@ -126,27 +127,29 @@ __global__ void __launch_bounds__(256) head2_bwd_kernel(ActView h, const float* 
             gl[i] = v;
         }
         __syncthreads();
+        // R[tx][ty][zz]: the x/y part of the clamp sets summed once per (tx,ty) line; G then needs <= 2 terms
+        for (int i = threadIdx.x; i < 9 * Hz; i += 256) {
+            const int r = i / Hz, zz = i % Hz;
+            const int tx = r / 3, ty = r % 3;
+            const int ex = (x == 0 && tx == 0) || (x == H - 1 && tx == 2);
+            const int ey = (y == 0 && ty == 0) || (y == H - 1 && ty == 2);
+            float s = gl[((2 - tx) * 3 + (2 - ty)) * Hz + zz];
+            if (ex) s += gl[(3 + (2 - ty)) * Hz + zz];
+            if (ey) s += gl[((2 - tx) * 3 + 1) * Hz + zz];
+            if (ex && ey) s += gl[4 * Hz + zz];
+            Rl[i] = s;
+        }
+        __syncthreads();
         for (int i = threadIdx.x; i < H * 28; i += 256) {
             const int z = i / 28, t = i % 28;
-            float s = 0.f;
+            float s;
             if (t == 27) {
                 s = gl[4 * Hz + z + 1];                      // g at the voxel itself (bias gradient)
             } else {
-                const int tx = t / 9, ty = (t / 3) % 3, tz = t % 3;
-                // offsets o = i - j contributing along each axis: 1 - t always (zero if out of range), plus 0
-                // again at the clamped ends
-                const int ex = (x == 0 && tx == 0) || (x == H - 1 && tx == 2);
-                const int ey = (y == 0 && ty == 0) || (y == H - 1 && ty == 2);
-                const int ez = (z == 0 && tz == 0) || (z == H - 1 && tz == 2);
-                for (int ax = 0; ax <= ex; ++ax) {
-                    const int rx = ax ? 1 : 2 - tx;              // row index = o + 1
-                    for (int ay = 0; ay <= ey; ++ay) {
-                        const int ry = ay ? 1 : 2 - ty;
-                        const float* gp = gl + (rx * 3 + ry) * Hz + z + 1;
-                        s += gp[1 - tz];
-                        if (ez) s += gp[0];
-                    }
-                }
+                const int tz = t % 3;
+                const float* rp = Rl + (t / 3) * Hz + z + 1;
+                s = rp[1 - tz];
+                if ((z == 0 && tz == 0) || (z == H - 1 && tz == 2)) s += rp[0];
             }
             Gs[i] = s;
         }
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(256) head2_bwd_kernel(ActView h, const float* 
                     const float4 v = G4p[k];
                     Gt[4 * k] = v.x; Gt[4 * k + 1] = v.y; Gt[4 * k + 2] = v.z; Gt[4 * k + 3] = v.w;
                 }
-                const float hv = hvp[u];
+                const float hv = join_f16(hph[u], hpl[u]);
                 float sa = 0.f;
 #pragma unroll
                 for (int t = 0; t < 27; ++t) {
@@ -644,7 +647,7 @@ cudaError_t launch_head2_bwd(ActView h, const float* g, int c, const float* w, f
     const int H = h.D;
     const int nlines = h.B * H * H;
     const unsigned nb = nlines < 592 ? nlines : 592;           // 148 SMs x 4 resident blocks
-    size_t smem = (size_t)((9 * (H + 2) + 3) / 4 * 4 + H * 28) * sizeof(float);
+    size_t smem = (size_t)((18 * (H + 2) + 3) / 4 * 4 + H * 28) * sizeof(float);
     if (smem < 4 * 29 * 64 * sizeof(float)) smem = 4 * 29 * 64 * sizeof(float);
     if (H > 128 || (split_out && (!split_exp || !gmax))) return cudaErrorInvalidValue;
     float* tmp = scratch + (size_t)nb * 29 * 64;   // reduced [29][64]
