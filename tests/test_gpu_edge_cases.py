@@ -156,3 +156,40 @@ def test_trainer_default_geometry_vs_oracle(pkg, oracle):
     got2 = np.concatenate([v.cpu().numpy().ravel() for _, v in eng.tensor_views(eng.grads)])
     assert np.linalg.norm(got2 - got) / np.linalg.norm(got) < 1e-4
     eng.close()
+
+
+def test_three_train_steps_follow_the_oracle_loop(pkg, oracle):
+    """Three consecutive TrainerController.train_step calls (forward, backward, Adam, refreshed tensor-core weight
+    images) against the oracle's fp64 loop: per-step loss trajectory and the accumulated weight update."""
+    import contextlib
+    import io
+    tcm = importlib.import_module("4dflownet_b200.Network.TrainerController")
+    P, r, low, hi, B, lr = 8, 2, 2, 1, 3, 1e-3
+    params = oracle.glorot_params(low, hi, seed=17, bias_scale=0.05)
+    batches = [oracle.synthetic_batch(B, P, r, seed=30 + i) for i in range(3)]
+    with contextlib.redirect_stdout(io.StringIO()):
+        ctl = tcm.TrainerController(P, r, lr, False, "t", low, hi, max_batch=B)
+    ctl.model.set_weights(params)
+    got_losses = []
+    for bt in batches:
+        ctl.reset_metrics()
+        ctl.train_step(bt)
+        got_losses.append(ctl.loss_metrics["train_loss"].result())
+    w_got = dict(zip(ctl.model.variable_names, ctl.model.get_weights()))
+    # oracle loop (fp64 autograd + numpy Adam)
+    w = {k: v.astype(np.float64) for k, v in params.items()}
+    m = {k: 0.0 for k in w}
+    v = {k: 0.0 for k in w}
+    want_losses = []
+    for t, bt in enumerate(batches, 1):
+        g, met = oracle.gradients(w, bt, r, low, hi)
+        want_losses.append(float(np.mean(met["loss"])))
+        for k in w:
+            w[k], m[k], v[k] = oracle.adam_step(w[k], g[k], m[k], v[k], t, lr)
+    np.testing.assert_allclose(got_losses, want_losses, rtol=2e-4)
+    assert want_losses[2] != want_losses[0]
+    num = sum(float(np.sum((w_got[k] - w[k]) ** 2)) for k in w)
+    den = sum(float(np.sum((w[k] - params[k]) ** 2)) for k in w)
+    assert (num / den) ** 0.5 < 2e-2          # accumulated update agrees to 2 % (Adam's sign-like first steps amplify
+    #                                           gradient noise near zero; the loss trajectory above is the tight check)
+    assert ctl.optimizer.iterations == 3
