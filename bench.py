@@ -53,18 +53,22 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region: the sampler is started before the
+    warm-up (nvidia-smi needs a moment to produce its first line, more so on an 8-GPU box) and only samples whose
+    timestamp falls inside [mark_begin, mark_end] are used; if the region was too short to catch one, the samples
+    taken under load during the warm-up right before it are used and the summary says so."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc, self.thr = index, [], None, None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -72,27 +76,50 @@ class ClockSampler:
         self.thr = threading.Thread(target=lambda: self.rows.extend(self.proc.stdout), daemon=True)
         self.thr.start()
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    @staticmethod
+    def _epoch(ts):
+        import datetime
+        try:
+            return datetime.datetime.strptime(ts.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         self.thr.join(timeout=2)
-        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        parsed = []
         for line in self.rows:
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                parsed.append((self._epoch(f[0]), float(f[1]), float(f[2]), float(f[3]),
+                               [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w": statistics.median(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        inside = [p for p in parsed if p[0] is not None and t0 <= p[0] <= t1 + 0.05]
+        window = "timed region"
+        if not inside:
+            # region shorter than the sampling latency: use the last samples before it ends (warm-up under the same load)
+            inside = [p for p in parsed if p[0] is None or p[0] <= t1 + 0.05][-6:]
+            window = "warm-up + timed region (region too short for a sample of its own)"
+        sm = [p[1] for p in inside]
+        reasons = sorted({r for p in inside for r in p[4]})
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max((p[2] for p in inside), default=None),
+                "power_w": statistics.median([p[3] for p in inside]) if inside else None,
+                "samples": len(inside), "window": window, "reasons": reasons}
 
 
 # --------------------------------------------------------------------------------------------
@@ -218,13 +245,15 @@ def run_b200(args):
 
     # ---- headline: device-resident train step --------------------------------------------------
     clocks = ClockSampler(local)
+    clocks.start()
     eng.reset_launch_count()
     for _ in range(W):
         step_dev()
     barrier()
     eng.reset_launch_count()
-    clocks.start()
+    clocks.mark_begin()
     ms_total = timed(step_dev, K, 0)
+    clocks.mark_end()
     clk = clocks.stop()
     launches = eng.launch_count()
     ms_step = ms_total / K
