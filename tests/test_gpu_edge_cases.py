@@ -193,3 +193,23 @@ def test_three_train_steps_follow_the_oracle_loop(pkg, oracle):
     assert (num / den) ** 0.5 < 2e-2          # accumulated update agrees to 2 % (Adam's sign-like first steps amplify
     #                                           gradient noise near zero; the loss trajectory above is the tight check)
     assert ctl.optimizer.iterations == 3
+
+
+def test_training_reduces_the_loss_on_a_fixed_batch(pkg, oracle):
+    """Overfit check through the public controller: 25 Adam steps on one fixed batch must cut the masked-MSE loss
+    (the regulariser is ~1e-3 of it) by a large factor -- catches sign / scale errors no single-step parity test sees."""
+    import contextlib
+    import io
+    tcm = importlib.import_module("4dflownet_b200.Network.TrainerController")
+    P, r = 12, 2
+    with contextlib.redirect_stdout(io.StringIO()):
+        ctl = tcm.TrainerController(P, r, 2e-3, False, "t", 2, 1, max_batch=4, seed=3)
+    batch = oracle.synthetic_batch(4, P, r, seed=8)
+    losses = []
+    for _ in range(25):
+        ctl.reset_metrics()
+        ctl.train_step(batch)
+        losses.append(ctl.loss_metrics["train_mse"].result())
+    assert np.isfinite(losses).all()
+    assert losses[-1] < 0.5 * losses[0], losses
+    assert losses[-1] == min(losses[-5:]) or losses[-1] < 0.6 * losses[0]
