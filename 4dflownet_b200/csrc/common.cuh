@@ -113,6 +113,35 @@ __device__ __forceinline__ void act_store4_halo(__half* hi, __half* lo, int D, i
     }
 }
 
+// 8 consecutive channels with 16-byte stores (same halo replication rule)
+__device__ __forceinline__ void act_store8_halo(__half* hi, __half* lo, int D, int b, int x, int y, int z,
+                                                int c, const float* v, bool halo) {
+    __align__(16) __half hh[8];
+    __align__(16) __half ll[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_f16(v[i], hh[i], ll[i]);
+    const uint4 H = *reinterpret_cast<const uint4*>(hh), L = *reinterpret_cast<const uint4*>(ll);
+    const bool edge = halo && (x == 0 || x == D - 1 || y == 0 || y == D - 1 || z == 0 || z == D - 1);
+    if (!edge) {
+        const size_t o = act_off(D, b, x, y, z) + c;
+        *reinterpret_cast<uint4*>(hi + o) = H;
+        *reinterpret_cast<uint4*>(lo + o) = L;
+        return;
+    }
+    for (int dx = -1; dx <= 1; ++dx) {
+        if ((dx == -1 && x != 0) || (dx == 1 && x != D - 1)) continue;
+        for (int dy = -1; dy <= 1; ++dy) {
+            if ((dy == -1 && y != 0) || (dy == 1 && y != D - 1)) continue;
+            for (int dz = -1; dz <= 1; ++dz) {
+                if ((dz == -1 && z != 0) || (dz == 1 && z != D - 1)) continue;
+                const size_t o = act_off(D, b, x + dx, y + dy, z + dz) + c;
+                *reinterpret_cast<uint4*>(hi + o) = H;
+                *reinterpret_cast<uint4*>(lo + o) = L;
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ float act_fn(float v, float slope) { return v > 0.f ? v : v * slope; }
 // derivative of the activation expressed through its OUTPUT (ReLU / LeakyReLU keep sign;
 // TF's ReluGrad / LeakyReluGrad test "> 0")

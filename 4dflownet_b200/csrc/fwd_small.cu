@@ -26,7 +26,7 @@ __global__ void prep_features_kernel(const float* __restrict__ u, const float* _
 __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ feat, int ch0,
                                                         const float* __restrict__ w,
                                                         const float* __restrict__ bias, ActView out) {
-    __shared__ float ws[27 * 3 * 64];
+    __shared__ __align__(16) float ws[27 * 3 * 64];
     for (int i = threadIdx.x; i < 27 * 3 * 64; i += 256) ws[i] = w[i];
     __syncthreads();
     const int P = out.D;
@@ -48,8 +48,15 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
                 float f0 = f[0], f1 = f[1], f2 = f[2];
                 const float* wp = ws + (((dx + 1) * 3 + (dy + 1)) * 3 + (dz + 1)) * 192 + cq;
 #pragma unroll
-                for (int n = 0; n < 16; ++n)
-                    acc[n] = fmaf(f0, wp[n], fmaf(f1, wp[64 + n], fmaf(f2, wp[128 + n], acc[n])));
+                for (int n4 = 0; n4 < 4; ++n4) {          // 16-byte shared-memory loads: 12 per tap for 48 FMAs
+                    const float4 w0 = *reinterpret_cast<const float4*>(wp + n4 * 4);
+                    const float4 w1 = *reinterpret_cast<const float4*>(wp + 64 + n4 * 4);
+                    const float4 w2 = *reinterpret_cast<const float4*>(wp + 128 + n4 * 4);
+                    acc[n4 * 4 + 0] = fmaf(f0, w0.x, fmaf(f1, w1.x, fmaf(f2, w2.x, acc[n4 * 4 + 0])));
+                    acc[n4 * 4 + 1] = fmaf(f0, w0.y, fmaf(f1, w1.y, fmaf(f2, w2.y, acc[n4 * 4 + 1])));
+                    acc[n4 * 4 + 2] = fmaf(f0, w0.z, fmaf(f1, w1.z, fmaf(f2, w2.z, acc[n4 * 4 + 2])));
+                    acc[n4 * 4 + 3] = fmaf(f0, w0.w, fmaf(f1, w1.w, fmaf(f2, w2.w, acc[n4 * 4 + 3])));
+                }
             }
         }
     }
@@ -66,7 +73,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
 // ---- 1x1 conv over concat[a(phase), b(pc)] 128->64 (+bias, ReLU): SR4DFlowNet.py:23-24
 __global__ void __launch_bounds__(256) conv1x1_cat_kernel(ActView a, ActView bq, const float* __restrict__ w,
                                                           const float* __restrict__ bias, ActView out) {
-    extern __shared__ float ws[];   // [128][64]
+    extern __shared__ __align__(16) float ws[];   // [128][64]
     for (int i = threadIdx.x; i < 128 * 64; i += 256) ws[i] = w[i];
     __syncthreads();
     const int D = out.D;
@@ -86,9 +93,15 @@ __global__ void __launch_bounds__(256) conv1x1_cat_kernel(ActView a, ActView bq,
             act_load8(hi, lo, off + c8 * 8, xv);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const float* wp = ws + (half * 64 + c8 * 8 + k) * 64 + cq;
+                const float4* wp = reinterpret_cast<const float4*>(ws + (half * 64 + c8 * 8 + k) * 64 + cq);
 #pragma unroll
-                for (int n = 0; n < 16; ++n) acc[n] = fmaf(xv[k], wp[n], acc[n]);
+                for (int n4 = 0; n4 < 4; ++n4) {
+                    const float4 wv = wp[n4];
+                    acc[n4 * 4 + 0] = fmaf(xv[k], wv.x, acc[n4 * 4 + 0]);
+                    acc[n4 * 4 + 1] = fmaf(xv[k], wv.y, acc[n4 * 4 + 1]);
+                    acc[n4 * 4 + 2] = fmaf(xv[k], wv.z, acc[n4 * 4 + 2]);
+                    acc[n4 * 4 + 3] = fmaf(xv[k], wv.w, acc[n4 * 4 + 3]);
+                }
             }
         }
     }
@@ -132,8 +145,7 @@ __global__ void __launch_bounds__(256) upsample_kernel(ActView in, ActView out, 
     float o[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = r[0][k] + (r[1][k] - r[0][k]) * fx;
-    act_store4_halo(out.hi, out.lo, H, b, x, y, z, c, o, true);
-    act_store4_halo(out.hi, out.lo, H, b, x, y, z, c + 4, o + 4, true);
+    act_store8_halo(out.hi, out.lo, H, b, x, y, z, c, o, true);
 }
 
 // ---- 64->1 head conv, linear (+bias), writes (B,H^3,3): SR4DFlowNet.py:40,43,46,49 -------
