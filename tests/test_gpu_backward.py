@@ -70,7 +70,7 @@ def test_train_step_gradients_vs_oracle(pkg, oracle, P, r, low, hi, B, impl):
     gref, met = oracle.gradients({k: v.astype(np.float64) for k, v in params.items()}, batch, r, low, hi)
     # fp32 autograd of the same graph (what the reference's TF fp32 path amounts to): its distance from
     # the fp64 truth calibrates the gradient tolerance -- through this depth fp32 itself is off by up to
-    # ~5e-4 on the (ill-conditioned, zero-mean-input) stem kernels (tools/diag_grads.py), so the per-tensor
+    # ~5e-4 on the (ill-conditioned, zero-mean-input) stem kernels (tests/diag_grads.py), so the per-tensor
     # bar is max(2e-4, 2x the fp32 error) and the 1e-4 bar is applied to the flat gradient as a whole.
     g32, _ = oracle.gradients(params, batch, r, low, hi, dtype=torch.float32)
     l2c = oracle.L2_COEFF
@@ -84,7 +84,7 @@ def test_train_step_gradients_vs_oracle(pkg, oracle, P, r, low, hi, B, impl):
         # ReLU / LeakyReLU gates make the gradient discontinuous in the forward activations: a forward
         # perturbation of relative size eps flips ~eps of the gates and moves a random-sign gradient sum by
         # ~sqrt(eps).  fp32 autograd (eps ~1e-7) is therefore 1e-4..5e-4 from fp64 on some tensors, and the
-        # tensor-core forward (eps ~3e-6: the tcgen05 fp32 accumulator truncates) 1e-3..3e-3 (tools/diag_grads.py).
+        # tensor-core forward (eps ~3e-6: the tcgen05 fp32 accumulator truncates) 1e-3..3e-3 (tests/diag_grads.py).
         # The backward KERNELS are held to 1e-5 given identical inputs in test_conv64_layer_bwd.
         tol = max(2e-4 if impl == "simt" else 5e-3, 2.0 * rel_l2(g32[name], gref[name]))
         assert rel_l2(got, want) < tol, (name, rel_l2(got, want), tol)
