@@ -145,6 +145,21 @@ class TrainerController:
         per = self.engine.loss_metrics(y_pred, y_true[..., 0], y_true[..., 1], y_true[..., 2], mask)
         return per[:, 2].cpu().numpy()
 
+    def calculate_mse(self, u, v, w, u_pred, v_pred, w_pred):
+        """Voxel-wise squared error summed over the three components (TrainerController.py:152-156).  Convenience
+        mirror only: the training path computes it inside the fused loss kernel."""
+        t = [torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).to(self.engine.device, torch.float32)
+             for a in (u, v, w, u_pred, v_pred, w_pred)]
+        return (t[3] - t[0]) ** 2 + (t[4] - t[1]) ** 2 + (t[5] - t[2]) ** 2
+
+    def calculate_and_update_metrics(self, hires, predictions, mask, metric_set):
+        """TrainerController.py:241-257: loss / mse / accuracy of a batch folded into the running means; returns the
+        (B,) loss vector (with the scalar l2 added for the train set)."""
+        hires = torch.as_tensor(np.asarray(hires) if not torch.is_tensor(hires) else hires)
+        per = self.engine.loss_metrics(predictions, hires[..., 0], hires[..., 1], hires[..., 2], mask)
+        l2 = self.calculate_regularizer_loss() if metric_set == 'train' else None
+        return self._update_metrics(per.cpu().numpy(), l2, metric_set)
+
     def calculate_regularizer_loss(self):
         """5e-7 * sum over the conv kernels of sum(w^2) — TrainerController.py:129-141."""
         tot = 0.0

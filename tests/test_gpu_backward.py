@@ -117,3 +117,33 @@ def test_train_step_gradients_vs_oracle(pkg, oracle, P, r, low, hi, B, impl):
         if np.abs(gref[name]).max() > 1e-3:
             assert np.percentile(np.abs(upd[big] - (p_ref - w0)[big]), 99) < 0.2 * lr, name
     eng.close()
+
+
+def test_reference_named_metric_entry_points(pkg, oracle):
+    """loss_utils.calculate_relative_error and TrainerController.calculate_and_update_metrics / calculate_mse with the
+    reference's argument conventions, against the oracle."""
+    import contextlib
+    import importlib
+    import io
+    lu = importlib.import_module("4dflownet_b200.Network.loss_utils")
+    tcm = importlib.import_module("4dflownet_b200.Network.TrainerController")
+    g = np.random.default_rng(3)
+    B, H = 3, 12
+    true = (g.standard_normal((B, H, H, H, 3)) * 0.1).astype(np.float32)
+    pred = (true + g.standard_normal(true.shape) * 0.02).astype(np.float32)
+    mask = (g.uniform(size=(B, H, H, H)) < 0.3).astype(np.float32)
+    true[mask == 0] = 0
+    want = oracle.calculate_relative_error(torch.tensor(true, dtype=torch.float64), torch.tensor(pred, dtype=torch.float64),
+                                           torch.tensor(mask, dtype=torch.float64)).numpy()
+    got = lu.calculate_relative_error(pred[..., 0:1], pred[..., 1:2], pred[..., 2:3], true[..., 0:1], true[..., 1:2],
+                                      true[..., 2:3], mask).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ctl = tcm.TrainerController(6, 2, 1e-4, False, "t", 0, 0, max_batch=B)
+    loss = ctl.calculate_and_update_metrics(true, pred, mask, 'val')
+    lw, _, _ = oracle.loss_function(torch.tensor(true, dtype=torch.float64), torch.tensor(pred, dtype=torch.float64),
+                                    torch.tensor(mask, dtype=torch.float64))
+    np.testing.assert_allclose(loss, lw.numpy(), rtol=1e-4)
+    assert abs(ctl.loss_metrics['val_loss'].result() - float(lw.mean())) < 1e-4 * float(lw.mean())
+    mse = ctl.calculate_mse(true[..., 0], true[..., 1], true[..., 2], pred[..., 0], pred[..., 1], pred[..., 2]).cpu().numpy()
+    np.testing.assert_allclose(mse, ((pred - true) ** 2).sum(-1), rtol=1e-5, atol=1e-9)
