@@ -331,6 +331,7 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                          "frac": ach / peak, "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16",
+                         "executed_tflops_fp16": 4.0 * ach, "executed_frac": 4.0 * ach / peak,
                          "ms_per_launch": dom_ms / max(dom_n, 1), "launches_per_step": dom_n,
                          "share_of_step": dom_ms / ms_step,
                          "note": "achieved = algorithmic fp32 FLOPs (2*27*64*64*B*D^3) / event time; the fp32-accurate "
