@@ -139,6 +139,12 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t_entry = p.dbg ? clock64() : 0;
+    if (p.dbg && threadIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        atomicMin(reinterpret_cast<unsigned long long*>(p.dbg + 148 * 8), gt);          // first CTA entry (ns)
+    }
 
     // the zero blocks are written once (generic proxy) and only ever read by the tensor core
     for (int i = threadIdx.x; i < C::NWS * (W_ZERO_BYTES / 16); i += NUM_THREADS) {
@@ -163,6 +169,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 4] = clock64() - t_entry;     // prologue
 
     const int tiles_per_x = p.nyt * p.nzt;
     const int tiles_per_b = p.nx * tiles_per_x;
@@ -255,8 +262,9 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                 tc_commit(&t_full[buf]);
             }
             if (p.dbg) {
-                p.dbg[blockIdx.x * 4 + 0] = wt; p.dbg[blockIdx.x * 4 + 1] = wx;
-                p.dbg[blockIdx.x * 4 + 2] = ww; p.dbg[blockIdx.x * 4 + 3] = clock64() - tbeg;
+                p.dbg[blockIdx.x * 8 + 0] = wt; p.dbg[blockIdx.x * 8 + 1] = wx;
+                p.dbg[blockIdx.x * 8 + 2] = ww; p.dbg[blockIdx.x * 8 + 3] = clock64() - tbeg;
+                p.dbg[blockIdx.x * 8 + 5] = clock64();          // MMA issue loop end (absolute)
             }
         }
     } else {
@@ -477,6 +485,14 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
 
     tc_fence_before();
     __syncthreads();
+    if (p.dbg && threadIdx.x == 64) {
+        const long long now = clock64();
+        p.dbg[blockIdx.x * 8 + 6] = now - t_entry;                                  // whole CTA lifetime
+        p.dbg[blockIdx.x * 8 + 7] = now - p.dbg[blockIdx.x * 8 + 5];                // tail after the last MMA was issued
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        atomicMax(reinterpret_cast<unsigned long long*>(p.dbg + 148 * 8 + 1), gt);      // last CTA exit (ns)
+    }
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                      : "memory");
@@ -686,8 +702,9 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
     static const bool debug = getenv("SR4D_TC_DEBUG") != nullptr;
     static long long* dbg_buf = nullptr;
     if (debug) {
-        if (!dbg_buf) cudaMalloc((void**)&dbg_buf, 148 * 4 * sizeof(long long));
-        cudaMemsetAsync(dbg_buf, 0, 148 * 4 * sizeof(long long), s);
+        if (!dbg_buf) cudaMalloc((void**)&dbg_buf, (148 * 8 + 2) * sizeof(long long));
+        cudaMemsetAsync(dbg_buf, 0, (148 * 8 + 2) * sizeof(long long), s);
+        cudaMemsetAsync(dbg_buf + 148 * 8, 0x7f, sizeof(long long), s);      // min slot starts high
         p.dbg = dbg_buf;
     }
     const int ty = pick_ty(Do);
@@ -702,13 +719,13 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
         default: e = launch_cfg<26>(map, p, s); break;
     }
     if (debug && e == cudaSuccess) {
-        long long hb[148 * 4];
+        long long hb[148 * 8 + 2];
         cudaStreamSynchronize(s);
         cudaMemcpy(hb, dbg_buf, sizeof hb, cudaMemcpyDeviceToHost);
-        double a4[4] = {0, 0, 0, 0};
-        for (int i = 0; i < 148; ++i) for (int k = 0; k < 4; ++k) a4[k] += (double)hb[i * 4 + k] / 148;
-        fprintf(stderr, "[tc dbg] Do=%d B=%d ty=%d dgrad=%d: MMA-warp wait cycles avg/CTA: t_empty %.0f  x_full %.0f  w_full %.0f  of total %.0f\n",
-                Do, B, ty, a.dgrad, a4[0], a4[1], a4[2], a4[3]);
+        double a4[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < 148; ++i) for (int k = 0; k < 8; ++k) a4[k] += (double)hb[i * 8 + k] / 148;
+        fprintf(stderr, "[tc dbg] Do=%d B=%d ty=%d dgrad=%d: MMA-warp wait cycles avg/CTA: t_empty %.0f  x_full %.0f  w_full %.0f  of total %.0f | prologue %.0f  tail after last MMA issue %.0f  CTA lifetime %.0f | first entry -> last exit %.1f us\n",
+                Do, B, ty, a.dgrad, a4[0], a4[1], a4[2], a4[3], a4[4], a4[7], a4[6], (double)(hb[148 * 8 + 1] - hb[148 * 8]) * 1e-3);
     }
     return e;
 }
