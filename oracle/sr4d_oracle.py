@@ -5,15 +5,27 @@ TEST INFRASTRUCTURE ONLY.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
 module.  The product path (``4dflownet_b200``) never does: it fails loudly when
 its CUDA library is missing.
 
-PARITY UNPINNED for the floating-point graph: the reference's arithmetic lives in
+PARITY STATUS of the floating-point graph.  The reference's arithmetic lives in
 TensorFlow 2.2 / Keras (README.md:4), which is not vendored under /root/reference
-and is not installable in this image (no tensorflow, keras, h5py; no network).
-The reference ships no tests, golden outputs or weights.  This file is therefore a
-*restatement* of the reference graph on torch-CPU, self-checked in
-``tests/test_oracle.py`` against (a) a naive numpy convolution, (b) a literal
-two-pass restatement of ``upsample3d``, (c) fp64 finite differences, (d) a hand
-computed Adam example.  The integer tiling logic (PatchGenerator) *is* pinned: the
-reference's own numpy code was imported to generate ``tests/golden/*.npz``.
+and is not installable in this image (no tensorflow, keras, h5py; no network); the
+reference ships no tests, golden outputs or weights.
+* PINNED to the reference's own Python code: forward graph wiring, ``upsample3d``
+  choreography, loss, relative-error metric, L2 term, running means and the Keras
+  variable creation order.  ``tests/golden/make_graph_golden.py`` imports
+  ``Network/SR4DFlowNet.py``, ``loss_utils.py`` and ``TrainerController.py``
+  unmodified and executes them in float64 on a numpy stand-in for the ~30 TF
+  symbols they call (``tests/golden/tf_numpy_shim.py``); this file agrees with
+  the resulting ``tests/golden/graph_golden.npz`` to 1e-12
+  (``tests/test_graph_golden.py``).
+* RESTATED, NOT PINNED ("parity unpinned" for these): the semantics of the TF
+  primitives themselves (Conv3D, tf.pad SYMMETRIC, resize_bilinear with
+  align_corners, LeakyReLU, tf.round), ``tape.gradient`` (here: torch autograd of
+  the pinned forward, checked against fp64 finite differences) and Keras Adam.
+  Self-checks in ``tests/test_oracle.py``: naive numpy convolution, a literal
+  two-pass restatement of ``upsample3d``, finite differences, a hand-computed
+  Adam example.
+* PINNED: the integer tiling / data-path logic (PatchGenerator, PatchHandler3D):
+  the reference's own numpy code generated ``tests/golden/patch*_golden.npz``.
 
 Every function cites the reference file:line it follows (paths relative to
 /root/reference/src).

@@ -39,3 +39,31 @@ ROWS = [
 ] + [["synth_LR.h5", "synth_HR.h5", str(i % 2), str(1 + p), str(2 + k), str(k), "1", str(p), str(k), "0.3"]
      for i, (p, k) in enumerate((p, k) for p in (1, 2, 3) for k in (1, 2, 3))]
 PATCH = 4
+
+
+# ---- floating-point graph golden (make_graph_golden.py and the tests that replay it) ----
+def graph_weight_source(seed):
+    """fn(kernel_shape, use_bias) -> (kernel, bias|None), drawn sequentially in layer creation order: glorot-uniform
+    kernels (Keras default) and small normal biases (so the bias path matters)."""
+    g = np.random.default_rng(seed)
+
+    def draw(shape, use_bias):
+        k3 = shape[0] * shape[1] * shape[2]
+        lim = np.sqrt(6.0 / (k3 * shape[3] + k3 * shape[4]))
+        kernel = g.uniform(-lim, lim, size=shape).astype(np.float32)
+        bias = (0.05 * g.standard_normal(shape[4])).astype(np.float32) if use_bias else None
+        return kernel, bias
+    return draw
+
+
+def graph_inputs(B, P, r, seed):
+    """6 LR inputs (B,P,P,P,1), 3 HR targets (B,rP,rP,rP,1) with exact zeros, binary mask (B,rP,rP,rP); float32
+    values held in float64 arrays."""
+    g = np.random.default_rng(seed + 1000)
+    lr = [g.uniform(-1, 1, (B, P, P, P, 1)).astype(np.float32).astype(np.float64) for _ in range(3)] + \
+         [g.uniform(0, 0.016, (B, P, P, P, 1)).astype(np.float32).astype(np.float64) for _ in range(3)]
+    H = P * r
+    keep = g.uniform(size=(B, H, H, H, 1)) < 0.7
+    hr = [(0.3 * g.standard_normal((B, H, H, H, 1)) * keep).astype(np.float32).astype(np.float64) for _ in range(3)]
+    mask = (g.uniform(size=(B, H, H, H)) < 0.3).astype(np.float64)
+    return lr, hr, mask

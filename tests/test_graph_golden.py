@@ -1,0 +1,154 @@
+"""Parity against golden vectors produced by the reference's OWN graph code.
+
+``tests/golden/graph_golden.npz`` was written by ``tests/golden/make_graph_golden.py``: the reference's
+``SR4DFlowNet.build_network`` / ``upsample3d`` / ``conv3d`` / ``resnet_block``, ``loss_utils.calculate_relative_error``
+and the loss / metric methods of ``TrainerController`` imported unmodified and executed in float64 on a numpy stand-in
+for the TensorFlow primitives (``tests/golden/tf_numpy_shim.py``).  The CPU tests hold the oracle restatement to it
+(1e-12: same arithmetic, different summation order), the GPU tests hold the CUDA engine to it through the C ABI
+(north-star tolerance 1e-4, max|d|/max|ref|)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import synth  # noqa: E402
+
+GOLD = np.load(os.path.join(HERE, "golden", "graph_golden.npz"))
+CASES = [str(c) for c in GOLD["cases"]]
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+
+
+def case(oracle, tag):
+    """Rebuild the weights in the ORACLE's parameter order from the generator's sequential stream (a layer-order or
+    bias-presence mismatch against the reference's creation order shows up as a shape / value mismatch)."""
+    P, r, low, hi, B, seed = (int(x) for x in GOLD[f"{tag}_cfg"])
+    draw = synth.graph_weight_source(seed)
+    table = oracle.param_table(low, hi)
+    params, i = {}, 0
+    while i < len(table):
+        name, shape = table[i]
+        assert name.endswith("/kernel")
+        has_bias = i + 1 < len(table) and table[i + 1][0] == name.replace("/kernel", "/bias")
+        k, b = draw(shape, has_bias)
+        params[name] = k
+        if has_bias:
+            params[table[i + 1][0]] = b
+        i += 2 if has_bias else 1
+    lr, hr, mask = synth.graph_inputs(B, P, r, seed)
+    assert np.float64(sum(a.sum() for a in lr + hr) + mask.sum()) == GOLD[f"{tag}_input_sum"]
+    return (P, r, low, hi, B), params, lr, hr, mask
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_oracle_layer_order_matches_reference_creation_order(oracle, tag):
+    (P, r, low, hi, B), *_ = case(oracle, tag)
+    ref_layers = [str(s).split("|") for s in GOLD[f"{tag}_layer_table"]]
+    table = oracle.param_table(low, hi)
+    kernels = [(n, s) for n, s in table if n.endswith("/kernel")]
+    biases = {n for n, _ in table if n.endswith("/bias")}
+    assert len(kernels) == len(ref_layers)
+    for (n, s), (rname, rshape, rbias) in zip(kernels, ref_layers):
+        assert n == rname + "/kernel"
+        assert "x".join(map(str, s)) == rshape
+        assert ((rname + "/bias") in biases) == bool(int(rbias))
+
+
+@pytest.mark.parametrize("tag", CASES)
+def test_oracle_forward_loss_metric_vs_reference_graph(oracle, tag):
+    (P, r, low, hi, B), params, lr, hr, mask = case(oracle, tag)
+    p64 = {k: torch.tensor(v, dtype=torch.float64) for k, v in params.items()}
+    pred = oracle.forward(p64, [torch.tensor(a) for a in lr], r, low, hi)
+    assert pred.shape == GOLD[f"{tag}_pred"].shape
+    assert relerr(pred.numpy(), GOLD[f"{tag}_pred"]) < 1e-12
+    hires = torch.tensor(np.concatenate(hr, axis=-1))
+    m = torch.tensor(mask)
+    gp = torch.tensor(GOLD[f"{tag}_pred"])          # feed the golden prediction: isolates the loss / metric formulas
+    tot, mse, div = oracle.loss_function(hires, gp, m)
+    np.testing.assert_allclose(tot.numpy(), GOLD[f"{tag}_loss"], rtol=1e-12)
+    np.testing.assert_allclose(mse.numpy(), GOLD[f"{tag}_mse"], rtol=1e-12)
+    assert div == 0
+    rel = oracle.calculate_relative_error(hires, gp, m)
+    np.testing.assert_allclose(rel.numpy(), GOLD[f"{tag}_rel"], rtol=1e-12)
+    l2 = float(oracle.regularizer_loss(p64))
+    assert abs(l2 - float(GOLD[f"{tag}_l2"])) < 1e-12 * l2
+    np.testing.assert_allclose(tot.numpy() + l2, GOLD[f"{tag}_loss_train"], rtol=1e-12)
+    # running means as TrainerController.calculate_and_update_metrics accumulates them (one train + one val call)
+    names = [str(n) for n in GOLD["metric_names"]]
+    got = dict(zip(names, GOLD[f"{tag}_metrics"]))
+    assert abs(got["train_loss"] - float((tot + l2).mean())) < 1e-12
+    assert abs(got["val_loss"] - float(tot.mean())) < 1e-12
+    assert abs(got["train_accuracy"] - float(rel.mean())) < 1e-10
+    assert abs(got["l2_reg_loss"] - l2) < 1e-15
+    assert got["train_div"] == 0 and got["val_div"] == 0
+
+
+def test_oracle_upsample_vs_reference_resize(oracle):
+    """The reference's upsample3d (two resize_bilinear passes + transposes) on a random 5-D tensor, via the shim, vs
+    the oracle's separable lerp -- an odd, anisotropy-revealing shape is impossible here (the reference assumes the
+    same factor on all axes) so the tensor is non-cubic instead."""
+    import tf_numpy_shim
+    mods = {k: sys.modules.get(k) for k in list(sys.modules) if k == "tensorflow" or k.startswith("tensorflow.")}
+    ref_src = "/root/reference/src"
+    if not os.path.isdir(ref_src):
+        pytest.skip("reference tree not present (GPU box)")
+    tf_numpy_shim.install()
+    sys.path.insert(0, ref_src)
+    try:
+        import importlib
+        net = importlib.import_module("Network.SR4DFlowNet")
+        g = np.random.default_rng(9)
+        for shape, r in [((2, 3, 5, 4, 2), 2), ((1, 4, 2, 3, 3), 3), ((1, 2, 2, 2, 1), 4)]:
+            x = g.standard_normal(shape)
+            want = net.upsample3d(x, r)
+            got = oracle.upsample3d(torch.tensor(x), r).numpy()
+            assert got.shape == want.shape
+            assert relerr(got, want) < 1e-13
+    finally:
+        sys.path.remove(ref_src)
+        for k in [k for k in sys.modules if k == "tensorflow" or k.startswith("tensorflow.") or k.startswith("Network")]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in mods.items() if v is not None})
+
+
+# ------------------------------------------------------------------ GPU: the CUDA engine against the same golden
+@pytest.mark.gpu
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+@pytest.mark.parametrize("tag", CASES)
+def test_engine_forward_vs_reference_graph(pkg, oracle, tag, impl):
+    (P, r, low, hi, B), params, lr, hr, mask = case(oracle, tag)
+    eng = pkg.Engine(P, r, low, hi, max_batch=B, training=False, device=0)
+    eng.set_option(pkg._lib.OPT_CONV_IMPL, pkg._lib.CONV_SIMT if impl == "simt" else pkg._lib.CONV_AUTO)
+    eng.set_weights(params)
+    y = eng.forward([a.astype(np.float32) for a in lr]).cpu().numpy()
+    assert y.shape == GOLD[f"{tag}_pred"].shape
+    assert relerr(y, GOLD[f"{tag}_pred"]) < 1e-4
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", CASES)
+def test_engine_train_metrics_vs_reference_graph(pkg, oracle, tag):
+    (P, r, low, hi, B), params, lr, hr, mask = case(oracle, tag)
+    eng = pkg.Engine(P, r, low, hi, max_batch=B, training=True, device=0)
+    eng.set_weights(params)
+    per, l2, pred = eng.train_fwd_bwd([a.astype(np.float32) for a in lr], [a[..., 0].astype(np.float32) for a in hr],
+                                      mask.astype(np.float32), want_pred=True)
+    per = per.cpu().numpy()
+    assert relerr(pred.cpu().numpy(), GOLD[f"{tag}_pred"]) < 1e-4
+    np.testing.assert_allclose(per[:, 0], GOLD[f"{tag}_loss"], rtol=1e-4)
+    np.testing.assert_allclose(per[:, 1], GOLD[f"{tag}_mse"], rtol=1e-4)
+    # the metric rounds every voxel to 1e-4 steps: a prediction 1e-6 away can flip single voxels
+    np.testing.assert_allclose(per[:, 2], GOLD[f"{tag}_rel"], rtol=1e-3)
+    np.testing.assert_allclose(per[:, 3], mask.sum(axis=(1, 2, 3)), rtol=0)
+    assert abs(float(l2) - float(GOLD[f"{tag}_l2"])) < 1e-5 * float(GOLD[f"{tag}_l2"])
+    np.testing.assert_allclose(per[:, 0] + float(l2), GOLD[f"{tag}_loss_train"], rtol=1e-4)
+    eng.close()
