@@ -67,3 +67,40 @@ def graph_inputs(B, P, r, seed):
     hr = [(0.3 * g.standard_normal((B, H, H, H, 1)) * keep).astype(np.float32).astype(np.float64) for _ in range(3)]
     mask = (g.uniform(size=(B, H, H, H)) < 0.3).astype(np.float64)
     return lr, hr, mask
+
+
+# ---- predictor.py golden (make_predictor_golden.py and tests/test_gpu_integration.py) ----
+EXAMPLE_LR_SHAPE = (42, 38, 36)      # the shape of the reference's data/example_data.h5
+
+
+def make_example_lr(path, seed=7):
+    """A one-row LR file with the column layout, shape and value ranges of the reference's data/example_data.h5
+    (u,v,w in [-1.5,1.5], magnitudes in [0,65], venc 1.5, dx 1.1875), written with the repo's HDF5 shim."""
+    h5io = importlib.import_module("4dflownet_b200.utils.h5io")
+    g = np.random.default_rng(seed)
+    if os.path.exists(path):
+        os.remove(path)
+    with h5io.File(path, "w") as f:
+        for c in "uvw":
+            f.create_dataset(c, data=g.uniform(-1.5, 1.5, (1,) + EXAMPLE_LR_SHAPE).astype(np.float32))
+            f.create_dataset("mag_" + c, data=g.uniform(0, 65, (1,) + EXAMPLE_LR_SHAPE).astype(np.float32))
+            f.create_dataset("venc_" + c, data=np.asarray([1.5], np.float32))
+        f.create_dataset("dx", data=np.full((1, 3), 1.1875, np.float32))
+
+
+def keras_weight_dict(low, hi, seed):
+    """{'conv3d_k/kernel'|'bias': array} for the 8/4 (or any) network in Keras creation order, drawn from
+    graph_weight_source; layer shapes follow Network/SR4DFlowNet.py:17-46."""
+    draw = graph_weight_source(seed)
+    C = 64
+    spec = [(3, 3, C, True), (3, C, C, True), (3, 3, C, True), (3, C, C, True), (1, 2 * C, C, True), (3, C, C, True)]
+    spec += [(3, C, C, False)] * (2 * low + 2 * hi)
+    spec += [(3, C, C, True), (3, C, 1, True)] * 3
+    out = {}
+    for i, (k, ci, co, bias) in enumerate(spec):
+        name = "conv3d" if i == 0 else f"conv3d_{i}"
+        kern, b = draw((k, k, k, ci, co), bias)
+        out[f"{name}/kernel"] = kern
+        if bias:
+            out[f"{name}/bias"] = b
+    return out

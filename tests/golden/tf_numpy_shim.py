@@ -4,7 +4,10 @@ hot path calls, so that the reference's OWN graph-wiring code -- ``Network/SR4DF
 metric methods of ``Network/TrainerController.py`` -- can be imported UNMODIFIED from /root/reference and
 executed eagerly here (TensorFlow itself is not installable in this image).
 
-TEST INFRASTRUCTURE, used only by ``tests/golden/make_graph_golden.py`` in the build container.
+TEST INFRASTRUCTURE, used only by ``tests/golden/make_graph_golden.py`` / ``make_predictor_golden.py`` in the
+build container.  Tensors are plain float64 numpy arrays; ``tf.keras.layers.Input`` returns a symbolic ``Sym`` node
+and every op below records itself instead of executing when it meets one, so ``tf.keras.Model(inputs, outputs)``
+(predictor.py:11-29) can replay the recorded graph on real batches later.
 
 What this pins and what it does not: the layer order, channel concat order, skip connections, activation
 placement, padding calls, the reshape/transpose choreography of ``upsample3d``, the loss / metric formulas
@@ -43,6 +46,101 @@ def created_layers():
     return list(_state["layers"])
 
 
+# ---------------------------------------------------------------- symbolic tensors (Input / Model)
+class Sym:
+    """A recorded op (fn, args, kwargs); ``probe`` is its value on a batch of one zero patch (static shapes)."""
+    __array_priority__ = 1000
+    __array_ufunc__ = None
+
+    def __init__(self, fn, args, kwargs, probe, name=None):
+        self.fn, self.args, self.kwargs, self.probe, self.name = fn, args, kwargs, probe, name
+
+    @property
+    def shape(self):
+        return (None,) + tuple(self.probe.shape[1:])
+
+    def __pow__(self, e): return _lazy(np.power)(self, e)
+    def __add__(self, o): return _lazy(np.add)(self, o)
+    def __radd__(self, o): return _lazy(np.add)(o, self)
+    def __sub__(self, o): return _lazy(np.subtract)(self, o)
+    def __rsub__(self, o): return _lazy(np.subtract)(o, self)
+    def __mul__(self, o): return _lazy(np.multiply)(self, o)
+    def __rmul__(self, o): return _lazy(np.multiply)(o, self)
+    def __truediv__(self, o): return _lazy(np.divide)(self, o)
+    def __getitem__(self, idx): return _lazy(lambda a: a[idx])(self)
+
+
+def _any_sym(obj):
+    if isinstance(obj, Sym):
+        return True
+    if isinstance(obj, (list, tuple)):
+        return any(_any_sym(o) for o in obj)
+    return False
+
+
+def _subst(obj, get):
+    if isinstance(obj, Sym):
+        return get(obj)
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_subst(o, get) for o in obj)
+    return obj
+
+
+def _lazy(fn):
+    def wrapped(*args, **kwargs):
+        if not (_any_sym(args) or _any_sym(list(kwargs.values()))):
+            return fn(*args, **kwargs)
+        probe = fn(*_subst(args, lambda n: n.probe), **{k: _subst(v, lambda n: n.probe) for k, v in kwargs.items()})
+        return Sym(fn, args, kwargs, probe)
+    return wrapped
+
+
+def _evaluate(node, env, memo):
+    if not isinstance(node, Sym):
+        return node
+    key = id(node)
+    if key not in memo:
+        if node.fn is None:
+            memo[key] = env[key]
+        else:
+            get = lambda n: _evaluate(n, env, memo)  # noqa: E731
+            memo[key] = node.fn(*_subst(node.args, get), **{k: _subst(v, get) for k, v in node.kwargs.items()})
+    return memo[key]
+
+
+def _Input(shape, name=None, **kw):
+    return Sym(None, (), {}, np.zeros((1,) + tuple(shape), F64), name=name)
+
+
+class _Model:
+    """tf.keras.Model(inputs, outputs) over a recorded graph: predict / __call__ / load_weights / layers."""
+
+    def __init__(self, inputs, outputs):
+        self.inputs, self.outputs = list(inputs), outputs
+        self.layers = created_layers()
+
+    def __call__(self, xs, training=False):
+        env = {id(i): np.asarray(x, F64) for i, x in zip(self.inputs, xs)}
+        return _evaluate(self.outputs, env, {})
+
+    def predict(self, xs, batch_size=None):
+        return self(xs)
+
+    @property
+    def variable_names(self):
+        return [f"{l.name}/{w}" for l in self.layers for w in (("kernel", "bias") if l.use_bias else ("kernel",))]
+
+    def load_weights(self, path):
+        import importlib
+        h5io = importlib.import_module("4dflownet_b200.utils.h5io")     # the repo's HDF5 reader (no h5py here)
+        w = h5io.load_keras_weights(path, self.variable_names)
+        for l in self.layers:
+            assert w[f"{l.name}/kernel"].shape == l.kernel.shape
+            l.kernel = w[f"{l.name}/kernel"]
+            if l.use_bias:
+                l.bias = w[f"{l.name}/bias"]
+
+
 # ---------------------------------------------------------------- primitive ops
 def _pad(x, paddings, mode="CONSTANT"):
     assert mode == "SYMMETRIC", mode
@@ -51,8 +149,17 @@ def _pad(x, paddings, mode="CONSTANT"):
 
 def _conv3d_valid(x, kernel):
     kd, kh, kw, ci, co = kernel.shape
-    win = np.lib.stride_tricks.sliding_window_view(x, (kd, kh, kw), axis=(1, 2, 3))  # (B,X',Y',Z',Ci,kd,kh,kw)
-    return np.einsum("bxyzcijk,ijkco->bxyzo", win, kernel, optimize=True)
+    B, X, Y, Z, _ = x.shape
+    ox, oy, oz = X - kd + 1, Y - kh + 1, Z - kw + 1
+    if B * ox * oy * oz * ci * kd * kh * kw * 8 <= (1 << 30):
+        win = np.lib.stride_tricks.sliding_window_view(x, (kd, kh, kw), axis=(1, 2, 3))  # (B,X',Y',Z',Ci,kd,kh,kw)
+        return np.einsum("bxyzcijk,ijkco->bxyzo", win, kernel, optimize=True)
+    out = np.zeros((B * ox * oy * oz, co), F64)          # big tensors: one GEMM per tap instead of an im2col copy
+    for i in range(kd):
+        for j in range(kh):
+            for k in range(kw):
+                out += np.ascontiguousarray(x[:, i:i + ox, j:j + oy, k:k + oz, :]).reshape(-1, ci) @ kernel[i, j, k]
+    return out.reshape(B, ox, oy, oz, co)
 
 
 class _Conv3D:
@@ -64,11 +171,17 @@ class _Conv3D:
         self.kernel = self.bias = None
 
     def __call__(self, x):
-        x = np.asarray(x, F64)
         shape = (self.k, self.k, self.k, x.shape[-1], self.filters)
-        self.kernel, self.bias = _state["weights"](shape, self.use_bias)
+        if _state["weights"] is None:       # no source: zeros until Model.load_weights fills them in
+            self.kernel, self.bias = np.zeros(shape, np.float32), (np.zeros(self.filters, np.float32) if self.use_bias else None)
+        else:
+            self.kernel, self.bias = _state["weights"](shape, self.use_bias)
         self.name = "conv3d" if not _state["layers"] else f"conv3d_{len(_state['layers'])}"
         _state["layers"].append(self)
+        return _lazy(self._apply)(x)
+
+    def _apply(self, x):
+        x = np.asarray(x, F64)
         y = _conv3d_valid(x, np.asarray(self.kernel, F64))
         if self.use_bias:
             y = y + np.asarray(self.bias, F64)
@@ -84,7 +197,7 @@ class _LeakyReLU:
         self.alpha = alpha
 
     def __call__(self, x):
-        return np.where(x > 0, x, self.alpha * x)
+        return _lazy(lambda a: np.where(a > 0, a, self.alpha * a))(x)
 
 
 def _resize_bilinear(images, size, align_corners=False, name=None):
@@ -144,10 +257,11 @@ def install():
     tf = types.ModuleType("tensorflow")
     tf.float32 = np.float32          # tf.cast(x, tf.float32): kept in float64 below on purpose (golden = fp64 truth)
     tf.function = lambda f: f
-    tf.pad = _pad
-    tf.reshape = lambda x, shape, name=None: np.reshape(x, shape)
-    tf.transpose = lambda x, perm: np.transpose(x, perm)
-    tf.concat = lambda xs, axis: np.concatenate(xs, axis=axis)
+    sys.setrecursionlimit(max(sys.getrecursionlimit(), 20000))      # replaying a ~40-layer recorded graph recurses
+    tf.pad = _lazy(_pad)
+    tf.reshape = _lazy(lambda x, shape, name=None: np.reshape(x, shape))
+    tf.transpose = _lazy(lambda x, perm: np.transpose(x, perm))
+    tf.concat = _lazy(lambda xs, axis: np.concatenate(xs, axis=axis))
     tf.constant = lambda v, dtype=None: np.asarray(v, F64)
     tf.less = np.less
     tf.equal = np.equal
@@ -164,7 +278,9 @@ def install():
     layers = types.ModuleType("tensorflow.keras.layers")
     layers.Conv3D = _Conv3D
     layers.LeakyReLU = _LeakyReLU
-    layers.concatenate = lambda xs, axis=-1: np.concatenate([np.asarray(a, F64) for a in xs], axis=axis)
+    layers.concatenate = _lazy(lambda xs, axis=-1: np.concatenate([np.asarray(a, F64) for a in xs], axis=axis))
+    layers.Input = _Input
+    keras.Model = _Model
     regularizers = types.ModuleType("tensorflow.keras.regularizers")
     regularizers.l2 = _L2
     metrics = types.ModuleType("tensorflow.keras.metrics")
@@ -174,7 +290,7 @@ def install():
     compat = types.ModuleType("tensorflow.compat")
     v1 = types.ModuleType("tensorflow.compat.v1")
     image = types.ModuleType("tensorflow.compat.v1.image")
-    image.resize_bilinear = _resize_bilinear
+    image.resize_bilinear = _lazy(_resize_bilinear)
     v1.image, compat.v1, tf.compat = image, v1, compat
     for m in (tf, keras, layers, regularizers, metrics, compat, v1, image):
         sys.modules[m.__name__] = m

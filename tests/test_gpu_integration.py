@@ -47,6 +47,42 @@ def test_predictor_main_on_hdf5_volume(pkg, oracle, tmp_path):
                 assert np.all(got[np.abs(want) < 0.5 * venc / 2048] == 0)
 
 
+def test_predictor_config0_vs_reference_script_golden(pkg, tmp_path):
+    """BASELINE configs[0] (patch 24, r=2, 8/4 blocks, 42x38x36 volume): the product's predictor.main against the
+    output file of the reference's own src/predictor.py run unmodified on the numpy TF stand-in
+    (tests/golden/make_predictor_golden.py).  Inputs are regenerated from the seeds stored with the golden."""
+    gold = np.load(os.path.join(HERE, "golden", "predictor_golden.npz"))
+    h5io = importlib.import_module("4dflownet_b200.utils.h5io")
+    predictor = importlib.import_module("4dflownet_b200.predictor")
+    d = str(tmp_path)
+    synth.make_example_lr(os.path.join(d, "example_data.h5"), int(gold["data_seed"]))
+    wpath = os.path.join(d, "4DFlowNet.h5")
+    h5io.save_keras_weights(wpath, synth.keras_weight_dict(8, 4, int(gold["weight_seed"])))
+    predictor.main(data_dir=d, filename="example_data.h5", output_dir=os.path.join(d, "result"),
+                   output_filename="example_result.h5", model_path=wpath)          # the reference's defaults otherwise
+    venc, flips = 1.5, 0
+    with h5io.open_file(os.path.join(d, "result", "example_result.h5"), "r") as res:
+        np.testing.assert_allclose(res["dx"][...], gold["dx"], rtol=1e-6)
+        for c in "uvw":
+            got = np.asarray(res[c][...])
+            assert got.shape == (1, 84, 76, 72) and got.dtype == np.float32
+            want = gold[c]
+            sub = got[0, ::2, ::2, ::2].astype(np.float64)
+            tol = 1e-4 * float(gold[c + "_moments"][4])                     # 1e-4 of max|ref| (north-star bar)
+            bad = np.abs(sub - want) > tol
+            # a value within tol of the venc/2048 zeroing threshold may be zeroed on one side only
+            flip = bad & ((sub == 0) | (want == 0)) & (np.maximum(np.abs(sub), np.abs(want)) < venc / 2048 + 2 * tol)
+            assert not np.any(bad & ~flip), float(np.abs(sub - want)[bad & ~flip].max())
+            flips += int(flip.sum())
+            g64 = got.astype(np.float64)
+            m = gold[c + "_moments"]
+            assert abs(g64.sum() - m[0]) < 1e-4 * m[1]
+            assert abs(np.abs(g64).sum() - m[1]) < 1e-4 * m[1]
+            assert abs((g64 ** 2).sum() - m[2]) < 2e-4 * m[2]
+            assert abs(float((got == 0).sum()) - m[3]) <= max(8.0, 0.02 * m[3])
+    assert flips <= 8
+
+
 def test_trainer_flow_and_restore(pkg, oracle, tmp_path, capsys):
     h5io = importlib.import_module("4dflownet_b200.utils.h5io")
     trainer = importlib.import_module("4dflownet_b200.trainer")

@@ -119,6 +119,36 @@ def test_oracle_upsample_vs_reference_resize(oracle):
         sys.modules.update({k: v for k, v in mods.items() if v is not None})
 
 
+def test_oracle_predictor_flow_vs_reference_script_golden(oracle, tmp_path):
+    """BASELINE configs[0] end to end: the oracle's patchify -> forward (fp32) -> patchup -> x venc -> zero small values
+    against the result file the reference's own src/predictor.py wrote (tests/golden/make_predictor_golden.py)."""
+    import importlib
+    gold = np.load(os.path.join(HERE, "golden", "predictor_golden.npz"))
+    h5io = importlib.import_module("4dflownet_b200.utils.h5io")
+    path = os.path.join(str(tmp_path), "example_data.h5")
+    synth.make_example_lr(path, int(gold["data_seed"]))
+    params = {k: torch.tensor(v) for k, v in synth.keras_weight_dict(8, 4, int(gold["weight_seed"])).items()}
+    with h5io.open_file(path, "r") as lr:
+        venc = np.float32(max(float(lr[k][0]) for k in ("venc_u", "venc_v", "venc_w")))
+        vel = [(np.asarray(lr[c][0]) / venc).astype(np.float32) for c in "uvw"]        # ImageDataset.py:11-35
+        mag = [(np.asarray(lr["mag_" + c][0]) / 4095.).astype(np.float32) for c in "uvw"]
+    stacks = [oracle.patchify(a, 24)[0] for a in vel + mag]
+    assert stacks[0].shape[0] == 12
+    with torch.no_grad():
+        y = torch.cat([oracle.forward(params, [torch.tensor(s[i:i + 4, ..., None]) for s in stacks], 2, 8, 4)
+                       for i in range(0, 12, 4)]).numpy()
+    for ci, c in enumerate("uvw"):
+        v = oracle.patchup(y[..., ci], vel[0].shape, 24, 2) * venc
+        v[np.abs(v) < venc / 2048] = 0                                                 # predictor.py:99-104
+        sub, want = v[::2, ::2, ::2].astype(np.float64), gold[c].astype(np.float64)
+        assert sub.shape == want.shape
+        tol = 1e-4 * float(gold[c + "_moments"][4])
+        bad = np.abs(sub - want) > tol
+        flip = bad & ((sub == 0) | (want == 0)) & (np.maximum(np.abs(sub), np.abs(want)) < venc / 2048 + 2 * tol)
+        assert not np.any(bad & ~flip), float(np.abs(sub - want)[bad & ~flip].max())
+        assert flip.sum() <= 4
+
+
 # ------------------------------------------------------------------ GPU: the CUDA engine against the same golden
 @pytest.mark.gpu
 @pytest.mark.parametrize("impl", ["simt", "auto"])
