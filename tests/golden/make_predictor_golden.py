@@ -41,7 +41,7 @@ def main():
     synth.make_example_lr(os.path.join(work, "data", "example_data.h5"), DATA_SEED)
     h5io.save_keras_weights(os.path.join(work, "models", "4DFlowNet", "4DFlowNet.h5"),
                             synth.keras_weight_dict(8, 4, WEIGHT_SEED))
-    assert h5io.install_as_h5py()          # before the TF stand-in, which would register an empty h5py
+    assert h5io.install_as_h5py()
     tf_numpy_shim.install()
     tf_numpy_shim.set_weight_source(None)
     sys.path.insert(0, REF)

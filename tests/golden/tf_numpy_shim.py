@@ -253,7 +253,8 @@ class _Mean:
 
 
 def install():
-    """Register the stand-in as ``tensorflow`` (and an empty ``h5py``) in sys.modules."""
+    """Register the stand-in as ``tensorflow`` in sys.modules (callers that import reference modules which
+    ``import h5py`` register a stand-in for it themselves)."""
     tf = types.ModuleType("tensorflow")
     tf.float32 = np.float32          # tf.cast(x, tf.float32): kept in float64 below on purpose (golden = fp64 truth)
     tf.function = lambda f: f
@@ -294,5 +295,4 @@ def install():
     v1.image, compat.v1, tf.compat = image, v1, compat
     for m in (tf, keras, layers, regularizers, metrics, compat, v1, image):
         sys.modules[m.__name__] = m
-    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
     return tf
