@@ -177,38 +177,59 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            uint32_t xi = 0, wi = 0;   // running stage counters
-            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+            // Issue order.  Weight taps run NWS stages ahead of the MMA warp.  The activation plane of the NEXT
+            // (tile, dx) pass is requested in the middle of the current pass (hi part before tap 3, lo part before
+            // tap 5): its stage was released when the previous pass finished, which is exactly when the slot of tap 3
+            // frees, so the wait never blocks the weight stream, the 2 x 33 KB transfers get a whole pass to land
+            // and they no longer queue three weight images behind one 66 KB burst on the SM's L2 port.
+            uint32_t wi = 0;           // running weight-stage counter
+            const int npass = p.ntiles > (int)blockIdx.x ? ((p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) * 3 : 0;
+            auto x_load = [&](int q, int part) {
+                const int t = blockIdx.x + (q / 3) * gridDim.x, dx = q % 3;
                 const int b = t / tiles_per_b;
                 int rem = t % tiles_per_b;
                 const int x = rem / tiles_per_x;
                 rem %= tiles_per_x;
                 const int y0 = (rem / p.nzt) * TY, z0 = (rem % p.nzt) * TZ;
-                for (int dx = 0; dx < 3; ++dx) {
-                    const uint32_t s = xi % C::NXS, ph = (xi / C::NXS) & 1;
+                const uint32_t s = (uint32_t)q % C::NXS, ph = ((uint32_t)q / C::NXS) & 1;
+                int plane = x + dx;
+                if (p.fused) {
+                    // interior plane x of dX: storage planes x+1..x+3 of the zero-haloed dY; at the two boundary
+                    // planes the all-zero halo pass is replaced by the pass that the folded halo plane would add
+                    plane = x + 1 + dx;
+                    if (dx == 0 && x == 0) plane = 2;
+                    if (dx == 2 && x == p.Dint - 1) plane = p.Dint + 1;
+                }
+                uint8_t* dst = xs + s * C::XSTAGE_BYTES;
+                if (part == 0) {
                     mbar_wait(&x_empty[s], ph ^ 1);
                     mbar_expect_tx(&x_full[s], 2 * C::ROWS * 128);
-                    uint8_t* dst = xs + s * C::XSTAGE_BYTES;
-                    int plane = x + dx, wsel = dx;
-                    if (p.fused) {
-                        // interior plane x of dX: storage planes x+1..x+3 of the zero-haloed dY; at the two boundary
-                        // planes the all-zero halo pass is replaced by the pass that the folded halo plane would add
-                        plane = x + 1 + dx;
-                        if (dx == 0 && x == 0) { plane = 2; wsel = 2; }
-                        if (dx == 2 && x == p.Dint - 1) { plane = p.Dint + 1; wsel = 0; }
-                    }
                     tma_load_5d(dst, &xmap, &x_full[s], 0, z0, y0, plane, b);
+                } else {
                     tma_load_5d(dst + C::PART_BYTES, &xmap, &x_full[s], 0, z0, y0, plane, p.B + b);
-                    ++xi;
-                    for (int tp = 0; tp < 9; ++tp) {
-                        const uint32_t ws = wi % C::NWS, wph = (wi / C::NWS) & 1;
-                        mbar_wait(&w_empty[ws], wph ^ 1);
-                        mbar_expect_tx(&w_full[ws], W_TAP_BYTES);
-                        bulk_load(wsm + ws * W_STAGE_BYTES,
-                                  reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)(wsel * 9 + tp) * W_TAP_BYTES,
-                                  W_TAP_BYTES, &w_full[ws]);
-                        ++wi;
+                }
+            };
+            if (npass) { x_load(0, 0); x_load(0, 1); }
+            for (int q = 0; q < npass; ++q) {
+                const int t = blockIdx.x + (q / 3) * gridDim.x, dx = q % 3;
+                int wsel = dx;
+                if (p.fused) {
+                    const int x = (t % tiles_per_b) / tiles_per_x;
+                    if (dx == 0 && x == 0) wsel = 2;
+                    if (dx == 2 && x == p.Dint - 1) wsel = 0;
+                }
+                for (int tp = 0; tp < 9; ++tp) {
+                    if (q + 1 < npass) {
+                        if (tp == 3) x_load(q + 1, 0);
+                        if (tp == 5) x_load(q + 1, 1);
                     }
+                    const uint32_t ws = wi % C::NWS, wph = (wi / C::NWS) & 1;
+                    mbar_wait(&w_empty[ws], wph ^ 1);
+                    mbar_expect_tx(&w_full[ws], W_TAP_BYTES);
+                    bulk_load(wsm + ws * W_STAGE_BYTES,
+                              reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)(wsel * 9 + tp) * W_TAP_BYTES,
+                              W_TAP_BYTES, &w_full[ws]);
+                    ++wi;
                 }
             }
         }

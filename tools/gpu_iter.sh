@@ -1,7 +1,8 @@
 #!/bin/bash
-# one optimisation iteration: backward parity tests, then the default bench (prints the per-class kernel times)
+# one optimisation iteration: parity tests that touch the changed kernels, MMA-warp wait breakdown, default bench
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_backward.py tests/test_gpu_edge_cases.py -m gpu -x -q --timeout 120 2>&1 | tail -12 > gpurun_out/pytest_iter.log; cat gpurun_out/pytest_iter.log
+timeout 400 python -m pytest tests/test_gpu_forward.py tests/test_gpu_backward.py tests/test_gpu_edge_cases.py tests/test_graph_golden.py -m gpu -x -q --timeout 120 2>&1 | tail -12 > gpurun_out/pytest_iter.log; cat gpurun_out/pytest_iter.log
+SR4D_TC_DEBUG=1 timeout 200 python tools/fwd_once.py 8 2 2>&1 | grep "tc dbg" | tail -30 | grep "B=8" | sort -u -k3,6 | cut -c1-330 > gpurun_out/tc_dbg_iter.txt; cat gpurun_out/tc_dbg_iter.txt
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_iter.json 2> gpurun_out/bench_iter.err; tail -3 gpurun_out/bench_iter.err
 python - <<'PY'
 import json
