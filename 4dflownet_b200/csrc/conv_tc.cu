@@ -100,6 +100,7 @@ struct KParams {
     const float* gain;
     const unsigned int* dy_amax;
     const unsigned int* add_amax;
+    int xsplit;              // producer order: 1 = next activation plane requested mid-pass (default), 0 = at the pass boundary (SR4D_TC_XSPLIT=0)
     long long* dbg;          // SR4D_TC_DEBUG=1: per-CTA cycles the MMA warp waited on {t_empty, x_full, w_full} and its total
 };
 
@@ -219,7 +220,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                     if (dx == 2 && x == p.Dint - 1) wsel = 0;
                 }
                 for (int tp = 0; tp < 9; ++tp) {
-                    if (q + 1 < npass) {
+                    if (q + 1 < npass && p.xsplit) {
                         if (tp == 3) x_load(q + 1, 0);
                         if (tp == 5) x_load(q + 1, 1);
                     }
@@ -231,6 +232,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                               W_TAP_BYTES, &w_full[ws]);
                     ++wi;
                 }
+                if (q + 1 < npass && !p.xsplit) { x_load(q + 1, 0); x_load(q + 1, 1); }
             }
         }
     } else if (warp == 1) {
@@ -719,6 +721,8 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
     p.split_lo = a.split_out ? a.split_out + act_plane_elems(B, Do) : nullptr;   // [2B][D+4]^3[64]: hi planes then lo planes
     p.split_exp = a.split_exp; p.gain = w->gain + a.layer; p.dy_amax = a.dy_amax; p.add_amax = a.add_amax;
     if (a.split_out && (!a.split_exp || !a.dy_amax || !a.fused)) return cudaErrorInvalidValue;
+    static const bool xsplit = !(getenv("SR4D_TC_XSPLIT") && atoi(getenv("SR4D_TC_XSPLIT")) == 0);
+    p.xsplit = xsplit;
     p.dbg = nullptr;
     static const bool debug = getenv("SR4D_TC_DEBUG") != nullptr;
     static long long* dbg_buf = nullptr;
