@@ -9,10 +9,11 @@
 //   Operands are split in fp16: W = Whi + Wlo/2048, X = Xhi + Xlo/2048.  ONE accumulator per tile:
 //     TMEM lanes 0..63   ("L", lane = co)      accumulate  Wlo*Xhi + Whi*Xlo   (both scaled by 2048)
 //     TMEM lanes 64..127 ("H", lane = 64 + co) accumulate  Whi*Xhi
-//   through two MMAs per K-step that share one 16 KB weight image [Wlo rows ; Whi rows] followed by an
-//   8 KB block of zeros in shared memory:
+//   through two MMAs per K-step that share one 16 KB weight image [Wlo rows ; Whi rows]:
 //     MMA_a: A = image            = [Wlo ; Whi],  B = the activation's hi plane
-//     MMA_b: A = image + 8 KB     = [Whi ; 0  ],  B = the activation's lo plane
+//     MMA_b: A = image + 8 KB     = [Whi ; the 8 KB that follow], B = the activation's lo plane, issued with the
+//            disable-output-lane vector masking lanes 64..127, so whatever the upper 64 rows read is never
+//            accumulated (no zero block behind the image: four 16 KB weight stages fit where three 24 KB did)
 //   out[co][v] = D[H] + D[L]/2048 (the Wlo*Xlo term, 2^-22 relative, is dropped).  With a single
 //   accumulator of N <= 208 columns the 512 TMEM columns hold TWO tiles, so the epilogue of tile i
 //   overlaps the MMAs of tile i+1 (the previous two-accumulator version stalled the tensor pipe for
@@ -41,8 +42,8 @@
 namespace {
 
 constexpr int W_TAP_BYTES = 128 * 64 * 2;            // 16 KB: [Wlo ; Whi] x 64 ci, fp16, swizzled
-constexpr int W_ZERO_BYTES = 64 * 64 * 2;            // 8 KB of zeros behind every staged image
-constexpr int W_STAGE_BYTES = W_TAP_BYTES + W_ZERO_BYTES;
+constexpr int W_HI_OFFSET = 64 * 64 * 2;             // the Whi rows start 8 KB into the image
+constexpr int W_STAGE_BYTES = W_TAP_BYTES;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_EPI = NUM_EPI_WARPS * 32;   // epilogue threads
 constexpr int NUM_THREADS = 64 + NUM_EPI;
@@ -58,7 +59,7 @@ struct Cfg {
     static constexpr int PART_BYTES = (ROWS * 128 + 1023) / 1024 * 1024;
     static constexpr int XSTAGE_BYTES = 2 * PART_BYTES;                // hi part | lo part
     static constexpr int NXS = 2;
-    static constexpr int NWS = 3;
+    static constexpr int NWS = 4;
     static constexpr int LPC = (TY % 4 == 0) ? 4 : 3;                  // y-lines per epilogue chunk
     static constexpr int CV = LPC * TZ;                                // voxels (TMEM columns) per chunk
     static constexpr int NCHUNK = (TY + LPC - 1) / LPC;
@@ -101,6 +102,8 @@ struct KParams {
     const unsigned int* dy_amax;
     const unsigned int* add_amax;
     int xsplit;              // producer order: 1 = next activation plane requested mid-pass (default), 0 = at the pass boundary (SR4D_TC_XSPLIT=0)
+    int exp_skip;            // TIMING EXPERIMENT ONLY (SR4D_TC_EXP_SKIP, wrong results): bit 0 = re-use stale weight slots
+                             // after the first fill, bit 1 = re-use stale activation stages (how much do the L2 streams cost?)
     long long* dbg;          // SR4D_TC_DEBUG=1: per-CTA cycles the MMA warp waited on {t_empty, x_full, w_full} and its total
 };
 
@@ -128,7 +131,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
     // align by OFFSET (not by pointer cast) so the compiler keeps the shared address space (STS/LDS, not generic)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* xs = smem;                                   // NXS x [hi part | lo part]
-    uint8_t* wsm = smem + C::NXS * C::XSTAGE_BYTES;       // NWS x (16 KB image + 8 KB zeros)
+    uint8_t* wsm = smem + C::NXS * C::XSTAGE_BYTES;       // NWS x 16 KB image
     float* stage = reinterpret_cast<float*>(wsm + C::NWS * W_STAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage) + C::STAGE_FLOATS * 4);
     uint64_t* x_full = bars;                 // [NXS]
@@ -147,12 +150,6 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
         atomicMin(reinterpret_cast<unsigned long long*>(p.dbg + 148 * 8), gt);          // first CTA entry (ns)
     }
 
-    // the zero blocks are written once (generic proxy) and only ever read by the tensor core
-    for (int i = threadIdx.x; i < C::NWS * (W_ZERO_BYTES / 16); i += NUM_THREADS) {
-        const int st = i / (W_ZERO_BYTES / 16), o = i % (W_ZERO_BYTES / 16);
-        *reinterpret_cast<uint4*>(wsm + st * W_STAGE_BYTES + W_TAP_BYTES + o * 16) = make_uint4(0, 0, 0, 0);
-    }
-    fence_proxy_async();
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NXS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
         for (int i = 0; i < C::NWS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
@@ -179,8 +176,8 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
         // ================= TMA producer =================
         if (lane == 0) {
             // Issue order.  Weight taps run NWS stages ahead of the MMA warp.  The activation plane of the NEXT
-            // (tile, dx) pass is requested in the middle of the current pass (hi part before tap 3, lo part before
-            // tap 5): its stage was released when the previous pass finished, which is exactly when the slot of tap 3
+            // (tile, dx) pass is requested in the middle of the current pass (hi part before tap NWS, lo part two taps
+            // later): its stage was released when the previous pass finished, which is exactly when the slot of tap NWS
             // frees, so the wait never blocks the weight stream, the 2 x 33 KB transfers get a whole pass to land
             // and they no longer queue three weight images behind one 66 KB burst on the SM's L2 port.
             uint32_t wi = 0;           // running weight-stage counter
@@ -202,7 +199,9 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                     if (dx == 2 && x == p.Dint - 1) plane = p.Dint + 1;
                 }
                 uint8_t* dst = xs + s * C::XSTAGE_BYTES;
-                if (part == 0) {
+                if ((p.exp_skip & 2) && q >= C::NXS) {
+                    if (part == 0) { mbar_wait(&x_empty[s], ph ^ 1); mbar_expect_tx(&x_full[s], 0); }
+                } else if (part == 0) {
                     mbar_wait(&x_empty[s], ph ^ 1);
                     mbar_expect_tx(&x_full[s], 2 * C::ROWS * 128);
                     tma_load_5d(dst, &xmap, &x_full[s], 0, z0, y0, plane, b);
@@ -221,15 +220,19 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                 }
                 for (int tp = 0; tp < 9; ++tp) {
                     if (q + 1 < npass && p.xsplit) {
-                        if (tp == 3) x_load(q + 1, 0);
-                        if (tp == 5) x_load(q + 1, 1);
+                        if (tp == C::NWS) x_load(q + 1, 0);
+                        if (tp == C::NWS + 2) x_load(q + 1, 1);
                     }
                     const uint32_t ws = wi % C::NWS, wph = (wi / C::NWS) & 1;
                     mbar_wait(&w_empty[ws], wph ^ 1);
-                    mbar_expect_tx(&w_full[ws], W_TAP_BYTES);
-                    bulk_load(wsm + ws * W_STAGE_BYTES,
-                              reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)(wsel * 9 + tp) * W_TAP_BYTES,
-                              W_TAP_BYTES, &w_full[ws]);
+                    if ((p.exp_skip & 1) && wi >= (uint32_t)C::NWS) {
+                        mbar_expect_tx(&w_full[ws], 0);
+                    } else {
+                        mbar_expect_tx(&w_full[ws], W_TAP_BYTES);
+                        bulk_load(wsm + ws * W_STAGE_BYTES,
+                                  reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)(wsel * 9 + tp) * W_TAP_BYTES,
+                                  W_TAP_BYTES, &w_full[ws]);
+                    }
                     ++wi;
                 }
                 if (q + 1 < npass && !p.xsplit) { x_load(q + 1, 0); x_load(q + 1, 1); }
@@ -270,11 +273,11 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint32_t acc = (dx | tp | k) != 0;
-                            // [Wlo ; Whi] x Xhi, then [Whi ; 0] x Xlo into the same accumulator
+                            // [Wlo ; Whi] x Xhi, then [Whi ; (next 8 KB, lanes 64-127 masked off)] x Xlo into the same accumulator
                             tc_mma_f16(dacc, make_desc_sbo(wa + k * 32, 1024),
                                        make_desc_sbo(xhi + boff + k * 32, ZP * 128), idesc, acc);
-                            tc_mma_f16(dacc, make_desc_sbo(wa + W_ZERO_BYTES + k * 32, 1024),
-                                       make_desc_sbo(xlo + boff + k * 32, ZP * 128), idesc, 1u);
+                            tc_mma_f16_masked(dacc, make_desc_sbo(wa + W_HI_OFFSET + k * 32, 1024),
+                                              make_desc_sbo(xlo + boff + k * 32, ZP * 128), idesc, 1u, 0u, 0u, ~0u, ~0u);
                         }
                         tc_commit(&w_empty[ws]);
                         ++wi;
@@ -723,6 +726,8 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
     if (a.split_out && (!a.split_exp || !a.dy_amax || !a.fused)) return cudaErrorInvalidValue;
     static const bool xsplit = !(getenv("SR4D_TC_XSPLIT") && atoi(getenv("SR4D_TC_XSPLIT")) == 0);
     p.xsplit = xsplit;
+    static const int exp_skip = getenv("SR4D_TC_EXP_SKIP") ? atoi(getenv("SR4D_TC_EXP_SKIP")) : 0;
+    p.exp_skip = exp_skip;
     p.dbg = nullptr;
     static const bool debug = getenv("SR4D_TC_DEBUG") != nullptr;
     static long long* dbg_buf = nullptr;

@@ -62,6 +62,18 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, with the disable-output-lane vector: bit j of m<i> set = accumulator lane 32*i + j is NOT written
+__device__ __forceinline__ void tc_mma_f16_masked(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                  uint32_t accumulate, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+        : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(
