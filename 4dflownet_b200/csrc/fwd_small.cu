@@ -22,7 +22,11 @@ __global__ void prep_features_kernel(const float* __restrict__ u, const float* _
 }
 
 // ---- 3->64 stem conv (+bias, ReLU): SR4DFlowNet.py:17,20 ---------------------------
-// 4 threads per voxel, 16 output channels each; weights [27][3][64] in shared memory.
+// 4 threads per run of STEM_VZ consecutive z voxels, 16 output channels each; weights [27][3][64] in shared memory.
+// The kernel is bound by the shared-memory weight fetches (a 16-byte load per 4 FMAs when a thread owns one voxel:
+// 12 LDS.128 per 48 FMAs, 4 LSU cycles each); with four voxels per thread every fetched weight feeds 16 FMAs and the
+// six clamped feature columns of a (dx,dy) row are read once for the three dz taps of all four voxels.
+constexpr int STEM_VZ = 4;
 __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ feat, int ch0,
                                                         const float* __restrict__ w,
                                                         const float* __restrict__ bias, ActView out) {
@@ -30,47 +34,67 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
     for (int i = threadIdx.x; i < 27 * 3 * 64; i += 256) ws[i] = w[i];
     __syncthreads();
     const int P = out.D;
-    const size_t nvox = (size_t)out.B * P * P * P;
+    const int nzr = (P + STEM_VZ - 1) / STEM_VZ;                    // z runs per line
+    const size_t nrun = (size_t)out.B * P * P * nzr;
     const int cq = (threadIdx.x & 3) * 16;
-    // grid-stride over groups of 64 voxels: the weights are staged once per CTA
-    for (size_t vi = (size_t)blockIdx.x * 64 + (threadIdx.x >> 2); vi < nvox; vi += (size_t)gridDim.x * 64) {
-    int z = vi % P, y = (vi / P) % P, x = (vi / ((size_t)P * P)) % P, b = vi / ((size_t)P * P * P);
-    float acc[16];
+    // grid-stride over groups of 64 runs: the weights are staged once per CTA
+    for (size_t ri = (size_t)blockIdx.x * 64 + (threadIdx.x >> 2); ri < nrun; ri += (size_t)gridDim.x * 64) {
+        const int z0 = (int)(ri % nzr) * STEM_VZ, y = (int)((ri / nzr) % P), x = (int)((ri / ((size_t)nzr * P)) % P);
+        const int b = (int)(ri / ((size_t)nzr * P * P));
+        float acc[STEM_VZ][16];
 #pragma unroll
-    for (int n = 0; n < 16; ++n) acc[n] = bias[cq + n];
-    for (int dx = -1; dx <= 1; ++dx) {
-        int xx = min(max(x + dx, 0), P - 1);
-        for (int dy = -1; dy <= 1; ++dy) {
-            int yy = min(max(y + dy, 0), P - 1);
-            for (int dz = -1; dz <= 1; ++dz) {
-                int zz = min(max(z + dz, 0), P - 1);
-                const float* f = feat + ((((size_t)b * P + xx) * P + yy) * P + zz) * 6 + ch0;
-                float f0 = f[0], f1 = f[1], f2 = f[2];
-                const float* wp = ws + (((dx + 1) * 3 + (dy + 1)) * 3 + (dz + 1)) * 192 + cq;
+        for (int v = 0; v < STEM_VZ; ++v)
 #pragma unroll
-                for (int n4 = 0; n4 < 4; ++n4) {          // 16-byte shared-memory loads: 12 per tap for 48 FMAs
-                    const float4 w0 = *reinterpret_cast<const float4*>(wp + n4 * 4);
-                    const float4 w1 = *reinterpret_cast<const float4*>(wp + 64 + n4 * 4);
-                    const float4 w2 = *reinterpret_cast<const float4*>(wp + 128 + n4 * 4);
-                    acc[n4 * 4 + 0] = fmaf(f0, w0.x, fmaf(f1, w1.x, fmaf(f2, w2.x, acc[n4 * 4 + 0])));
-                    acc[n4 * 4 + 1] = fmaf(f0, w0.y, fmaf(f1, w1.y, fmaf(f2, w2.y, acc[n4 * 4 + 1])));
-                    acc[n4 * 4 + 2] = fmaf(f0, w0.z, fmaf(f1, w1.z, fmaf(f2, w2.z, acc[n4 * 4 + 2])));
-                    acc[n4 * 4 + 3] = fmaf(f0, w0.w, fmaf(f1, w1.w, fmaf(f2, w2.w, acc[n4 * 4 + 3])));
+            for (int n = 0; n < 16; ++n) acc[v][n] = bias[cq + n];
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = min(max(x + dx, 0), P - 1);
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int yy = min(max(y + dy, 0), P - 1);
+                const float* row = feat + (((size_t)b * P + xx) * P + yy) * P * 6 + ch0;
+                float f[STEM_VZ + 2][3];
+#pragma unroll
+                for (int j = 0; j < STEM_VZ + 2; ++j) {
+                    const float* fp = row + (size_t)min(max(z0 + j - 1, 0), P - 1) * 6;
+                    f[j][0] = fp[0]; f[j][1] = fp[1]; f[j][2] = fp[2];
+                }
+#pragma unroll
+                for (int dz = 0; dz < 3; ++dz) {
+                    const float* wp = ws + (((dx + 1) * 3 + (dy + 1)) * 3 + dz) * 192 + cq;
+#pragma unroll
+                    for (int n4 = 0; n4 < 4; ++n4) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(wp + n4 * 4);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wp + 64 + n4 * 4);
+                        const float4 w2 = *reinterpret_cast<const float4*>(wp + 128 + n4 * 4);
+#pragma unroll
+                        for (int v = 0; v < STEM_VZ; ++v) {
+                            const float f0 = f[v + dz][0], f1 = f[v + dz][1], f2 = f[v + dz][2];
+                            acc[v][n4 * 4 + 0] = fmaf(f0, w0.x, fmaf(f1, w1.x, fmaf(f2, w2.x, acc[v][n4 * 4 + 0])));
+                            acc[v][n4 * 4 + 1] = fmaf(f0, w0.y, fmaf(f1, w1.y, fmaf(f2, w2.y, acc[v][n4 * 4 + 1])));
+                            acc[v][n4 * 4 + 2] = fmaf(f0, w0.z, fmaf(f1, w1.z, fmaf(f2, w2.z, acc[v][n4 * 4 + 2])));
+                            acc[v][n4 * 4 + 3] = fmaf(f0, w0.w, fmaf(f1, w1.w, fmaf(f2, w2.w, acc[v][n4 * 4 + 3])));
+                        }
+                    }
                 }
             }
         }
-    }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        float vv[4];
+        for (int v = 0; v < STEM_VZ; ++v) {
+            if (z0 + v >= P) break;
 #pragma unroll
-        for (int n = 0; n < 4; ++n) vv[n] = fmaxf(acc[q * 4 + n], 0.f);
-        act_store4_halo(out.hi, out.lo, P, b, x, y, z, cq + q * 4, vv, true);
-    }
+            for (int q = 0; q < 4; ++q) {
+                float vv[4];
+#pragma unroll
+                for (int n = 0; n < 4; ++n) vv[n] = fmaxf(acc[v][q * 4 + n], 0.f);
+                act_store4_halo(out.hi, out.lo, P, b, x, y, z0 + v, cq + q * 4, vv, true);
+            }
+        }
     }
 }
 
 // ---- 1x1 conv over concat[a(phase), b(pc)] 128->64 (+bias, ReLU): SR4DFlowNet.py:23-24
+// 4 threads per group of C1_NV consecutive voxels, 16 output channels each: every 16-byte weight fetch from shared
+// memory feeds 4 * C1_NV FMAs (the one-voxel version was bound by those fetches).
+constexpr int C1_NV = 4;
 __global__ void __launch_bounds__(256) conv1x1_cat_kernel(ActView a, ActView bq, const float* __restrict__ w,
                                                           const float* __restrict__ bias, ActView out) {
     extern __shared__ __align__(16) float ws[];   // [128][64]
@@ -78,40 +102,59 @@ __global__ void __launch_bounds__(256) conv1x1_cat_kernel(ActView a, ActView bq,
     __syncthreads();
     const int D = out.D;
     const size_t nvox = (size_t)out.B * D * D * D;
+    const size_t ngrp = (nvox + C1_NV - 1) / C1_NV;
     const int cq = (threadIdx.x & 3) * 16;
-    for (size_t vi = (size_t)blockIdx.x * 64 + (threadIdx.x >> 2); vi < nvox; vi += (size_t)gridDim.x * 64) {
-    int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
-    size_t off = act_off(D, b, x, y, z);
-    float acc[16];
+    for (size_t gi = (size_t)blockIdx.x * 64 + (threadIdx.x >> 2); gi < ngrp; gi += (size_t)gridDim.x * 64) {
+        size_t off[C1_NV];
+        int vx[C1_NV], vy[C1_NV], vz[C1_NV], vb[C1_NV];
 #pragma unroll
-    for (int n = 0; n < 16; ++n) acc[n] = bias[cq + n];
-    for (int half = 0; half < 2; ++half) {
-        const __half* hi = half ? bq.hi : a.hi;
-        const __half* lo = half ? bq.lo : a.lo;
-        for (int c8 = 0; c8 < 8; ++c8) {
-            float xv[8];
-            act_load8(hi, lo, off + c8 * 8, xv);
+        for (int v = 0; v < C1_NV; ++v) {
+            size_t vi = gi * C1_NV + v;
+            if (vi >= nvox) vi = nvox - 1;                       // tail: recompute the last voxel, store skipped below
+            vz[v] = (int)(vi % D); vy[v] = (int)((vi / D) % D); vx[v] = (int)((vi / ((size_t)D * D)) % D);
+            vb[v] = (int)(vi / ((size_t)D * D * D));
+            off[v] = act_off(D, vb[v], vx[v], vy[v], vz[v]);
+        }
+        float acc[C1_NV][16];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float4* wp = reinterpret_cast<const float4*>(ws + (half * 64 + c8 * 8 + k) * 64 + cq);
+        for (int v = 0; v < C1_NV; ++v)
 #pragma unroll
-                for (int n4 = 0; n4 < 4; ++n4) {
-                    const float4 wv = wp[n4];
-                    acc[n4 * 4 + 0] = fmaf(xv[k], wv.x, acc[n4 * 4 + 0]);
-                    acc[n4 * 4 + 1] = fmaf(xv[k], wv.y, acc[n4 * 4 + 1]);
-                    acc[n4 * 4 + 2] = fmaf(xv[k], wv.z, acc[n4 * 4 + 2]);
-                    acc[n4 * 4 + 3] = fmaf(xv[k], wv.w, acc[n4 * 4 + 3]);
+            for (int n = 0; n < 16; ++n) acc[v][n] = bias[cq + n];
+        for (int half = 0; half < 2; ++half) {
+            const __half* hi = half ? bq.hi : a.hi;
+            const __half* lo = half ? bq.lo : a.lo;
+            for (int c8 = 0; c8 < 8; ++c8) {
+                float xv[C1_NV][8];
+#pragma unroll
+                for (int v = 0; v < C1_NV; ++v) act_load8(hi, lo, off[v] + c8 * 8, xv[v]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4* wp = reinterpret_cast<const float4*>(ws + (half * 64 + c8 * 8 + k) * 64 + cq);
+#pragma unroll
+                    for (int n4 = 0; n4 < 4; ++n4) {
+                        const float4 wv = wp[n4];
+#pragma unroll
+                        for (int v = 0; v < C1_NV; ++v) {
+                            acc[v][n4 * 4 + 0] = fmaf(xv[v][k], wv.x, acc[v][n4 * 4 + 0]);
+                            acc[v][n4 * 4 + 1] = fmaf(xv[v][k], wv.y, acc[v][n4 * 4 + 1]);
+                            acc[v][n4 * 4 + 2] = fmaf(xv[v][k], wv.z, acc[v][n4 * 4 + 2]);
+                            acc[v][n4 * 4 + 3] = fmaf(xv[v][k], wv.w, acc[v][n4 * 4 + 3]);
+                        }
+                    }
                 }
             }
         }
-    }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        float vv[4];
+        for (int v = 0; v < C1_NV; ++v) {
+            if (gi * C1_NV + v >= nvox) break;
 #pragma unroll
-        for (int n = 0; n < 4; ++n) vv[n] = fmaxf(acc[q * 4 + n], 0.f);
-        act_store4_halo(out.hi, out.lo, D, b, x, y, z, cq + q * 4, vv, true);
-    }
+            for (int q = 0; q < 4; ++q) {
+                float vv[4];
+#pragma unroll
+                for (int n = 0; n < 4; ++n) vv[n] = fmaxf(acc[v][q * 4 + n], 0.f);
+                act_store4_halo(out.hi, out.lo, D, vb[v], vx[v], vy[v], vz[v], cq + q * 4, vv, true);
+            }
+        }
     }
 }
 
@@ -324,14 +367,14 @@ cudaError_t launch_prep_features(const float* u, const float* v, const float* w,
 }
 cudaError_t launch_stem_conv(const float* feat, int ch0, const float* w, const float* bias, ActView out,
                              cudaStream_t s) {
-    size_t nvox = (size_t)out.B * out.D * out.D * out.D;
-    const size_t ngrp = (nvox + 63) / 64;
+    const size_t nrun = (size_t)out.B * out.D * out.D * ((out.D + STEM_VZ - 1) / STEM_VZ);
+    const size_t ngrp = (nrun + 63) / 64;
     stem_conv_kernel<<<(unsigned)(ngrp < 2368 ? ngrp : 2368), 256, 0, s>>>(feat, ch0, w, bias, out);
     return cudaGetLastError();
 }
 cudaError_t launch_conv1x1_cat(ActView a, ActView b, const float* w, const float* bias, ActView out, cudaStream_t s) {
     size_t nvox = (size_t)out.B * out.D * out.D * out.D;
-    const size_t ngrp = (nvox + 63) / 64;
+    const size_t ngrp = ((nvox + C1_NV - 1) / C1_NV + 63) / 64;
     conv1x1_cat_kernel<<<(unsigned)(ngrp < 2368 ? ngrp : 2368), 256, 128 * 64 * 4, s>>>(a, b, w, bias, out);
     return cudaGetLastError();
 }
