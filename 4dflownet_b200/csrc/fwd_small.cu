@@ -159,36 +159,63 @@ __global__ void __launch_bounds__(256) conv1x1_cat_kernel(ActView a, ActView bq,
 }
 
 // ---- trilinear upsample, align_corners=True, lerp order z,y,x: SR4DFlowNet.py:53-90 ----
-// 8 threads per HR voxel, 8 channels each.
+// 8 threads per HR z-line (b, x, y), 8 channels each, marching along z.  The four (x,y) corner columns of a line are
+// fixed, and the LR z index pair (lo, hi) advances by at most one per output voxel (scale <= 1), so the thread keeps the
+// corner values at LR indices i0 and i0+1 in registers and loads every LR voxel of its four columns exactly once:
+// 2 instead of 8 corner loads per output voxel, same lerp expressions and order as the one-voxel-per-thread version.
 __global__ void __launch_bounds__(256) upsample_kernel(ActView in, ActView out, UpsampleTables t) {
     const int H = out.D, D = in.D;
-    const size_t nvox = (size_t)out.B * H * H * H;
-    size_t vi = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3);
-    if (vi >= nvox) return;
+    const size_t nline = (size_t)out.B * H * H;
+    const size_t li = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3);
+    if (li >= nline) return;
     const int c = (threadIdx.x & 7) * 8;
-    int z = vi % H, y = (vi / H) % H, x = (vi / ((size_t)H * H)) % H, b = vi / ((size_t)H * H * H);
-    const int xl = t.lo[x], xh = t.hi[x], yl = t.lo[y], yh = t.hi[y], zl = t.lo[z], zh = t.hi[z];
-    const float fx = t.lerp[x], fy = t.lerp[y], fz = t.lerp[z];
-    float r[2][8];
+    const int y = (int)(li % H), x = (int)((li / H) % H), b = (int)(li / ((size_t)H * H));
+    const int xl = t.lo[x], xh = t.hi[x], yl = t.lo[y], yh = t.hi[y];
+    const float fx = t.lerp[x], fy = t.lerp[y];
+    size_t col[4];                                   // [ix][iy] column bases at z = 0
+    col[0] = act_off(D, b, xl, yl, 0) + c; col[1] = act_off(D, b, xl, yh, 0) + c;
+    col[2] = act_off(D, b, xh, yl, 0) + c; col[3] = act_off(D, b, xh, yh, 0) + c;
+    float v0[4][8], v1[4][8];
+    int i0 = 0;
 #pragma unroll
-    for (int ix = 0; ix < 2; ++ix) {
-        float q[2][8];
-#pragma unroll
-        for (int iy = 0; iy < 2; ++iy) {
-            float p0[8], p1[8];
-            int xx = ix ? xh : xl, yy = iy ? yh : yl;
-            act_load8(in.hi, in.lo, act_off(D, b, xx, yy, zl) + c, p0);
-            act_load8(in.hi, in.lo, act_off(D, b, xx, yy, zh) + c, p1);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) q[iy][k] = p0[k] + (p1[k] - p0[k]) * fz;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) r[ix][k] = q[0][k] + (q[1][k] - q[0][k]) * fy;
+    for (int k = 0; k < 4; ++k) {
+        act_load8(in.hi, in.lo, col[k], v0[k]);
+        act_load8(in.hi, in.lo, col[k] + (size_t)min(1, D - 1) * SR4D_C, v1[k]);
     }
-    float o[8];
+    for (int z = 0; z < H; ++z) {
+        const int zl = t.lo[z], zh = t.hi[z];
+        const float fz = t.lerp[z];
+        if (zl > i0) {                               // warp-uniform: every thread of the block walks the same z
+            ++i0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = r[0][k] + (r[1][k] - r[0][k]) * fx;
-    act_store8_halo(out.hi, out.lo, H, b, x, y, z, c, o, true);
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v0[k][j] = v1[k][j];
+                act_load8(in.hi, in.lo, col[k] + (size_t)min(i0 + 1, D - 1) * SR4D_C, v1[k]);
+            }
+        }
+        const bool same = zh == zl;
+        float r[2][8];
+#pragma unroll
+        for (int ix = 0; ix < 2; ++ix) {
+            float q[2][8];
+#pragma unroll
+            for (int iy = 0; iy < 2; ++iy) {
+                const int k = ix * 2 + iy;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float p0 = v0[k][j], p1 = same ? v0[k][j] : v1[k][j];
+                    q[iy][j] = p0 + (p1 - p0) * fz;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[ix][j] = q[0][j] + (q[1][j] - q[0][j]) * fy;
+        }
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = r[0][j] + (r[1][j] - r[0][j]) * fx;
+        act_store8_halo(out.hi, out.lo, H, b, x, y, z, c, o, true);
+    }
 }
 
 // ---- 64->1 head conv, linear (+bias), writes (B,H^3,3): SR4DFlowNet.py:40,43,46,49 -------
@@ -380,8 +407,8 @@ cudaError_t launch_conv1x1_cat(ActView a, ActView b, const float* w, const float
 }
 cudaError_t launch_upsample(ActView in, ActView out, int r, UpsampleTables t, cudaStream_t s) {
     (void)r;
-    size_t nvox = (size_t)out.B * out.D * out.D * out.D;
-    upsample_kernel<<<(unsigned)((nvox + 31) / 32), 256, 0, s>>>(in, out, t);
+    size_t nline = (size_t)out.B * out.D * out.D;
+    upsample_kernel<<<(unsigned)((nline + 31) / 32), 256, 0, s>>>(in, out, t);
     return cudaGetLastError();
 }
 cudaError_t launch_head_out(ActView h0, ActView h1, ActView h2, const float* w0, const float* w1,
