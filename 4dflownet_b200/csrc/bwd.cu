@@ -450,6 +450,7 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restri
 
 // ---- 1x1 (128->64) backward ----------------------------------------------------------------
 // input gradient: d_cat[v][k] = sum_co dy[v][co] W[k][co]; 8 threads per voxel, k = kg*4 + 32q + (0..3)
+constexpr int C1D_NV = 4;
 __global__ void __launch_bounds__(256) conv1x1_dgrad_kernel(const float* __restrict__ dy, ActView a, ActView bq,
                                                             const float* __restrict__ w, float* __restrict__ da,
                                                             float* __restrict__ db, unsigned int* amax_a,
@@ -464,38 +465,65 @@ __global__ void __launch_bounds__(256) conv1x1_dgrad_kernel(const float* __restr
     const size_t nvox = (size_t)a.B * D * D * D;
     float ma = 0.f, mb = 0.f;
     const int kg = threadIdx.x & 7;
-    // grid-stride over groups of 32 voxels: the transposed weights are staged once per CTA
-    for (size_t vi = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3); vi < nvox; vi += (size_t)gridDim.x * 32) {
-    int z = vi % D, y = (vi / D) % D, x = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
-    const float* dyp = dy + g4_off(D, b, x, y, z);
-    float acc[4][4];
+    // grid-stride over groups of 32 runs of C1D_NV consecutive voxels (8 threads per run): the transposed weights are
+    // staged once per CTA and every 16-byte weight fetch feeds 4 * C1D_NV FMAs
+    const size_t nrun = (nvox + C1D_NV - 1) / C1D_NV;
+    for (size_t ri = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3); ri < nrun; ri += (size_t)gridDim.x * 32) {
+        size_t go[C1D_NV];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[q][j] = 0.f;
-    for (int co = 0; co < 64; ++co) {
-        float d = dyp[co];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float4 wv = *reinterpret_cast<const float4*>(wt + co * 128 + q * 32 + kg * 4);
-            acc[q][0] = fmaf(d, wv.x, acc[q][0]); acc[q][1] = fmaf(d, wv.y, acc[q][1]);
-            acc[q][2] = fmaf(d, wv.z, acc[q][2]); acc[q][3] = fmaf(d, wv.w, acc[q][3]);
+        for (int v = 0; v < C1D_NV; ++v) {
+            size_t vi = ri * C1D_NV + v;
+            if (vi >= nvox) vi = nvox - 1;                       // tail: recomputed, store skipped below
+            go[v] = g4_off(D, (int)(vi / ((size_t)D * D * D)), (int)((vi / ((size_t)D * D)) % D), (int)((vi / D) % D),
+                           (int)(vi % D));
         }
-    }
-    const size_t ao = act_off(D, b, x, y, z), go = g4_off(D, b, x, y, z);
+        float acc[C1D_NV][4][4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        int k = q * 32 + kg * 4;
-        const bool second = k >= 64;
-        int kk = second ? k - 64 : k;
-        float sv[4];
-        act_load4(second ? bq.hi : a.hi, second ? bq.lo : a.lo, ao + kk, sv);
-        float4 o = make_float4(sv[0] > 0.f ? acc[q][0] : 0.f, sv[1] > 0.f ? acc[q][1] : 0.f,
-                               sv[2] > 0.f ? acc[q][2] : 0.f, sv[3] > 0.f ? acc[q][3] : 0.f);
-        *reinterpret_cast<float4*>((second ? db : da) + go + kk) = o;
-        const float mo = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w)));
-        if (second) mb = fmaxf(mb, mo); else ma = fmaxf(ma, mo);
-    }
+        for (int v = 0; v < C1D_NV; ++v)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[v][q][j] = 0.f;
+        for (int c4 = 0; c4 < 16; ++c4) {
+            float4 d4[C1D_NV];
+#pragma unroll
+            for (int v = 0; v < C1D_NV; ++v) d4[v] = *reinterpret_cast<const float4*>(dy + go[v] + c4 * 4);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const int co = c4 * 4 + cc;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wt + co * 128 + q * 32 + kg * 4);
+#pragma unroll
+                    for (int v = 0; v < C1D_NV; ++v) {
+                        const float d = cc == 0 ? d4[v].x : cc == 1 ? d4[v].y : cc == 2 ? d4[v].z : d4[v].w;
+                        acc[v][q][0] = fmaf(d, wv.x, acc[v][q][0]); acc[v][q][1] = fmaf(d, wv.y, acc[v][q][1]);
+                        acc[v][q][2] = fmaf(d, wv.z, acc[v][q][2]); acc[v][q][3] = fmaf(d, wv.w, acc[v][q][3]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < C1D_NV; ++v) {
+            const size_t vi = ri * C1D_NV + v;
+            if (vi >= nvox) break;
+            const int z = (int)(vi % D), y = (int)((vi / D) % D), x = (int)((vi / ((size_t)D * D)) % D);
+            const int b = (int)(vi / ((size_t)D * D * D));
+            const size_t ao = act_off(D, b, x, y, z);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int k = q * 32 + kg * 4;
+                const bool second = k >= 64;
+                int kk = second ? k - 64 : k;
+                float sv[4];
+                act_load4(second ? bq.hi : a.hi, second ? bq.lo : a.lo, ao + kk, sv);
+                float4 o = make_float4(sv[0] > 0.f ? acc[v][q][0] : 0.f, sv[1] > 0.f ? acc[v][q][1] : 0.f,
+                                       sv[2] > 0.f ? acc[v][q][2] : 0.f, sv[3] > 0.f ? acc[v][q][3] : 0.f);
+                *reinterpret_cast<float4*>((second ? db : da) + go[v] + kk) = o;
+                const float mo = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w)));
+                if (second) mb = fmaxf(mb, mo); else ma = fmaxf(ma, mo);
+            }
+        }
     }
     if (amax_a) { absmax_commit(ma, amax_a); __syncthreads(); absmax_commit(mb, amax_b); }
 }
@@ -705,7 +733,7 @@ cudaError_t launch_conv1x1_bwd(const float* dy_g4, ActView a, ActView b, const f
                                float* db_g4, unsigned int* amax_a, unsigned int* amax_b, float* dw, float* dbias,
                                float* scratch, cudaStream_t s) {
     size_t nvox = (size_t)a.B * a.D * a.D * a.D;
-    const unsigned ngrp = nblocks(nvox, 32);
+    const unsigned ngrp = nblocks((nvox + C1D_NV - 1) / C1D_NV, 32);
     conv1x1_dgrad_kernel<<<ngrp < 592 ? ngrp : 592, 256, 128 * 64 * 4, s>>>(dy_g4, a, b, w, da_g4, db_g4, amax_a, amax_b);
     unsigned nb = red_blocks(nvox, C1_VOX_PER_BLOCK);
     conv1x1_wgrad_kernel<<<nb, 256, 0, s>>>(dy_g4, a, b, scratch);

@@ -1,0 +1,6 @@
+#!/bin/bash
+# final check of a session: smoke, the whole gpu suite, both bench arms (no profiler)
+mkdir -p gpurun_out
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+timeout 600 python -m pytest tests -m gpu -x -q --timeout 200 2>&1 | tail -4 > gpurun_out/pytest_gpu.log; cat gpurun_out/pytest_gpu.log
+timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -2 gpurun_out/bench_n1.err; cut -c1-200 gpurun_out/bench_n1.json
