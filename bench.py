@@ -130,6 +130,13 @@ def cpu_train_steps(n_steps, warmup, batch=1):
     restatement (oracle/sr4d_oracle.py) on all host cores, `batch` patches per step."""
     import numpy as np
     import torch
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # silently turn the CPU arm into a single-threaded run
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    torch.set_num_threads(max(1, ncpu))
     oracle = importlib.import_module("oracle.sr4d_oracle")
     params = {k: torch.tensor(v, requires_grad=True) for k, v in oracle.glorot_params(LOW, HI, seed=1234).items()}
     m = {k: np.zeros(v.shape, np.float32) for k, v in params.items()}
