@@ -1,50 +1,51 @@
-"""Mirror of the reference's utils/ImageDataset.py (class ImageDataset, :4-85): loads one low-resolution
-velocity + magnitude volume of a 4D-flow HDF5 file and normalises it for the network (velocity / max venc,
-magnitude / 4095).  File access goes through `h5io.open_file` (h5py when installed, the pure-Python shim
-otherwise); everything else is the numpy arithmetic the predictor feeds to `PatchGenerator.patchify`."""
+"""One low-resolution 4D-flow volume, normalised the way the network expects it.
+
+Drop-in for the reference's utils/ImageDataset.py (class ImageDataset, :4-85) as used by predictor.py:50-76 and
+PatchGenerator.patchify: `get_dataset_len(path)`, `load_vectorfield(path, row)` and afterwards the attributes
+u, v, w, mag_u, mag_v, mag_w (float32 volumes), venc, velocity_per_px, dx, plus the column-name lists.
+Velocities are divided by the largest of the three vencs of the row, magnitudes by 4095 (12-bit images); files
+are opened through `h5io.open_file` (h5py when installed, the pure-Python HDF5 shim otherwise)."""
 import numpy as np
 
 from . import h5io
 
+_AXES = ("u", "v", "w")
+_MAG_FULL_SCALE = 4095.0        # magnitude images are 12-bit
+_PHASE_LEVELS = 2048            # venc / 2048 = one quantisation step of the phase image
+
 
 class ImageDataset:
-    def __init__(self):
-        self.velocity_colnames = ['u', 'v', 'w']
-        self.venc_colnames = ['venc_u', 'venc_v', 'venc_w']
-        self.mag_colnames = ['mag_u', 'mag_v', 'mag_w']
-        self.dx_colname = 'dx'
-
-    def _normalize(self, velocity, venc):
-        return velocity / venc
-
-    def _set_images(self, velocity_images, mag_images, venc, dx):
-        velocity_images = self._normalize(velocity_images, venc)
-        mag_images = mag_images / 4095.          # magnitude 0 .. 1
-        self.u, self.v, self.w = (velocity_images[i].astype('float32') for i in range(3))
-        self.mag_u, self.mag_v, self.mag_w = (mag_images[i].astype('float32') for i in range(3))
-        self.venc = venc.astype('float32')       # kept to de-normalise the prediction
-        self.velocity_per_px = self.venc / 2048  # one phase-image quantum: smaller predictions are zeroed
-        self.dx = dx
-
-    def postprocess_result(self, results, zerofy=True):
-        results = results * self.venc
-        if zerofy:
-            print(f"Zero out velocity component less than {self.velocity_per_px}")
-            results[np.abs(results) < self.velocity_per_px] = 0
-        return results
+    velocity_colnames = list(_AXES)
+    venc_colnames = [f"venc_{a}" for a in _AXES]
+    mag_colnames = [f"mag_{a}" for a in _AXES]
+    dx_colname = "dx"
 
     def get_dataset_len(self, filepath):
-        with h5io.open_file(filepath, 'r') as hl:
-            return hl[self.velocity_colnames[0]].shape[0]
+        """Number of rows (time frames) in the file."""
+        with h5io.open_file(filepath, "r") as f:
+            return f[self.velocity_colnames[0]].shape[0]
 
     def load_vectorfield(self, filepath, idx):
-        lowres, mags, vencs = [], [], []
-        dx = None
-        with h5io.open_file(filepath, 'r') as hl:
-            if self.dx_colname in hl:
-                dx = hl.get(self.dx_colname)[idx]
-            for vel, mag, venc in zip(self.velocity_colnames, self.mag_colnames, self.venc_colnames):
-                lowres.append(np.asarray(hl.get(vel)[idx]))
-                mags.append(np.asarray(hl.get(mag)[idx]))
-                vencs.append(np.asarray(hl.get(venc)[idx]))
-        self._set_images(np.asarray(lowres), np.asarray(mags), np.max(vencs), dx)
+        """Read row `idx` and set the normalised attributes."""
+        with h5io.open_file(filepath, "r") as f:
+            spacing = f[self.dx_colname][idx] if self.dx_colname in f else None
+            read = lambda names: np.stack([np.asarray(f[n][idx]) for n in names])    # noqa: E731
+            velocity, magnitude = read(self.velocity_colnames), read(self.mag_colnames)
+            venc = np.max([np.asarray(f[n][idx]) for n in self.venc_colnames])
+        self._assign(velocity / venc, magnitude / _MAG_FULL_SCALE, venc, spacing)
+
+    def _assign(self, velocity, magnitude, venc, spacing):
+        for axis, vel, mag in zip(_AXES, velocity, magnitude):
+            setattr(self, axis, vel.astype(np.float32))
+            setattr(self, "mag_" + axis, mag.astype(np.float32))
+        self.venc = np.float32(venc)                      # needed again to de-normalise the prediction
+        self.velocity_per_px = self.venc / _PHASE_LEVELS  # predictions below one phase step are zeroed
+        self.dx = spacing
+
+    def postprocess_result(self, results, zerofy=True):
+        """De-normalise a prediction (x venc) and optionally zero what is below one phase quantisation step."""
+        out = results * self.venc
+        if zerofy:
+            print(f"Zero out velocity component less than {self.velocity_per_px}")
+            out[np.abs(out) < self.velocity_per_px] = 0
+        return out
