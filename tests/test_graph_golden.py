@@ -119,6 +119,27 @@ def test_oracle_upsample_vs_reference_resize(oracle):
         sys.modules.update({k: v for k, v in mods.items() if v is not None})
 
 
+def test_committed_graph_golden_is_reproducible(tmp_path):
+    """Where the reference tree is present (the build container), re-run the generator and compare every array with the
+    committed file: guards the fixture against drifting away from the reference's code."""
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("reference tree not present (GPU box)")
+    import subprocess
+    script = os.path.join(HERE, "golden", "make_graph_golden.py")
+    code = ("import runpy, sys, numpy as np, os; sys.argv=['x']; m = runpy.run_path(%r); "
+            "m['HERE'] = %r; m['main'].__globals__['HERE'] = %r; m['main']()") % (script, str(tmp_path), str(tmp_path))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    fresh = np.load(os.path.join(str(tmp_path), "graph_golden.npz"))
+    assert sorted(fresh.files) == sorted(GOLD.files)
+    for k in GOLD.files:
+        a, b = GOLD[k], fresh[k]
+        if a.dtype.kind in "fc":
+            np.testing.assert_allclose(b, a, rtol=1e-13, atol=0, err_msg=k)
+        else:
+            assert np.array_equal(a, b), k
+
+
 def test_oracle_predictor_flow_vs_reference_script_golden(oracle, tmp_path):
     """BASELINE configs[0] end to end: the oracle's patchify -> forward (fp32) -> patchup -> x venc -> zero small values
     against the result file the reference's own src/predictor.py wrote (tests/golden/make_predictor_golden.py)."""
