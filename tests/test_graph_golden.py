@@ -91,6 +91,20 @@ def test_oracle_forward_loss_metric_vs_reference_graph(oracle, tag):
     assert got["train_div"] == 0 and got["val_div"] == 0
 
 
+@pytest.mark.parametrize("tag", [t for t in CASES if f"{t}_fd_grad" in GOLD.files])
+def test_oracle_gradient_vs_finite_differences_of_the_reference_objective(oracle, tag):
+    """d/dw of sum_b(loss_b + l2) -- the objective TrainerController.train_step gives to tape.gradient, assembled by the
+    reference's own calculate_and_update_metrics(..., 'train') -- by central differences through the reference code
+    (stored with the golden) against the oracle's autograd gradient, incl. its B * 2 * 5e-7 * w regulariser share."""
+    (P, r, low, hi, B), params, lr, hr, mask = case(oracle, tag)
+    batch = [*lr, *hr, np.float64(1.0), mask]
+    grads, _ = oracle.gradients({k: v.astype(np.float64) for k, v in params.items()}, batch, r, low, hi)
+    for pick, want in zip(GOLD[f"{tag}_fd_picks"], GOLD[f"{tag}_fd_grad"]):
+        name, fi = str(pick).split("|")
+        got = grads[name].reshape(-1)[int(fi)]
+        assert abs(got - want) <= 2e-6 * abs(want) + 1e-9, (name, fi, got, want)
+
+
 def test_oracle_upsample_vs_reference_resize(oracle):
     """The reference's upsample3d (two resize_bilinear passes + transposes) on a random 5-D tensor, via the shim, vs
     the oracle's separable lerp -- an odd, anisotropy-revealing shape is impossible here (the reference assumes the
@@ -128,11 +142,13 @@ def test_committed_graph_golden_is_reproducible(tmp_path):
     script = os.path.join(HERE, "golden", "make_graph_golden.py")
     code = ("import runpy, sys, numpy as np, os; sys.argv=['x']; m = runpy.run_path(%r); "
             "m['HERE'] = %r; m['main'].__globals__['HERE'] = %r; m['main']()") % (script, str(tmp_path), str(tmp_path))
-    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, GRAPH_GOLDEN_NO_FD="1"))      # the finite-difference entries take a minute
     assert out.returncode == 0, out.stderr[-2000:]
     fresh = np.load(os.path.join(str(tmp_path), "graph_golden.npz"))
-    assert sorted(fresh.files) == sorted(GOLD.files)
-    for k in GOLD.files:
+    keys = [k for k in GOLD.files if "_fd_" not in k]
+    assert sorted(fresh.files) == sorted(keys)
+    for k in keys:
         a, b = GOLD[k], fresh[k]
         if a.dtype.kind in "fc":
             np.testing.assert_allclose(b, a, rtol=1e-13, atol=0, err_msg=k)
