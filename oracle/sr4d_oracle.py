@@ -17,10 +17,14 @@ reference ships no tests, golden outputs or weights.
   symbols they call (``tests/golden/tf_numpy_shim.py``); this file agrees with
   the resulting ``tests/golden/graph_golden.npz`` to 1e-12
   (``tests/test_graph_golden.py``).
+  The gradient of the training objective (sum over the batch of loss_b + l2, as
+  ``calculate_and_update_metrics(..., 'train')`` assembles it) is checked against
+  central finite differences taken through the reference code (stored in the
+  same file): 2e-6.
 * RESTATED, NOT PINNED ("parity unpinned" for these): the semantics of the TF
   primitives themselves (Conv3D, tf.pad SYMMETRIC, resize_bilinear with
-  align_corners, LeakyReLU, tf.round), ``tape.gradient`` (here: torch autograd of
-  the pinned forward, checked against fp64 finite differences) and Keras Adam.
+  align_corners, LeakyReLU, tf.round), that ``tape.gradient`` of a vector target
+  differentiates its sum, and Keras Adam.
   Self-checks in ``tests/test_oracle.py``: naive numpy convolution, a literal
   two-pass restatement of ``upsample3d``, finite differences, a hand-computed
   Adam example.
