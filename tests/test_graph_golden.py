@@ -219,3 +219,25 @@ def test_engine_train_metrics_vs_reference_graph(pkg, oracle, tag):
     assert abs(float(l2) - float(GOLD[f"{tag}_l2"])) < 1e-5 * float(GOLD[f"{tag}_l2"])
     np.testing.assert_allclose(per[:, 0] + float(l2), GOLD[f"{tag}_loss_train"], rtol=1e-4)
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", [t for t in CASES if f"{t}_fd_grad" in GOLD.files])
+def test_engine_gradient_vs_finite_differences_of_the_reference_objective(pkg, oracle, tag):
+    """The engine's flat gradient (sum over the batch, the L2 share is added by the Adam kernel) plus B*2*5e-7*w against
+    the finite differences of the reference code's training objective.  Tolerance: 5e-3 of the entry plus 5e-3 of the
+    tensor's rms gradient (the bar tests/test_gpu_backward.py applies per tensor)."""
+    (P, r, low, hi, B), params, lr, hr, mask = case(oracle, tag)
+    eng = pkg.Engine(P, r, low, hi, max_batch=B, training=True, device=0)
+    eng.set_weights(params)
+    eng.train_fwd_bwd([a.astype(np.float32) for a in lr], [a[..., 0].astype(np.float32) for a in hr],
+                      mask.astype(np.float32))
+    grads = {name: view.cpu().numpy().astype(np.float64) for name, view in eng.tensor_views(eng.grads)}
+    for pick, want in zip(GOLD[f"{tag}_fd_picks"], GOLD[f"{tag}_fd_grad"]):
+        name, fi = str(pick).split("|")
+        g = grads[name]
+        l2_share = B * 2 * oracle.L2_COEFF * float(params[name].reshape(-1)[int(fi)]) if name.endswith("kernel") else 0.0
+        got = g.reshape(-1)[int(fi)] + l2_share
+        rms = float(np.sqrt(np.mean(g ** 2)))
+        assert abs(got - want) <= 5e-3 * abs(want) + 5e-3 * rms, (name, fi, got, want, rms)
+    eng.close()
