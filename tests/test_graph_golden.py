@@ -241,3 +241,27 @@ def test_engine_gradient_vs_finite_differences_of_the_reference_objective(pkg, o
         rms = float(np.sqrt(np.mean(g ** 2)))
         assert abs(got - want) <= 5e-3 * abs(want) + 5e-3 * rms, (name, fi, got, want, rms)
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["a", "c"])
+def test_trainer_controller_running_means_vs_reference_graph(pkg, oracle, tag):
+    """The product TrainerController's calculate_and_update_metrics / loss_metrics (the reference's names) after one
+    'train' and one 'val' call on the golden prediction problem, against the running means the reference's own
+    calculate_and_update_metrics accumulated in tf.keras.metrics.Mean (stand-in) objects."""
+    import importlib
+    tcm = importlib.import_module("4dflownet_b200.Network.TrainerController")
+    (P, r, low, hi, B), params, lr, hr, mask = case(oracle, tag)
+    tc = tcm.TrainerController(P, r, 1e-4, False, "golden", low, hi, max_batch=B)
+    tc.model.set_weights([params[n] for n in tc.model.variable_names])
+    pred = tc.model([a.astype(np.float32) for a in lr], training=False)
+    hires = np.concatenate(hr, axis=-1).astype(np.float32)
+    m32 = mask.astype(np.float32)
+    loss_train = tc.calculate_and_update_metrics(hires, pred, m32, "train")
+    tc.calculate_and_update_metrics(hires, pred, m32, "val")
+    np.testing.assert_allclose(np.asarray(loss_train, dtype=np.float64), GOLD[f"{tag}_loss_train"], rtol=1e-4)
+    want = dict(zip([str(n) for n in GOLD["metric_names"]], GOLD[f"{tag}_metrics"]))
+    for name, ref in want.items():
+        got = float(tc.loss_metrics[name].result())
+        tol = 1e-3 if "accuracy" in name else 1e-4        # the metric rounds every voxel to 1e-4 steps
+        assert abs(got - ref) <= tol * abs(ref) + 1e-12, (name, got, ref)
