@@ -123,6 +123,17 @@ def test_adam_hand_example(oracle):
     assert abs(v2[0] - (0.00025 + (0.0625 - 0.00025) * 0.001)) < 1e-12
 
 
+def test_adam_tensorflow_documentation_example(oracle):
+    """tf.keras.optimizers.Adam API docs: `opt = Adam(learning_rate=0.1); var1 = tf.Variable(10.0);
+    loss = lambda: (var1 ** 2) / 2.0  # d(loss)/d(var1) == var1; opt.minimize(loss, [var1]);
+    # The first step is -learning_rate * sign(grad)` and `var1.numpy()` prints 9.9."""
+    p, m, v = oracle.adam_step(np.array([10.0]), np.array([10.0]), np.array([0.0]), np.array([0.0]), t=1, lr=0.1)
+    assert abs(p[0] - 9.9) < 1e-6
+    # a gradient of the other sign and a different magnitude moves by the same 0.1 in the other direction
+    p, m, v = oracle.adam_step(np.array([-3.0]), np.array([-0.002]), np.array([0.0]), np.array([0.0]), t=1, lr=0.1)
+    assert abs(p[0] - (-2.9)) < 1e-4
+
+
 def test_loss_and_metric_small_example(oracle):
     yt = torch.zeros(1, 2, 1, 1, 3)
     yp = torch.zeros(1, 2, 1, 1, 3)
