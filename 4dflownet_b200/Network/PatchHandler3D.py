@@ -50,13 +50,18 @@ def rotate_object(img, rotation_idx, plane_nr):
 class _BatchedDataset:
     """Re-iterable (one pass per epoch) batched view over the index rows."""
 
-    def __init__(self, handler, indexes, shuffle, n_parallel, seed=None):
+    def __init__(self, handler, indexes, shuffle, n_parallel, seed=None, shard=None):
         self.h, self.rows, self.shuffle = handler, list(indexes), shuffle
         self.n_parallel = n_parallel or 4
         self.rng = np.random.default_rng(seed)
+        self.shard = shard              # (rank, world): load only this rank's contiguous slice of every global batch
 
     def __len__(self):
-        return -(-len(self.rows) // self.h.batch_size)
+        n, bs = len(self.rows), self.h.batch_size
+        full, tail = divmod(n, bs)
+        if self.shard is not None and 0 < tail < self.shard[1]:
+            return full                 # a tail batch with fewer rows than ranks is dropped (see __iter__)
+        return full + (1 if tail else 0)
 
     def _load_batch(self, rows):
         items = [self.h.load_patches_from_index_file(r) for r in rows]
@@ -70,6 +75,13 @@ class _BatchedDataset:
         order = self.rng.permutation(len(self.rows)) if self.shuffle else np.arange(len(self.rows))
         bs = self.h.batch_size
         chunks = [[self.rows[i] for i in order[s:s + bs]] for s in range(0, len(order), bs)]
+        if self.shard is not None:
+            # data parallel: every rank draws the same permutation (same seed) and reads only the rows of its shard,
+            # i.e. exactly parallel.shard_batch() of the global batch without loading the other ranks' patches
+            from .. import parallel
+            # (a ragged tail batch with fewer rows than ranks would leave a rank without work in a step that still
+            # needs its all-reduce: it is dropped, at most world-1 rows per epoch)
+            chunks = [c[slice(*parallel.shard_bounds(len(c), *self.shard))] for c in chunks if len(c) >= self.shard[1]]
         with cf.ThreadPoolExecutor(max_workers=self.n_parallel) as pool:
             pending = []
             it = iter(chunks)
@@ -101,9 +113,9 @@ class PatchHandler3D:
         self.pin_memory = pin_memory
         self.prefetch = prefetch
 
-    def initialize_dataset(self, indexes, shuffle, n_parallel=None, seed=None):
+    def initialize_dataset(self, indexes, shuffle, n_parallel=None, seed=None, shard=None):
         print("Total dataset:", len(indexes), 'shuffle', shuffle)
-        return _BatchedDataset(self, indexes, shuffle, n_parallel, seed)
+        return _BatchedDataset(self, indexes, shuffle, n_parallel, seed, shard)
 
     # -- one CSV row -> one sample (PatchHandler3D.py:49-81) -------------------------------------------
     def load_patches_from_index_file(self, indexes):

@@ -3,8 +3,9 @@
 Flow: read the three patch-index CSVs, wrap them in PatchHandler3D iterators (train / validation shuffled, the
 benchmark set in file order so the first batch can be re-predicted after every best epoch), build a
 TrainerController with the reference's positional arguments, optionally restore, train.  Under `torchrun` every
-rank runs this function: all ranks iterate the same global batches (same shuffle seed), each keeps its
-contiguous slice (`parallel.shard_batch`) and the controller all-reduces the flat gradient buffer once per step."""
+rank runs this function: all ranks draw the same global batches (same shuffle seed), each loads only the rows of its
+contiguous shard (the `shard=` argument of `initialize_dataset`, equal to `parallel.shard_batch` of the global batch)
+and the controller all-reduces the flat gradient buffer once per step."""
 import numpy as np
 
 from . import parallel
@@ -21,23 +22,12 @@ def load_indexes(index_file):
     return np.genfromtxt(index_file, dtype="unicode", delimiter=",", skip_header=True)
 
 
-class _RankSlice:
-    """Iterates the wrapped global-batch iterator and yields this rank's slice of every batch."""
-
-    def __init__(self, batches):
-        self._batches = batches
-
-    def __len__(self):
-        return len(self._batches)
-
-    def __iter__(self):
-        return (parallel.shard_batch(b) for b in self._batches)
-
-
-def _iterator(csv_path, geometry, shuffle, seed=None, pinned=False):
+def _iterator(csv_path, geometry, shuffle, seed=None, pinned=False, sharded=False):
     data_dir, patch_size, res_increase, batch_size, mask_threshold = geometry
     handler = PatchHandler3D(data_dir, patch_size, res_increase, batch_size, mask_threshold, pin_memory=pinned)
     kwargs = {} if seed is None else {"n_parallel": None, "seed": seed}
+    if sharded and parallel.world_size() > 1:
+        kwargs["shard"] = (parallel.rank(), parallel.world_size())
     return handler.initialize_dataset(load_indexes(csv_path), shuffle=shuffle, **kwargs)
 
 
@@ -53,8 +43,8 @@ def main(data_dir='../data', training_file=None, validate_file=None, benchmark_f
              "benchmark": f"{data_dir}/benchmark.csv" if benchmark_file is None else benchmark_file}
     geometry = (data_dir, patch_size, res_increase, batch_size, mask_threshold)
 
-    train_batches = _RankSlice(_iterator(paths["train"], geometry, shuffle=True, seed=seed, pinned=True))
-    val_batches = _RankSlice(_iterator(paths["validate"], geometry, shuffle=True, seed=seed + 1, pinned=True))
+    train_batches = _iterator(paths["train"], geometry, shuffle=True, seed=seed, pinned=True, sharded=True)
+    val_batches = _iterator(paths["validate"], geometry, shuffle=True, seed=seed + 1, pinned=True, sharded=True)
     bench_batches = None
     if QUICKSAVE and paths["benchmark"]:
         bench_batches = _iterator(paths["benchmark"], geometry, shuffle=False)

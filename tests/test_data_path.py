@@ -168,6 +168,28 @@ def test_patchhandler_batches_and_shuffle(data_dir):
     assert not all(np.array_equal(x, y) for x, y in zip(a, [bb[0] for bb in batches]))
 
 
+def test_patchhandler_row_level_sharding_equals_shard_batch(data_dir):
+    """Data parallel feeding: with shard=(rank, world) a rank loads only its rows of every global batch; the result is
+    exactly parallel.shard_batch() of the batch a single process would have loaded (same seed, same order)."""
+    ph = importlib.import_module("4dflownet_b200.Network.PatchHandler3D")
+    parallel = importlib.import_module("4dflownet_b200.parallel")
+    rows = np.asarray(synth.ROWS)                                                # 11 rows
+    full = list(ph.PatchHandler3D(data_dir, synth.PATCH, synth.R, 4, 0.6).initialize_dataset(rows, shuffle=True, seed=3))
+    assert [len(b[0]) for b in full] == [4, 4, 3]
+    for world in (2, 3):
+        for rank in range(world):
+            ds = ph.PatchHandler3D(data_dir, synth.PATCH, synth.R, 4, 0.6).initialize_dataset(
+                rows, shuffle=True, seed=3, shard=(rank, world))
+            got = list(ds)
+            assert len(got) == len(ds) == 3
+            for g, f in zip(got, full):
+                want = parallel.shard_batch(f, rank, world)
+                assert all(np.array_equal(a, b) for a, b in zip(g, want))
+    # a tail batch with fewer rows than ranks is dropped on every rank alike
+    ds = ph.PatchHandler3D(data_dir, synth.PATCH, synth.R, 5, 0.6).initialize_dataset(rows, shuffle=False, shard=(1, 2))
+    assert len(ds) == 2 and [len(b[0]) for b in ds] == [2, 2]                    # 11 = 5 + 5 + 1: the 1-row tail goes
+
+
 def test_image_dataset_and_result_writer(h5io, data_dir, tmp_path):
     ids = importlib.import_module("4dflownet_b200.utils.ImageDataset")
     pu = importlib.import_module("4dflownet_b200.utils.prediction_utils")
