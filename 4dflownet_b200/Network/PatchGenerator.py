@@ -53,6 +53,35 @@ class PatchGenerator:
         self.nr_x, self.nr_y, self.nr_z = i, j, k
         return tuple(stacks[:3]), tuple(stacks[3:])
 
+    def patchify_device(self, dataset, device, lo=None, hi=None):
+        """`patchify` with the copying done on `device`: the six volumes go up once (one page-locked staging buffer,
+        one async copy), are zero-padded there and the (P,P,P) windows are gathered by a strided view -- the same
+        integer plan, so the result equals `patchify` bit for bit.  Returns six (n,P,P,P) float32 tensors
+        (u, v, w, mag_u, mag_v, mag_w); `lo, hi` select patches [lo, hi) of the x-major list (one rank's shard).
+        On the host the six window copies of a 160x160x64 volume cost ~80 ms, more than a B200 needs for the
+        forward pass of the patches of one rank."""
+        import torch
+        import torch.nn.functional as F
+        imgs = (dataset.u, dataset.v, dataset.w, dataset.mag_u, dataset.mag_v, dataset.mag_w)
+        shape = imgs[0].shape
+        side, far, nr = self._plan(shape)
+        self.padding = tuple(f * self.res_increase for f in far)
+        self.nr_x, self.nr_y, self.nr_z = nr
+        dev = torch.device(device)
+        host = torch.empty((6,) + tuple(shape), dtype=torch.float32, pin_memory=dev.type == "cuda")
+        for k, img in enumerate(imgs):
+            host[k].copy_(torch.from_numpy(np.ascontiguousarray(img, dtype=np.float32)))
+        vol = host.to(dev, non_blocking=True)
+        padded = F.pad(vol, (side, side + far[2], side, side + far[1], side, side + far[0]))
+        P, e = self.patch_size, self.effective_patch_size
+        win = padded.unfold(1, P, e).unfold(2, P, e).unfold(3, P, e)[:, :nr[0], :nr[1], :nr[2]]
+        if lo is None:
+            sel = win.reshape(6, -1, P, P, P)
+        else:
+            ix, iy, iz = (torch.from_numpy(a).to(dev) for a in np.unravel_index(np.arange(lo, hi), nr))
+            sel = win[:, ix, iy, iz]
+        return tuple(sel[k].contiguous() for k in range(6))
+
     def count_patches(self, shape):
         nr = self._plan(shape)[2]
         return nr[0] * nr[1] * nr[2]

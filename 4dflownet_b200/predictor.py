@@ -42,12 +42,13 @@ def predict_volume(network, pgen, dataset, batch_size=8, round_small_values=True
     H = eng.H
     n = pgen.count_patches(dataset.u.shape)
     lo, hi = parallel.shard_bounds(n)
-    velocities, magnitudes = pgen.patchify(dataset, lo, hi) if parallel.world_size() > 1 else pgen.patchify(dataset)
+    # tiling on the device: one upload of the six volumes, the window copies happen there (bit-identical to patchify)
+    stacks = pgen.patchify_device(dataset, eng.device, lo, hi) if parallel.world_size() > 1 else \
+        pgen.patchify_device(dataset, eng.device)
     local = torch.empty((hi - lo, H, H, H, 3), device=eng.device, dtype=torch.float32)
     for i in range(0, hi - lo, batch_size):
         sl = slice(i, min(i + batch_size, hi - lo))
-        eng.forward([velocities[0][sl], velocities[1][sl], velocities[2][sl],
-                     magnitudes[0][sl], magnitudes[1][sl], magnitudes[2][sl]], out=local[sl])
+        eng.forward([t[sl] for t in stacks], out=local[sl])
     results = parallel.gather_rows(local, n, dst=None if all_ranks else 0)
     if results is None:
         return None

@@ -190,6 +190,33 @@ def test_patchhandler_row_level_sharding_equals_shard_batch(data_dir):
     assert len(ds) == 2 and [len(b[0]) for b in ds] == [2, 2]                    # 11 = 5 + 5 + 1: the 1-row tail goes
 
 
+def test_patchify_device_equals_patchify():
+    """The torch (device) tiling used by predict_volume against the numpy tiling that is pinned to the reference's
+    golden vectors: bit-identical stacks, padding and patch counts, whole list and per-rank ranges."""
+    import torch
+    pgm = importlib.import_module("4dflownet_b200.Network.PatchGenerator")
+
+    class DS:
+        pass
+    g = np.random.default_rng(4)
+    for shape, P, r in [((42, 38, 36), 24, 2), ((10, 9, 11), 8, 2), ((21, 22, 23), 12, 3), ((7, 13, 5), 8, 1)]:
+        ds = DS()
+        for n in ("u", "v", "w", "mag_u", "mag_v", "mag_w"):
+            setattr(ds, n, g.standard_normal(shape).astype(np.float32))
+        a, b = pgm.PatchGenerator(P, r), pgm.PatchGenerator(P, r)
+        vel, mag = a.patchify(ds)
+        dev = b.patchify_device(ds, "cpu")
+        assert (a.nr_x, a.nr_y, a.nr_z, a.padding) == (b.nr_x, b.nr_y, b.nr_z, b.padding)
+        for want, got in zip((*vel, *mag), dev):
+            assert got.dtype == torch.float32 and got.is_contiguous()
+            assert np.array_equal(got.numpy(), want[..., 0])
+        n = a.count_patches(shape)
+        lo, hi = n // 3, n - 1
+        vel, mag = a.patchify(ds, lo, hi)
+        for want, got in zip((*vel, *mag), b.patchify_device(ds, "cpu", lo, hi)):
+            assert np.array_equal(got.numpy(), want[..., 0])
+
+
 def test_image_dataset_and_result_writer(h5io, data_dir, tmp_path):
     ids = importlib.import_module("4dflownet_b200.utils.ImageDataset")
     pu = importlib.import_module("4dflownet_b200.utils.prediction_utils")
