@@ -101,6 +101,7 @@ struct KParams {
     const float* gain;
     const unsigned int* dy_amax;
     const unsigned int* add_amax;
+    int single_b;            // 1: the B operand has no lo part (dgrad with a single-fp16 gradient): no second MMA, no lo load
     int xsplit;              // producer order: 1 = next activation plane requested mid-pass (default), 0 = at the pass boundary (SR4D_TC_XSPLIT=0)
     int exp_skip;            // TIMING EXPERIMENT ONLY (SR4D_TC_EXP_SKIP, wrong results): bit 0 = re-use stale weight slots
                              // after the first fill, bit 1 = re-use stale activation stages (how much do the L2 streams cost?)
@@ -203,9 +204,9 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                     if (part == 0) { mbar_wait(&x_empty[s], ph ^ 1); mbar_expect_tx(&x_full[s], 0); }
                 } else if (part == 0) {
                     mbar_wait(&x_empty[s], ph ^ 1);
-                    mbar_expect_tx(&x_full[s], 2 * C::ROWS * 128);
+                    mbar_expect_tx(&x_full[s], (p.single_b ? 1 : 2) * C::ROWS * 128);
                     tma_load_5d(dst, &xmap, &x_full[s], 0, z0, y0, plane, b);
-                } else {
+                } else if (!p.single_b) {
                     tma_load_5d(dst + C::PART_BYTES, &xmap, &x_full[s], 0, z0, y0, plane, p.B + b);
                 }
             };
@@ -276,8 +277,9 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                             // [Wlo ; Whi] x Xhi, then [Whi ; (next 8 KB, lanes 64-127 masked off)] x Xlo into the same accumulator
                             tc_mma_f16(dacc, make_desc_sbo(wa + k * 32, 1024),
                                        make_desc_sbo(xhi + boff + k * 32, ZP * 128), idesc, acc);
-                            tc_mma_f16_masked(dacc, make_desc_sbo(wa + W_HI_OFFSET + k * 32, 1024),
-                                              make_desc_sbo(xlo + boff + k * 32, ZP * 128), idesc, 1u, 0u, 0u, ~0u, ~0u);
+                            if (!p.single_b)
+                                tc_mma_f16_masked(dacc, make_desc_sbo(wa + W_HI_OFFSET + k * 32, 1024),
+                                                  make_desc_sbo(xlo + boff + k * 32, ZP * 128), idesc, 1u, 0u, 0u, ~0u, ~0u);
                         }
                         tc_commit(&w_empty[ws]);
                         ++wi;
@@ -718,6 +720,7 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
     p.slope = a.slope; p.B = B; p.Do = Do; p.halo = a.halo;
     p.nx = a.fused ? Do - 2 : Do;
     p.fused = a.fused; p.Dint = Do - 2;
+    p.single_b = (a.dgrad && a.single_b) ? 1 : 0;
     p.dy_exp = a.dy_exp; p.add_pre = a.add_pre; p.add_post = a.add_post;
     p.sav_hi = a.sav_hi; p.sav_lo = a.sav_lo; p.out_g4 = a.out_g4;
     p.split_hi = a.split_out;

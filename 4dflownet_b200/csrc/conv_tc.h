@@ -20,6 +20,9 @@ struct TcConvArgs {
     // D+2; the halo fold, the skip add, the activation derivative and the accumulation happen in the epilogue:
     //   out_g4(interior) = (fold(dgrad) * 2^-(*dy_exp) + add_pre) * act'(saved; slope) + add_post
     int fused = 0;
+    // dgrad only: use just the hi plane of the split gradient (one scaled fp16 value per element) -- one
+    // [Wlo;Whi] x dYhi instruction per K-step instead of two.  Weights stay split; see SR4D_OPT_DGRAD_SINGLE.
+    int single_b = 0;
     const int* dy_exp = nullptr;
     const float* add_pre = nullptr;    // fp32 G4 [B][D+4]^3[64] or NULL
     const float* add_post = nullptr;   // fp32 G4 or NULL (may alias out_g4)

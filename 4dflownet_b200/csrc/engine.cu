@@ -85,6 +85,7 @@ struct sr4d_handle {
     int conv_impl = SR4D_CONV_AUTO;
     int save_acts = 0;
     int fused_dgrad = 1;       // SR4D_OPT_FUSED_DGRAD
+    int dgrad_single = 0;      // SR4D_OPT_DGRAD_SINGLE
     bool have_fwd_state = false;
     int64_t launches = 0;
     // per-kernel-class device timing (SR4D_OPT_PROFILE): event pairs on the launch stream
@@ -393,7 +394,7 @@ int conv64_dgrad(sr4d_t* h, int layer, const GBuf& dy, RawBuf& raw, int B, int D
     if (use_tc(h)) {
         TcConvArgs a;
         a.in.hi = dy.s; a.in.lo = dy.s + act_plane_elems(B, D + 2); a.in.B = B; a.in.D = D + 2;
-        a.layer = layer; a.dgrad = 1;
+        a.layer = layer; a.dgrad = 1; a.single_b = h->dgrad_single;
         a.out_raw = raw.p;
         raw.exp = dy.exp;
         CK(h, tc_conv64(h->tcw, a, s), 1);
@@ -439,7 +440,7 @@ int conv64_dgrad_fused(sr4d_t* h, int layer, const GBuf& dy, const GBuf* add_pre
     ProfScope prof(h, D == h->P ? SR4D_PROF_CONV64_DGRAD_LR : SR4D_PROF_CONV64_DGRAD_HR, s);
     TcConvArgs a;
     a.in.hi = dy.s; a.in.lo = dy.s + act_plane_elems(B, D + 2); a.in.B = B; a.in.D = D + 2;
-    a.layer = layer; a.dgrad = 1; a.fused = 1;
+    a.layer = layer; a.dgrad = 1; a.fused = 1; a.single_b = h->dgrad_single;
     a.dy_exp = dy.exp; a.add_pre = add_pre ? add_pre->f : nullptr; a.add_post = add_post;
     if (with_split) {
         a.split_out = out.s; a.split_exp = out.exp; a.dy_amax = dy.amax;
@@ -739,6 +740,9 @@ int sr4d_set_option(sr4d_t* h, int option, int value) {
         case SR4D_OPT_FUSED_DGRAD:
             h->fused_dgrad = value != 0;
             return SR4D_OK;
+        case SR4D_OPT_DGRAD_SINGLE:
+            h->dgrad_single = value != 0;
+            return SR4D_OK;
     }
     return fail(h, SR4D_EINVAL, "unknown option");
 }
@@ -748,6 +752,7 @@ int sr4d_get_option(const sr4d_t* h, int option, int* value) {
     if (option == SR4D_OPT_SAVE_ACTS) { *value = h->save_acts; return SR4D_OK; }
     if (option == SR4D_OPT_PROFILE) { *value = h->profile; return SR4D_OK; }
     if (option == SR4D_OPT_FUSED_DGRAD) { *value = h->fused_dgrad; return SR4D_OK; }
+    if (option == SR4D_OPT_DGRAD_SINGLE) { *value = h->dgrad_single; return SR4D_OK; }
     return SR4D_EINVAL;
 }
 
