@@ -38,6 +38,7 @@ MODES = {
     "bf16 (1 pass)": lambda x, w, conv: conv(x.bfloat16().float(), w.bfloat16().float()),
     "fp16 (1 pass)": lambda x, w, conv: conv(x.half().float(), w.half().float()),
     "fp16 split, 2 products (no Wlo*Xhi)": lambda x, w, conv: (lambda xs, ws: conv(xs[0], ws[0]) + conv(xs[1], ws[0]) / 2048.0)(split16(x), split16(w)),
+    "fp16 split, 2 products (no Whi*Xlo)": lambda x, w, conv: (lambda xs, ws: conv(xs[0], ws[0]) + conv(xs[0], ws[1]) / 2048.0)(split16(x), split16(w)),
     "fp16 split, 3 products (conv_tc.cu)": lambda x, w, conv: (lambda xs, ws: conv(xs[0], ws[0]) + (conv(xs[0], ws[1]) + conv(xs[1], ws[0])) / 2048.0)(split16(x), split16(w)),
 }
 
