@@ -53,4 +53,6 @@ bool tc_dgrad_fusable(int D);
 // split-fp16 gradient [2B][D+4]^3[64] with device exponent *dy_exp; writes tc_wgrad_slabs() partial
 // dW[27][64][64] into `partial` (slab-major) for a row reduction.
 int tc_wgrad_slabs();
-cudaError_t tc_wgrad64(ActView x, const __half* dy_split, const int* dy_exp, float* partial, cudaStream_t s);
+// single = 1 (EXPERIMENTAL, SR4D_OPT_WGRAD_SINGLE): dYhi x Xhi only.
+cudaError_t tc_wgrad64(ActView x, const __half* dy_split, const int* dy_exp, float* partial, cudaStream_t s,
+                       int single = 0);

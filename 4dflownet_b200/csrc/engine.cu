@@ -86,6 +86,7 @@ struct sr4d_handle {
     int save_acts = 0;
     int fused_dgrad = 1;       // SR4D_OPT_FUSED_DGRAD
     int dgrad_single = 0;      // SR4D_OPT_DGRAD_SINGLE
+    int wgrad_single = 0;      // SR4D_OPT_WGRAD_SINGLE
     bool have_fwd_state = false;
     int64_t launches = 0;
     // per-kernel-class device timing (SR4D_OPT_PROFILE): event pairs on the launch stream
@@ -412,7 +413,7 @@ int conv64_wgrad(sr4d_t* h, int layer, ActView x, const GBuf& dy, bool bias, cud
     ProfScope prof(h, x.D == h->P ? SR4D_PROF_CONV64_WGRAD_LR : SR4D_PROF_CONV64_WGRAD_HR, s);
     static const bool wgrad_simt = getenv("SR4D_WGRAD_SIMT") != nullptr;   // debugging aid
     if (use_tc(h) && !wgrad_simt) {
-        CK(h, tc_wgrad64(x, dy.s, dy.exp, h->scratch, s), 1);
+        CK(h, tc_wgrad64(x, dy.s, dy.exp, h->scratch, s, h->wgrad_single), 1);
         CK(h, launch_reduce_rows(h->scratch, tc_wgrad_slabs(), 27 * 4096, GW(h, layer), s), 1);
     } else {
         CK(h, launch_wgrad64_simt(x, dy.f, GW(h, layer), h->scratch, h->wgrad_chunks, s), 2);
@@ -743,6 +744,9 @@ int sr4d_set_option(sr4d_t* h, int option, int value) {
         case SR4D_OPT_DGRAD_SINGLE:
             h->dgrad_single = value != 0;
             return SR4D_OK;
+        case SR4D_OPT_WGRAD_SINGLE:
+            h->wgrad_single = value != 0;
+            return SR4D_OK;
     }
     return fail(h, SR4D_EINVAL, "unknown option");
 }
@@ -753,6 +757,7 @@ int sr4d_get_option(const sr4d_t* h, int option, int* value) {
     if (option == SR4D_OPT_PROFILE) { *value = h->profile; return SR4D_OK; }
     if (option == SR4D_OPT_FUSED_DGRAD) { *value = h->fused_dgrad; return SR4D_OK; }
     if (option == SR4D_OPT_DGRAD_SINGLE) { *value = h->dgrad_single; return SR4D_OK; }
+    if (option == SR4D_OPT_WGRAD_SINGLE) { *value = h->wgrad_single; return SR4D_OK; }
     return SR4D_EINVAL;
 }
 

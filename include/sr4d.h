@@ -53,6 +53,9 @@ extern "C" {
                                     stay split): one MMA per K-step instead of two.  CPU emulation
                                     (tools/gradient_precision_emulation.py): costs ~0.4e-5 of the flat gradient at
                                     48^3 voxels (fp32 autograd itself: 1e-5 from float64), ~1/sqrt(#voxels). */
+#define SR4D_OPT_WGRAD_SINGLE 6  /* EXPERIMENTAL, default 0, not yet validated on hardware: the tensor-core wgrad multiplies
+                                    only the hi planes (dYhi x Xhi): per-voxel rounding errors of both operands average
+                                    out over the 10^5..10^6-voxel sum (same emulation: 1.14e-5 vs 1.05e-5 for fp32). */
 
 /* kernel classes timed under SR4D_OPT_PROFILE (index into sr4d_profile_read's arrays):
  * the 64->64 3x3x3 convolution forward / input-gradient / weight-gradient, on the LR

@@ -63,6 +63,16 @@ def make_conv(mode):
                 wh = w.half().float(); wl = w - wh
                 xh = x.half().float(); xl = x - xh
                 return dgrad(g16, wh) + dgrad(g16, wl.half().float()), wgrad(xh, g16) + wgrad(xl.half().float(), g16)
+            if mode == "dgrad: W split x gradient single; wgrad: gradient split x X single":
+                g16 = fp16_scaled(gy)
+                gh, gl = split16_scaled(gy)
+                wh = w.half().float(); wl = (w - wh).half().float()
+                x16 = x.half().float()
+                return dgrad(g16, wh) + dgrad(g16, wl), wgrad(x16, gh) + wgrad(x16, gl)
+            if mode == "dgrad: W split x gradient single; wgrad: gradient single x X single":
+                g16 = fp16_scaled(gy)
+                wh = w.half().float(); wl = (w - wh).half().float()
+                return dgrad(g16, wh) + dgrad(g16, wl), wgrad(x.half().float(), g16)
             if mode == "fp16 split, 3 products (csrc)":
                 gh, gl = split16_scaled(gy)
                 wh = w.half().float(); wl = ((w - wh) * 2048).half().float() / 2048
@@ -73,7 +83,9 @@ def make_conv(mode):
 
 
 MODES = ["fp32", "fp16 split, 3 products (csrc)", "fp16 split, 2 products (gradient split, W / X single)",
-         "fp16 split, 2 products (W / X split, gradient single)", "fp16 (1 pass)"]
+         "fp16 split, 2 products (W / X split, gradient single)",
+         "dgrad: W split x gradient single; wgrad: gradient split x X single",
+         "dgrad: W split x gradient single; wgrad: gradient single x X single", "fp16 (1 pass)"]
 
 
 def run(P=12, r=2, low=2, hi=2, B=2, modes=MODES):
