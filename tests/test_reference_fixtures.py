@@ -84,3 +84,60 @@ def test_product_data_path_equals_reference_modules_on_the_real_file(h5io):
     dev = ppg.patchify_device(pds, "cpu")
     for a, b in zip((*rvel, *rmag), dev):
         assert np.array_equal(a[..., 0], b.numpy())
+
+
+def test_product_patch_loader_equals_reference_loader_on_the_real_training_rows(h5io):
+    """Every row of the reference's data/train.csv, validate.csv and benchmark.csv (real LR / HR files, rotations
+    included) through the reference's own PatchHandler3D.load_patches_from_index_file (tf stubbed: only tf.newaxis is
+    touched) and through the product loader: the 11 arrays of a sample are bit-identical."""
+
+    class FakeTensor:                       # what tf.py_function hands to the reference loader
+        def __init__(self, s):
+            self.s = s
+
+        def numpy(self):
+            return self.s.encode()
+
+        def __int__(self):
+            return int(self.s)
+
+        def __float__(self):
+            return float(self.s)
+
+    saved = {k: sys.modules.get(k) for k in ("h5py", "tensorflow", "Network", "Network.PatchHandler3D")}
+    shim = types.ModuleType("h5py")
+    shim.File, shim.Group, shim.Dataset, shim.__shim__ = h5io.File, h5io.Group, h5io.Dataset, True
+    tf = types.ModuleType("tensorflow")
+    tf.newaxis = None
+    sys.modules["h5py"], sys.modules["tensorflow"] = shim, tf
+    for k in ("Network", "Network.PatchHandler3D"):
+        sys.modules.pop(k, None)
+    sys.path.insert(0, os.path.join(REF, "src"))
+    data_dir = os.path.join(REF, "data")
+    rows = []
+    for name in ("train.csv", "validate.csv", "benchmark.csv"):
+        rows += [ln.strip().split(",") for ln in open(os.path.join(data_dir, name)).read().splitlines()[1:] if ln.strip()]
+    assert len(rows) == 70
+    try:
+        ref = importlib.import_module("Network.PatchHandler3D")                 # reference code, unmodified
+        rh = ref.PatchHandler3D(data_dir, 16, 2, 4, 0.6)                       # trainer.py defaults: patch 16, r 2
+        want = [[np.asarray(a) for a in rh.load_patches_from_index_file([FakeTensor(x) for x in row])] for row in rows]
+    finally:
+        sys.path.remove(os.path.join(REF, "src"))
+        for k in ("Network", "Network.PatchHandler3D"):
+            sys.modules.pop(k, None)
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
+            else:
+                sys.modules.pop(k, None)
+    ph = importlib.import_module("4dflownet_b200.Network.PatchHandler3D").PatchHandler3D(data_dir, 16, 2, 4, 0.6)
+    rotated = 0
+    for row, w in zip(rows, want):
+        got = ph.load_patches_from_index_file(np.asarray(row))
+        assert len(got) == len(w) == 11
+        for k, (a, b) in enumerate(zip(got, w)):
+            a = np.asarray(a)
+            assert a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b), (row, k)
+        rotated += int(row[6])
+    assert rotated > 10                     # the CSVs do exercise the rotation augmentation
