@@ -342,7 +342,7 @@ def run_b200(args):
                          "ms_per_launch": dom_ms / max(dom_n, 1), "launches_per_step": dom_n,
                          "share_of_step": dom_ms / ms_step,
                          "note": "achieved = algorithmic fp32 FLOPs (2*27*64*64*B*D^3) / event time; the fp32-accurate "
-                                 "split-fp16 path issues 4 fp16 tcgen05 products per fp32 MAC (3 useful + zero rows), so the "
+                                 "split-fp16 path issues 4 fp16 tcgen05 products per fp32 MAC (3 useful + 64 masked-off rows), so the "
                                  "tensor pipe saturates at frac ~0.25; the dgrad launch also folds the halo, adds the skip "
                                  "gradient, applies act' and writes the split copy"},
             "kernel_classes_ms_per_step": {k: round(v[0], 4) for k, v in prof_step.items()},
