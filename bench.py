@@ -212,6 +212,12 @@ def run_b200(args):
     with contextlib.redirect_stdout(io.StringIO()):
         ctl = tcm.TrainerController(P, R, 1e-4, False, "4DFlowNet", LOW, HI, max_batch=B, device=local, seed=1234)
     eng = ctl.engine
+    if args.experimental_backward:
+        # EXPERIMENTAL (default off, see DESIGN.md "what would come next" item 0): single-fp16 gradient operand in the
+        # tensor-core dgrad / hi-planes-only wgrad.  The line is labelled; it is not the headline configuration.
+        L = importlib.import_module("4dflownet_b200._lib")
+        eng.set_option(L.OPT_DGRAD_SINGLE, 1)
+        eng.set_option(L.OPT_WGRAD_SINGLE, 1)
     host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in synthetic_batch(B, P, R, seed=rank)]
     devb = [h.to(dev) for h in host]
     h2d = sum(h.numel() * 4 for i, h in enumerate(host) if i != 9)     # venc is not an input of the step
@@ -331,7 +337,9 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(world, B),
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(world, B), **({"experimental_backward": "single-fp16 gradient operand in dgrad, "
+                                                         "hi planes only in wgrad"} if args.experimental_backward else {})),
             "clocks": clk,
             "e2e": {"value": e2e_val, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
@@ -366,6 +374,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="patches per GPU per step (configs[1]: 8)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--experimental-backward", action="store_true",
+                    help="turn on SR4D_OPT_DGRAD_SINGLE / SR4D_OPT_WGRAD_SINGLE (not validated on hardware yet)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
