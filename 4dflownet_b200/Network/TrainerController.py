@@ -103,6 +103,13 @@ class AdamOptimizer:
         self.engine.adam_step(float(self.lr), self.iterations, global_batch * 2.0 * L2_COEFF,
                               self.beta_1, self.beta_2, self.epsilon)
 
+    def apply_counted(self, tail_index):
+        """Same, with the global batch size read on the device from the metric tail of the gradient buffer (what the
+        all-reduce left there): no host synchronisation between the collective and the update."""
+        self.iterations += 1
+        self.engine.adam_step_counted(float(self.lr), self.iterations, 2.0 * L2_COEFF, tail_index,
+                                      self.beta_1, self.beta_2, self.epsilon)
+
 
 def _squeeze_last(a):
     return a[..., 0] if a.shape[-1] == 1 and a.ndim == 5 else a
@@ -132,6 +139,7 @@ class TrainerController:
         self.learning_rate = initial_learning_rate
         self.optimizer = AdamOptimizer(self.engine, lr=self.learning_rate)
         self._last = None    # device tensors of the most recent step (per_sample, l2)
+        self._metric_tail = None
 
     # ---- loss / metric entry points with the reference's names -------------------------------
     def loss_function(self, y_true, y_pred, mask):
@@ -169,29 +177,44 @@ class TrainerController:
         return L2_COEFF * tot
 
     # ---- steps --------------------------------------------------------------------------------
+    def _tail(self):
+        if self._metric_tail is None or self._metric_tail.world != parallel.world_size():
+            self._metric_tail = parallel.MetricTail(self.engine.grad_tail, self.engine.max_batch)
+        return self._metric_tail
+
     def train_step_async(self, data_pairs):
-        """Enqueue forward + loss + backward (+ all-reduce) + Adam; returns device tensors
-        (per_sample (B,4), l2 (1,)) without synchronising."""
+        """Enqueue forward + loss + backward + the step's ONE collective + Adam; returns device views
+        (per_sample (B,4), l2 (1,)) of this rank's metrics without synchronising.
+
+        Data parallel: every rank holds a shard of the global batch and leaves the SUM of its samples'
+        gradients in the flat buffer; the per-sample metrics, the l2 value and the local batch size go into the
+        rank's slot of the metric tail behind the gradients, so ONE all-reduce(SUM) of `grads_full` delivers the
+        global gradient, gathers the metrics of every sample and the global batch size; Adam then runs identically on
+        every rank with the L2 gradient of the GLOBAL batch (TrainerController.py:223,249) read from the tail on the
+        device."""
         u, v, w, u_mag, v_mag, w_mag, u_hr, v_hr, w_hr, venc, mask = data_pairs
-        per, l2, _ = self.engine.train_fwd_bwd([u, v, w, u_mag, v_mag, w_mag],
-                                                [_squeeze_last(a) for a in (u_hr, v_hr, w_hr)], mask)
-        # data parallel (SURVEY 8e): every rank holds an equal shard of the global batch; ONE all-reduce (SUM) of
-        # the flat gradient buffer, then the same Adam step everywhere with the L2 gradient of the GLOBAL batch
-        parallel.allreduce_gradients(self.engine.grads)
-        self.optimizer.apply(per.shape[0] * parallel.world_size())
+        tail = self._tail()
+        per, l2 = tail.begin(len(u))
+        self.engine.train_fwd_bwd([u, v, w, u_mag, v_mag, w_mag], [_squeeze_last(a) for a in (u_hr, v_hr, w_hr)], mask,
+                                  per_out=per, l2_out=l2)
+        parallel.allreduce_gradients(self.engine.grads_full)
+        self.optimizer.apply_counted(tail.count_index)
         self._last = (per, l2)
         return per, l2
 
     def train_step(self, data_pairs):
-        per, l2 = self.train_step_async(data_pairs)
-        per = parallel.gather_metrics(per)          # running means cover every sample of the global batch
-        self._update_metrics(per.cpu().numpy(), float(l2.item()), 'train')
+        self.train_step_async(data_pairs)
+        per, l2, _ = self._tail().read()     # running means cover every sample of the global batch
+        self._update_metrics(per, l2, 'train')
 
     def test_step(self, data_pairs):
         u, v, w, u_mag, v_mag, w_mag, u_hr, v_hr, w_hr, venc, mask = data_pairs
         predictions = self.model([u, v, w, u_mag, v_mag, w_mag], training=False)
-        per = self.engine.loss_metrics(predictions, *[_squeeze_last(a) for a in (u_hr, v_hr, w_hr)], mask)
-        self._update_metrics(parallel.gather_metrics(per).cpu().numpy(), None, 'val')
+        tail = self._tail()
+        per, _ = tail.begin(len(u))
+        self.engine.loss_metrics(predictions, *[_squeeze_last(a) for a in (u_hr, v_hr, w_hr)], mask, per_out=per)
+        tail.exchange()
+        self._update_metrics(tail.read()[0], None, 'val')
         return predictions
 
     def _update_metrics(self, per, l2, metric_set):
@@ -214,11 +237,39 @@ class TrainerController:
     # ---- model directory, logging ---------------------------------------------------------------
     def init_model_dir(self, root="../models"):
         timestamp = datetime.datetime.now().strftime("%Y%m%d-%H%M")
+        if parallel.world_size() > 1:
+            # one directory per run: every rank uses rank 0's timestamp; only rank 0 writes into it
+            import torch.distributed as dist
+            box = [timestamp]
+            dist.broadcast_object_list(box, src=0)
+            timestamp = box[0]
         self.unique_model_name = f'{self.network_name}_{timestamp}'
         self.model_dir = f"{root}/{self.unique_model_name}"
         self.model_path = f"{self.model_dir}/{self.network_name}"
-        os.makedirs(self.model_dir, exist_ok=True)
-        self._prepare_logfile_and_summary()
+        self.train_writer = self.val_writer = None
+        self.logfile = self.model_dir + '/loss.csv'
+        if parallel.is_main():
+            os.makedirs(self.model_dir, exist_ok=True)
+            self._prepare_logfile_and_summary()
+        parallel.barrier()
+
+    def _log(self, text):
+        if parallel.is_main():
+            utility.log_to_file(self.logfile, text)
+
+    def sync_ranks(self):
+        """Data parallel: rank 0's weights, Adam moments and iteration count on every rank (after the random
+        initialisation and after restore_model); the derived tensor-core weight images are rebuilt."""
+        if parallel.world_size() == 1:
+            return
+        for t in (self.engine.params, self.engine.adam_m, self.engine.adam_v):
+            parallel.broadcast_(t, 0)
+        it = torch.tensor([self.optimizer.iterations, 0], dtype=torch.int64, device=self.engine.device)
+        it[1] = int(np.float32(float(self.optimizer.lr)).view(np.int32))
+        parallel.broadcast_(it, 0)
+        self.optimizer.iterations = int(it[0].item())
+        self.optimizer.lr.assign(float(np.int32(int(it[1].item())).view(np.float32)))
+        self.engine.params_changed()
 
     def _prepare_logfile_and_summary(self):
         self.train_writer = self.val_writer = None
@@ -286,24 +337,29 @@ class TrainerController:
                     message += f' Benchmark loss: {q[0]:.5f} ({q[1]:.1f} %)'
                     log_line += f', {q[0]:.7f}, {q[1]:.2f}%, {q[2]:.7f}, {q[3]:.7f}'
             print(message)
-            utility.log_to_file(self.logfile, log_line + "\n")
+            self._log(log_line + "\n")
         hrs, mins, secs = utility.calculate_time_elapsed(start_time)
         message = (f"\nTraining {self.network_name} completed! - name: {self.unique_model_name}"
                    f"\nTotal training time: {hrs} hrs {mins} mins {secs} secs."
                    f"\nFinished at {time.ctime()}\n==================== END TRAINING =================")
-        utility.log_to_file(self.logfile, message)
+        self._log(message)
         print(message)
 
     # ---- checkpoints (TrainerController.py:347-394) -------------------------------------------------
     def save_latest_model(self, epoch):
         if epoch > 0 and epoch % 10 == 0:
-            self.model.save(f'{self.model_path}-latest.h5')
-            print(f'Saving current model - {time.ctime()}\n')
+            if parallel.is_main():
+                self.model.save(f'{self.model_path}-latest.h5')
+                print(f'Saving current model - {time.ctime()}\n')
+            parallel.barrier()
 
     def save_best_model(self):
-        self.model.save(f'{self.model_path}-best.h5')
-        with open(f'{self.model_dir}/optimizer.pkl', 'wb') as f:
-            pickle.dump(self.optimizer.weights, f)
+        """Rank 0 writes (weights are identical on every rank after the all-reduced Adam step); the others wait."""
+        if parallel.is_main():
+            self.model.save(f'{self.model_path}-best.h5')
+            with open(f'{self.model_dir}/optimizer.pkl', 'wb') as f:
+                pickle.dump(self.optimizer.weights, f)
+        parallel.barrier()
 
     def restore_model(self, old_model_dir, old_model_file):
         with open(f"{old_model_dir}/optimizer.pkl", 'rb') as f:

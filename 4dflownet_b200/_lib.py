@@ -14,6 +14,7 @@ OPT_CONV_IMPL, OPT_SAVE_ACTS, OPT_PROFILE, OPT_FUSED_DGRAD, OPT_DGRAD_SINGLE, OP
 PROF_CLASSES = ("conv64_fwd_lr", "conv64_fwd_hr", "conv64_dgrad_lr", "conv64_dgrad_hr", "conv64_wgrad_lr",
                 "conv64_wgrad_hr")
 CONV_AUTO, CONV_SIMT, CONV_TCGEN05 = 0, 1, 2
+METRIC_TAIL = 4096     # SR4D_METRIC_TAIL
 
 ERRNAMES = {EINVAL: "SR4D_EINVAL", ENODEVICE: "SR4D_ENODEVICE", ECUDA: "SR4D_ECUDA",
             ENOMEM: "SR4D_ENOMEM", ESTATE: "SR4D_ESTATE"}
@@ -45,7 +46,11 @@ SYMBOLS = {
     "sr4d_forward": (C.c_int, [_P] + [_P] * 6 + [_P, C.c_int, _P]),
     "sr4d_loss_metrics": (C.c_int, [_P] + [_P] * 5 + [C.c_int, _P, _P]),
     "sr4d_train_fwd_bwd": (C.c_int, [_P] + [_P] * 10 + [C.c_int, _P, _P, _P, _P]),
+    "sr4d_train_forward": (C.c_int, [_P] + [_P] * 6 + [C.c_int, _P, _P]),
+    "sr4d_train_backward": (C.c_int, [_P] + [_P] * 4 + [C.c_int, _P, _P, _P]),
     "sr4d_adam_step": (C.c_int, [_P, _F, _F, _F, _F, C.c_int64, _F, _P]),
+    "sr4d_adam_step_counted": (C.c_int, [_P, _F, _F, _F, _F, C.c_int64, _F, C.c_int, _P]),
+    "sr4d_grads_size": (C.c_int64, [_P]),
     "sr4d_stitch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _F, C.c_int, _P, _P]),
     "sr4d_conv64_layer": (C.c_int, [_P, _P, _P, _P, _P, _F, _P, C.c_int, C.c_int, C.c_int, _P]),
     "sr4d_upsample_layer": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),

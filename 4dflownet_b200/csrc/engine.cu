@@ -88,6 +88,7 @@ struct sr4d_handle {
     int dgrad_single = 0;      // SR4D_OPT_DGRAD_SINGLE
     int wgrad_single = 0;      // SR4D_OPT_WGRAD_SINGLE
     bool have_fwd_state = false;
+    int fwd_batch = 0;         // batch of the forward whose activations are saved
     int64_t launches = 0;
     // per-kernel-class device timing (SR4D_OPT_PROFILE): event pairs on the launch stream
     int profile = 0;
@@ -377,7 +378,8 @@ int forward_impl(sr4d_t* h, const float* u, const float* v, const float* w, cons
     }
     CK(h, launch_head_out(hd[0], hd[1], hd[2], W(h, li + 1), W(h, li + 3), W(h, li + 5), Bv(h, li + 1),
                           Bv(h, li + 3), Bv(h, li + 5), out, s), 1);                     // :40,43,46,49
-    h->have_fwd_state = h->training != 0;
+    h->have_fwd_state = h->training != 0 && out == h->pred;   // backward differentiates h->pred
+    h->fwd_batch = B;
     return SR4D_OK;
 }
 
@@ -664,8 +666,8 @@ int sr4d_create(sr4d_t** out, int patch_size, int res_increase, int low_resblock
             if (tc_alloc_weights(&h->tcw, (int)h->layers.size()) != cudaSuccess) { rc = SR4D_ENOMEM; break; }
         }
         if (training) {
-            if (dmalloc(&h->grads, h->flat) || dmalloc(&h->m, h->flat) || dmalloc(&h->v, h->flat)) { rc = SR4D_ENOMEM; break; }
-            cudaMemset(h->grads, 0, h->flat * sizeof(float));
+            if (dmalloc(&h->grads, h->flat + SR4D_METRIC_TAIL) || dmalloc(&h->m, h->flat) || dmalloc(&h->v, h->flat)) { rc = SR4D_ENOMEM; break; }
+            cudaMemset(h->grads, 0, (h->flat + SR4D_METRIC_TAIL) * sizeof(float));
             cudaMemset(h->m, 0, h->flat * sizeof(float));
             cudaMemset(h->v, 0, h->flat * sizeof(float));
             const size_t g4l = (size_t)h->maxB * (h->P + 4) * (h->P + 4) * (h->P + 4) * 64;
@@ -763,6 +765,7 @@ int sr4d_get_option(const sr4d_t* h, int option, int* value) {
 
 int64_t sr4d_param_count(const sr4d_t* h) { return h ? h->nparam : 0; }
 int64_t sr4d_flat_size(const sr4d_t* h) { return h ? h->flat : 0; }
+int64_t sr4d_grads_size(const sr4d_t* h) { return h && h->training ? h->flat + SR4D_METRIC_TAIL : 0; }
 int sr4d_num_tensors(const sr4d_t* h) { return h ? (int)h->table.size() : 0; }
 int sr4d_param_table(const sr4d_t* h, sr4d_tensor_desc* out, int capacity) {
     if (!h || !out) return SR4D_EINVAL;
@@ -813,19 +816,58 @@ int sr4d_train_fwd_bwd(sr4d_t* h, const float* u, const float* v, const float* w
     return backward_impl(h, hu, hv, hw, mask, B, per_sample, l2_out, s);
 }
 
-int sr4d_adam_step(sr4d_t* h, float lr, float beta1, float beta2, float eps, int64_t t, float l2_grad_scale,
-                   void* stream) {
-    if (!h) return SR4D_EINVAL;
+int sr4d_train_forward(sr4d_t* h, const float* u, const float* v, const float* w, const float* um, const float* vm,
+                       const float* wm, int B, float* pred_out, void* stream) {
+    if (!h || !u || !v || !w || !um || !vm || !wm) return fail(h, SR4D_EINVAL, "null argument");
+    if (!h->training) return fail(h, SR4D_ESTATE, "handle was not created for training");
+    cudaSetDevice(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = forward_impl(h, u, v, w, um, vm, wm, h->pred, B, s);
+    if (rc) return rc;
+    if (pred_out)
+        CK(h, cudaMemcpyAsync(pred_out, h->pred, (size_t)B * h->H * h->H * h->H * 3 * sizeof(float),
+                              cudaMemcpyDeviceToDevice, s), 0);
+    return SR4D_OK;
+}
+
+int sr4d_train_backward(sr4d_t* h, const float* hu, const float* hv, const float* hw, const float* mask, int B,
+                        float* per_sample, float* l2_out, void* stream) {
+    if (!h || !hu || !hv || !hw || !mask || !per_sample) return fail(h, SR4D_EINVAL, "null argument");
+    if (!h->training) return fail(h, SR4D_ESTATE, "handle was not created for training");
+    if (!h->have_fwd_state || h->fwd_batch != B)
+        return fail(h, SR4D_ESTATE, "sr4d_train_backward needs a preceding sr4d_train_forward of the same batch");
+    cudaSetDevice(h->device);
+    int rc = ensure_tc_weights(h, (cudaStream_t)stream);   // the forward may have run with the SIMT kernels
+    if (rc) return rc;
+    return backward_impl(h, hu, hv, hw, mask, B, per_sample, l2_out, (cudaStream_t)stream);
+}
+
+static int adam_impl(sr4d_t* h, float lr, float beta1, float beta2, float eps, int64_t t, float l2_grad_scale,
+                     const float* count_dev, cudaStream_t s) {
     if (!h->training) return fail(h, SR4D_ESTATE, "handle was not created for training");
     if (t < 1) return fail(h, SR4D_EINVAL, "t must be >= 1 (iterations + 1)");
     cudaSetDevice(h->device);
-    cudaStream_t s = (cudaStream_t)stream;
     const double alpha = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)t)) /
                          (1.0 - std::pow((double)beta1, (double)t));
     CK(h, launch_adam(h->params, h->grads, h->m, h->v, h->kflag, h->flat, (float)alpha, beta1, beta2, eps,
-                      l2_grad_scale, s), 1);
+                      l2_grad_scale, count_dev, s), 1);
     h->tcw_dirty = true;
     return ensure_tc_weights(h, s);
+}
+
+int sr4d_adam_step(sr4d_t* h, float lr, float beta1, float beta2, float eps, int64_t t, float l2_grad_scale,
+                   void* stream) {
+    if (!h) return SR4D_EINVAL;
+    return adam_impl(h, lr, beta1, beta2, eps, t, l2_grad_scale, nullptr, (cudaStream_t)stream);
+}
+
+int sr4d_adam_step_counted(sr4d_t* h, float lr, float beta1, float beta2, float eps, int64_t t,
+                           float l2_grad_per_sample, int tail_index, void* stream) {
+    if (!h) return SR4D_EINVAL;
+    if (tail_index < 0 || tail_index >= SR4D_METRIC_TAIL) return fail(h, SR4D_EINVAL, "tail_index out of range");
+    if (!h->training) return fail(h, SR4D_ESTATE, "handle was not created for training");
+    return adam_impl(h, lr, beta1, beta2, eps, t, l2_grad_per_sample, h->grads + h->flat + tail_index,
+                     (cudaStream_t)stream);
 }
 
 int sr4d_stitch(sr4d_t* h, const float* pred, int nx, int ny, int nz, int side_pad_hr, int VX, int VY, int VZ,

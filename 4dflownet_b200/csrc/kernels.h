@@ -60,7 +60,8 @@ cudaError_t launch_loss_grad(const float* pred, const float* hu, const float* hv
 cudaError_t launch_sumsq(const float* p, const unsigned char* kflag, int64_t n, double* partial, int nblk,
                          float coeff, float* out, cudaStream_t s);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, const unsigned char* kflag, int64_t n,
-                        float alpha, float beta1, float beta2, float eps, float l2_scale, cudaStream_t s);
+                        float alpha, float beta1, float beta2, float eps, float l2_scale, const float* count_dev,
+                        cudaStream_t s);
 cudaError_t launch_stitch(const float* pred, int nx, int ny, int nz, int H, int crop, int VX, int VY, int VZ,
                           float venc, int round_small, float* vol, cudaStream_t s);
 

@@ -118,9 +118,12 @@ __global__ void sumsq_final_kernel(const double* __restrict__ partial, int nblk,
 // ---- Keras Adam (ResourceApplyAdam): TrainerController.py:73,225 ----------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, const unsigned char* __restrict__ kflag, int64_t n4, float alpha,
-                            float beta1, float beta2, float eps, float l2s) {
+                            float beta1, float beta2, float eps, float l2s, const float* __restrict__ count) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
+    // data parallel: l2s is the regulariser gradient PER SAMPLE and *count the global batch size the all-reduce
+    // left in the gradient buffer's metric tail (no host round trip for ragged shards)
+    if (count) l2s *= *count;
     float4 pp = reinterpret_cast<float4*>(p)[i];
     float4 gg = reinterpret_cast<const float4*>(g)[i];
     float4 mm = reinterpret_cast<float4*>(m)[i];
@@ -185,9 +188,10 @@ cudaError_t launch_sumsq(const float* p, const unsigned char* kflag, int64_t n, 
     return cudaGetLastError();
 }
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, const unsigned char* kflag, int64_t n,
-                        float alpha, float beta1, float beta2, float eps, float l2_scale, cudaStream_t s) {
+                        float alpha, float beta1, float beta2, float eps, float l2_scale, const float* count_dev,
+                        cudaStream_t s) {
     int64_t n4 = n / 4;   // flat size is a multiple of 32 floats
-    adam_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(p, g, m, v, kflag, n4, alpha, beta1, beta2, eps, l2_scale);
+    adam_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(p, g, m, v, kflag, n4, alpha, beta1, beta2, eps, l2_scale, count_dev);
     return cudaGetLastError();
 }
 cudaError_t launch_stitch(const float* pred, int nx, int ny, int nz, int H, int crop, int VX, int VY, int VZ,

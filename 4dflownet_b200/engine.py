@@ -55,7 +55,12 @@ class Engine:
         with torch.cuda.device(self.device):
             self.params = torch.as_tensor(_DevArray(self.lib.sr4d_params(h), self.flat_size, self), device=self.device)
             if self.training:
-                self.grads = torch.as_tensor(_DevArray(self.lib.sr4d_grads(h), self.flat_size, self), device=self.device)
+                # gradients + metric tail (include/sr4d.h SR4D_METRIC_TAIL): `grads_full` is what the data-parallel
+                # all-reduce operates on, `grads` the flat_size gradient floats, `grad_tail` the caller-owned tail
+                gsz = int(self.lib.sr4d_grads_size(h))
+                self.grads_full = torch.as_tensor(_DevArray(self.lib.sr4d_grads(h), gsz, self), device=self.device)
+                self.grads = self.grads_full[:self.flat_size]
+                self.grad_tail = self.grads_full[self.flat_size:]
                 self.adam_m = torch.as_tensor(_DevArray(self.lib.sr4d_adam_m(h), self.flat_size, self), device=self.device)
                 self.adam_v = torch.as_tensor(_DevArray(self.lib.sr4d_adam_v(h), self.flat_size, self), device=self.device)
 
@@ -143,28 +148,33 @@ class Engine:
         self._check(rc, "sr4d_forward")
         return out
 
-    def loss_metrics(self, pred, hr_u, hr_v, hr_w, mask):
+    def loss_metrics(self, pred, hr_u, hr_v, hr_w, mask, per_out=None):
         H = self.H
         pred = self._dev(pred).reshape(-1, H, H, H, 3)
         B = pred.shape[0]
         t = [self._dev(a).reshape(B, H, H, H) for a in (hr_u, hr_v, hr_w, mask)]
-        per = torch.empty((B, 4), device=self.device, dtype=torch.float32)
+        per = torch.empty((B, 4), device=self.device, dtype=torch.float32) if per_out is None else per_out
+        if tuple(per.shape) != (B, 4) or not per.is_contiguous():
+            raise ValueError("per_out must be a contiguous (B,4) tensor")
         with torch.cuda.device(self.device):
             rc = self.lib.sr4d_loss_metrics(self._h, C.c_void_p(pred.data_ptr()), *[C.c_void_p(x.data_ptr()) for x in t],
                                             B, C.c_void_p(per.data_ptr()), _stream_ptr(self.device))
         self._check(rc, "sr4d_loss_metrics")
         return per
 
-    def train_fwd_bwd(self, inputs, hr, mask, want_pred=False):
+    def train_fwd_bwd(self, inputs, hr, mask, want_pred=False, per_out=None, l2_out=None):
         """Returns (per_sample (B,4) [loss, mse, rel_err%, sum mask], l2 (1,), pred or None);
-        gradients (sum over the batch, no L2 term) are left in self.grads."""
+        gradients (sum over the batch, no L2 term) are left in self.grads.  per_out / l2_out: optional
+        preallocated device tensors (e.g. views into self.grad_tail) that receive the metrics."""
         P, H = self.patch_size, self.H
         xs = [self._dev(a).reshape(-1, P, P, P) for a in inputs]
         B = xs[0].shape[0]
         ys = [self._dev(a).reshape(B, H, H, H) for a in hr]
         mk = self._dev(mask).reshape(B, H, H, H)
-        per = torch.empty((B, 4), device=self.device, dtype=torch.float32)
-        l2 = torch.empty((1,), device=self.device, dtype=torch.float32)
+        per = torch.empty((B, 4), device=self.device, dtype=torch.float32) if per_out is None else per_out
+        l2 = torch.empty((1,), device=self.device, dtype=torch.float32) if l2_out is None else l2_out
+        if tuple(per.shape) != (B, 4) or not per.is_contiguous() or l2.numel() != 1:
+            raise ValueError("per_out must be a contiguous (B,4) tensor and l2_out a single float")
         pred = torch.empty((B, H, H, H, 3), device=self.device, dtype=torch.float32) if want_pred else None
         with torch.cuda.device(self.device):
             rc = self.lib.sr4d_train_fwd_bwd(
@@ -174,11 +184,46 @@ class Engine:
         self._check(rc, "sr4d_train_fwd_bwd")
         return per, l2, pred
 
+    def train_forward(self, inputs, want_pred=False):
+        """First half of train_fwd_bwd (the taped forward, TrainerController.py:213-217)."""
+        P, H = self.patch_size, self.H
+        xs = [self._dev(a).reshape(-1, P, P, P) for a in inputs]
+        B = xs[0].shape[0]
+        pred = torch.empty((B, H, H, H, 3), device=self.device, dtype=torch.float32) if want_pred else None
+        with torch.cuda.device(self.device):
+            rc = self.lib.sr4d_train_forward(self._h, *[C.c_void_p(x.data_ptr()) for x in xs], B,
+                                             C.c_void_p(pred.data_ptr()) if want_pred else None,
+                                             _stream_ptr(self.device))
+        self._check(rc, "sr4d_train_forward")
+        return pred
+
+    def train_backward(self, hr, mask):
+        """Second half (loss + tape.gradient, TrainerController.py:218-223) on the activations train_forward saved."""
+        H = self.H
+        mk = self._dev(mask).reshape(-1, H, H, H)
+        B = mk.shape[0]
+        ys = [self._dev(a).reshape(B, H, H, H) for a in hr]
+        per = torch.empty((B, 4), device=self.device, dtype=torch.float32)
+        l2 = torch.empty((1,), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.sr4d_train_backward(self._h, *[C.c_void_p(y.data_ptr()) for y in ys],
+                                              C.c_void_p(mk.data_ptr()), B, C.c_void_p(per.data_ptr()),
+                                              C.c_void_p(l2.data_ptr()), _stream_ptr(self.device))
+        self._check(rc, "sr4d_train_backward")
+        return per, l2
+
     def adam_step(self, lr, t, l2_grad_scale, beta1=0.9, beta2=0.999, eps=1e-7):
         with torch.cuda.device(self.device):
             rc = self.lib.sr4d_adam_step(self._h, lr, beta1, beta2, eps, int(t), float(l2_grad_scale),
                                          _stream_ptr(self.device))
         self._check(rc, "sr4d_adam_step")
+
+    def adam_step_counted(self, lr, t, l2_grad_per_sample, tail_index, beta1=0.9, beta2=0.999, eps=1e-7):
+        """Adam with the regulariser scale l2_grad_per_sample * grad_tail[tail_index] read on the device."""
+        with torch.cuda.device(self.device):
+            rc = self.lib.sr4d_adam_step_counted(self._h, lr, beta1, beta2, eps, int(t), float(l2_grad_per_sample),
+                                                 int(tail_index), _stream_ptr(self.device))
+        self._check(rc, "sr4d_adam_step_counted")
 
     def stitch(self, pred, nr, vol_shape, side_pad_hr, venc, round_small=True):
         H = self.H

@@ -10,8 +10,44 @@ The path shards on the patch / batch axis and nothing else:
     embarrassingly parallel), results are gathered for the unchanged stitcher.
 Everything here works on CPU tensors with the gloo backend too (tests/test_parallel_gloo.py).
 """
+import numpy as np
 import torch
 import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Join the process group `torchrun` describes (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*), once; returns the
+    local device index this rank must use.  Without WORLD_SIZE > 1 in the environment nothing is initialised and the
+    current CUDA device (or 0) is returned, so the single-process entry points behave as before.  backend: "nccl"
+    when CUDA is available, else "gloo" (CPU tests)."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cuda = torch.cuda.is_available()
+    if cuda:
+        torch.cuda.set_device(local)
+    if world > 1 and not initialized():
+        backend = backend or ("nccl" if cuda else "gloo")
+        kwargs = {"device_id": torch.device("cuda", local)} if backend == "nccl" else {}
+        dist.init_process_group(backend, **kwargs)
+    return local
+
+
+def is_main():
+    """Rank 0 owns every file the run writes (model directory, loss.csv, checkpoints, quicksave, results)."""
+    return rank() == 0
+
+
+def barrier():
+    if world_size() > 1:
+        dist.barrier()
+
+
+def broadcast_(tensor, src=0):
+    """In-place broadcast from `src` (initial weights / restored checkpoints must be identical on every rank)."""
+    if world_size() > 1:
+        dist.broadcast(tensor, src)
+    return tensor
 
 
 def initialized():
@@ -48,6 +84,71 @@ def allreduce_gradients(flat_grads):
     if world_size() > 1:
         dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
     return flat_grads
+
+
+class MetricTail:
+    """The caller-owned floats behind the flat gradients (include/sr4d.h SR4D_METRIC_TAIL), laid out so that the
+    step's ONE all-reduce(SUM) of `engine.grads_full` also gathers the metrics (SURVEY 8e "+ metric tail"):
+
+        slot r = [count_r, l2_r, per_sample rows of rank r (max_batch x 4)]   for r < world
+        last float = sum over ranks of the local batch sizes (the global batch Adam's L2 term needs,
+                     TrainerController.py:249; read on the device by sr4d_adam_step_counted)
+
+    Every rank zeroes the tail and fills only its own slot, so the SUM is a gather.  Works on CPU tensors (gloo
+    tests) and on the engine's device view alike."""
+
+    def __init__(self, tail, max_batch, rank_=None, world=None):
+        self.tail = tail
+        self.rank = rank() if rank_ is None else int(rank_)
+        self.world = world_size() if world is None else int(world)
+        self.max_batch = int(max_batch)
+        self.slot = 2 + 4 * self.max_batch
+        if self.world * self.slot + 1 > tail.numel():
+            raise ValueError(f"metric tail of {tail.numel()} floats cannot hold {self.world} ranks x {self.max_batch} samples")
+        self.count_index = tail.numel() - 1
+        self._template = torch.zeros_like(tail)
+        self._template_batch = None
+        self._host = torch.empty(tail.numel(), dtype=tail.dtype)
+        if tail.is_cuda:
+            self._host = self._host.pin_memory()
+
+    def begin(self, local_batch):
+        """Reset the tail for a step of `local_batch` samples on this rank; returns the (B,4) per-sample view and the
+        (1,) l2 view the engine writes its metrics into."""
+        B = int(local_batch)
+        if B > self.max_batch:
+            raise ValueError(f"local batch {B} exceeds the tail slot ({self.max_batch})")
+        if B != self._template_batch:
+            t = torch.zeros(self.tail.numel(), dtype=self.tail.dtype)
+            t[self.rank * self.slot] = B
+            t[self.count_index] = B
+            self._template.copy_(t)
+            self._template_batch = B
+        self.tail.copy_(self._template)
+        base = self.rank * self.slot
+        return self.tail[base + 2:base + 2 + 4 * B].view(B, 4), self.tail[base + 1:base + 2]
+
+    def exchange(self):
+        """All-reduce of the tail alone (validation steps, which move no gradients)."""
+        if self.world > 1:
+            dist.all_reduce(self.tail, op=dist.ReduceOp.SUM)
+
+    def read(self):
+        """After the all-reduce: ((B_global,4) per-sample metrics in rank order == global batch order, l2, B_global).
+        One small device->host copy and one stream synchronisation -- the step's only host round trip."""
+        n_used = self.world * self.slot
+        self._host[:n_used].copy_(self.tail[:n_used], non_blocking=True)
+        self._host[self.count_index:].copy_(self.tail[self.count_index:], non_blocking=True)
+        if self.tail.is_cuda:
+            torch.cuda.current_stream(self.tail.device).synchronize()
+        h = self._host.numpy()
+        rows = []
+        for r in range(self.world):
+            base = r * self.slot
+            n = int(round(float(h[base])))
+            rows.append(h[base + 2:base + 2 + 4 * n].reshape(n, 4))
+        per = np.concatenate(rows, axis=0).copy()
+        return per, float(h[self.rank * self.slot + 1]), int(round(float(h[self.count_index])))
 
 
 def l2_grad_scale(local_batch, l2_coeff=5e-7):

@@ -76,15 +76,19 @@ def main(data_dir="../data", filename="example_data.h5", output_dir="../result",
          round_small_values=True, low_resblock=8, hi_resblock=4):
     from .utils.ImageDataset import ImageDataset
     from .utils import prediction_utils
+    from . import parallel
+    local_device = parallel.init_from_env()      # under torchrun: one rank per GPU, patch list sharded per rank
     input_filepath = f"{data_dir}/{filename}"
     pgen = PatchGenerator(patch_size, res_increase)
     dataset = ImageDataset()
     nr_rows = dataset.get_dataset_len(input_filepath)
     print(f"Number of rows in dataset: {nr_rows}")
     print(f"Loading 4DFlowNet: {res_increase}x upsample")
-    network = prepare_network(patch_size, res_increase, low_resblock, hi_resblock, max_batch=batch_size)
+    network = prepare_network(patch_size, res_increase, low_resblock, hi_resblock, max_batch=batch_size,
+                              device=local_device)
     network.load_weights(model_path)
-    os.makedirs(output_dir, exist_ok=True)
+    if parallel.is_main():
+        os.makedirs(output_dir, exist_ok=True)
     for nrow in range(nr_rows):
         print(f"\nProcessed ({nrow + 1}/{nr_rows}) - {time.ctime()}")
         dataset.load_vectorfield(input_filepath, nrow)

@@ -5,7 +5,9 @@ benchmark set in file order so the first batch can be re-predicted after every b
 TrainerController with the reference's positional arguments, optionally restore, train.  Under `torchrun` every
 rank runs this function: all ranks draw the same global batches (same shuffle seed), each loads only the rows of its
 contiguous shard (the `shard=` argument of `initialize_dataset`, equal to `parallel.shard_batch` of the global batch)
-and the controller all-reduces the flat gradient buffer once per step."""
+and the controller all-reduces the flat gradient buffer once per step.  `main` joins the process group itself
+(`parallel.init_from_env`), binds the rank to its LOCAL_RANK device, broadcasts rank 0's initial (or restored) weights
+and optimizer state, and lets only rank 0 write the model directory."""
 import numpy as np
 
 from . import parallel
@@ -35,6 +37,7 @@ def main(data_dir='../data', training_file=None, validate_file=None, benchmark_f
          restore=False, model_dir="../models/4DFlowNet", model_file="4DFlowNet-best.h5",
          initial_learning_rate=2e-4, epochs=60, batch_size=20, mask_threshold=0.6, network_name='4DFlowNet',
          patch_size=16, res_increase=2, low_resblock=8, hi_resblock=4, models_root="../models", seed=0):
+    local_device = parallel.init_from_env()
     ranks = parallel.world_size()
     if batch_size % ranks:
         raise ValueError(f"batch_size {batch_size} must be a multiple of the number of ranks {ranks}")
@@ -51,12 +54,14 @@ def main(data_dir='../data', training_file=None, validate_file=None, benchmark_f
 
     print(f"4DFlowNet Patch {patch_size}, lr {initial_learning_rate}, batch {batch_size}")
     controller = TrainerController(patch_size, res_increase, initial_learning_rate, QUICKSAVE, network_name,
-                                   low_resblock, hi_resblock, max_batch=max(1, batch_size // ranks))
+                                   low_resblock, hi_resblock, max_batch=max(1, batch_size // ranks),
+                                   device=local_device)
     controller.init_model_dir(models_root)
     if restore:
         print(f"Restoring model {model_file}...")
         controller.restore_model(model_dir, model_file)
         print("Learning rate", controller.optimizer.lr.numpy())
+    controller.sync_ranks()          # rank 0's weights / Adam state everywhere (no-op in a single process)
     controller.train_network(train_batches, val_batches, n_epoch=epochs, testset=bench_batches)
     return controller
 

@@ -101,7 +101,13 @@ int64_t sr4d_flat_size(const sr4d_t* h);          /* floats in the padded flat b
 int     sr4d_num_tensors(const sr4d_t* h);        /* 48 for 8/4 */
 int     sr4d_param_table(const sr4d_t* h, sr4d_tensor_desc* out, int capacity);
 float*  sr4d_params(sr4d_t* h);                   /* borrowed device pointers, flat_size floats */
-float*  sr4d_grads(sr4d_t* h);                    /* NULL unless training */
+float*  sr4d_grads(sr4d_t* h);                    /* NULL unless training; sr4d_grads_size() floats */
+/* The gradient buffer is flat_size floats of gradients followed by a SR4D_METRIC_TAIL-float "metric tail" the
+ * engine never touches: the data-parallel caller points per_sample / l2_out of sr4d_train_fwd_bwd into its
+ * rank's slot of the tail, so ONE all-reduce(SUM) of the whole buffer moves the gradients and gathers the
+ * per-sample metrics and the global sample count ("13.37 MB + metric tail"). */
+#define SR4D_METRIC_TAIL 4096
+int64_t sr4d_grads_size(const sr4d_t* h);         /* flat_size + SR4D_METRIC_TAIL (0 unless training) */
 float*  sr4d_adam_m(sr4d_t* h);
 float*  sr4d_adam_v(sr4d_t* h);
 /* must be called after the caller wrote into sr4d_params() so derived weight images
@@ -133,12 +139,29 @@ int  sr4d_train_fwd_bwd(sr4d_t* h, const float* u, const float* v, const float* 
                         const float* mask, int B, float* per_sample, float* l2_out,
                         float* pred_out, void* stream);
 
+/* The two halves of sr4d_train_fwd_bwd as separate calls: `with tf.GradientTape() as tape: predictions =
+ * self.model(inputs, training=True)` (TrainerController.py:213-217) and `loss ...; tape.gradient`
+ * (TrainerController.py:218-223).  sr4d_train_backward differentiates the activations the last
+ * sr4d_train_forward of the same batch saved; options (e.g. SR4D_OPT_CONV_IMPL) may change in between, which
+ * is how the parity tests feed the tensor-core backward the fp32 SIMT forward's activations. */
+int  sr4d_train_forward(sr4d_t* h, const float* u, const float* v, const float* w,
+                        const float* u_mag, const float* v_mag, const float* w_mag, int B,
+                        float* pred_out, void* stream);
+int  sr4d_train_backward(sr4d_t* h, const float* hr_u, const float* hr_v, const float* hr_w,
+                         const float* mask, int B, float* per_sample, float* l2_out, void* stream);
+
 /* Keras Adam (TrainerController.py:73,225): t = iterations+1;
  * g = grad + l2_grad_scale * w on kernels only (l2_grad_scale = B_global * 2 * 5e-7, the
  * gradient of the regulariser added to each of the B_global loss entries,
  * TrainerController.py:249). */
 int  sr4d_adam_step(sr4d_t* h, float lr, float beta1, float beta2, float eps, int64_t t,
                     float l2_grad_scale, void* stream);
+
+/* Same step with the regulariser scale taken from the device: g = grad + l2_grad_per_sample * tail[tail_index] * w,
+ * where tail[tail_index] is a float in the metric tail of sr4d_grads() (the all-reduced global batch size), so
+ * ragged data-parallel shards need no host synchronisation between the all-reduce and Adam. */
+int  sr4d_adam_step_counted(sr4d_t* h, float lr, float beta1, float beta2, float eps, int64_t t,
+                            float l2_grad_per_sample, int tail_index, void* stream);
 
 /* ---- inference post-processing: PatchGenerator._patchup_with_overlap + predictor.py:99-107
  * Crops side_pad*r voxels per side of every predicted patch, scatters component c into

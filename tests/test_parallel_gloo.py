@@ -106,6 +106,40 @@ def _ragged_gather(rank, world):
         assert torch.equal(only0, full)
 
 
+def _metric_tail_one_collective(rank, world):
+    """The layout TrainerController.train_step uses: [flat gradients | metric tail] all-reduced ONCE; the SUM gathers
+    every rank's per-sample rows, its l2 value and the global sample count (ragged shards: 3 + 2 samples)."""
+    par = _par()
+    flat_n, tail_n, max_b, n = 40, 4096, 3, 5
+    lo, hi = par.shard_bounds(n)
+    full = torch.arange(n * 4, dtype=torch.float32).reshape(n, 4) + 0.25
+    buf = torch.full((flat_n + tail_n,), float("nan"))
+    buf[:flat_n] = float(rank + 1)                                   # "gradients" of this rank
+    tail = par.MetricTail(buf[flat_n:], max_b)
+    for rep in range(2):                                             # second pass: the tail is reset, not accumulated
+        buf[:flat_n] = float(rank + 1)
+        per, l2 = tail.begin(hi - lo)
+        per.copy_(full[lo:hi])
+        l2.fill_(0.5)
+        par.allreduce_gradients(buf)                                 # the step's one collective
+        assert torch.equal(buf[:flat_n], torch.full((flat_n,), float(sum(range(1, world + 1)))))
+        assert float(buf[flat_n + tail.count_index]) == n            # what sr4d_adam_step_counted reads
+        got, l2v, cnt = tail.read()
+        assert cnt == n and l2v == 0.5
+        np.testing.assert_array_equal(got, full.numpy())
+    # validation steps exchange the tail alone
+    per, _ = tail.begin(hi - lo)
+    per.copy_(full[lo:hi] * 2)
+    tail.exchange()
+    np.testing.assert_array_equal(tail.read()[0], full.numpy() * 2)
+    with pytest.raises(ValueError):
+        par.MetricTail(torch.zeros(64), 16)                          # 2 ranks x 16 samples do not fit 64 floats
+
+
+def test_metric_tail_single_collective():
+    _run("_metric_tail_one_collective")
+
+
 def test_dp_allreduce_reproduces_full_batch_gradient():
     _run("_dp_gradient_identity")
 
