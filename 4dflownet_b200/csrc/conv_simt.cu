@@ -9,6 +9,7 @@
 // brick and the 27x8x64 weight slab of one 8-channel K chunk are staged in shared
 // memory; each of the 256 threads owns 4 z-consecutive voxels x 8 output channels.
 #include "kernels.h"
+#include "tc_host.h"
 
 namespace {
 constexpr int TX = 2, TY = 8, TZ = 8, CK = 8;
@@ -148,13 +149,8 @@ __global__ void __launch_bounds__(256, 2) conv64_simt_kernel(Conv64Args a) {
 
 template <bool IN_ACT, bool OUT_ACT>
 cudaError_t launch_t(const Conv64Args& a, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv64_simt_kernel<IN_ACT, OUT_ACT>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(conv64_simt_kernel<IN_ACT, OUT_ACT>), SMEM_BYTES);
+    if (ea != cudaSuccess) return ea;
     dim3 grid((a.Do + TZ - 1) / TZ, (a.Do + TY - 1) / TY, ((a.Do + TX - 1) / TX) * a.B);
     conv64_simt_kernel<IN_ACT, OUT_ACT><<<grid, 256, SMEM_BYTES, s>>>(a);
     return cudaGetLastError();

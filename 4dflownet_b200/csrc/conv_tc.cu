@@ -37,6 +37,7 @@
 #include <vector>
 
 #include "conv_tc.h"
+#include "tc_host.h"
 #include "tc_ptx.cuh"
 
 namespace {
@@ -585,62 +586,16 @@ __global__ void __launch_bounds__(256) weight_gain_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-// 5-D map over the packed [2B][Dp][Dp][Dp][64] fp16 planes of an Act (hi planes then lo planes)
-bool make_xmap(CUtensorMap* map, const __half* base, int B, int Dp, int ty2, int tz2) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) return false;
-    cuuint64_t dims[5] = {64, (cuuint64_t)Dp, (cuuint64_t)Dp, (cuuint64_t)Dp, (cuuint64_t)(2 * B)};
-    cuuint64_t strides[4] = {128, (cuuint64_t)128 * Dp, (cuuint64_t)128 * Dp * Dp, (cuuint64_t)128 * Dp * Dp * Dp};
-    cuuint32_t box[5] = {64, (cuuint32_t)tz2, (cuuint32_t)ty2, 1, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS;
-}
-
-int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return n;
-}
-
 template <int TY>
 cudaError_t launch_cfg(const CUtensorMap& map, KParams p, cudaStream_t s) {
     using C = Cfg<TY>;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv64_tc_kernel<TY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             C::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
+    cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(conv64_tc_kernel<TY>), C::SMEM_BYTES);
+    if (ea != cudaSuccess) return ea;
     p.nyt = (p.Do + TY - 1) / TY;
     p.nzt = (p.Do + TZ - 1) / TZ;
     p.ntiles = p.B * p.nx * p.nyt * p.nzt;
-    int grid = p.ntiles < num_sms() ? p.ntiles : num_sms();
+    const int sms = tc_num_sms();
+    int grid = p.ntiles < sms ? p.ntiles : sms;
     conv64_tc_kernel<TY><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(map, p);
     return cudaGetLastError();
 }
@@ -652,8 +607,6 @@ struct TcWeights {
     __half* img = nullptr;   // [nlayers][2 (fwd, dgrad)][27*128*64]
     float* gain = nullptr;   // [nlayers] dgrad gain bound (weight_gain_kernel)
 };
-
-bool tc_available() { return true; }
 
 cudaError_t tc_alloc_weights(TcWeights** w, int nlayers) {
     TcWeights* t = new TcWeights();
@@ -742,7 +695,7 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
     }
     const int ty = pick_ty(Do);
     CUtensorMap map;
-    if (!make_xmap(&map, a.in.hi, B, Dp, ty + 2, ZP)) return cudaErrorUnknown;
+    if (!tc_make_act_map(&map, a.in.hi, B, Dp, ty + 2, ZP)) return cudaErrorUnknown;
     if (a.in.lo != a.in.hi + act_plane_elems(B, a.in.D)) return cudaErrorInvalidValue;   // planes must be packed
     cudaError_t e;
     switch (ty) {

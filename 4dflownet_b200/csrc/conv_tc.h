@@ -37,7 +37,6 @@ struct TcConvArgs {
     const unsigned int* add_amax = nullptr;
 };
 
-bool tc_available();
 cudaError_t tc_alloc_weights(TcWeights** w, int nlayers);
 void tc_free_weights(TcWeights* w);
 // (re)build the operand images (forward + dgrad) of n layers in one launch: entry i is image slot layers[i],
@@ -50,9 +49,15 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s);
 bool tc_dgrad_fusable(int D);
 
 // tcgen05 weight gradient (wgrad_tc.cu): x = the layer's saved input Act (edge D), dy_split = the scaled
-// split-fp16 gradient [2B][D+4]^3[64] with device exponent *dy_exp; writes tc_wgrad_slabs() partial
+// split-fp16 gradient [2B][D+4]^3[64] with device exponent *dy_exp; writes tc_wgrad_slabs(B, D) partial
 // dW[27][64][64] into `partial` (slab-major) for a row reduction.
-int tc_wgrad_slabs();
-// single = 1 (EXPERIMENTAL, SR4D_OPT_WGRAD_SINGLE): dYhi x Xhi only.
+int tc_wgrad_slabs(int B, int D);
+// single = 1: dYhi x Xhi only, same kernel with the lo planes and the second instruction left out (kept as the
+// cross-check of tc_wgrad64_single).
 cudaError_t tc_wgrad64(ActView x, const __half* dy_split, const int* dy_exp, float* partial, cudaStream_t s,
                        int single = 0);
+// single-operand weight gradient (wgrad_tc2.cu, SR4D_OPT_WGRAD_SINGLE = 1, the default): two x-planes of dYhi stacked on
+// M against Xhi, operands re-used out of shared memory across x, accumulator chains flushed to fp32 every 384
+// accumulations; writes tc_wgrad2_slabs(B, D) partial dW[27][64][64] (slab-major) for a row reduction.
+int tc_wgrad2_slabs(int B, int D);
+cudaError_t tc_wgrad64_single(ActView x, const __half* dy_split, const int* dy_exp, float* partial, cudaStream_t s);

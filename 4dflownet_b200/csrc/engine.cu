@@ -1,6 +1,7 @@
 // libsr4d engine: owns parameters, optimizer state and workspace; sequences the kernels
 // of the 4DFlowNet SR graph (Network/SR4DFlowNet.py:7-51) forward and backward, and
 // implements the C ABI of include/sr4d.h.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -85,8 +86,8 @@ struct sr4d_handle {
     int conv_impl = SR4D_CONV_AUTO;
     int save_acts = 0;
     int fused_dgrad = 1;       // SR4D_OPT_FUSED_DGRAD
-    int dgrad_single = 0;      // SR4D_OPT_DGRAD_SINGLE
-    int wgrad_single = 0;      // SR4D_OPT_WGRAD_SINGLE
+    int dgrad_single = 1;      // SR4D_OPT_DGRAD_SINGLE
+    int wgrad_single = 1;      // SR4D_OPT_WGRAD_SINGLE
     bool have_fwd_state = false;
     int fwd_batch = 0;         // batch of the forward whose activations are saved
     int64_t launches = 0;
@@ -292,12 +293,10 @@ float* GB(sr4d_t* h, int layer) { return h->grads + h->layers[layer].b_off; }
 
 bool use_tc(sr4d_t* h, int impl_override = -1) {
     int impl = impl_override >= 0 ? impl_override : h->conv_impl;
-    if (impl == SR4D_CONV_SIMT) return false;
-    return tc_available();
+    return impl != SR4D_CONV_SIMT;
 }
 
 int ensure_tc_weights(sr4d_t* h, cudaStream_t s) {
-    if (!tc_available()) return SR4D_OK;
     if (!h->tcw_dirty) return SR4D_OK;
     std::vector<int> idx;
     std::vector<long long> off;
@@ -415,8 +414,13 @@ int conv64_wgrad(sr4d_t* h, int layer, ActView x, const GBuf& dy, bool bias, cud
     ProfScope prof(h, x.D == h->P ? SR4D_PROF_CONV64_WGRAD_LR : SR4D_PROF_CONV64_WGRAD_HR, s);
     static const bool wgrad_simt = getenv("SR4D_WGRAD_SIMT") != nullptr;   // debugging aid
     if (use_tc(h) && !wgrad_simt) {
-        CK(h, tc_wgrad64(x, dy.s, dy.exp, h->scratch, s, h->wgrad_single), 1);
-        CK(h, launch_reduce_rows(h->scratch, tc_wgrad_slabs(), 27 * 4096, GW(h, layer), s), 1);
+        if (h->wgrad_single == 1) {
+            CK(h, tc_wgrad64_single(x, dy.s, dy.exp, h->scratch, s), 1);
+            CK(h, launch_reduce_rows(h->scratch, tc_wgrad2_slabs(x.B, x.D), 27 * 4096, GW(h, layer), s), 1);
+        } else {
+            CK(h, tc_wgrad64(x, dy.s, dy.exp, h->scratch, s, h->wgrad_single == 2), 1);
+            CK(h, launch_reduce_rows(h->scratch, tc_wgrad_slabs(x.B, x.D), 27 * 4096, GW(h, layer), s), 1);
+        }
     } else {
         CK(h, launch_wgrad64_simt(x, dy.f, GW(h, layer), h->scratch, h->wgrad_chunks, s), 2);
     }
@@ -662,9 +666,7 @@ int sr4d_create(sr4d_t** out, int patch_size, int res_increase, int low_resblock
         for (auto& b : h->hr) if (b.base) cudaMemset(b.base, 0, 2 * act_plane_elems(h->maxB, b.D) * sizeof(__half));
         if (dmalloc(&h->dpartial, (size_t)64 * 5 * h->maxB + 256) || dmalloc(&h->norm, (size_t)2 * h->maxB) ||
             dmalloc(&h->per_sample_int, (size_t)4 * h->maxB)) { rc = SR4D_ENOMEM; break; }
-        if (tc_available()) {
-            if (tc_alloc_weights(&h->tcw, (int)h->layers.size()) != cudaSuccess) { rc = SR4D_ENOMEM; break; }
-        }
+        if (tc_alloc_weights(&h->tcw, (int)h->layers.size()) != cudaSuccess) { rc = SR4D_ENOMEM; break; }
         if (training) {
             if (dmalloc(&h->grads, h->flat + SR4D_METRIC_TAIL) || dmalloc(&h->m, h->flat) || dmalloc(&h->v, h->flat)) { rc = SR4D_ENOMEM; break; }
             cudaMemset(h->grads, 0, (h->flat + SR4D_METRIC_TAIL) * sizeof(float));
@@ -698,6 +700,10 @@ int sr4d_create(sr4d_t** out, int patch_size, int res_increase, int low_resblock
             bad |= dmalloc(&h->pred, (size_t)h->maxB * nvoxH * 3) != cudaSuccess;
             bad |= dmalloc(&h->gpred, (size_t)h->maxB * nvoxH * 3) != cudaSuccess;
             h->scratch_floats = (size_t)h->wgrad_chunks * 27 * 4096;
+            for (int D : {h->P, h->H}) {
+                const size_t need = (size_t)std::max(tc_wgrad_slabs(h->maxB, D), tc_wgrad2_slabs(h->maxB, D)) * 27 * 4096;
+                if (need > h->scratch_floats) h->scratch_floats = need;
+            }
             size_t need2 = (size_t)1184 * 8192 + 8192;
             if (need2 > h->scratch_floats) h->scratch_floats = need2;
             bad |= dmalloc(&h->scratch, h->scratch_floats) != cudaSuccess;
@@ -729,7 +735,6 @@ int sr4d_set_option(sr4d_t* h, int option, int value) {
     switch (option) {
         case SR4D_OPT_CONV_IMPL:
             if (value < 0 || value > 2) return fail(h, SR4D_EINVAL, "bad conv impl");
-            if (value == SR4D_CONV_TCGEN05 && !tc_available()) return fail(h, SR4D_EINVAL, "tcgen05 conv not built");
             h->conv_impl = value;
             return SR4D_OK;
         case SR4D_OPT_SAVE_ACTS:
@@ -747,7 +752,8 @@ int sr4d_set_option(sr4d_t* h, int option, int value) {
             h->dgrad_single = value != 0;
             return SR4D_OK;
         case SR4D_OPT_WGRAD_SINGLE:
-            h->wgrad_single = value != 0;
+            if (value < 0 || value > 2) return fail(h, SR4D_EINVAL, "SR4D_OPT_WGRAD_SINGLE takes 0, 1 or 2");
+            h->wgrad_single = value;
             return SR4D_OK;
     }
     return fail(h, SR4D_EINVAL, "unknown option");
@@ -898,7 +904,6 @@ int sr4d_conv64_layer(sr4d_t* h, const float* x, const float* kernel, const floa
             if (e) { rc = SR4D_ECUDA; h->err = cudaGetErrorString(e); break; }
             h->launches += residual ? 2 : 1;
             if (impl == SR4D_CONV_TCGEN05) {
-                if (!tc_available()) { rc = fail(h, SR4D_EINVAL, "tcgen05 conv not built"); break; }
                 if (tc_alloc_weights(&tw, 1) != cudaSuccess) { rc = SR4D_ENOMEM; break; }
                 { const int l0 = 0; const long long o0 = 0; e = tc_prepare_weights(tw, kernel, &l0, &o0, 1, s); }
                 TcConvArgs a;
@@ -951,7 +956,6 @@ int sr4d_conv64_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const 
                           float* dkernel, float* dbias, int B, int D, int impl, void* stream) {
     if (!h || !x || !kernel || !dy || B < 1 || D < 2) return fail(h, SR4D_EINVAL, "bad argument");
     const bool tc = impl == SR4D_CONV_TCGEN05;
-    if (tc && !tc_available()) return fail(h, SR4D_EINVAL, "tcgen05 conv not built");
     cudaStream_t s = (cudaStream_t)stream;
     ActBuf bi;
     float *g4 = nullptr, *raw = nullptr, *g4o = nullptr, *scr = nullptr, *dwb = nullptr;
@@ -962,7 +966,7 @@ int sr4d_conv64_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const 
     const int nchunk = 16;
     int rc = SR4D_OK;
     if (alloc_act(bi, B, D) || dmalloc(&g4, n4) || dmalloc(&raw, n2) || dmalloc(&g4o, n4) ||
-        dmalloc(&scr, (size_t)nchunk * 27 * 4096 + 1184 * 64) || dmalloc(&dwb, 27 * 4096 + 64) || dmalloc(&meta, 2) ||
+        dmalloc(&scr, (size_t)std::max(nchunk, std::max(tc_wgrad_slabs(B, D), tc_wgrad2_slabs(B, D))) * 27 * 4096 + 1184 * 64) || dmalloc(&dwb, 27 * 4096 + 64) || dmalloc(&meta, 2) ||
         (tc && (dmalloc(&g4s, 2 * n4) || tc_alloc_weights(&tw, 1) != cudaSuccess)))
         rc = SR4D_ENOMEM;
     if (!rc) {
@@ -980,7 +984,7 @@ int sr4d_conv64_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const 
                 if (!e) { const int l0 = 0; const long long o0 = 0; e = tc_prepare_weights(tw, kernel, &l0, &o0, 1, s); }
                 TcConvArgs a;
                 a.in.hi = g4s; a.in.lo = g4s + act_plane_elems(B, D + 2); a.in.B = B; a.in.D = D + 2;
-                a.layer = 0; a.dgrad = 1; a.out_raw = raw;
+                a.layer = 0; a.dgrad = 1; a.out_raw = raw; a.single_b = h->dgrad_single;
                 if (!e) e = tc_conv64(tw, a, s);
                 rexp = meta + 1;
                 h->launches += 3;
@@ -996,8 +1000,11 @@ int sr4d_conv64_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const 
         }
         if (!e && dkernel && tc) {
             if (!dx) e = launch_g4_split(g4, reinterpret_cast<unsigned int*>(meta), g4s, meta + 1, B, D, s);
-            if (!e) e = tc_wgrad64(vi, g4s, meta + 1, scr, s);
-            if (!e) e = launch_reduce_rows(scr, tc_wgrad_slabs(), 27 * 4096, dwb, s);
+            // the handle's SR4D_OPT_WGRAD_SINGLE picks the kernel, as in the training path
+            if (!e) e = h->wgrad_single == 1 ? tc_wgrad64_single(vi, g4s, meta + 1, scr, s)
+                                             : tc_wgrad64(vi, g4s, meta + 1, scr, s, h->wgrad_single == 2);
+            if (!e) e = launch_reduce_rows(scr, h->wgrad_single == 1 ? tc_wgrad2_slabs(B, D) : tc_wgrad_slabs(B, D),
+                                           27 * 4096, dwb, s);
             if (!e) e = cudaMemcpyAsync(dkernel, dwb, 27 * 4096 * 4, cudaMemcpyDeviceToDevice, s);
             h->launches += 3;
         } else if (!e && dkernel) {

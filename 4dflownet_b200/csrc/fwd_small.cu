@@ -2,6 +2,7 @@
 // input features, the two 3->64 stems, the 128->64 1x1 fuse, the trilinear upsample,
 // the three 64->1 output heads, and fp32 <-> Act conversions.
 #include "kernels.h"
+#include "tc_host.h"
 
 namespace {
 
@@ -419,12 +420,8 @@ cudaError_t launch_head_out(ActView h0, ActView h1, ActView h2, const float* w0,
     a.lo[0] = h0.lo; a.lo[1] = h1.lo; a.lo[2] = h2.lo;
     a.w[0] = w0; a.w[1] = w1; a.w[2] = w2;
     a.b[0] = b0; a.b[1] = b1; a.b[2] = b2;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(head_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
+    cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(head_out_kernel), HEAD_SMEM);
+    if (ea != cudaSuccess) return ea;
     const int nt = (h0.D + HO_T - 1) / HO_T, nseg = (h0.D + HO_SEG - 1) / HO_SEG;
     head_out_kernel<<<(unsigned)(h0.B * 3 * nseg * nt * nt), HO_THREADS, HEAD_SMEM, s>>>(a, out, h0.B, h0.D);
     return cudaGetLastError();

@@ -1,0 +1,17 @@
+// Host-side launch helpers shared by the kernel translation units: everything that is cached is cached PER DEVICE
+// (a process may hold handles on several GPUs), and TMA descriptors are encoded once per (buffer, geometry).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+// multiprocessor count of the CURRENT device
+int tc_num_sms();
+// cudaFuncSetAttribute(func, MaxDynamicSharedMemorySize, bytes), issued once per (current device, func)
+cudaError_t tc_func_smem(const void* func, int bytes);
+// 5-D tiled map over packed [2B][E][E][E][64] fp16 planes (hi planes then lo planes), box {64, bz, by, 1, 1},
+// SWIZZLE_128B; encoded once per (device, base, B, E, by, bz) and copied from the cache afterwards
+bool tc_make_act_map(CUtensorMap* map, const __half* base, int B, int E, int by, int bz);
+// drop every cached descriptor that points into [base, base + bytes) (call before freeing device memory that was
+// used as a TMA source, so a recycled address never meets a stale descriptor with another geometry)
+void tc_forget_maps(const void* base, size_t bytes);

@@ -160,18 +160,24 @@ def cpu_train_steps(n_steps, warmup, batch=1):
 
 
 def run_reference(args):
+    """The reference graph on the host CPU, same workload as the B200 arm: one train step of `--batch` (8) patches.
+    Under torchrun only rank 0 works (ONE CPU process on the box's host cores, whatever N); `n_gpus` repeats the
+    launch's N so the driver can pair the lines, `cpu_processes` says what actually ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    times, cores = cpu_train_steps(args.steps, args.warmup, batch=1)
+    times, cores = cpu_train_steps(args.steps, args.warmup, batch=args.batch)
     total = sum(times)
-    val = len(times) * 1 / total
-    sample = "1 patch per step (full train step: fwd+loss+bwd+Adam) of the same P=24,r=2,8/4 network"
+    val = len(times) * args.batch / total
+    sample = (f"{args.batch} patches per step (full train step: fwd+loss+bwd+Adam) of the same P=24,r=2,8/4 network, "
+              f"{len(times)} timed steps after {args.warmup} warm-up")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "patches/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "cpu_processes": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus, 1),
+        "config": dict(workload_config(args.gpus, args.batch),
+                       note="CPU arm: one process on rank 0's host cores steps ONE shard (batch_per_gpu patches) per step; "
+                            "its patches/s does not grow with N"),
         "cpu_baseline": {"value": val, "unit": "patches/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "TensorFlow is not installable here; torch-CPU (oneDNN) restatement of the "
                                  "reference graph stands in for the TF-CPU path"},
@@ -186,6 +192,116 @@ def workload_config(n_gpus, batch_per_gpu):
                         "patch_size=24, res_increase=2, 8 low / 4 hi resblocks, fp32",
             "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * n_gpus, "parallelism": f"dp{n_gpus}",
             "l2": "no explicit flush: one step streams ~3.3 GB of saved activations per GPU (>> 126 MB L2)"}
+
+
+
+# --------------------------------------------------------------------------------------------
+# the other BASELINE.json configs, measured in the same run (extra keys of the one JSON line)
+# --------------------------------------------------------------------------------------------
+def run_extra_configs(pkg, dev, local, world, timed, steps):
+    """configs[0] (predictor forward, batch 1), configs[2] (r=4, batch 16) and configs[4] (tiled 160x160x64 volume,
+    sharded over the ranks); configs[1]/[3] are the headline itself.  Device timing, max over ranks."""
+    import numpy as np
+    import torch
+    predictor = importlib.import_module("4dflownet_b200.predictor")
+    g = torch.Generator().manual_seed(0)
+    out = {}
+    for key, (Pp, r, Bc, n) in {"configs[0]": (24, 2, 1, 12), "configs[2]": (24, 4, 16, 16)}.items():
+        # configs[0]: the 12 patches of the 42x38x36 example volume one by one (predictor.py batch loop at batch 1)
+        model = pkg.prepare_network(Pp, r, LOW, HI, max_batch=Bc, device=local)
+        xs = [(torch.rand((n, Pp, Pp, Pp), generator=g) * 2 - 1) for _ in range(3)] + \
+             [(torch.rand((n, Pp, Pp, Pp), generator=g) * 0.016) for _ in range(3)]
+        xd = [x.to(dev) for x in xs]
+        y = torch.empty((n, Pp * r, Pp * r, Pp * r, 3), device=dev)
+
+        def step():
+            for i in range(0, n, Bc):
+                model.engine.forward([x[i:i + Bc] for x in xd], out=y[i:i + Bc])
+        ms = timed(step, steps, 2) / steps
+        host_np = [x.numpy() for x in xs]
+
+        def step_e2e():
+            model.predict(host_np, batch_size=Bc)
+        ms_e2e = timed(step_e2e, max(1, steps // 2), 1) / max(1, steps // 2)
+        flops = {2: 328.83e9, 4: 2220.4e9}[r]
+        out[key] = {"workload": f"forward patch_size={Pp} res_increase={r} batch={Bc} ({n} patches per step per GPU)",
+                    "value": n * world / ms * 1e3, "unit": "patches/s", "ms_per_step": ms,
+                    "tflops_fp32_equiv": flops * n * world / ms / 1e9,
+                    "e2e": {"value": n * world / ms_e2e * 1e3, "unit": "patches/s",
+                            "note": "model.predict: numpy patches in, numpy predictions out"}}
+        del model, xd, y
+        torch.cuda.empty_cache()
+
+    class DS:
+        pass
+    rng = np.random.default_rng(0)
+    ds = DS()
+    for nme in ("u", "v", "w"):
+        setattr(ds, nme, rng.uniform(-1, 1, (160, 160, 64)).astype(np.float32))
+    for nme in ("mag_u", "mag_v", "mag_w"):
+        setattr(ds, nme, rng.uniform(0, 0.016, (160, 160, 64)).astype(np.float32))
+    ds.venc = np.float32(1.5)
+    ds.velocity_per_px = ds.venc / 2048
+    model = pkg.prepare_network(24, 2, LOW, HI, max_batch=8, device=local)
+    pg = pkg.PatchGenerator(24, 2)
+
+    def step_vol():
+        predictor.predict_volume(model, pg, ds, batch_size=8, reuse_host_buffer=True)
+    ms = timed(step_vol, steps, 1) / steps
+    npatch = pg.nr_x * pg.nr_y * pg.nr_z
+    out["configs[4]"] = {"workload": "tiled inference of a 160x160x64 volume, patch_size=24 (reference tiling, stride 20: 256 "
+                         "patches) sharded over the ranks: host volume in -> stitched 320x320x128 host volume out "
+                         "(patchify + H2D + forward + gather + GPU stitch + D2H inside the timed region)",
+                         "value": npatch / ms * 1e3, "unit": "patches/s", "ms_per_volume": ms, "patches": npatch,
+                         "scaling": "strong"}
+    return out
+
+
+def dp_parity_preflight(pkg, tcm, dev, local, rank, world):
+    """Data-parallel pre-flight (N > 1), small geometry: after the step's one all-reduce every rank must hold the
+    bit-identical flat gradient, and it must equal the single-GPU gradient of the concatenated global batch up to
+    fp32 summation order.  Run once with the default (tensor-core) kernels and once with the fp32 SIMT anchor."""
+    import contextlib
+    import io
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    par = importlib.import_module("4dflownet_b200.parallel")
+    synthetic_batch = importlib.import_module("4dflownet_b200.utils.synthetic").synthetic_batch
+    Pp, r, low, hi, Bl = 8, 2, 1, 1, 2
+    glob = synthetic_batch(Bl * world, Pp, r, seed=77)
+    shard = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in par.shard_batch(glob)]
+    res = {"geometry": f"patch_size={Pp} res_increase={r} {low}/{hi} blocks, {Bl} samples per rank"}
+    for label, impl in (("default", pkg._lib.CONV_AUTO), ("simt_fp32", pkg._lib.CONV_SIMT)):
+        with contextlib.redirect_stdout(io.StringIO()):
+            ctl = tcm.TrainerController(Pp, r, 1e-4, False, "dp", low, hi, max_batch=Bl, device=local, seed=5)
+        ctl.engine.set_option(pkg._lib.OPT_CONV_IMPL, impl)
+        tail = ctl._tail()
+        per, l2 = tail.begin(Bl)
+        ctl.engine.train_fwd_bwd(shard[:6], [a[..., 0] for a in shard[6:9]], shard[10], per_out=per, l2_out=l2)
+        par.allreduce_gradients(ctl.engine.grads_full)
+        flat = ctl.engine.grads.clone()
+        allf = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(allf, flat)
+        same = all(torch.equal(allf[0], f) for f in allf)
+        _, _, count = tail.read()
+        rel = None
+        if rank == 0:
+            eng1 = pkg.Engine(Pp, r, low, hi, max_batch=Bl * world, training=True, device=local)
+            eng1.set_option(pkg._lib.OPT_CONV_IMPL, impl)
+            eng1.set_weights(ctl.model.get_weights())
+            eng1.train_fwd_bwd(glob[:6], [a[..., 0] for a in glob[6:9]], glob[10])
+            rel = float(((flat.double() - eng1.grads.double()).norm() / eng1.grads.double().norm()).item())
+            eng1.close()
+        res[label] = {"bit_identical_across_ranks": bool(same), "rel_l2_vs_single_gpu": rel,
+                      "global_count_in_tail": count}
+        ctl.engine.close()
+    if rank == 0:
+        res["ok"] = bool(res["default"]["bit_identical_across_ranks"] and res["simt_fp32"]["bit_identical_across_ranks"]
+                         and res["simt_fp32"]["rel_l2_vs_single_gpu"] <= 1e-6
+                         and res["default"]["rel_l2_vs_single_gpu"] <= 1e-5
+                         and res["default"]["global_count_in_tail"] == Bl * world)
+    return res
 
 
 # --------------------------------------------------------------------------------------------
@@ -212,18 +328,18 @@ def run_b200(args):
     with contextlib.redirect_stdout(io.StringIO()):
         ctl = tcm.TrainerController(P, R, 1e-4, False, "4DFlowNet", LOW, HI, max_batch=B, device=local, seed=1234)
     eng = ctl.engine
-    if args.experimental_backward:
-        # EXPERIMENTAL (default off, see DESIGN.md "what would come next" item 0): single-fp16 gradient operand in the
-        # tensor-core dgrad / hi-planes-only wgrad.  The line is labelled; it is not the headline configuration.
+    if args.two_plane_backward:
+        # A/B switch: the round-1 backward (both planes of the split gradient in the dgrad, two-plane wgrad kernel).
+        # The line is labelled; the default since round 2 is the single-plane backward (same gradient parity,
+        # profiles/r02_grad_parity.txt).
         L = importlib.import_module("4dflownet_b200._lib")
-        eng.set_option(L.OPT_DGRAD_SINGLE, 1)
-        eng.set_option(L.OPT_WGRAD_SINGLE, 1)
+        eng.set_option(L.OPT_DGRAD_SINGLE, 0)
+        eng.set_option(L.OPT_WGRAD_SINGLE, 0)
     host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in synthetic_batch(B, P, R, seed=rank)]
     devb = [h.to(dev) for h in host]
     h2d = sum(h.numel() * 4 for i, h in enumerate(host) if i != 9)     # venc is not an input of the step
-    per_host = torch.empty((B, 4), dtype=torch.float32).pin_memory()
-    l2_host = torch.empty((1,), dtype=torch.float32).pin_memory()
-    d2h = per_host.numel() * 4 + 4
+    tail = ctl._tail()
+    d2h = (world * tail.slot + 1) * 4            # the metric tail read back per step (every rank's slot + the count)
 
     def barrier():
         if world > 1:
@@ -249,12 +365,10 @@ def run_b200(args):
         ctl.train_step_async(devb)
 
     def step_e2e():
-        db = [h.to(dev, non_blocking=True) for h in host]
-        per, l2 = ctl.train_step_async(db)
-        per_host.copy_(per, non_blocking=True)
-        l2_host.copy_(l2, non_blocking=True)
-        torch.cuda.current_stream().synchronize()       # the caller reads the metrics every step
-        ctl._update_metrics(per_host.numpy(), float(l2_host[0]), 'train')
+        # the call a user makes: TrainerController.train_step on a batch that lives in (pinned) host memory.  The
+        # step uploads the 11-tuple, runs forward + loss + backward + the ONE all-reduce + Adam, and reads the
+        # all-reduced metric tail back (one small D2H + the step's only stream synchronisation) for the running means.
+        ctl.train_step([h.to(dev, non_blocking=True) for h in host])
 
     # ---- headline: device-resident train step --------------------------------------------------
     clocks = ClockSampler(local)
@@ -302,6 +416,9 @@ def run_b200(args):
         ctl.model.predict(host_np, batch_size=B)
     ms_fwd_e2e = timed(fwd_e2e, max(1, K // 2), 1) / max(1, K // 2) / NB
 
+    extra = {} if args.no_extra_configs else run_extra_configs(pkg, dev, local, world, timed, max(3, K // 3))
+    dp = dp_parity_preflight(pkg, tcm, dev, local, rank, world) if world > 1 else None
+
     peaks = measured_peaks()
     if rank == 0:
         # dominant kernel class of the train step
@@ -338,14 +455,17 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(world, B), **({"experimental_backward": "single-fp16 gradient operand in dgrad, "
-                                                         "hi planes only in wgrad"} if args.experimental_backward else {})),
+            "config": dict(workload_config(world, B), **({"two_plane_backward": "round-1 backward kernels (A/B run)"}
+                                                        if args.two_plane_backward else {})),
             "clocks": clk,
             "e2e": {"value": e2e_val, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                         "frac": ach / peak, "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16",
+                         "frac": ach / peak, "traffic": traffic,
+                         "traffic_source": "profiles/traffic.json: dram bytes per launch of this kernel class from an "
+                                           "ncu --set full capture (not re-measured in this run)",
+                         "peak_source": peaks["source"] + ", sustained bf16",
                          "executed_tflops_fp16": 4.0 * ach, "executed_frac": 4.0 * ach / peak,
                          "ms_per_launch": dom_ms / max(dom_n, 1), "launches_per_step": dom_n,
                          "share_of_step": dom_ms / ms_step,
@@ -355,12 +475,15 @@ def run_b200(args):
                                  "gradient, applies act' and writes the split copy"},
             "kernel_classes_ms_per_step": {k: round(v[0], 4) for k, v in prof_step.items()},
             "forward": fwd,
+            "other_configs": extra,
         }
+        if dp is not None:
+            line["dp_parity"] = dp
         if world == 1 and not args.no_cpu_baseline:
-            times, cores = cpu_train_steps(12, 1, batch=1)
-            line["cpu_baseline"] = {"value": len(times) / sum(times), "unit": "patches/s", "cores": cores,
-                                    "kind": "port", "sample": "12 timed train steps of 1 patch (after 1 warm-up, ~10 s of CPU "
-                                    "work) on the torch-CPU restatement of the reference graph (TF not installable)"}
+            times, cores = cpu_train_steps(3, 1, batch=B)
+            line["cpu_baseline"] = {"value": len(times) * B / sum(times), "unit": "patches/s", "cores": cores,
+                                    "kind": "port", "sample": f"3 timed train steps of {B} patches (after 1 warm-up, ~20 s of "
+                                    "CPU work) on the torch-CPU restatement of the reference graph (TF not installable)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -374,8 +497,10 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="patches per GPU per step (configs[1]: 8)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--experimental-backward", action="store_true",
-                    help="turn on SR4D_OPT_DGRAD_SINGLE / SR4D_OPT_WGRAD_SINGLE (not validated on hardware yet)")
+    ap.add_argument("--no-extra-configs", action="store_true",
+                    help="skip the configs[0] / configs[2] / configs[4] legs (quick A/B runs)")
+    ap.add_argument("--two-plane-backward", action="store_true",
+                    help="A/B: SR4D_OPT_DGRAD_SINGLE = SR4D_OPT_WGRAD_SINGLE = 0 (the round-1 backward kernels)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -19,7 +19,7 @@ def _baseline():
 
 def test_reference_arm_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--warmup", "0", "--batch", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert BASE_KEYS <= set(line) and line["impl"] == "reference"
@@ -29,6 +29,8 @@ def test_reference_arm_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
+    assert line["config"]["batch_per_gpu"] == 2 and line["cpu_processes"] == 1      # same per-step batch as the B200 arm
+    assert abs(line["value"] - 2 / line["ms_per_step"] * 1e3) < 1e-6 * line["value"]
     assert line["metric"].split(" at ")[0] in _baseline()["metric"]
 
 

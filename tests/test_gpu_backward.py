@@ -14,17 +14,26 @@ def rel_l2(a, b):
     return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
 
 
-@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
-@pytest.mark.parametrize("D,B,dy_scale", [(6, 2, 1.0), (9, 1, 1.0), (24, 1, 3e-7), (26, 1, 1e3)])
+@pytest.mark.parametrize("impl", ["simt", "tcgen05_full", "tcgen05", "tcgen05_hi_only_old_kernel"])
+@pytest.mark.parametrize("D,B,dy_scale", [(6, 2, 1.0), (9, 1, 1.0), (24, 1, 3e-7), (26, 1, 1e3), (24, 3, 1.0), (48, 1, 1.0)])
 def test_conv64_layer_bwd(pkg, D, B, dy_scale, impl):
-    """dy_scale exercises the power-of-two rescaling of the split-fp16 gradient operand: loss gradients
-    of this network are ~1e-6, far below the fp16 normal range."""
+    """Backward kernels of one 64->64 layer given identical inputs, against float64 autograd.
+    dy_scale exercises the power-of-two rescaling of the split-fp16 gradient operand: loss gradients of this network
+    are ~1e-6, far below the fp16 normal range.
+    tcgen05_full: both gradient planes in the dgrad, the two-plane weight-gradient kernel (1e-5, like the fp32 SIMT
+    anchor).  tcgen05 (the default since round 2): single scaled-fp16 gradient plane in the dgrad and the stacked
+    hi-plane weight-gradient kernel -- their rounding errors are independent per element (2^-12 relative) and average
+    out over the 1728-term (dgrad) / B*D^3-term (wgrad) sums, so the bar scales with 1/sqrt(#terms)."""
+    L = pkg._lib
     eng = pkg.Engine(8, 2, 0, 0, max_batch=2, training=False, device=0)
+    single = {"tcgen05_full": (0, 0), "tcgen05": (1, 1), "tcgen05_hi_only_old_kernel": (1, 2)}.get(impl, (0, 0))
+    eng.set_option(L.OPT_DGRAD_SINGLE, single[0])
+    eng.set_option(L.OPT_WGRAD_SINGLE, single[1])
     g = np.random.default_rng(D)
     x = g.standard_normal((B, D, D, D, 64)).astype(np.float32)
     k = (g.standard_normal((3, 3, 3, 64, 64)) * 0.05).astype(np.float32)
     dy = (g.standard_normal((B, D, D, D, 64)) * dy_scale).astype(np.float32)
-    dx, dk, db = eng.conv64_layer_bwd(x, k, dy, impl=pkg._lib.CONV_SIMT if impl == "simt" else pkg._lib.CONV_TCGEN05)
+    dx, dk, db = eng.conv64_layer_bwd(x, k, dy, impl=L.CONV_SIMT if impl == "simt" else L.CONV_TCGEN05)
     import importlib
     oracle = importlib.import_module("oracle.sr4d_oracle")
     xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
@@ -32,8 +41,15 @@ def test_conv64_layer_bwd(pkg, D, B, dy_scale, impl):
     bt = torch.zeros(64, dtype=torch.float64, requires_grad=True)
     y = oracle.conv3d(xt, kt, bt)
     (y * torch.tensor(dy, dtype=torch.float64)).sum().backward()
-    assert rel_l2(dx.cpu().numpy(), xt.grad.numpy()) < 1e-5
-    assert rel_l2(dk.cpu().numpy(), kt.grad.numpy()) < 1e-5
+    nvox = B * D ** 3
+    # single gradient plane: every dY element carries an independent fp16 rounding error (rms 2^-11/sqrt(3) = 2.8e-4
+    # relative), and a random-sign sum inherits the relative error of its terms -- the per-voxel input gradient is
+    # 2e-4 off (measured 2.1e-4), independently per voxel; it averages out in the weight gradients downstream,
+    # which is what the reference API exposes (test_backward_kernels_given_identical_gates holds those)
+    tol_dx = 1e-5 if not single[0] else 4e-4
+    tol_dk = 1e-5 if not single[1] else max(1e-5, 6e-4 / nvox ** 0.5)   # both operands rounded: ~2 * 2^-12/sqrt(3) / sqrt(nvox)
+    assert rel_l2(dx.cpu().numpy(), xt.grad.numpy()) < tol_dx
+    assert rel_l2(dk.cpu().numpy(), kt.grad.numpy()) < tol_dk
     assert rel_l2(db.cpu().numpy(), bt.grad.numpy()) < 1e-5
     eng.close()
 
@@ -56,45 +72,92 @@ def test_loss_metrics(pkg, oracle):
     eng.close()
 
 
-@pytest.mark.parametrize("impl", ["simt", "auto", "auto_unfused"])
-@pytest.mark.parametrize("P,r,low,hi,B", [(8, 2, 1, 1, 2), (6, 1, 1, 1, 2), (6, 2, 0, 1, 1), (6, 2, 2, 0, 2), (6, 1, 0, 0, 1),
-                                          (12, 2, 2, 2, 1)])
-def test_train_step_gradients_vs_oracle(pkg, oracle, P, r, low, hi, B, impl):
+def _flat(grads, names):
+    return np.concatenate([np.asarray(grads[n], np.float64).ravel() for n in names])
+
+
+def _engine_grads(pkg, P, r, low, hi, B, params, batch, fwd_impl, bwd_impl, dgrad_single=1, wgrad_single=1, fused=1):
+    """Gradient of one train step with the forward and the backward convolutions on possibly different kernels
+    (sr4d_train_forward / sr4d_train_backward)."""
+    L = pkg._lib
+    eng = pkg.Engine(P, r, low, hi, max_batch=B, training=True, device=0)
+    eng.set_option(L.OPT_FUSED_DGRAD, fused)
+    eng.set_option(L.OPT_DGRAD_SINGLE, dgrad_single)
+    eng.set_option(L.OPT_WGRAD_SINGLE, wgrad_single)
+    eng.set_weights(params)
+    eng.set_option(L.OPT_CONV_IMPL, fwd_impl)
+    eng.train_forward(batch[:6])
+    eng.set_option(L.OPT_CONV_IMPL, bwd_impl)
+    eng.train_backward([b[..., 0] for b in batch[6:9]], batch[10])
+    g = {n: v.cpu().numpy().astype(np.float64) for n, v in eng.tensor_views(eng.grads)}
+    eng.close()
+    return g
+
+
+GEOMS = [(8, 2, 1, 1, 2), (6, 1, 1, 1, 2), (6, 2, 0, 1, 1), (6, 2, 2, 0, 2), (6, 1, 0, 0, 1), (12, 2, 2, 2, 1)]
+
+
+@pytest.mark.parametrize("P,r,low,hi,B", GEOMS + [(24, 2, 2, 1, 2)])
+def test_backward_kernels_given_identical_gates(pkg, oracle, bars, P, r, low, hi, B):
+    """The decisive separation: the tensor-core BACKWARD fed the fp32 SIMT forward's saved
+    activations -- identical ReLU / LeakyReLU gates -- against the SIMT backward on the same activations.  What is
+    left is the backward kernels' own arithmetic: split-fp16 weights, one scaled fp16 gradient plane, hi-plane weight
+    gradient, truncating tcgen05 accumulators with chains cut at 384 accumulations."""
+    L = pkg._lib
+    params = oracle.glorot_params(low, hi, seed=P + r, bias_scale=0.05)
+    batch = oracle.synthetic_batch(B, P, r, seed=4)
+    names = [n for n, _ in oracle.param_table(low, hi)]
+    ref = _flat(_engine_grads(pkg, P, r, low, hi, B, params, batch, L.CONV_SIMT, L.CONV_SIMT), names)
+    tag = f"P{P}r{r}l{low}h{hi}B{B}"
+    for label, kw in (("default", {}), ("full", dict(dgrad_single=0, wgrad_single=0)), ("unfused", dict(fused=0))):
+        got = _flat(_engine_grads(pkg, P, r, low, hi, B, params, batch, L.CONV_SIMT, L.CONV_AUTO, **kw), names)
+        # ceiling: the north-star 1e-4 at real patch sizes; the single-plane operands' averaging is weaker on toy grids
+        ceiling = 1e-4 if B * (P * r) ** 3 >= 48 ** 3 else 3e-4
+        bars(f"identical_gates/{tag}/{label}", rel_l2(got, ref), ceiling)
+
+
+@pytest.mark.parametrize("impl", ["simt", "auto", "auto_unfused", "auto_full"])
+@pytest.mark.parametrize("P,r,low,hi,B", GEOMS)
+def test_train_step_gradients_vs_oracle(pkg, oracle, bars, P, r, low, hi, B, impl):
     params = oracle.glorot_params(low, hi, seed=P + r, bias_scale=0.05)
     batch = oracle.synthetic_batch(B, P, r, seed=4)
     eng = pkg.Engine(P, r, low, hi, max_batch=B, training=True, device=0)
     eng.set_option(pkg._lib.OPT_CONV_IMPL, pkg._lib.CONV_SIMT if impl == "simt" else pkg._lib.CONV_AUTO)
-    # "auto": tensor-core kernels with the halo fold / skip add / activation gradient fused into the dgrad
-    # epilogue; "auto_unfused": the same kernels with the separate raw-dgrad + fold kernel
+    # "auto": the default tensor-core path (fused dgrad epilogue, single gradient plane, stacked hi-plane wgrad);
+    # "auto_unfused": separate raw-dgrad + fold kernel; "auto_full": both gradient planes / two-plane wgrad kernel
     eng.set_option(pkg._lib.OPT_FUSED_DGRAD, 0 if impl == "auto_unfused" else 1)
+    if impl == "auto_full":
+        eng.set_option(pkg._lib.OPT_DGRAD_SINGLE, 0)
+        eng.set_option(pkg._lib.OPT_WGRAD_SINGLE, 0)
     eng.set_weights(params)
     per, l2, pred = eng.train_fwd_bwd(batch[:6], [b[..., 0] for b in batch[6:9]], batch[10], want_pred=True)
+    # everything is compared with the FLOAT64 oracle.  fp32 autograd of the same graph (what the reference's TF fp32
+    # path amounts to) is computed next to it: on these toy grids fp32 itself is 1e-4..5e-4 off on the ill-conditioned
+    # stem kernels, because a forward perturbation of relative size eps flips ~eps of the ReLU / LeakyReLU gates and
+    # moves a random-sign gradient sum by ~sqrt(eps).
     gref, met = oracle.gradients({k: v.astype(np.float64) for k, v in params.items()}, batch, r, low, hi)
-    # fp32 autograd of the same graph (what the reference's TF fp32 path amounts to): its distance from
-    # the fp64 truth calibrates the gradient tolerance -- through this depth fp32 itself is off by up to
-    # ~5e-4 on the (ill-conditioned, zero-mean-input) stem kernels (tests/diag_grads.py), so the per-tensor
-    # bar is max(2e-4, 2x the fp32 error) and the 1e-4 bar is applied to the flat gradient as a whole.
     g32, _ = oracle.gradients(params, batch, r, low, hi, dtype=torch.float32)
     l2c = oracle.L2_COEFF
     assert abs(float(l2) - float(met["l2"])) <= 1e-5 * float(met["l2"])
     np.testing.assert_allclose(per[:, 0].cpu().numpy() + float(l2), met["loss"], rtol=1e-4)
     np.testing.assert_allclose(per[:, 2].cpu().numpy(), met["rel_err"], rtol=1e-3, atol=1e-3)
     assert np.abs(pred.cpu().numpy() - met["pred"]).max() / np.abs(met["pred"]).max() < 1e-4
+    tag = f"P{P}r{r}l{low}h{hi}B{B}/{impl}"
+    worst, worst32 = 0.0, 0.0
     for name, view in eng.tensor_views(eng.grads):
         got = view.cpu().numpy()
         want = gref[name] - (B * 2 * l2c * params[name] if name.endswith("kernel") else 0.0)
-        # ReLU / LeakyReLU gates make the gradient discontinuous in the forward activations: a forward
-        # perturbation of relative size eps flips ~eps of the gates and moves a random-sign gradient sum by
-        # ~sqrt(eps).  fp32 autograd (eps ~1e-7) is therefore 1e-4..5e-4 from fp64 on some tensors, and the
-        # tensor-core forward (eps ~3e-6: the tcgen05 fp32 accumulator truncates) 1e-3..3e-3 (tests/diag_grads.py).
-        # The backward KERNELS are held to 1e-5 given identical inputs in test_conv64_layer_bwd.
-        tol = max(2e-4 if impl == "simt" else 5e-3, 2.0 * rel_l2(g32[name], gref[name]))
-        assert rel_l2(got, want) < tol, (name, rel_l2(got, want), tol)
-    # the flat gradient the optimizer consumes: 1e-4 relative
+        worst = max(worst, rel_l2(got, want))
+        worst32 = max(worst32, rel_l2(g32[name], gref[name]))
+    # the flat gradient the optimizer consumes, and the worst single tensor (small bias tensors of these toy grids feel
+    # individual gate flips: fp32 autograd's own worst tensor is printed next to it when the check fails)
     flat_got = np.concatenate([v.cpu().numpy().ravel() for _, v in eng.tensor_views(eng.grads)])
     flat_want = np.concatenate([(gref[n] - (B * 2 * l2c * params[n] if n.endswith("kernel") else 0.0)).ravel()
                                 for n, *_ in eng.table])
-    assert rel_l2(flat_got, flat_want) < (1e-4 if impl == "simt" else 3e-3)
+    flat = rel_l2(flat_got, flat_want)
+    bars(f"train_step/{tag}/flat", flat, 1e-4 if impl == "simt" else 3e-4)
+    bars(f"train_step/{tag}/worst_tensor", worst, 1e-3 if impl == "simt" else 5e-3)
+    assert worst32 < 1e-3, worst32      # sanity of the calibration: fp32 autograd itself on the worst tensor
     # one Adam step (Keras semantics, L2 gradient folded in) vs the oracle's numpy Adam, fed the gradient the
     # engine itself produced: the first step moves a weight by lr*g/(|g|+3.2e-6), so near g ~ 1e-6 the update
     # amplifies gradient noise that the checks above already bound; this isolates the Adam kernel.
@@ -149,35 +212,3 @@ def test_reference_named_metric_entry_points(pkg, oracle):
     assert abs(ctl.loss_metrics['val_loss'].result() - float(lw.mean())) < 1e-4 * float(lw.mean())
     mse = ctl.calculate_mse(true[..., 0], true[..., 1], true[..., 2], pred[..., 0], pred[..., 1], pred[..., 2]).cpu().numpy()
     np.testing.assert_allclose(mse, ((pred - true) ** 2).sum(-1), rtol=1e-5, atol=1e-9)
-
-
-@pytest.mark.skipif(not os.environ.get("SR4D_TEST_EXPERIMENTAL"),
-                    reason="SR4D_OPT_DGRAD_SINGLE / SR4D_OPT_WGRAD_SINGLE have not been validated on hardware yet "
-                           "(set SR4D_TEST_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("fused", [1, 0])
-@pytest.mark.parametrize("dgrad_single,wgrad_single", [(1, 0), (0, 1), (1, 1)])
-@pytest.mark.parametrize("P,r,low,hi,B", [(8, 2, 1, 1, 2), (12, 2, 2, 2, 1), (24, 2, 2, 1, 1)])
-def test_single_operand_backward_options(pkg, oracle, P, r, low, hi, B, dgrad_single, wgrad_single, fused):
-    """EXPERIMENTAL options: the tensor-core dgrad reads only the hi plane of the scaled split gradient, the wgrad only
-    the hi planes of both operands.  CPU emulation (tools/gradient_precision_emulation.py) predicts a cost of about
-    1e-5 * sqrt(48^3 / #voxels) on the flat gradient; the options must meet the default path's tolerance against the
-    oracle and stay close to the default path's own gradient."""
-    params = oracle.glorot_params(low, hi, seed=P + r, bias_scale=0.05)
-    batch = oracle.synthetic_batch(B, P, r, seed=4)
-    gref, _ = oracle.gradients({k: v.astype(np.float64) for k, v in params.items()}, batch, r, low, hi)
-    l2c = oracle.L2_COEFF
-    flats = {}
-    for on in (0, 1):
-        eng = pkg.Engine(P, r, low, hi, max_batch=B, training=True, device=0)
-        eng.set_option(pkg._lib.OPT_FUSED_DGRAD, fused)
-        eng.set_option(pkg._lib.OPT_DGRAD_SINGLE, dgrad_single * on)
-        eng.set_option(pkg._lib.OPT_WGRAD_SINGLE, wgrad_single * on)
-        eng.set_weights(params)
-        eng.train_fwd_bwd(batch[:6], [b[..., 0] for b in batch[6:9]], batch[10])
-        flats[on] = np.concatenate([v.cpu().numpy().ravel().astype(np.float64) for _, v in eng.tensor_views(eng.grads)])
-        eng.close()
-    want = np.concatenate([(gref[n] - (B * 2 * l2c * params[n] if n.endswith("kernel") else 0.0)).ravel()
-                           for n, _ in oracle.param_table(low, hi)])
-    assert rel_l2(flats[1], want) < 3e-3
-    voxels = B * (P * r) ** 3
-    assert rel_l2(flats[1], flats[0]) < 1e-4 * max(1.0, (48 ** 3 / voxels) ** 0.5)

@@ -115,50 +115,65 @@ def test_forward_r4_full_geometry_vs_oracle(pkg, oracle):
     eng.close()
 
 
-def test_train_step_full_geometry_vs_oracle(pkg, oracle):
-    """BASELINE config 2 geometry (P=24, r=2, 8/4 blocks), one sample: loss, metric and the flat gradient against
-    fp32 autograd of the oracle (tolerances as in test_gpu_backward: ReLU gate flips bound the gradient parity)."""
+def _rel_l2(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300))
+
+
+def _flat_vs_fp64(eng, oracle, params, batch, r, low, hi):
+    """(flat rel-L2, worst per-tensor rel-L2, metrics) of the engine's gradient buffer against float64 autograd."""
+    B = len(batch[0])
+    g64, met = oracle.gradients({k: v.astype(np.float64) for k, v in params.items()}, batch, r, low, hi)
+    l2c = oracle.L2_COEFF
+    want = {n: g64[n] - (B * 2 * l2c * params[n].astype(np.float64) if n.endswith("kernel") else 0.0) for n, *_ in eng.table}
+    got = {n: v.cpu().numpy().astype(np.float64) for n, v in eng.tensor_views(eng.grads)}
+    flat = _rel_l2(np.concatenate([got[n].ravel() for n in want]), np.concatenate([want[n].ravel() for n in want]))
+    worst = max(_rel_l2(got[n], want[n]) for n in want)
+    return flat, worst, met
+
+
+def test_train_step_full_geometry_vs_oracle(pkg, oracle, bars):
+    """BASELINE configs[1] geometry (P=24, r=2, 8/4 blocks), two samples: loss, metric and the gradient of the
+    default (tensor-core) path against FLOAT64 autograd of the oracle; flat gradient within the north-star 1e-4.
+    (tools/grad_parity.py prints the same comparison at B=1 and B=8 with the SIMT anchor, fp32 autograd and the
+    identical-gates variants next to it: profiles/r02_grad_parity.txt.)"""
     params = oracle.glorot_params(8, 4, seed=1234, bias_scale=0.02)
-    batch = oracle.synthetic_batch(1, 24, 2, seed=9)
-    eng = pkg.Engine(24, 2, 8, 4, max_batch=1, training=True, device=0)
+    batch = oracle.synthetic_batch(2, 24, 2, seed=9)
+    eng = pkg.Engine(24, 2, 8, 4, max_batch=2, training=True, device=0)
     eng.set_weights(params)
     per, l2, pred = eng.train_fwd_bwd(batch[:6], [b[..., 0] for b in batch[6:9]], batch[10], want_pred=True)
-    g32, met = oracle.gradients(params, batch, 2, 8, 4, dtype=torch.float32)
+    flat, worst, met = _flat_vs_fp64(eng, oracle, params, batch, 2, 8, 4)
     assert relerr(pred.cpu().numpy(), met["pred"]) < 1e-4
     np.testing.assert_allclose(per[:, 0].cpu().numpy() + float(l2), met["loss"], rtol=1e-4)
     np.testing.assert_allclose(per[:, 2].cpu().numpy(), met["rel_err"], rtol=1e-3, atol=1e-3)
-    l2c = oracle.L2_COEFF
-    got = np.concatenate([v.cpu().numpy().ravel() for _, v in eng.tensor_views(eng.grads)])
-    want = np.concatenate([(g32[n] - (2 * l2c * params[n] if n.endswith("kernel") else 0.0)).ravel() for n, *_ in eng.table])
-    err = np.linalg.norm(got - want) / np.linalg.norm(want)
-    assert err < 5e-3, err
+    bars("full_geometry/P24r2l8h4B2/flat", flat, 1e-4)
+    bars("full_geometry/P24r2l8h4B2/worst_tensor", worst, 2e-3)
     eng.close()
 
 
-def test_trainer_default_geometry_vs_oracle(pkg, oracle):
+def test_trainer_default_geometry_vs_oracle(pkg, oracle, bars):
     """trainer.py's own defaults (patch_size=16, res_increase=2, 8/4 blocks; trainer.py:28-39), two samples: exercises the
-    TY=16 forward tiles and the 18^3 / 34^3 fused-dgrad grids against fp32 autograd of the oracle."""
+    TY=16 forward tiles and the 18^3 / 34^3 fused-dgrad grids against FLOAT64 autograd of the oracle."""
     params = oracle.glorot_params(8, 4, seed=21, bias_scale=0.02)
     batch = oracle.synthetic_batch(2, 16, 2, seed=4)
     eng = pkg.Engine(16, 2, 8, 4, max_batch=2, training=True, device=0)
     eng.set_weights(params)
     per, l2, pred = eng.train_fwd_bwd(batch[:6], [b[..., 0] for b in batch[6:9]], batch[10], want_pred=True)
-    g32, met = oracle.gradients(params, batch, 2, 8, 4, dtype=torch.float32)
+    flat, worst, met = _flat_vs_fp64(eng, oracle, params, batch, 2, 8, 4)
     assert relerr(pred.cpu().numpy(), met["pred"]) < 1e-4
     np.testing.assert_allclose(per[:, 0].cpu().numpy() + float(l2), met["loss"], rtol=1e-4)
-    l2c = oracle.L2_COEFF
-    got = np.concatenate([v.cpu().numpy().ravel() for _, v in eng.tensor_views(eng.grads)])
-    want = np.concatenate([(g32[n] - (2 * 2 * l2c * params[n] if n.endswith("kernel") else 0.0)).ravel() for n, *_ in eng.table])
-    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 5e-3
+    bars("trainer_default/P16r2l8h4B2/flat", flat, 2e-4)
+    bars("trainer_default/P16r2l8h4B2/worst_tensor", worst, 3e-3)
+    got = eng.grads.clone()
     # the unfused path gives the same gradient up to rounding of the split copies' exponents
     eng.set_option(pkg._lib.OPT_FUSED_DGRAD, 0)
     eng.train_fwd_bwd(batch[:6], [b[..., 0] for b in batch[6:9]], batch[10])
-    got2 = np.concatenate([v.cpu().numpy().ravel() for _, v in eng.tensor_views(eng.grads)])
-    assert np.linalg.norm(got2 - got) / np.linalg.norm(got) < 1e-4
+    bars("trainer_default/P16r2l8h4B2/unfused_vs_fused", float((eng.grads - got).norm() / got.norm()), 1e-4)
     eng.close()
 
 
-def test_three_train_steps_follow_the_oracle_loop(pkg, oracle):
+def test_three_train_steps_follow_the_oracle_loop(pkg, oracle, bars):
     """Three consecutive TrainerController.train_step calls (forward, backward, Adam, refreshed tensor-core weight
     images) against the oracle's fp64 loop: per-step loss trajectory and the accumulated weight update."""
     import contextlib
@@ -190,8 +205,9 @@ def test_three_train_steps_follow_the_oracle_loop(pkg, oracle):
     assert want_losses[2] != want_losses[0]
     num = sum(float(np.sum((w_got[k] - w[k]) ** 2)) for k in w)
     den = sum(float(np.sum((w[k] - params[k]) ** 2)) for k in w)
-    assert (num / den) ** 0.5 < 2e-2          # accumulated update agrees to 2 % (Adam's sign-like first steps amplify
-    #                                           gradient noise near zero; the loss trajectory above is the tight check)
+    # accumulated update (Adam's sign-like first steps amplify gradient noise near zero: the update of a weight whose
+    # gradient is ~1e-6 flips with the gradient's last bits; the loss trajectory above is the tight check)
+    bars("three_steps/P8r2l2h1B3/update_rel_l2", (num / den) ** 0.5, 2e-2)
     assert ctl.optimizer.iterations == 3
 
 

@@ -8,8 +8,7 @@ loss vector) for
   * the engine's default tensor-core (tcgen05 split-fp16) path,
   * the tensor-core BACKWARD fed the SIMT forward's saved activations (identical ReLU / LeakyReLU gates): separates
     kernel error from gate flips caused by the forward's rounding,
-  * the single-fp16-gradient-operand options (SR4D_OPT_DGRAD_SINGLE / SR4D_OPT_WGRAD_SINGLE),
-and, per variant, the error on "gate-robust" coordinates excluded (none) -- everything is on the full flat gradient.
+  * the two-plane backward (SR4D_OPT_DGRAD_SINGLE = SR4D_OPT_WGRAD_SINGLE = 0) and the old kernel's hi-only mode.
 Writes a text table (committed as profiles/r02_grad_parity.txt).
 
 usage: python tools/grad_parity.py [--cases P,r,low,hi,B;...] [--out FILE]
@@ -85,13 +84,13 @@ def main():
         variants = {"torch-cpu fp32 autograd": ({n: np.asarray(g32[n], np.float64) - corr[n] for n in names}, None)}
         specs = [
             ("engine SIMT fp32 anchor", dict(fwd_impl=L.CONV_SIMT, bwd_impl=L.CONV_SIMT)),
-            ("engine tcgen05 (default)", dict(fwd_impl=L.CONV_AUTO, bwd_impl=L.CONV_AUTO)),
-            ("tcgen05 bwd on SIMT fwd acts", dict(fwd_impl=L.CONV_SIMT, bwd_impl=L.CONV_AUTO)),
+            ("engine tcgen05 (default)", dict(fwd_impl=L.CONV_AUTO, bwd_impl=L.CONV_AUTO, dgrad_single=1, wgrad_single=1)),
+            ("tcgen05 bwd on SIMT fwd acts", dict(fwd_impl=L.CONV_SIMT, bwd_impl=L.CONV_AUTO, dgrad_single=1, wgrad_single=1)),
             ("SIMT bwd on tcgen05 fwd acts", dict(fwd_impl=L.CONV_AUTO, bwd_impl=L.CONV_SIMT)),
-            ("tcgen05 + dgrad_single", dict(fwd_impl=L.CONV_AUTO, bwd_impl=L.CONV_AUTO, dgrad_single=1)),
-            ("tcgen05 + wgrad_single", dict(fwd_impl=L.CONV_AUTO, bwd_impl=L.CONV_AUTO, wgrad_single=1)),
-            ("tcgen05 + both single", dict(fwd_impl=L.CONV_AUTO, bwd_impl=L.CONV_AUTO, dgrad_single=1, wgrad_single=1)),
-            ("both single on SIMT fwd acts", dict(fwd_impl=L.CONV_SIMT, bwd_impl=L.CONV_AUTO, dgrad_single=1, wgrad_single=1)),
+            ("tcgen05 two-plane backward", dict(fwd_impl=L.CONV_AUTO, bwd_impl=L.CONV_AUTO, dgrad_single=0, wgrad_single=0)),
+            ("two-plane bwd on SIMT fwd acts", dict(fwd_impl=L.CONV_SIMT, bwd_impl=L.CONV_AUTO, dgrad_single=0, wgrad_single=0)),
+            ("dgrad two-plane, wgrad default", dict(fwd_impl=L.CONV_SIMT, bwd_impl=L.CONV_AUTO, dgrad_single=0, wgrad_single=1)),
+            ("old hi-only wgrad on SIMT acts", dict(fwd_impl=L.CONV_SIMT, bwd_impl=L.CONV_AUTO, dgrad_single=1, wgrad_single=2)),
         ]
         preds = {}
         for label, kw in specs:
@@ -111,17 +110,16 @@ def main():
             worst = max(per_t, key=per_t.get)
             emit(f"{label:34s} {rel(flat, flat_want):12.3e} {per_t[worst]:13.3e}  {worst:18s} "
                  f"{float(np.median(list(per_t.values()))):13.3e}")
-        # the decisive comparison: same activations, different backward arithmetic
-        ga = variants["engine SIMT fp32 anchor"][0]
-        gb = variants["tcgen05 bwd on SIMT fwd acts"][0]
-        gs = variants["both single on SIMT fwd acts"][0]
-        fa = np.concatenate([ga[n].ravel() for n in names])
-        emit(f"identical gates: tcgen05 backward vs SIMT backward (both on SIMT activations): flat rel-L2 = "
-             f"{rel(np.concatenate([gb[n].ravel() for n in names]), fa):.3e}; single-operand backward: "
-             f"{rel(np.concatenate([gs[n].ravel() for n in names]), fa):.3e}")
-        emit("per tensor (default tcgen05 | tcgen05 bwd on SIMT acts | both single | torch fp32):")
+        # the decisive comparison: same activations (identical gates), different backward arithmetic
+        fa = np.concatenate([variants["engine SIMT fp32 anchor"][0][n].ravel() for n in names])
+        for label in ("tcgen05 bwd on SIMT fwd acts", "two-plane bwd on SIMT fwd acts", "dgrad two-plane, wgrad default",
+                      "old hi-only wgrad on SIMT acts"):
+            fb = np.concatenate([variants[label][0][n].ravel() for n in names])
+            emit(f"identical gates: {label:32s} vs SIMT backward on the same activations: flat rel-L2 = {rel(fb, fa):.3e}")
+        emit("per tensor (default tcgen05 | default bwd on SIMT acts | two-plane bwd on SIMT acts | torch fp32):")
         gd = variants["engine tcgen05 (default)"][0]
-        g2 = variants["tcgen05 + both single"][0]
+        gb = variants["tcgen05 bwd on SIMT fwd acts"][0]
+        g2 = variants["two-plane bwd on SIMT fwd acts"][0]
         gt = variants["torch-cpu fp32 autograd"][0]
         for n in names:
             emit(f"  {n:22s} {rel(gd[n], want[n]):10.2e} {rel(gb[n], want[n]):10.2e} {rel(g2[n], want[n]):10.2e} "
