@@ -66,7 +66,14 @@ class _LearningRate:
 class AdamOptimizer:
     """The slice of tf.keras.optimizers.Adam the reference touches (TrainerController.py:73,
     225,269,359,391): `lr`, `iterations`, `weights` = [iterations, m_0..m_n, v_0..v_n],
-    `set_weights`, and an apply step.  State lives in the engine's flat m / v buffers."""
+    `set_weights`, and an apply step.  State lives in the engine's flat m / v buffers.
+
+    ORDER.  The m / v lists follow this package's parameter table, i.e. Keras layer-CREATION order (conv3d,
+    conv3d_1, ...).  A Keras functional model lists `trainable_variables` / `optimizer.weights` by graph depth
+    instead (parallel branches interleave), which cannot be reproduced here without TensorFlow: an `optimizer.pkl`
+    written by the reference's own training run is therefore NOT restorable through `set_weights` (named `.h5` weight
+    files are: they are matched by layer name).  Files this package wrote round-trip.  `set_weights` validates every
+    shape before it touches the state, so a foreign list fails cleanly instead of half-overwriting the moments."""
 
     def __init__(self, engine, lr=1e-4, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
         self.engine = engine
@@ -91,11 +98,17 @@ class AdamOptimizer:
         n = len(self.engine.table)
         if len(weights) != 1 + 2 * n:
             raise ValueError(f"expected {1 + 2 * n} optimizer tensors, got {len(weights)}")
+        mviews = self.engine.tensor_views(self.engine.adam_m)
+        vviews = self.engine.tensor_views(self.engine.adam_v)
+        staged = [torch.as_tensor(np.asarray(w, dtype=np.float32)) for w in weights[1:]]
+        for (name, view), w in zip(mviews + vviews, staged):           # validate all shapes before the first copy
+            if tuple(w.shape) != tuple(view.shape):
+                raise ValueError(f"optimizer slot of {name}: shape {tuple(w.shape)} != {tuple(view.shape)}; the list must be "
+                                 "[iterations, m..., v...] in this package's table order (layer-creation order), not "
+                                 "the graph-depth order of a Keras-written optimizer.pkl")
         self.iterations = int(weights[0])
-        for (_, view), w in zip(self.engine.tensor_views(self.engine.adam_m), weights[1:1 + n]):
-            view.copy_(torch.as_tensor(np.asarray(w, dtype=np.float32)))
-        for (_, view), w in zip(self.engine.tensor_views(self.engine.adam_v), weights[1 + n:]):
-            view.copy_(torch.as_tensor(np.asarray(w, dtype=np.float32)))
+        for (_, view), w in zip(mviews + vviews, staged):
+            view.copy_(w)
 
     def apply(self, global_batch):
         """apply_gradients on the engine's gradient buffer (TrainerController.py:225)."""

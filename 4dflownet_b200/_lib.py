@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsr4d.so")
 
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5
-OPT_CONV_IMPL, OPT_SAVE_ACTS, OPT_PROFILE, OPT_FUSED_DGRAD, OPT_DGRAD_SINGLE, OPT_WGRAD_SINGLE = 1, 2, 3, 4, 5, 6
+OPT_CONV_IMPL, OPT_SAVE_ACTS, OPT_PROFILE, OPT_FUSED_DGRAD, OPT_DGRAD_SINGLE, OPT_WGRAD_SINGLE, OPT_NVTX = 1, 2, 3, 4, 5, 6, 7
 PROF_CLASSES = ("conv64_fwd_lr", "conv64_fwd_hr", "conv64_dgrad_lr", "conv64_dgrad_hr", "conv64_wgrad_lr",
                 "conv64_wgrad_hr")
 CONV_AUTO, CONV_SIMT, CONV_TCGEN05 = 0, 1, 2
@@ -56,6 +56,7 @@ SYMBOLS = {
     "sr4d_upsample_layer": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "sr4d_conv64_layer_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "sr4d_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
+    "sr4d_activation_overflow": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int, _P]),
     "sr4d_launch_count": (C.c_int64, [_P]),
     "sr4d_reset_launch_count": (None, [_P]),
 }

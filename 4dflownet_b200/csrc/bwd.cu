@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) head2_bwd_kernel(ActView h, const float* 
                     __half sh, sl;
                     split_f16(d * ksplit, sh, sl);
                     split_hi[go] = sh;
-                    split_lo[go] = sl;
+                    if (split_lo) split_lo[go] = sl;
                 }
                 dw[28] += d;
                 m = fmaxf(m, fabsf(d));
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256) g4_split_kernel(const float* __restrict__
     uint2 h, l;
     act_pack4(vv, h, l);
     *reinterpret_cast<uint2*>(hi + go) = h;
-    *reinterpret_cast<uint2*>(lo + go) = l;
+    if (lo) *reinterpret_cast<uint2*>(lo + go) = l;
 }
 
 // ---- 64->64 3x3x3 weight gradient: dW[t][ci][co] = sum_{b,v} Xp[b,v+t][ci] dY[b,v][co] ------
@@ -671,7 +671,7 @@ inline unsigned red_blocks(size_t n, int per) { unsigned b = nblocks(n, per); re
 
 cudaError_t launch_head2_bwd(ActView h, const float* g, int c, const float* w, float* out_g4, unsigned int* amax,
                              float* dw, float* db, float* db1, __half* split_out, int* split_exp,
-                             const unsigned int* gmax, float* scratch, cudaStream_t s) {
+                             const unsigned int* gmax, float* scratch, cudaStream_t s, bool hi_only) {
     const int H = h.D;
     const int nlines = h.B * H * H;
     const unsigned nb = nlines < 592 ? nlines : 592;           // 148 SMs x 4 resident blocks
@@ -680,7 +680,7 @@ cudaError_t launch_head2_bwd(ActView h, const float* g, int c, const float* w, f
     if (H > 128 || (split_out && (!split_exp || !gmax))) return cudaErrorInvalidValue;
     float* tmp = scratch + (size_t)nb * 29 * 64;   // reduced [29][64]
     __half* shi = split_out;
-    __half* slo = split_out ? split_out + (size_t)h.B * (H + 4) * (H + 4) * (H + 4) * 64 : nullptr;
+    __half* slo = (split_out && !hi_only) ? split_out + (size_t)h.B * (H + 4) * (H + 4) * (H + 4) * 64 : nullptr;
     if (H <= 48) head2_bwd_kernel<12><<<nb, 256, smem, s>>>(h, g, c, w, out_g4, amax, scratch, shi, slo, split_exp, gmax);
     else head2_bwd_kernel<32><<<nb, 256, smem, s>>>(h, g, c, w, out_g4, amax, scratch, shi, slo, split_exp, gmax);
     launch_reduce_rows(scratch, nb, 29 * 64, tmp, s);
@@ -698,10 +698,10 @@ cudaError_t launch_fold_act(const float* raw0, const float* raw1, const float* r
     return cudaGetLastError();
 }
 cudaError_t launch_g4_split(const float* g4, const unsigned int* amax, __half* split, int* exp_out, int B, int D,
-                            cudaStream_t s) {
+                            cudaStream_t s, bool hi_only) {
     size_t n = (size_t)B * D * D * D * 16;
     const size_t plane = (size_t)B * (D + 4) * (D + 4) * (D + 4) * 64;
-    g4_split_kernel<<<nblocks(n, 256), 256, 0, s>>>(g4, amax, split, split + plane, exp_out, B, D);
+    g4_split_kernel<<<nblocks(n, 256), 256, 0, s>>>(g4, amax, split, hi_only ? nullptr : split + plane, exp_out, B, D);
     return cudaGetLastError();
 }
 cudaError_t launch_wgrad64_simt(ActView x, const float* dy_g4, float* dw, float* scratch, int nchunk,

@@ -24,6 +24,10 @@ struct ActView {
     __half* hi;
     __half* lo;
     int B, D;   // D = interior edge; storage edge is D + 2
+    // handle-owned device flag, set to 1 by any producer that had to clamp a value to the fp16 range (+-65504) while
+    // splitting it (NULL: not tracked).  The fp32 reference would carry such values on; sr4d_activation_overflow()
+    // reports it instead of saturating silently.
+    unsigned int* ovf = nullptr;
 };
 
 __host__ __device__ inline size_t act_plane_elems(int B, int D) {
@@ -41,6 +45,12 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
     x = fminf(fmaxf(x, -65504.f), 65504.f);
     hi = __float2half_rn(x);
     lo = __float2half_rn((x - __half2float(hi)) * SR4D_LO_SCALE);
+}
+// same, reporting whether the value was outside the representable range (NaN counts)
+__device__ __forceinline__ bool split_f16_chk(float x, __half& hi, __half& lo) {
+    const bool over = !(fabsf(x) <= 65504.f);
+    split_f16(x, hi, lo);
+    return over;
 }
 __device__ __forceinline__ float join_f16(__half hi, __half lo) {
     return fmaf(__half2float(lo), SR4D_LO_INV, __half2float(hi));
@@ -73,10 +83,12 @@ __device__ __forceinline__ void act_load4(const __half* hi, const __half* lo, si
         v[2 * i + 1] = fmaf(b.y, SR4D_LO_INV, a.y);
     }
 }
-__device__ __forceinline__ void act_pack4(const float* v, uint2& h, uint2& l) {
+__device__ __forceinline__ void act_pack4(const float* v, uint2& h, uint2& l, unsigned int* ovf = nullptr) {
     __half hh[4], ll[4];
+    bool over = false;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) split_f16(v[i], hh[i], ll[i]);
+    for (int i = 0; i < 4; ++i) over |= split_f16_chk(v[i], hh[i], ll[i]);
+    if (over && ovf) *ovf = 1u;
     h = *reinterpret_cast<uint2*>(hh);
     l = *reinterpret_cast<uint2*>(ll);
 }
@@ -84,9 +96,9 @@ __device__ __forceinline__ void act_pack4(const float* v, uint2& h, uint2& l) {
 // Store 4 consecutive channels of interior voxel (x,y,z) and replicate them into the
 // halo positions this voxel is the clamp image of (faces, edges, corners).
 __device__ __forceinline__ void act_store4_halo(__half* hi, __half* lo, int D, int b, int x, int y, int z,
-                                                int c, const float* v, bool halo) {
+                                                int c, const float* v, bool halo, unsigned int* ovf = nullptr) {
     uint2 h, l;
-    act_pack4(v, h, l);
+    act_pack4(v, h, l, ovf);
     if (!halo) {
         size_t o = act_off(D, b, x, y, z) + c;
         *reinterpret_cast<uint2*>(hi + o) = h;
@@ -115,11 +127,13 @@ __device__ __forceinline__ void act_store4_halo(__half* hi, __half* lo, int D, i
 
 // 8 consecutive channels with 16-byte stores (same halo replication rule)
 __device__ __forceinline__ void act_store8_halo(__half* hi, __half* lo, int D, int b, int x, int y, int z,
-                                                int c, const float* v, bool halo) {
+                                                int c, const float* v, bool halo, unsigned int* ovf = nullptr) {
     __align__(16) __half hh[8];
     __align__(16) __half ll[8];
+    bool over = false;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) split_f16(v[i], hh[i], ll[i]);
+    for (int i = 0; i < 8; ++i) over |= split_f16_chk(v[i], hh[i], ll[i]);
+    if (over && ovf) *ovf = 1u;
     const uint4 H = *reinterpret_cast<const uint4*>(hh), L = *reinterpret_cast<const uint4*>(ll);
     const bool edge = halo && (x == 0 || x == D - 1 || y == 0 || y == D - 1 || z == 0 || z == D - 1);
     if (!edge) {

@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(256, 2) conv64_simt_kernel(Conv64Args a) {
             }
 #pragma unroll
             for (int n = 0; n < 4; ++n) { v0[n] = act_fn(v0[n], a.slope); v1[n] = act_fn(v1[n], a.slope); }
-            act_store4_halo(a.out_hi, a.out_lo, Do, b, x, y, z, c0, v0, a.halo);
-            act_store4_halo(a.out_hi, a.out_lo, Do, b, x, y, z, c1, v1, a.halo);
+            act_store4_halo(a.out_hi, a.out_lo, Do, b, x, y, z, c0, v0, a.halo, a.ovf);
+            act_store4_halo(a.out_hi, a.out_lo, Do, b, x, y, z, c1, v1, a.halo, a.ovf);
         } else {
             size_t o = ((((size_t)b * Do + x) * Do + y) * Do + z) * 64;
             *reinterpret_cast<float4*>(a.out_raw + o + c0) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);

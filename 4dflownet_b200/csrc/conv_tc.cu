@@ -53,21 +53,40 @@ constexpr int ZP = TZ + 2;                  // plane row pitch in voxels
 constexpr int TMEM_COLS = 512;              // two accumulators of up to 256 columns
 constexpr int ACC_STRIDE = 256;             // column offset of the second accumulator
 
-template <int TY>
+template <int TY, bool SINGLE>
 struct Cfg {
     static constexpr int N = TY * TZ;                                  // voxels per tile = MMA N
     static constexpr int ROWS = (TY + 2) * ZP;                         // rows of one staged plane part
     static constexpr int PART_BYTES = (ROWS * 128 + 1023) / 1024 * 1024;
-    static constexpr int XSTAGE_BYTES = 2 * PART_BYTES;                // hi part | lo part
+    static constexpr int XSTAGE_BYTES = (SINGLE ? 1 : 2) * PART_BYTES; // hi part | lo part (SINGLE: the B operand has no lo plane)
     static constexpr int NXS = 2;
-    static constexpr int NWS = 4;
-    static constexpr int LPC = (TY % 4 == 0) ? 4 : 3;                  // y-lines per epilogue chunk
+    // Weight taps stream through NWS 16 KB stages that are handed back to the producer in GROUPS of WG taps: every
+    // tcgen05.commit costs the tensor pipe ~100 cycles (tools/probe/wgrad_probe.cu on B200: 8 MMAs + 1 commit take 870
+    // cycles instead of 770, + 2 commits 1008), so one commit per tap was a 13 % (two-plane: 8 instructions per tap) to
+    // 24 % (single-plane dgrad: 4 per tap) tax.  Two groups are in flight (NWS = 2 WG); the activation stages need no
+    // commit of their own: by the time the producer may refill the weight stage of a tap it has seen the group commit
+    // that covers the whole previous-but-one pass (checked exhaustively when the schedule was written).
+    static constexpr int WG = SINGLE ? 3 : 2;
+    static constexpr int NGW = 2;
+    static constexpr int NWS = NGW * WG;
+    static constexpr int LPC = 4;                                      // y-lines per epilogue chunk
     static constexpr int CV = LPC * TZ;                                // voxels (TMEM columns) per chunk
     static constexpr int NCHUNK = (TY + LPC - 1) / LPC;
-    static constexpr int STAGE_FLOATS = 2 * CV * 64;                   // [H | L][voxel][channel]
+    // Epilogue organisation.  Two-plane kernels (forward, two-plane dgrad) spend >= 22k cycles of MMAs per tile and
+    // run ONE group of 8 warps chunk by chunk.  The single-plane dgrad has half the MMA time per tile (11k cycles),
+    // which the latency-bound chunk loop (global loads of the skip gradient / saved activation -> fold -> stores) of one
+    // group does not fit into: there TWO groups of 4 warps work on alternate chunks, each with its own staging buffer
+    // and named barrier, and every thread carries two (voxel, 8-channel) items -- four times the loads in flight.
+    static constexpr int NG = SINGLE ? 2 : 1;
+    static constexpr int GT = NUM_EPI / NG;                            // threads per group
+    static constexpr int IT = CV * 8 / GT;                             // items per thread per chunk (1 or 2)
+    static constexpr int CP = NUM_EPI_WARPS / NG / 4;                  // warps sharing one TMEM lane quadrant (2 or 1)
+    static constexpr int COLS = CV / CP;                               // TMEM columns a warp reads per chunk (16 or 32)
+    static constexpr int GSTAGE_FLOATS = 2 * CV * 64;                  // per group: [H | L][voxel][channel]
+    static constexpr int STAGE_FLOATS = NG * GSTAGE_FLOATS;
     static constexpr int SMEM_BYTES = 1024 + NXS * XSTAGE_BYTES + NWS * W_STAGE_BYTES + STAGE_FLOATS * 4 + 256;
     static_assert(N % 16 == 0 && N >= 16 && N <= 256, "UMMA N constraint for M=128");
-    static_assert(CV == 32 || CV == 24, "epilogue chunk shapes");
+    static_assert(IT * GT == CV * 8 && COLS * CP == CV, "epilogue work split");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -80,6 +99,7 @@ struct KParams {
     const float* bias;
     float* out_raw;          // optional fp32 [B][Do^3][64] output instead of Act
     unsigned int* absmax;    // optional: atomicMax of |out_raw| bit patterns
+    unsigned int* ovf;       // optional: set to 1 when an output activation had to be clamped to the fp16 range
     float slope;
     int B, Do, halo;
     int nyt, nzt, ntiles;
@@ -104,8 +124,6 @@ struct KParams {
     const unsigned int* add_amax;
     int single_b;            // 1: the B operand has no lo part (dgrad with a single-fp16 gradient): no second MMA, no lo load
     int xsplit;              // producer order: 1 = next activation plane requested mid-pass (default), 0 = at the pass boundary (SR4D_TC_XSPLIT=0)
-    int exp_skip;            // TIMING EXPERIMENT ONLY (SR4D_TC_EXP_SKIP, wrong results): bit 0 = re-use stale weight slots
-                             // after the first fill, bit 1 = re-use stale activation stages (how much do the L2 streams cost?)
     long long* dbg;          // SR4D_TC_DEBUG=1: per-CTA cycles the MMA warp waited on {t_empty, x_full, w_full} and its total
 };
 
@@ -125,10 +143,10 @@ __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo) 
     return d;
 }
 
-template <int TY>
+template <int TY, bool SINGLE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
-    using C = Cfg<TY>;
+    using C = Cfg<TY, SINGLE>;
     extern __shared__ uint8_t smem_raw[];
     // align by OFFSET (not by pointer cast) so the compiler keeps the shared address space (STS/LDS, not generic)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -137,10 +155,9 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
     float* stage = reinterpret_cast<float*>(wsm + C::NWS * W_STAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage) + C::STAGE_FLOATS * 4);
     uint64_t* x_full = bars;                 // [NXS]
-    uint64_t* x_empty = bars + C::NXS;       // [NXS]
-    uint64_t* w_full = bars + 2 * C::NXS;    // [NWS]
-    uint64_t* w_empty = w_full + C::NWS;     // [NWS]
-    uint64_t* t_full = w_empty + C::NWS;     // [2]
+    uint64_t* w_full = bars + C::NXS;        // [NWS]
+    uint64_t* w_empty = w_full + C::NWS;     // [NGW] one per group of WG stages
+    uint64_t* t_full = w_empty + C::NGW;     // [2]
     uint64_t* t_empty = t_full + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
@@ -153,8 +170,9 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
     }
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < C::NXS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-        for (int i = 0; i < C::NWS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < C::NXS; ++i) mbar_init(&x_full[i], 1);
+        for (int i = 0; i < C::NWS; ++i) mbar_init(&w_full[i], 1);
+        for (int i = 0; i < C::NGW; ++i) mbar_init(&w_empty[i], 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&xmap);
@@ -177,12 +195,12 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            // Issue order.  Weight taps run NWS stages ahead of the MMA warp.  The activation plane of the NEXT
-            // (tile, dx) pass is requested in the middle of the current pass (hi part before tap NWS, lo part two taps
-            // later): its stage was released when the previous pass finished, which is exactly when the slot of tap NWS
-            // frees, so the wait never blocks the weight stream, the 2 x 33 KB transfers get a whole pass to land
-            // and they no longer queue three weight images behind one 66 KB burst on the SM's L2 port.
-            uint32_t wi = 0;           // running weight-stage counter
+            // Issue order.  Weight taps run up to NWS stages ahead of the MMA warp, released WG at a time.  The activation
+            // plane of the NEXT (tile, dx) pass is requested in the middle of the current pass (hi part at tap NWS, lo part
+            // two taps later): its stage was last read by the previous pass, whose completion the producer has seen through
+            // the weight-group barriers by then, the transfers get half a pass to land and they do not queue the
+            // weight images behind one 66 KB burst on the SM's L2 port.
+            uint32_t wi = 0;           // running weight-tap counter
             const int npass = p.ntiles > (int)blockIdx.x ? ((p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) * 3 : 0;
             auto x_load = [&](int q, int part) {
                 const int t = blockIdx.x + (q / 3) * gridDim.x, dx = q % 3;
@@ -191,7 +209,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                 const int x = rem / tiles_per_x;
                 rem %= tiles_per_x;
                 const int y0 = (rem / p.nzt) * TY, z0 = (rem % p.nzt) * TZ;
-                const uint32_t s = (uint32_t)q % C::NXS, ph = ((uint32_t)q / C::NXS) & 1;
+                const uint32_t s = (uint32_t)q % C::NXS;
                 int plane = x + dx;
                 if (p.fused) {
                     // interior plane x of dX: storage planes x+1..x+3 of the zero-haloed dY; at the two boundary
@@ -201,13 +219,10 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                     if (dx == 2 && x == p.Dint - 1) plane = p.Dint + 1;
                 }
                 uint8_t* dst = xs + s * C::XSTAGE_BYTES;
-                if ((p.exp_skip & 2) && q >= C::NXS) {
-                    if (part == 0) { mbar_wait(&x_empty[s], ph ^ 1); mbar_expect_tx(&x_full[s], 0); }
-                } else if (part == 0) {
-                    mbar_wait(&x_empty[s], ph ^ 1);
-                    mbar_expect_tx(&x_full[s], (p.single_b ? 1 : 2) * C::ROWS * 128);
+                if (part == 0) {
+                    mbar_expect_tx(&x_full[s], (SINGLE ? 1 : 2) * C::ROWS * 128);
                     tma_load_5d(dst, &xmap, &x_full[s], 0, z0, y0, plane, b);
-                } else if (!p.single_b) {
+                } else if (!SINGLE) {
                     tma_load_5d(dst + C::PART_BYTES, &xmap, &x_full[s], 0, z0, y0, plane, p.B + b);
                 }
             };
@@ -221,20 +236,17 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                     if (dx == 2 && x == p.Dint - 1) wsel = 0;
                 }
                 for (int tp = 0; tp < 9; ++tp) {
+                    const uint32_t ws = wi % C::NWS;
+                    if (wi % C::WG == 0)                 // first stage of a group: wait until the group's previous round was consumed
+                        mbar_wait(&w_empty[(wi / C::WG) % C::NGW], ((wi / C::NWS) & 1) ^ 1);
                     if (q + 1 < npass && p.xsplit) {
-                        if (tp == C::NWS) x_load(q + 1, 0);
-                        if (tp == C::NWS + 2) x_load(q + 1, 1);
+                        if (tp == 4) x_load(q + 1, 0);
+                        if (tp == 6) x_load(q + 1, 1);
                     }
-                    const uint32_t ws = wi % C::NWS, wph = (wi / C::NWS) & 1;
-                    mbar_wait(&w_empty[ws], wph ^ 1);
-                    if ((p.exp_skip & 1) && wi >= (uint32_t)C::NWS) {
-                        mbar_expect_tx(&w_full[ws], 0);
-                    } else {
-                        mbar_expect_tx(&w_full[ws], W_TAP_BYTES);
-                        bulk_load(wsm + ws * W_STAGE_BYTES,
-                                  reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)(wsel * 9 + tp) * W_TAP_BYTES,
-                                  W_TAP_BYTES, &w_full[ws]);
-                    }
+                    mbar_expect_tx(&w_full[ws], W_TAP_BYTES);
+                    bulk_load(wsm + ws * W_STAGE_BYTES,
+                              reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)(wsel * 9 + tp) * W_TAP_BYTES,
+                              W_TAP_BYTES, &w_full[ws]);
                     ++wi;
                 }
                 if (q + 1 < npass && !p.xsplit) { x_load(q + 1, 0); x_load(q + 1, 1); }
@@ -278,14 +290,13 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                             // [Wlo ; Whi] x Xhi, then [Whi ; (next 8 KB, lanes 64-127 masked off)] x Xlo into the same accumulator
                             tc_mma_f16(dacc, make_desc_sbo(wa + k * 32, 1024),
                                        make_desc_sbo(xhi + boff + k * 32, ZP * 128), idesc, acc);
-                            if (!p.single_b)
+                            if (!SINGLE)
                                 tc_mma_f16_masked(dacc, make_desc_sbo(wa + W_HI_OFFSET + k * 32, 1024),
                                                   make_desc_sbo(xlo + boff + k * 32, ZP * 128), idesc, 1u, 0u, 0u, ~0u, ~0u);
                         }
-                        tc_commit(&w_empty[ws]);
+                        if (wi % C::WG == C::WG - 1) tc_commit(&w_empty[(wi / C::WG) % C::NGW]);   // hand the group of stages back
                         ++wi;
                     }
-                    tc_commit(&x_empty[s]);
                     ++xi;
                 }
                 tc_commit(&t_full[buf]);
@@ -297,31 +308,34 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
             }
         }
     } else {
-        // ================= epilogue (warps 2..9, 256 threads) =================
+        // ================= epilogue (warps 2..9): C::NG groups working on alternate chunks =================
         // warp w may only read TMEM lanes 32*(w%4)..+31: quadrants 0,1 hold the L rows (co = 32e + lane),
-        // quadrants 2,3 the H rows; the two warps of a quadrant split a chunk's columns
+        // quadrants 2,3 the H rows; the C::CP warps of a quadrant (within a group) split a chunk's columns
+        const int ew = warp - 2;                                   // 0..7
+        const int grp = C::NG == 2 ? (ew >> 2) : 0;                // which group
+        const int cpart = C::NG == 2 ? 0 : (ew >> 2);              // which part of the chunk's columns this warp reads
         const int e = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const int et = threadIdx.x - 64;             // 0..255
+        const int gt = threadIdx.x - 64 - grp * C::GT;             // thread within the group
         const bool is_h = e >= 2;
         const int co = 32 * (e & 1) + lane;
         const float bias = (is_h && p.bias) ? p.bias[co] : 0.f;
         const float s1 = is_h ? 1.f : SR4D_LO_INV;
         const int Do = p.Do;
-        const int g8 = et & 7;                       // 8-channel group handled in the store phase
-        const int vq = et >> 3;                      // voxel of the chunk handled in the store phase
-        float* my_stage = stage + (is_h ? 0 : C::CV * 64) + co;
+        const int Di = p.Dint;
+        float* gstage = stage + grp * C::GSTAGE_FLOATS;
+        float* my_stage = gstage + (is_h ? 0 : C::CV * 64) + co;
         float amax = 0.f;
         float ksplit = 0.f;
         if (p.fused && p.split_hi) {
             float bound = 8.f * *p.gain * __uint_as_float(*p.dy_amax);
             if (p.add_amax) bound += __uint_as_float(*p.add_amax);
-            int e = 0;
-            if (bound > 0.f && bound < 3.0e38f) e = 14 - ilogbf(bound);     // bound * 2^e < 2^15
-            e = max(-120, min(120, e));
-            ksplit = exp2f((float)e);
-            if (blockIdx.x == 0 && et == 0) *p.split_exp = e;
+            int ex = 0;
+            if (bound > 0.f && bound < 3.0e38f) ex = 14 - ilogbf(bound);     // bound * 2^e < 2^15
+            ex = max(-120, min(120, ex));
+            ksplit = exp2f((float)ex);
+            if (blockIdx.x == 0 && threadIdx.x == 64) *p.split_exp = ex;
         }
+        const float ks = (p.fused && p.dy_exp) ? exp2f((float)(-*p.dy_exp)) : 1.f;
         uint32_t ti = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
             const int b = t / tiles_per_b;
@@ -334,73 +348,80 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
             mbar_wait(&t_full[buf], (ti >> 1) & 1);
             tc_fence_after();
             const uint32_t trow = tmem_base + buf * ACC_STRIDE + ((uint32_t)(32 * e) << 16);
+            if (grp >= C::NCHUNK) {
+                // this group has no chunk of the tile: hand the accumulator back right away
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&t_empty[buf]);
+            }
 #pragma unroll 1
-            for (int ch = 0; ch < C::NCHUNK; ++ch) {
-                const int line = ch * C::LPC + (vq >> 3);
-                const int y = y0 + line, z = z0 + (vq & 7);
-                bool active = vq < C::CV && line < TY && y < Do && z < Do;
-                // fused dgrad: (y, z) are padded-grid coordinates; only interior voxels produce output
-                const int Di = p.Dint;
-                if (p.fused) active = active && y >= 1 && y <= Di && z >= 1 && z <= Di;
-                float4 ap0, ap1, aq0, aq1;
-                // residual prefetch for the (voxel, channel-group) item this thread stores
-                uint4 rh, rl;
-                if (p.fused) {
-                    if (active) {
-                        const size_t go = g4_off(Di, b, x, y - 1, z - 1) + g8 * 8;
-                        if (p.add_pre) {
-                            ap0 = *reinterpret_cast<const float4*>(p.add_pre + go);
-                            ap1 = *reinterpret_cast<const float4*>(p.add_pre + go + 4);
+            for (int ch = grp; ch < C::NCHUNK; ch += C::NG) {
+                // ---- the (voxel, 8-channel group) items this thread stores, and the prefetch of what they add ----
+                bool active[C::IT];
+                int vy[C::IT], vz[C::IT];
+                float4 ap0[C::IT], ap1[C::IT], aq0[C::IT], aq1[C::IT];
+                uint4 rh[C::IT], rl[C::IT];
+#pragma unroll
+                for (int k = 0; k < C::IT; ++k) {
+                    const int item = gt + k * C::GT;
+                    const int vq = item >> 3, g8 = item & 7;
+                    const int line = ch * C::LPC + (vq >> 3);
+                    const int y = y0 + line, z = z0 + (vq & 7);
+                    vy[k] = y; vz[k] = z;
+                    bool act = line < TY && y < Do && z < Do;
+                    // fused dgrad: (y, z) are padded-grid coordinates; only interior voxels produce output
+                    if (p.fused) act = act && y >= 1 && y <= Di && z >= 1 && z <= Di;
+                    active[k] = act;
+                    if (p.fused) {
+                        if (act) {
+                            const size_t go = g4_off(Di, b, x, y - 1, z - 1) + g8 * 8;
+                            if (p.add_pre) {
+                                ap0[k] = *reinterpret_cast<const float4*>(p.add_pre + go);
+                                ap1[k] = *reinterpret_cast<const float4*>(p.add_pre + go + 4);
+                            }
+                            if (p.add_post) {
+                                aq0[k] = *reinterpret_cast<const float4*>(p.add_post + go);
+                                aq1[k] = *reinterpret_cast<const float4*>(p.add_post + go + 4);
+                            }
+                            if (p.sav_hi) {
+                                const size_t o = act_off(Di, b, x, y - 1, z - 1) + g8 * 8;
+                                rh[k] = *reinterpret_cast<const uint4*>(p.sav_hi + o);
+                                rl[k] = *reinterpret_cast<const uint4*>(p.sav_lo + o);
+                            }
                         }
-                        if (p.add_post) {
-                            aq0 = *reinterpret_cast<const float4*>(p.add_post + go);
-                            aq1 = *reinterpret_cast<const float4*>(p.add_post + go + 4);
-                        }
-                        if (p.sav_hi) {
-                            const size_t o = act_off(Di, b, x, y - 1, z - 1) + g8 * 8;
-                            rh = *reinterpret_cast<const uint4*>(p.sav_hi + o);
-                            rl = *reinterpret_cast<const uint4*>(p.sav_lo + o);
-                        }
+                    } else if (p.res_hi && act) {
+                        const size_t o = act_off(Do, b, x, y, z) + g8 * 8;
+                        rh[k] = *reinterpret_cast<const uint4*>(p.res_hi + o);
+                        rl[k] = *reinterpret_cast<const uint4*>(p.res_lo + o);
                     }
-                } else if (p.res_hi && active) {
-                    const size_t o = act_off(Do, b, x, y, z) + g8 * 8;
-                    rh = *reinterpret_cast<const uint4*>(p.res_hi + o);
-                    rl = *reinterpret_cast<const uint4*>(p.res_lo + o);
                 }
                 // ---- phase A: TMEM -> registers -> fp32 staging [part][voxel][channel] ----
-                const int c0 = ch * C::CV;
-                const int ncols = (C::N - c0) < C::CV ? (C::N - c0) : C::CV;
-                if (half == 0) {
-                    float a[16];
-                    tc_ld16(trow + c0, a);
-                    tc_ld_wait();
+                const int c0 = ch * C::CV + cpart * C::COLS;           // first accumulator column this warp reads
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) my_stage[j * 64] = fmaf(a[j], s1, bias);
-                } else if (ncols > 16) {
-                    if (C::CV == 32) {
+                for (int cc = 0; cc < C::COLS; cc += 16) {
+                    if (c0 + cc < C::N) {                              // N is a multiple of 16
                         float a[16];
-                        tc_ld16(trow + c0 + 16, a);
+                        tc_ld16(trow + c0 + cc, a);
                         tc_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) my_stage[(16 + j) * 64] = fmaf(a[j], s1, bias);
-                    } else {
-                        float a[8];
-                        tc_ld8(trow + c0 + 16, a);
-                        tc_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) my_stage[(16 + j) * 64] = fmaf(a[j], s1, bias);
+                        for (int j = 0; j < 16; ++j) my_stage[(cpart * C::COLS + cc + j) * 64] = fmaf(a[j], s1, bias);
                     }
                 }
-                if (ch == C::NCHUNK - 1) {
-                    // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+                if (ch + C::NG >= C::NCHUNK) {
+                    // all TMEM reads of this tile by this warp are done: hand the accumulator back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&t_empty[buf]);
                 }
-                named_bar(1, NUM_EPI);
+                named_bar(1 + grp, C::GT);
                 // ---- phase B: coalesced residual / activation / split / store ----
-                if (active) {
-                    const float* sp = stage + vq * 64 + g8 * 8;
+#pragma unroll
+                for (int k = 0; k < C::IT; ++k) {
+                    if (!active[k]) continue;
+                    const int item = gt + k * C::GT;
+                    const int vq = item >> 3, g8 = item & 7;
+                    const int y = vy[k], z = vz[k];
+                    const float* sp = gstage + vq * 64 + g8 * 8;
                     const float4 h0 = *reinterpret_cast<const float4*>(sp);
                     const float4 h1 = *reinterpret_cast<const float4*>(sp + 4);
                     const float4 l0 = *reinterpret_cast<const float4*>(sp + C::CV * 64);
@@ -423,26 +444,25 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                         if (yhi) fold(8);
                         if (zlo) { fold(-1); if (ylo) fold(-9); if (yhi) fold(7); }
                         if (zhi) { fold(1); if (ylo) fold(-7); if (yhi) fold(9); }
-                        const float ks = p.dy_exp ? exp2f((float)(-*p.dy_exp)) : 1.f;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) val[k] *= ks;
+                        for (int c = 0; c < 8; ++c) val[c] *= ks;
                         if (p.add_pre) {
-                            val[0] += ap0.x; val[1] += ap0.y; val[2] += ap0.z; val[3] += ap0.w;
-                            val[4] += ap1.x; val[5] += ap1.y; val[6] += ap1.z; val[7] += ap1.w;
+                            val[0] += ap0[k].x; val[1] += ap0[k].y; val[2] += ap0[k].z; val[3] += ap0[k].w;
+                            val[4] += ap1[k].x; val[5] += ap1[k].y; val[6] += ap1[k].z; val[7] += ap1[k].w;
                         }
                         if (p.sav_hi) {
-                            const __half2* hh = reinterpret_cast<const __half2*>(&rh);
-                            const __half2* ll = reinterpret_cast<const __half2*>(&rl);
+                            const __half2* hh = reinterpret_cast<const __half2*>(&rh[k]);
+                            const __half2* ll = reinterpret_cast<const __half2*>(&rl[k]);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const float2 ha = __half22float2(hh[k]), la = __half22float2(ll[k]);
-                                val[2 * k] *= act_grad_from_out(fmaf(la.x, SR4D_LO_INV, ha.x), p.slope);
-                                val[2 * k + 1] *= act_grad_from_out(fmaf(la.y, SR4D_LO_INV, ha.y), p.slope);
+                            for (int c = 0; c < 4; ++c) {
+                                const float2 ha = __half22float2(hh[c]), la = __half22float2(ll[c]);
+                                val[2 * c] *= act_grad_from_out(fmaf(la.x, SR4D_LO_INV, ha.x), p.slope);
+                                val[2 * c + 1] *= act_grad_from_out(fmaf(la.y, SR4D_LO_INV, ha.y), p.slope);
                             }
                         }
                         if (p.add_post) {
-                            val[0] += aq0.x; val[1] += aq0.y; val[2] += aq0.z; val[3] += aq0.w;
-                            val[4] += aq1.x; val[5] += aq1.y; val[6] += aq1.z; val[7] += aq1.w;
+                            val[0] += aq0[k].x; val[1] += aq0[k].y; val[2] += aq0[k].z; val[3] += aq0[k].w;
+                            val[4] += aq1[k].x; val[5] += aq1[k].y; val[6] += aq1[k].z; val[7] += aq1[k].w;
                         }
                         const size_t go = g4_off(Di, b, x, y - 1, z - 1) + g8 * 8;
                         float* o = p.out_g4 + go;
@@ -452,33 +472,35 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                             __align__(16) __half hv[8];
                             __align__(16) __half lv[8];
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) split_f16(val[k] * ksplit, hv[k], lv[k]);
+                            for (int c = 0; c < 8; ++c) split_f16(val[c] * ksplit, hv[c], lv[c]);
                             *reinterpret_cast<uint4*>(p.split_hi + go) = *reinterpret_cast<const uint4*>(hv);
-                            *reinterpret_cast<uint4*>(p.split_lo + go) = *reinterpret_cast<const uint4*>(lv);
+                            if (p.split_lo) *reinterpret_cast<uint4*>(p.split_lo + go) = *reinterpret_cast<const uint4*>(lv);
                         }
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(val[k]));
+                        for (int c = 0; c < 8; ++c) amax = fmaxf(amax, fabsf(val[c]));
                     } else if (p.out_raw) {
                         float* o = p.out_raw + ((((size_t)b * Do + x) * Do + y) * Do + z) * 64 + g8 * 8;
                         *reinterpret_cast<float4*>(o) = make_float4(val[0], val[1], val[2], val[3]);
                         *reinterpret_cast<float4*>(o + 4) = make_float4(val[4], val[5], val[6], val[7]);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(val[k]));
+                        for (int c = 0; c < 8; ++c) amax = fmaxf(amax, fabsf(val[c]));
                     } else {
                         if (p.res_hi) {
-                            const __half2* hh = reinterpret_cast<const __half2*>(&rh);
-                            const __half2* ll = reinterpret_cast<const __half2*>(&rl);
+                            const __half2* hh = reinterpret_cast<const __half2*>(&rh[k]);
+                            const __half2* ll = reinterpret_cast<const __half2*>(&rl[k]);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                float2 ha = __half22float2(hh[k]), la = __half22float2(ll[k]);
-                                val[2 * k] += fmaf(la.x, SR4D_LO_INV, ha.x);
-                                val[2 * k + 1] += fmaf(la.y, SR4D_LO_INV, ha.y);
+                            for (int c = 0; c < 4; ++c) {
+                                float2 ha = __half22float2(hh[c]), la = __half22float2(ll[c]);
+                                val[2 * c] += fmaf(la.x, SR4D_LO_INV, ha.x);
+                                val[2 * c + 1] += fmaf(la.y, SR4D_LO_INV, ha.y);
                             }
                         }
                         __align__(16) __half hv[8];
                         __align__(16) __half lv[8];
+                        bool over = false;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) split_f16(act_fn(val[k], p.slope), hv[k], lv[k]);
+                        for (int c = 0; c < 8; ++c) over |= split_f16_chk(act_fn(val[c], p.slope), hv[c], lv[c]);
+                        if (over && p.ovf) *p.ovf = 1u;
                         const uint4 H = *reinterpret_cast<const uint4*>(hv), L = *reinterpret_cast<const uint4*>(lv);
                         const size_t o = act_off(Do, b, x, y, z) + g8 * 8;
                         *reinterpret_cast<uint4*>(p.out_hi + o) = H;
@@ -502,7 +524,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                         }
                     }
                 }
-                named_bar(1, NUM_EPI);
+                named_bar(1 + grp, C::GT);
             }
         }
         if (p.absmax) {
@@ -586,17 +608,17 @@ __global__ void __launch_bounds__(256) weight_gain_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-template <int TY>
+template <int TY, bool SINGLE>
 cudaError_t launch_cfg(const CUtensorMap& map, KParams p, cudaStream_t s) {
-    using C = Cfg<TY>;
-    cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(conv64_tc_kernel<TY>), C::SMEM_BYTES);
+    using C = Cfg<TY, SINGLE>;
+    cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(conv64_tc_kernel<TY, SINGLE>), C::SMEM_BYTES);
     if (ea != cudaSuccess) return ea;
     p.nyt = (p.Do + TY - 1) / TY;
     p.nzt = (p.Do + TZ - 1) / TZ;
     p.ntiles = p.B * p.nx * p.nyt * p.nzt;
     const int sms = tc_num_sms();
     int grid = p.ntiles < sms ? p.ntiles : sms;
-    conv64_tc_kernel<TY><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(map, p);
+    conv64_tc_kernel<TY, SINGLE><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(map, p);
     return cudaGetLastError();
 }
 
@@ -653,10 +675,32 @@ int pick_ty(int Do) {
 }
 }  // namespace
 
+// forward grids: the tile height that finishes first on this machine.  A tile of N = 8*TY voxels costs
+// 27 taps x 4 K-steps x 2 instructions of max(N/2, 32 + N/4) cycles (tensor pipe vs shared-memory operand fetch,
+// profiles/r01_tcgen05_probe.txt); the persistent grid runs ceil(tiles / SMs) rounds.  At batch 8 the tall tiles win
+// (TY = 24 on the 24^3 / 48^3 grids); at batch 1 the 24^3 grid has only 72 such tiles for 148 SMs and TY = 12 (144
+// tiles, one round of cheaper tiles) is ~40 % faster (configs[0], predictor.py at batch 1).
+int pick_ty_fwd(int Do, int B) {
+    if (Do <= 8) return 8;
+    const int sms = tc_num_sms();
+    const int cand[5] = {8, 12, 16, 24, 26};
+    int best = 24;
+    long best_cost = -1;
+    for (int c : cand) {
+        const long tiles = (long)B * Do * ((Do + c - 1) / c) * ((Do + TZ - 1) / TZ);
+        const long rounds = (tiles + sms - 1) / sms;
+        const int n = c * TZ;
+        const long per_tile = 216L * (n / 2 > 32 + n / 4 ? n / 2 : 32 + n / 4) + 3000;    // + epilogue / pipeline fill
+        const long cost = rounds * per_tile;
+        if (best_cost < 0 || cost < best_cost || (cost == best_cost && c > best)) { best_cost = cost; best = c; }
+    }
+    return best;
+}
+
 bool tc_dgrad_fusable(int D) {
     if (D < 2) return false;
     const int ty = pick_ty(D + 2);
-    const int lpc = ty % 4 == 0 ? 4 : 3;
+    const int lpc = 4;
     auto chunk = [&](int line) { return (line / ty) * 1000 + (line % ty) / lpc; };
     return chunk(0) == chunk(1) && chunk(D) == chunk(D + 1) && D / TZ == (D + 1) / TZ;
 }
@@ -669,7 +713,7 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
     p.w_img = w->img + ((size_t)a.layer * 2 + (a.dgrad ? 1 : 0)) * 27 * 128 * 64;
     p.out_hi = a.out.hi; p.out_lo = a.out.lo;
     p.res_hi = a.res_hi; p.res_lo = a.res_lo;
-    p.bias = a.bias; p.out_raw = a.out_raw; p.absmax = a.absmax;
+    p.bias = a.bias; p.out_raw = a.out_raw; p.absmax = a.absmax; p.ovf = a.out.ovf;
     p.slope = a.slope; p.B = B; p.Do = Do; p.halo = a.halo;
     p.nx = a.fused ? Do - 2 : Do;
     p.fused = a.fused; p.Dint = Do - 2;
@@ -677,13 +721,11 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
     p.dy_exp = a.dy_exp; p.add_pre = a.add_pre; p.add_post = a.add_post;
     p.sav_hi = a.sav_hi; p.sav_lo = a.sav_lo; p.out_g4 = a.out_g4;
     p.split_hi = a.split_out;
-    p.split_lo = a.split_out ? a.split_out + act_plane_elems(B, Do) : nullptr;   // [2B][D+4]^3[64]: hi planes then lo planes
+    p.split_lo = (a.split_out && !a.split_hi_only) ? a.split_out + act_plane_elems(B, Do) : nullptr;   // [2B][D+4]^3[64]: hi planes then lo planes
     p.split_exp = a.split_exp; p.gain = w->gain + a.layer; p.dy_amax = a.dy_amax; p.add_amax = a.add_amax;
     if (a.split_out && (!a.split_exp || !a.dy_amax || !a.fused)) return cudaErrorInvalidValue;
     static const bool xsplit = !(getenv("SR4D_TC_XSPLIT") && atoi(getenv("SR4D_TC_XSPLIT")) == 0);
     p.xsplit = xsplit;
-    static const int exp_skip = getenv("SR4D_TC_EXP_SKIP") ? atoi(getenv("SR4D_TC_EXP_SKIP")) : 0;
-    p.exp_skip = exp_skip;
     p.dbg = nullptr;
     static const bool debug = getenv("SR4D_TC_DEBUG") != nullptr;
     static long long* dbg_buf = nullptr;
@@ -693,16 +735,26 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
         cudaMemsetAsync(dbg_buf + 148 * 8, 0x7f, sizeof(long long), s);      // min slot starts high
         p.dbg = dbg_buf;
     }
-    const int ty = pick_ty(Do);
+    const int ty = a.dgrad ? pick_ty(Do) : pick_ty_fwd(Do, B);
     CUtensorMap map;
     if (!tc_make_act_map(&map, a.in.hi, B, Dp, ty + 2, ZP)) return cudaErrorUnknown;
     if (a.in.lo != a.in.hi + act_plane_elems(B, a.in.D)) return cudaErrorInvalidValue;   // planes must be packed
     cudaError_t e;
-    switch (ty) {
-        case 8: e = launch_cfg<8>(map, p, s); break;
-        case 16: e = launch_cfg<16>(map, p, s); break;
-        case 24: e = launch_cfg<24>(map, p, s); break;
-        default: e = launch_cfg<26>(map, p, s); break;
+    if (p.single_b) {
+        switch (ty) {
+            case 8: e = launch_cfg<8, true>(map, p, s); break;
+            case 16: e = launch_cfg<16, true>(map, p, s); break;
+            case 24: e = launch_cfg<24, true>(map, p, s); break;
+            default: e = launch_cfg<26, true>(map, p, s); break;
+        }
+    } else {
+        switch (ty) {
+            case 8: e = launch_cfg<8, false>(map, p, s); break;
+            case 12: e = launch_cfg<12, false>(map, p, s); break;
+            case 16: e = launch_cfg<16, false>(map, p, s); break;
+            case 24: e = launch_cfg<24, false>(map, p, s); break;
+            default: e = launch_cfg<26, false>(map, p, s); break;
+        }
     }
     if (debug && e == cudaSuccess) {
         long long hb[148 * 8 + 2];

@@ -32,6 +32,7 @@ struct TcConvArgs {
     // optional: also write the scaled split-fp16 copy [2B][D+4]^3[64] of out_g4 (what g4_split_kernel produces) with
     // an exponent derived in-kernel from max|dy| (*dy_amax), the layer's weight gain and max|add_pre| (*add_amax)
     __half* split_out = nullptr;
+    int split_hi_only = 0;             // the lo plane of split_out has no consumer (single-plane dgrad + wgrad): skip it
     int* split_exp = nullptr;
     const unsigned int* dy_amax = nullptr;
     const unsigned int* add_amax = nullptr;

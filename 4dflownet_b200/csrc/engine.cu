@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/sr4d.h"
 #include "kernels.h"
 #include "conv_tc.h"
@@ -23,12 +25,14 @@ struct Layer {
 struct ActBuf {
     __half* base = nullptr;   // hi plane then lo plane, sized for maxB
     int D = 0;
+    unsigned int* ovf = nullptr;   // the handle's fp16-range overflow flag (see ActView::ovf)
     ActView view(int B) const {
         ActView v;
         v.hi = base;
         v.lo = base + act_plane_elems(B, D);   // planes packed for the CURRENT batch
         v.B = B;
         v.D = D;
+        v.ovf = ovf;
         return v;
     }
 };
@@ -58,6 +62,7 @@ struct sr4d_handle {
     int64_t flat = 0, nparam = 0;
     float *params = nullptr, *grads = nullptr, *m = nullptr, *v = nullptr;
     unsigned char* kflag = nullptr;
+    unsigned int* ovf = nullptr;       // device: set to 1 when an activation was clamped to the fp16 range
     float* feat = nullptr;
     std::vector<ActBuf> lr, hr;        // storage slots
     std::vector<int> lr_slot, hr_slot; // tensor index -> slot
@@ -93,6 +98,7 @@ struct sr4d_handle {
     int64_t launches = 0;
     // per-kernel-class device timing (SR4D_OPT_PROFILE): event pairs on the launch stream
     int profile = 0;
+    int nvtx = 0;              // SR4D_OPT_NVTX
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     std::vector<int> ev_class;        // class of pair i (events 2i, 2i+1)
@@ -116,9 +122,15 @@ int fail(sr4d_t* h, int code, const std::string& msg) {
     return code;
 }
 
+const char* const kProfNames[SR4D_PROF_NCLASSES] = {"conv64_fwd_lr", "conv64_fwd_hr", "conv64_dgrad_lr", "conv64_dgrad_hr",
+                                                    "conv64_wgrad_lr", "conv64_wgrad_hr"};
+
+// Brackets the launches of one 64->64 layer call: CUDA events per kernel class (SR4D_OPT_PROFILE) and / or an NVTX
+// range named after the class (SR4D_OPT_NVTX; the ranges show up in Nsight Systems / ncu --nvtx next to the kernels).
 struct ProfScope {
-    sr4d_t* h; cudaStream_t s; bool on;
-    ProfScope(sr4d_t* h_, int cls, cudaStream_t s_) : h(h_), s(s_), on(h_->profile != 0) {
+    sr4d_t* h; cudaStream_t s; bool on; bool nvtx;
+    ProfScope(sr4d_t* h_, int cls, cudaStream_t s_) : h(h_), s(s_), on(h_->profile != 0), nvtx(h_->nvtx != 0) {
+        if (nvtx) nvtxRangePushA(kProfNames[cls]);
         if (!on) return;
         if (h->ev_used + 2 > h->ev_pool.size()) {
             for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
@@ -127,10 +139,18 @@ struct ProfScope {
         cudaEventRecord(h->ev_pool[h->ev_used], s);
     }
     ~ProfScope() {
-        if (!on) return;
-        cudaEventRecord(h->ev_pool[h->ev_used + 1], s);
-        h->ev_used += 2;
+        if (on) {
+            cudaEventRecord(h->ev_pool[h->ev_used + 1], s);
+            h->ev_used += 2;
+        }
+        if (nvtx) nvtxRangePop();
     }
+};
+// NVTX range around a whole phase of a step (forward / loss / backward / adam)
+struct NvtxPhase {
+    bool on;
+    NvtxPhase(const sr4d_t* h, const char* name) : on(h->nvtx != 0) { if (on) nvtxRangePushA(name); }
+    ~NvtxPhase() { if (on) nvtxRangePop(); }
 };
 
 void build_table(sr4d_t* h) {
@@ -218,8 +238,9 @@ int build_upsample_tables(sr4d_t* h) {
     return SR4D_OK;
 }
 
-int alloc_act(ActBuf& b, int maxB, int D) {
+int alloc_act(ActBuf& b, int maxB, int D, unsigned int* ovf = nullptr) {
     b.D = D;
+    b.ovf = ovf;
     size_t n = 2 * act_plane_elems(maxB, D);
     if (dmalloc(&b.base, n) != cudaSuccess) return SR4D_ENOMEM;
     return SR4D_OK;
@@ -263,19 +284,19 @@ int plan_buffers(sr4d_t* h) {
     }
     h->lr.resize(n_lr_slots);
     for (auto& b : h->lr)
-        if (alloc_act(b, h->maxB, h->P)) return SR4D_ENOMEM;
+        if (alloc_act(b, h->maxB, h->P, h->ovf)) return SR4D_ENOMEM;
     if (h->r == 1) {
         // upsample is the identity (SR4DFlowNet.py:72-74): HR tensor 0 aliases the LR trunk
         h->hr.resize(n_hr_slots);
         for (int i = 0; i < n_hr_slots; ++i) {
             bool is_up_slot = (i == h->hr_slot[0]);
             if (h->training && is_up_slot) { h->hr[i].D = h->H; continue; }   // aliased at run time
-            if (alloc_act(h->hr[i], h->maxB, h->H)) return SR4D_ENOMEM;
+            if (alloc_act(h->hr[i], h->maxB, h->H, h->ovf)) return SR4D_ENOMEM;
         }
     } else {
         h->hr.resize(n_hr_slots);
         for (auto& b : h->hr)
-            if (alloc_act(b, h->maxB, h->H)) return SR4D_ENOMEM;
+            if (alloc_act(b, h->maxB, h->H, h->ovf)) return SR4D_ENOMEM;
     }
     return SR4D_OK;
 }
@@ -324,7 +345,7 @@ int conv64_fwd(sr4d_t* h, int layer, ActView in, ActView out, const ActView* res
     Conv64Args a;
     a.in_hi = in.hi; a.in_lo = in.lo; a.B = in.B; a.Do = in.D;
     a.w = W(h, layer);
-    a.out_hi = out.hi; a.out_lo = out.lo; a.halo = 1;
+    a.out_hi = out.hi; a.out_lo = out.lo; a.halo = 1; a.ovf = out.ovf;
     a.bias = Bv(h, layer);
     if (res) { a.res_hi = res->hi; a.res_lo = res->lo; }
     a.slope = slope;
@@ -335,6 +356,7 @@ int conv64_fwd(sr4d_t* h, int layer, ActView in, ActView out, const ActView* res
 int forward_impl(sr4d_t* h, const float* u, const float* v, const float* w, const float* um, const float* vm,
                  const float* wm, float* out, int B, cudaStream_t s) {
     if (B < 1 || B > h->maxB) return fail(h, SR4D_EINVAL, "batch size out of range (1..max_batch)");
+    NvtxPhase nvtx_phase(h, "sr4d forward");
     int rc = ensure_tc_weights(h, s);
     if (rc) return rc;
     const int P = h->P;
@@ -382,11 +404,14 @@ int forward_impl(sr4d_t* h, const float* u, const float* v, const float* w, cons
     return SR4D_OK;
 }
 
+// with the single-plane dgrad and the stacked single-plane wgrad nobody reads the lo plane of a split gradient
+bool lo_plane_dead(const sr4d_t* h) { return h->dgrad_single == 1 && h->wgrad_single == 1; }
+
 // A gradient tensor has just been written to g.f (and its |max| to g.amax): make the scaled
 // split-fp16 copy the tensor-core dgrad / wgrad kernels consume.
 int grad_ready(sr4d_t* h, GBuf& g, int B, int D, cudaStream_t s) {
     if (!use_tc(h)) return SR4D_OK;
-    CK(h, launch_g4_split(g.f, g.amax, g.s, g.exp, B, D, s), 1);
+    CK(h, launch_g4_split(g.f, g.amax, g.s, g.exp, B, D, s, lo_plane_dead(h)), 1);
     return SR4D_OK;
 }
 
@@ -450,7 +475,7 @@ int conv64_dgrad_fused(sr4d_t* h, int layer, const GBuf& dy, const GBuf* add_pre
     a.layer = layer; a.dgrad = 1; a.fused = 1; a.single_b = h->dgrad_single;
     a.dy_exp = dy.exp; a.add_pre = add_pre ? add_pre->f : nullptr; a.add_post = add_post;
     if (with_split) {
-        a.split_out = out.s; a.split_exp = out.exp; a.dy_amax = dy.amax;
+        a.split_out = out.s; a.split_exp = out.exp; a.dy_amax = dy.amax; a.split_hi_only = lo_plane_dead(h);
         // bound on |out|: this call's contribution plus what it is added to (skip gradient, or the in-place partial sum,
         // whose |max| the caller copied to amax_copy before this launch started updating out.amax)
         a.add_amax = add_pre ? add_pre->amax : (add_post ? h->amax_copy : nullptr);
@@ -507,6 +532,7 @@ int blocks_bwd(sr4d_t* h, int nblk, int l0, bool hr, GBuf* bufs[3], RawBuf& raw,
 int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, const float* mask, int B,
                   float* per_sample, float* l2_out, cudaStream_t s) {
     if (!h->training) return fail(h, SR4D_ESTATE, "handle was not created for training");
+    NvtxPhase nvtx_phase(h, "sr4d loss + backward");
     const int P = h->P, H = h->H;
     const int nvoxH = H * H * H;
     int rc;
@@ -534,7 +560,7 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
         // the head's first conv and (tensor-core path) the scaled split copy
         CK(h, cudaMemsetAsync(A.amax, 0, sizeof(int), s), 0);
         CK(h, launch_head2_bwd(hd, h->gpred, c, W(h, l2), A.f, A.amax, GW(h, l2), GB(h, l2), GB(h, l1),
-                               use_tc(h) ? A.s : nullptr, A.exp, h->gmax, h->scratch, s), 5);
+                               use_tc(h) ? A.s : nullptr, A.exp, h->gmax, h->scratch, s, lo_plane_dead(h)), 5);
         if ((rc = conv64_wgrad(h, l1, trunk, A, false, s))) return rc;
         if (fused_heads) {
             // the three heads accumulate act'(trunk) * fold(dgrad_c) in place (the activation gradient is linear);
@@ -607,7 +633,7 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
 }
 
 void free_all(sr4d_t* h) {
-    cudaFree(h->params); cudaFree(h->grads); cudaFree(h->m); cudaFree(h->v); cudaFree(h->kflag);
+    cudaFree(h->params); cudaFree(h->grads); cudaFree(h->m); cudaFree(h->v); cudaFree(h->kflag); cudaFree(h->ovf);
     cudaFree(h->feat);
     for (auto& b : h->lr) cudaFree(b.base);
     for (auto& b : h->hr) cudaFree(b.base);
@@ -659,6 +685,8 @@ int sr4d_create(sr4d_t** out, int patch_size, int res_increase, int low_resblock
             if (d.is_kernel)
                 for (int64_t i = d.offset / 32; i < (d.offset + d.count + 31) / 32; ++i) kf[i] = 1;
         cudaMemcpy(h->kflag, kf.data(), kf.size(), cudaMemcpyHostToDevice);
+        if (dmalloc(&h->ovf, 1)) { rc = SR4D_ENOMEM; break; }
+        cudaMemset(h->ovf, 0, sizeof(unsigned int));
         if ((rc = plan_buffers(h))) break;
         if ((rc = build_upsample_tables(h))) break;
         // zero-initialise activations once so halos of never-written regions are defined
@@ -748,6 +776,9 @@ int sr4d_set_option(sr4d_t* h, int option, int value) {
         case SR4D_OPT_FUSED_DGRAD:
             h->fused_dgrad = value != 0;
             return SR4D_OK;
+        case SR4D_OPT_NVTX:
+            h->nvtx = value != 0;
+            return SR4D_OK;
         case SR4D_OPT_DGRAD_SINGLE:
             h->dgrad_single = value != 0;
             return SR4D_OK;
@@ -764,6 +795,7 @@ int sr4d_get_option(const sr4d_t* h, int option, int* value) {
     if (option == SR4D_OPT_SAVE_ACTS) { *value = h->save_acts; return SR4D_OK; }
     if (option == SR4D_OPT_PROFILE) { *value = h->profile; return SR4D_OK; }
     if (option == SR4D_OPT_FUSED_DGRAD) { *value = h->fused_dgrad; return SR4D_OK; }
+    if (option == SR4D_OPT_NVTX) { *value = h->nvtx; return SR4D_OK; }
     if (option == SR4D_OPT_DGRAD_SINGLE) { *value = h->dgrad_single; return SR4D_OK; }
     if (option == SR4D_OPT_WGRAD_SINGLE) { *value = h->wgrad_single; return SR4D_OK; }
     return SR4D_EINVAL;
@@ -853,6 +885,7 @@ static int adam_impl(sr4d_t* h, float lr, float beta1, float beta2, float eps, i
     if (!h->training) return fail(h, SR4D_ESTATE, "handle was not created for training");
     if (t < 1) return fail(h, SR4D_EINVAL, "t must be >= 1 (iterations + 1)");
     cudaSetDevice(h->device);
+    NvtxPhase nvtx_phase(h, "sr4d adam");
     const double alpha = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)t)) /
                          (1.0 - std::pow((double)beta1, (double)t));
     CK(h, launch_adam(h->params, h->grads, h->m, h->v, h->kflag, h->flat, (float)alpha, beta1, beta2, eps,
@@ -1041,6 +1074,18 @@ int sr4d_profile_read(sr4d_t* h, double* ms, int64_t* launches, int nclasses) {
     }
     h->ev_used = 0;
     h->ev_class.clear();
+    return SR4D_OK;
+}
+
+int sr4d_activation_overflow(sr4d_t* h, int* flag, int reset, void* stream) {
+    if (!h || !flag) return SR4D_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned int v = 0;
+    cudaSetDevice(h->device);
+    CK(h, cudaMemcpyAsync(&v, h->ovf, sizeof v, cudaMemcpyDeviceToHost, s), 0);
+    CK(h, cudaStreamSynchronize(s), 0);
+    if (reset && v) CK(h, cudaMemsetAsync(h->ovf, 0, sizeof v, s), 0);
+    *flag = v != 0;
     return SR4D_OK;
 }
 

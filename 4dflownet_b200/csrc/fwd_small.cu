@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
                 float vv[4];
 #pragma unroll
                 for (int n = 0; n < 4; ++n) vv[n] = fmaxf(acc[v][q * 4 + n], 0.f);
-                act_store4_halo(out.hi, out.lo, P, b, x, y, z0 + v, cq + q * 4, vv, true);
+                act_store4_halo(out.hi, out.lo, P, b, x, y, z0 + v, cq + q * 4, vv, true, out.ovf);
             }
         }
     }
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) conv1x1_cat_kernel(ActView a, ActView bq,
                 float vv[4];
 #pragma unroll
                 for (int n = 0; n < 4; ++n) vv[n] = fmaxf(acc[v][q * 4 + n], 0.f);
-                act_store4_halo(out.hi, out.lo, D, vb[v], vx[v], vy[v], vz[v], cq + q * 4, vv, true);
+                act_store4_halo(out.hi, out.lo, D, vb[v], vx[v], vy[v], vz[v], cq + q * 4, vv, true, out.ovf);
             }
         }
     }
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) upsample_kernel(ActView in, ActView out, 
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = r[0][j] + (r[1][j] - r[0][j]) * fx;
-        act_store8_halo(out.hi, out.lo, H, b, x, y, z, c, o, true);
+        act_store8_halo(out.hi, out.lo, H, b, x, y, z, c, o, true, out.ovf);
     }
 }
 
@@ -371,7 +371,7 @@ __global__ void pack_act_kernel(const float* __restrict__ x, ActView out) {
     int z = vi % D, y = (vi / D) % D, xx = (vi / ((size_t)D * D)) % D, b = vi / ((size_t)D * D * D);
     float4 v = *reinterpret_cast<const float4*>(x + vi * 64 + c);
     float vv[4] = {v.x, v.y, v.z, v.w};
-    act_store4_halo(out.hi, out.lo, D, b, xx, y, z, c, vv, true);
+    act_store4_halo(out.hi, out.lo, D, b, xx, y, z, c, vv, true, out.ovf);
 }
 __global__ void unpack_act_kernel(ActView in, float* __restrict__ yv) {
     const int D = in.D;

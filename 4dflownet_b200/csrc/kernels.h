@@ -14,6 +14,7 @@ struct Conv64Args {
     // output A: Act planes with interior edge Do (storage Do+2), optional replicate halo
     __half* out_hi = nullptr;
     __half* out_lo = nullptr;
+    unsigned int* ovf = nullptr;   // fp16-range overflow flag of the output Act (ActView::ovf)
     int halo = 1;
     const float* bias = nullptr;
     const __half* res_hi = nullptr;
@@ -73,7 +74,7 @@ cudaError_t launch_stitch(const float* pred, int nx, int ny, int nz, int H, int 
 // split_out (optional) = scaled split-fp16 copy [2B][H+4]^3[64] of out_g4 with *split_exp derived from *gmax
 cudaError_t launch_head2_bwd(ActView h, const float* g, int c, const float* w, float* out_g4, unsigned int* amax,
                              float* dw, float* db, float* db1, __half* split_out, int* split_exp,
-                             const unsigned int* gmax, float* scratch, cudaStream_t s);
+                             const unsigned int* gmax, float* scratch, cudaStream_t s, bool hi_only = false);
 // out(G4 interior) = (fold(raw0*2^-e0 + raw1*2^-e1 + raw2*2^-e2) + add) * act'(saved); e_i are device
 // exponents (NULL = 0) of the scaled split-fp16 gradients the raws were computed from; amax (optional)
 // receives atomicMax of |out|
@@ -82,8 +83,9 @@ cudaError_t launch_fold_act(const float* raw0, const float* raw1, const float* r
                             float slope, float* out_g4, unsigned int* amax, int B, int D, cudaStream_t s);
 // split-fp16 copy [2B][D+4]^3[64] (hi planes then lo planes, zero halo kept) of a fp32 G4 tensor, scaled by
 // 2^e with e derived from *amax so max|x|*2^e is in [2^13, 2^14); *exp_out = e
+// hi_only: the lo plane has no consumer (single-plane dgrad + wgrad): it is not written
 cudaError_t launch_g4_split(const float* g4, const unsigned int* amax, __half* split, int* exp_out, int B, int D,
-                            cudaStream_t s);
+                            cudaStream_t s, bool hi_only = false);
 // dW[27][64][64] (+= nothing; overwrite) from x Act and dy G4; scratch >= nchunk*27*64*64 floats
 cudaError_t launch_wgrad64_simt(ActView x, const float* dy_g4, float* dw, float* scratch, int nchunk,
                                 cudaStream_t s);

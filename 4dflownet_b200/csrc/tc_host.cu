@@ -29,7 +29,7 @@ EncodeTiledFn get_encode() {
 std::mutex g_mu;
 std::map<int, int> g_sms;                                   // device -> SM count
 std::set<std::pair<int, const void*>> g_attr;               // (device, func) whose smem attribute is set
-typedef std::tuple<int, const void*, int, int, int, int> MapKey;
+typedef std::tuple<int, const void*, int, int, int, int, int> MapKey;
 std::map<MapKey, CUtensorMap> g_maps;
 
 int cur_dev() {
@@ -60,8 +60,8 @@ cudaError_t tc_func_smem(const void* func, int bytes) {
     return e;
 }
 
-bool tc_make_act_map(CUtensorMap* map, const __half* base, int B, int E, int by, int bz) {
-    const MapKey key(cur_dev(), base, B, E, by, bz);
+bool tc_make_act_map(CUtensorMap* map, const __half* base, int B, int E, int by, int bz, int bx) {
+    const MapKey key(cur_dev(), base, B, E, by, bz, bx);
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *map = it->second; return true; }
@@ -69,7 +69,7 @@ bool tc_make_act_map(CUtensorMap* map, const __half* base, int B, int E, int by,
     if (!enc) return false;
     cuuint64_t dims[5] = {64, (cuuint64_t)E, (cuuint64_t)E, (cuuint64_t)E, (cuuint64_t)(2 * B)};
     cuuint64_t strides[4] = {128, (cuuint64_t)128 * E, (cuuint64_t)128 * E * E, (cuuint64_t)128 * E * E * E};
-    cuuint32_t box[5] = {64, (cuuint32_t)bz, (cuuint32_t)by, 1, 1};
+    cuuint32_t box[5] = {64, (cuuint32_t)bz, (cuuint32_t)by, (cuuint32_t)bx, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     if (enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

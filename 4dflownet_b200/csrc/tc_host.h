@@ -9,9 +9,9 @@
 int tc_num_sms();
 // cudaFuncSetAttribute(func, MaxDynamicSharedMemorySize, bytes), issued once per (current device, func)
 cudaError_t tc_func_smem(const void* func, int bytes);
-// 5-D tiled map over packed [2B][E][E][E][64] fp16 planes (hi planes then lo planes), box {64, bz, by, 1, 1},
+// 5-D tiled map over packed [2B][E][E][E][64] fp16 planes (hi planes then lo planes), box {64, bz, by, bx, 1},
 // SWIZZLE_128B; encoded once per (device, base, B, E, by, bz) and copied from the cache afterwards
-bool tc_make_act_map(CUtensorMap* map, const __half* base, int B, int E, int by, int bz);
+bool tc_make_act_map(CUtensorMap* map, const __half* base, int B, int E, int by, int bz, int bx = 1);
 // drop every cached descriptor that points into [base, base + bytes) (call before freeing device memory that was
 // used as a TMA source, so a recycled address never meets a stale descriptor with another geometry)
 void tc_forget_maps(const void* base, size_t bytes);

@@ -5,7 +5,7 @@
 //     dW[dx,dy,dz][ci][co] = sum_{b,v} Xpad[b, v + (dx,dy,dz)][ci] * dY[b, v][co]                
 //
 // Both operands are the hi planes of the split-fp16 tensors (their rounding errors are independent per voxel and
-// average out over the 10^5..10^6-voxel sum: tools/gradient_precision_emulation.py, profiles/r02_grad_parity*.txt).
+// average out over the 10^5..10^6-voxel sum: tools/gradient_precision_emulation.py, profiles/r02_grad_parity.txt).
 //
 // GEMM view (K = voxels, both operands MN-major: a shared-memory row is one voxel's 64 channels = 128 B, straight
 // from TMA).  With a single gradient plane the M = 128 rows of the tensor-core instruction would be half empty, so
@@ -16,10 +16,17 @@
 //     MMA-2: B = Xpad plane x+2   rows 64..127 -> tap dx=2   (rows 0..63 would be "tap 3": never read)
 // i.e. 2 instructions per K-step give the 9 (dx,dz) taps of one dy, 24 instructions per 64-voxel tile for all 27 taps
 // (the two-plane kernel in wgrad_tc.cu needs 72, its hi-only mode 36).  A CTA of kind dy walks (column, x) units,
-// x = 0..D (the extra iteration x = D pairs dY[D-1] with the zero halo plane dY[D]), so every loaded tile is used by
-// the following iterations out of shared memory: per iteration ONE new dY tile (8 KB) and ONE new Xpad tile (10 KB)
-// arrive for 8 instructions -- 23 B/clk per SM against the ~43 B/clk the L2 delivers chip-wide (the previous kernel
-// sat at that limit).
+// x = 0..D (the extra iteration x = D pairs dY[D-1] with the zero halo plane dY[D]); every loaded plane tile is used by
+// the following iterations out of shared memory, so per iteration ONE new dY tile (8 KB) and ONE new Xpad tile (10 KB)
+// are needed for 8 instructions.
+//
+// Data movement.  The tiles arrive in GROUPS of four consecutive x-planes, one TMA box per tensor and group (32 KB of
+// dY, 40 KB of Xpad): the first version issued one 8 / 10 KB box per plane and ran at half speed -- the MMA warp spent
+// 35 % of its cycles waiting for tiles that had been requested five iterations earlier, because the TMA unit works
+// through small boxes nearly one memory latency at a time (SR4D_TC_DEBUG stamps, profiles/r02_wgrad2_notes.txt).  Three
+// groups form the ring (12 plane slots per tensor, + a copy of slot 0 behind slot 11 so the (previous, current) pair of
+// dY tiles is always adjacent for the A descriptor); a group is handed back with ONE tcgen05.commit after the
+// iteration that read its last plane (a commit costs the tensor pipe ~100 cycles: tools/probe/wgrad_probe.cu).
 //
 // Accumulator chains: the tcgen05 fp32 accumulator truncates after every instruction (measured: ~6e-8 relative loss
 // per accumulation), so a chain is cut after FLUSH_ITERS iterations (4 accumulations each): the epilogue warps drain
@@ -29,6 +36,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 
 #include "conv_tc.h"
 #include "tc_host.h"
@@ -39,12 +47,14 @@ namespace {
 constexpr int TY = 8, TZ = 8, ZP = TZ + 2;
 constexpr int DY_SLOT = TY * TZ * 128;              // 8 KB: 64 voxel rows
 constexpr int X_SLOT = TY * ZP * 128;               // 10 KB: 8 y-lines x 10 z rows
-constexpr int RY = 8;                               // dY ring slots (+ 1 mirror of slot 0 so (prev, cur) are always adjacent)
-constexpr int RX = 10;                              // Xpad ring slots
-constexpr int SMEM_BYTES = 1024 + (RY + 1) * DY_SLOT + RX * X_SLOT + 512;
+constexpr int GP = 4;                               // planes per group (one TMA box per tensor)
+constexpr int NGR = 3;                              // groups in the ring
+constexpr int NSLOT = NGR * GP;                     // plane slots per tensor
+constexpr int SMEM_BYTES = 1024 + (NSLOT + 1) * DY_SLOT + NSLOT * X_SLOT + 512;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NTHREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int FLUSH_ITERS = 96;                     // 384 accumulations per chain
+constexpr int GROUP_BYTES = GP * (DY_SLOT + X_SLOT);
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct W2Params {
@@ -53,6 +63,8 @@ struct W2Params {
     int B, D, nyt, nzt;
     int total;               // (column, x) iterations: B * nyt * nzt * (D + 1)
     int nslab;
+    int flush_iters;         // accumulator chain length in iterations (FLUSH_ITERS; SR4D_WGRAD_FLUSH overrides it for experiments)
+    long long* dbg;          // SR4D_TC_DEBUG=1: per-CTA cycles of the MMA warp {tile waits, acc_empty waits, issue (MMAs + commits), total, iterations}
 };
 
 __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -65,36 +77,25 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo, uint32
     return d;
 }
 
-// A CTA's iteration range [t0, t1) over t = column * (D+1) + x is a list of segments (one per column touched).  Both
-// the producer and the MMA warp walk it with this helper so their element counters agree.
-struct Seg {
-    int col, xa, len;        // iterations x = xa .. xa+len-1 of column col
-    int nx;                  // Xpad planes xa .. xa+nx-1 are loaded (up to plane D+1)
-};
-__device__ __forceinline__ Seg seg_at(int t, int t1, int D) {
-    Seg s;
-    s.col = t / (D + 1);
-    s.xa = t - s.col * (D + 1);
-    const int xend = min(D + 1, s.xa + (t1 - t));
-    s.len = xend - s.xa;
-    // planes read: x (MMA-1) and x+2 (MMA-2, while x+2 <= D+1) for x = xa..xend-1
-    const int last = s.xa <= D - 1 ? min(xend + 1, D + 1) : D;
-    s.nx = last - s.xa + 1;
-    return s;
-}
+// A CTA's iteration range [t0, t1) over t = column * (D+1) + x is a list of segments (one per column touched):
+// iterations x = xa .. xa+len-1 of one column.  Element k of a segment is dY plane xa-1+k and Xpad plane xa+k; iteration i
+// reads dY elements i (previous) and i+1 (current) and Xpad elements i (MMA-1) and i+2 (MMA-2; at x == D, where plane D+2
+// does not exist and the current dY plane is the zero halo, MMA-2 re-reads element i).  Elements 0 .. len+1 are loaded,
+// four per group; every segment starts on a fresh group.
+__device__ __forceinline__ int seg_len(int xa, int remaining, int D) { return min(D + 1 - xa, remaining); }
+__device__ __forceinline__ int seg_groups(int len) { return (len + 2 + GP - 1) / GP; }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap gmap, W2Params p) {
+wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap gmap,
+                   const __grid_constant__ CUtensorMap gmap1, W2Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* ysm = smem;                                   // (RY + 1) x 8 KB
-    uint8_t* xsm = smem + (RY + 1) * DY_SLOT;              // RX x 10 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xsm + RX * X_SLOT);
-    uint64_t* y_full = bars;                 // [RY]
-    uint64_t* y_empty = y_full + RY;         // [RY]
-    uint64_t* x_full = y_empty + RY;         // [RX]
-    uint64_t* x_empty = x_full + RX;         // [RX]
-    uint64_t* acc_full = x_empty + RX;       // [1]
+    uint8_t* ysm = smem;                                   // (NSLOT + 1) x 8 KB; slot NSLOT mirrors slot 0
+    uint8_t* xsm = smem + (NSLOT + 1) * DY_SLOT;           // NSLOT x 10 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xsm + NSLOT * X_SLOT);
+    uint64_t* full = bars;                   // [NGR]
+    uint64_t* empty = full + NGR;            // [NGR]
+    uint64_t* acc_full = empty + NGR;        // [1]
     uint64_t* acc_empty = acc_full + 1;      // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
@@ -107,13 +108,13 @@ wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     const int cols_per_b = p.nyt * p.nzt;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < RY; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
-        for (int i = 0; i < RX; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+        for (int i = 0; i < NGR; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, NUM_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&xmap);
         prefetch_tmap(&gmap);
+        prefetch_tmap(&gmap1);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -129,37 +130,29 @@ wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            uint32_t eY = 0, eX = 0;                  // elements issued so far
-            auto load_y = [&](int b, int y0, int z0, int plane) {
-                const uint32_t s = eY % RY, ph = (eY / RY) & 1;
-                mbar_wait(&y_empty[s], ph ^ 1);
-                mbar_expect_tx(&y_full[s], s == 0 ? 2 * DY_SLOT : DY_SLOT);
-                // interior voxel (plane, y0.., z0..) sits at +2 in the zero-haloed gradient tensor (plane in -1..D)
-                tma_load_5d(ysm + s * DY_SLOT, &gmap, &y_full[s], 0, z0 + 2, y0 + 2, plane + 2, b);
-                if (s == 0) tma_load_5d(ysm + RY * DY_SLOT, &gmap, &y_full[s], 0, z0 + 2, y0 + 2, plane + 2, b);
-                ++eY;
-            };
-            auto load_x = [&](int b, int y0, int z0, int plane) {
-                const uint32_t s = eX % RX, ph = (eX / RX) & 1;
-                mbar_wait(&x_empty[s], ph ^ 1);
-                mbar_expect_tx(&x_full[s], X_SLOT);
-                // padded coordinates: plane in 0..D+1, lines y0+dy.., rows z0..z0+9
-                tma_load_5d(xsm + s * X_SLOT, &xmap, &x_full[s], 0, z0, y0 + dy, plane, b);
-                ++eX;
-            };
+            uint32_t gq = 0;                          // groups issued so far
+            int col = t0 / (D + 1);
+            int xa = t0 - col * (D + 1);
             for (int t = t0; t < t1;) {
-                const Seg sg = seg_at(t, t1, D);
-                const int b = sg.col / cols_per_b;
-                const int rem = sg.col % cols_per_b;
+                const int len = seg_len(xa, t1 - t, D);
+                const int ngrp = seg_groups(len);
+                const int b = col / cols_per_b;
+                const int rem = col - b * cols_per_b;
                 const int y0 = (rem / p.nzt) * TY, z0 = (rem % p.nzt) * TZ;
-                load_y(b, y0, z0, sg.xa - 1);
-                load_x(b, y0, z0, sg.xa);
-                if (sg.nx > 1) load_x(b, y0, z0, sg.xa + 1);     // nx == 1 only for a segment that is the lone iteration x == D
-                for (int i = 0; i < sg.len; ++i) {
-                    load_y(b, y0, z0, sg.xa + i);
-                    if (i + 2 < sg.nx) load_x(b, y0, z0, sg.xa + i + 2);
+                for (int g = 0; g < ngrp; ++g, ++gq) {
+                    const uint32_t r = gq % NGR, ph = (gq / NGR) & 1;
+                    mbar_wait(&empty[r], ph ^ 1);
+                    mbar_expect_tx(&full[r], GROUP_BYTES + (r == 0 ? DY_SLOT : 0));
+                    // dY planes xa-1+4g ..+3: interior voxel (plane, y0.., z0..) sits at +2 in the zero-haloed gradient tensor;
+                    // Xpad planes xa+4g ..+3 (padded coordinates), lines y0+dy.., rows z0..z0+9.  Planes past the tensor are
+                    // zero-filled by the TMA unit and never read.
+                    tma_load_5d(ysm + r * GP * DY_SLOT, &gmap, &full[r], 0, z0 + 2, y0 + 2, xa - 1 + GP * g + 2, b);
+                    if (r == 0) tma_load_5d(ysm + NSLOT * DY_SLOT, &gmap1, &full[r], 0, z0 + 2, y0 + 2, xa - 1 + GP * g + 2, b);
+                    tma_load_5d(xsm + r * GP * X_SLOT, &xmap, &full[r], 0, z0, y0 + dy, xa + GP * g, b);
                 }
-                t += sg.len;
+                t += len;
+                xa = 0;                                // every further segment starts a new column
+                ++col;
             }
         }
     } else if (warp == 1) {
@@ -168,54 +161,68 @@ wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
             // D=f32, A=B=f16, both MN-major, M=128, N=192
             const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(192 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t d1 = tmem_base, d2 = tmem_base + 192;
-            uint32_t bY = 0, bX = 0;                  // element index of the current segment's element 0
-            uint32_t wY = 0, wX = 0;                  // elements whose full barrier has been waited for
+            const uint64_t adesc0 = desc_mn(0, DY_SLOT, TZ * 128);            // address field filled in per instruction
+            const uint64_t bdesc0 = desc_mn(0, 128, ZP * 128);
+            const uint32_t ybase = smem_u32(ysm) >> 4, xbase = smem_u32(xsm) >> 4;
+            uint32_t gq = 0;                          // group counter at the start of the current segment
+            uint32_t wq = 0;                          // groups whose full barrier has been waited for
             int chain_it = 0;                         // iterations issued into the current accumulator chain
             uint32_t nchain = 0;                      // chains completed
-            auto need_y = [&](uint32_t upto) {        // wait until dY elements [0, upto] have landed
-                while (wY <= upto) { mbar_wait(&y_full[wY % RY], (wY / RY) & 1); ++wY; }
-            };
-            auto need_x = [&](uint32_t upto) {
-                while (wX <= upto) { mbar_wait(&x_full[wX % RX], (wX / RX) & 1); ++wX; }
-            };
+            int xa = t0 % (D + 1);
+            long long dwf = 0, dwa = 0, dis = 0;
+            const long long tbeg = p.dbg ? clock64() : 0;
             for (int t = t0; t < t1;) {
-                const Seg sg = seg_at(t, t1, D);
-                for (int i = 0; i < sg.len; ++i) {
-                    const uint32_t gcur = bY + i + 1;                       // dY[x]; dY[x-1] is gcur - 1
-                    const int k2 = (i + 2 < sg.nx) ? i + 2 : i;            // x == D: MMA-2 re-uses plane x (rows 64..127 = zero plane)
-                    need_y(gcur);
-                    need_x(bX + (uint32_t)max(i, k2));
+                const int len = seg_len(xa, t1 - t, D);
+                const int ngrp = seg_groups(len);
+                const bool has_x2_last = xa + len - 1 + 2 <= D + 1;         // false only when the segment ends at x == D
+                uint32_t sprev = (gq % NGR) * GP;                           // ring slot of element i (starts at element 0)
+                for (int i = 0; i < len; ++i) {
+                    const int k2 = (i < len - 1 || has_x2_last) ? i + 2 : i;
+                    long long c0 = p.dbg ? clock64() : 0, c1;
+                    const uint32_t gneed = gq + (uint32_t)(k2 > i + 1 ? k2 : i + 1) / GP;
+                    while (wq <= gneed) { mbar_wait(&full[wq % NGR], (wq / NGR) & 1); ++wq; }
+                    if (p.dbg) { c1 = clock64(); dwf += c1 - c0; c0 = c1; }
                     if (chain_it == 0 && nchain > 0) mbar_wait(acc_empty, (nchain - 1) & 1);
+                    if (p.dbg) { c1 = clock64(); dwa += c1 - c0; c0 = c1; }
                     tc_fence_after();
-                    const uint32_t sc = gcur % RY;
-                    const uint32_t a0 = smem_u32(ysm + (sc == 0 ? RY - 1 : sc - 1) * DY_SLOT);   // (prev, cur) adjacent; slot 0's mirror sits behind slot RY-1
-                    const uint32_t x1 = smem_u32(xsm + ((bX + i) % RX) * X_SLOT);
-                    const uint32_t x2 = smem_u32(xsm + ((bX + k2) % RX) * X_SLOT);
+                    uint32_t s2 = sprev + (uint32_t)(k2 - i);               // slot of Xpad element k2
+                    if (s2 >= NSLOT) s2 -= NSLOT;
+                    // (previous, current) dY tiles are adjacent slots; when the current tile sits in slot 0 (sprev == NSLOT-1)
+                    // the A descriptor's second atom lands on the copy of slot 0 kept behind slot NSLOT-1
+                    const uint32_t a0 = ybase + sprev * (DY_SLOT >> 4);
+                    const uint32_t x1 = xbase + sprev * (X_SLOT >> 4);
+                    const uint32_t x2 = xbase + s2 * (X_SLOT >> 4);
 #pragma unroll
                     for (int j = 0; j < TY / 2; ++j) {
-                        const uint64_t ad = desc_mn(a0 + j * 2 * TZ * 128, DY_SLOT, TZ * 128);
+                        const uint64_t ad = adesc0 | (uint64_t)(a0 + j * (2 * TZ * 128 >> 4));
                         const uint32_t acc = (chain_it | j) != 0;
-                        tc_mma_f16(d1, ad, desc_mn(x1 + j * 2 * ZP * 128, 128, ZP * 128), idesc, acc);
-                        tc_mma_f16(d2, ad, desc_mn(x2 + j * 2 * ZP * 128, 128, ZP * 128), idesc, acc);
+                        tc_mma_f16(d1, ad, bdesc0 | (uint64_t)(x1 + j * (2 * ZP * 128 >> 4)), idesc, acc);
+                        tc_mma_f16(d2, ad, bdesc0 | (uint64_t)(x2 + j * (2 * ZP * 128 >> 4)), idesc, acc);
                     }
-                    // releases: dY element i of the segment (last read as "previous" here), Xpad element i (MMA-1), and the
-                    // elements only MMA-2 reads at the end of a segment
-                    tc_commit(&y_empty[(bY + i) % RY]);
-                    if (i == sg.len - 1) tc_commit(&y_empty[(bY + i + 1) % RY]);
-                    tc_commit(&x_empty[(bX + i) % RX]);
-                    if (i == sg.len - 1)
-                        for (int k = sg.len; k < sg.nx; ++k) tc_commit(&x_empty[(bX + k) % RX]);
+                    // hand a group back after the iteration that read its last plane (dY as "previous", Xpad in MMA-1), the
+                    // rest of the segment's groups after its last iteration
+                    if ((i & (GP - 1)) == GP - 1) tc_commit(&empty[(gq + i / GP) % NGR]);
+                    if (i == len - 1) {
+                        // (a trailing group may hold only planes nobody read: see its load land before giving it back)
+                        while (wq < gq + (uint32_t)ngrp) { mbar_wait(&full[wq % NGR], (wq / NGR) & 1); ++wq; }
+                        for (int g = len / GP; g < ngrp; ++g) tc_commit(&empty[(gq + g) % NGR]);
+                    }
+                    if (p.dbg) dis += clock64() - c0;
                     ++chain_it;
-                    const bool last = (t + i + 1 == t1);
-                    if (chain_it == FLUSH_ITERS || last) {
+                    if (chain_it == p.flush_iters || t + i + 1 == t1) {
                         tc_commit(acc_full);
                         chain_it = 0;
                         ++nchain;
                     }
+                    if (++sprev == NSLOT) sprev = 0;
                 }
-                bY += sg.len + 1;
-                bX += sg.nx;
-                t += sg.len;
+                gq += ngrp;
+                t += len;
+                xa = 0;
+            }
+            if (p.dbg) {
+                long long* d = p.dbg + (size_t)(blockIdx.y * 3 + blockIdx.x) * 8;
+                d[0] = dwf; d[1] = dwa; d[2] = dis; d[3] = clock64() - tbeg; d[4] = t1 - t0;
             }
         }
     } else {
@@ -229,7 +236,7 @@ wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
         float* out = p.partial + (size_t)slab * 27 * 4096 + co;
         const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16);
         const int nit = t1 - t0;
-        const int nchains = (nit + FLUSH_ITERS - 1) / FLUSH_ITERS;
+        const int nchains = (nit + p.flush_iters - 1) / p.flush_iters;
         auto flush = [&](uint32_t col0, int dx, bool first) {
             // columns n = dz*64 + ci of this accumulator -> partial[(dx*3+dy)*3+dz][ci][co]
 #pragma unroll 1
@@ -288,16 +295,38 @@ cudaError_t tc_wgrad64_single(ActView x, const __half* dy_split, const int* dy_e
     const int B = x.B, D = x.D;
     cudaError_t e = tc_func_smem(reinterpret_cast<const void*>(wgrad64_tc2_kernel), SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    CUtensorMap xmap, gmap;
-    // hi planes only: the maps cover the first B "samples" of the packed [2B] plane arrays
-    if (!tc_make_act_map(&xmap, x.hi, B, D + 2, TY, ZP)) return cudaErrorUnknown;
-    if (!tc_make_act_map(&gmap, dy_split, B, D + 4, TY, TZ)) return cudaErrorUnknown;
+    CUtensorMap xmap, gmap, gmap1;
+    // hi planes only: the maps cover the packed [2B] plane arrays, the kernel addresses samples b < B
+    if (!tc_make_act_map(&xmap, x.hi, B, D + 2, TY, ZP, GP)) return cudaErrorUnknown;
+    if (!tc_make_act_map(&gmap, dy_split, B, D + 4, TY, TZ, GP)) return cudaErrorUnknown;
+    if (!tc_make_act_map(&gmap1, dy_split, B, D + 4, TY, TZ, 1)) return cudaErrorUnknown;
     W2Params p;
     p.partial = partial; p.exp = dy_exp; p.B = B; p.D = D;
     p.nyt = (D + TY - 1) / TY; p.nzt = (D + TZ - 1) / TZ;
     p.total = B * p.nyt * p.nzt * (D + 1);
     p.nslab = tc_wgrad2_slabs(B, D);
+    static const int flush_env = getenv("SR4D_WGRAD_FLUSH") ? atoi(getenv("SR4D_WGRAD_FLUSH")) : 0;
+    p.flush_iters = flush_env > 0 ? flush_env : FLUSH_ITERS;
     dim3 grid(3, p.nslab);
-    wgrad64_tc2_kernel<<<grid, NTHREADS, SMEM_BYTES, s>>>(xmap, gmap, p);
-    return cudaGetLastError();
+    static const bool debug = getenv("SR4D_TC_DEBUG") != nullptr;
+    static long long* dbg_buf = nullptr;
+    p.dbg = nullptr;
+    if (debug) {
+        if (!dbg_buf) cudaMalloc((void**)&dbg_buf, 3 * 64 * 8 * sizeof(long long));
+        cudaMemsetAsync(dbg_buf, 0, 3 * 64 * 8 * sizeof(long long), s);
+        p.dbg = dbg_buf;
+    }
+    wgrad64_tc2_kernel<<<grid, NTHREADS, SMEM_BYTES, s>>>(xmap, gmap, gmap1, p);
+    cudaError_t e2 = cudaGetLastError();
+    if (debug && e2 == cudaSuccess) {
+        long long hb[3 * 64 * 8];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(hb, dbg_buf, sizeof hb, cudaMemcpyDeviceToHost);
+        double a[5] = {0, 0, 0, 0, 0};
+        const int n = 3 * p.nslab;
+        for (int i = 0; i < n; ++i) for (int k = 0; k < 5; ++k) a[k] += (double)hb[i * 8 + k] / n;
+        fprintf(stderr, "[wgrad2 dbg] D=%d B=%d: MMA-warp cycles avg/CTA: tile waits %.0f  acc_empty %.0f  issue %.0f  of total %.0f for %.0f iterations (%.0f per iteration)\n",
+                D, B, a[0], a[1], a[2], a[3], a[4], a[3] / (a[4] > 0 ? a[4] : 1));
+    }
+    return e2;
 }

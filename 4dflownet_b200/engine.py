@@ -103,6 +103,15 @@ class Engine:
         self._check(self.lib.sr4d_profile_read(self._h, ms, cnt, n), "sr4d_profile_read")
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(_lib.PROF_CLASSES)}
 
+    def activation_overflow(self, reset=True):
+        """True when some activation had to be clamped to the split-fp16 range (+-65504) or was NaN since the last
+        reset -- the fp32 reference would have carried the value on (synchronises the current stream)."""
+        flag = C.c_int(0)
+        with torch.cuda.device(self.device):
+            rc = self.lib.sr4d_activation_overflow(self._h, C.byref(flag), int(bool(reset)), _stream_ptr(self.device))
+        self._check(rc, "sr4d_activation_overflow")
+        return bool(flag.value)
+
     def launch_count(self):
         return int(self.lib.sr4d_launch_count(self._h))
 
@@ -121,10 +130,13 @@ class Engine:
             weights = [weights[n] for n, *_ in self.table]
         if len(weights) != len(self.table):
             raise ValueError(f"expected {len(self.table)} tensors, got {len(weights)}")
-        for (n, view), wv in zip(self.tensor_views(), weights):
-            wv = torch.as_tensor(np.asarray(wv, dtype=np.float32))
+        views = self.tensor_views()
+        staged = [torch.as_tensor(np.asarray(wv, dtype=np.float32)) for wv in weights]
+        for (n, view), wv in zip(views, staged):          # validate everything before the first copy
             if tuple(wv.shape) != tuple(view.shape):
-                raise ValueError(f"{n}: shape {tuple(wv.shape)} != {tuple(view.shape)}")
+                raise ValueError(f"{n}: shape {tuple(wv.shape)} != {tuple(view.shape)} (lists must be in this "
+                                 "package's table order = Keras layer-creation order)")
+        for (n, view), wv in zip(views, staged):
             view.copy_(wv)
         self.params_changed()
 

@@ -350,7 +350,13 @@ class Group:
         return self[path] if path in self else self.create_group(path)
 
     def create_dataset(self, path, data=None, shape=None, dtype=None, maxshape=None, compression=None, **_):
-        """`compression` is accepted and ignored: the shim writes contiguous data."""
+        """`compression` is accepted and ignored: the shim writes contiguous data (the reference writes gzip,
+        utils/prediction_utils.py:15-28; h5py reads either).  Said once per process so nobody expects small files."""
+        global _WARNED_COMPRESSION
+        if compression is not None and not _WARNED_COMPRESSION:
+            _WARNED_COMPRESSION = True
+            print(f"h5io: compression={compression!r} requested; the built-in HDF5 writer stores datasets uncompressed "
+                  "(install h5py to get the reference's gzip files)")
         self._file._require_write()
         if data is None:
             data = np.zeros(shape, dtype or np.float32)
@@ -374,6 +380,9 @@ class Group:
                 if r is not None:
                     return r
         return None
+
+
+_WARNED_COMPRESSION = False
 
 
 class File(Group):
@@ -422,6 +431,13 @@ class File(Group):
                         continue
                     group._items[name] = Dataset(self, group.name.rstrip("/") + "/" + name, rd.read_dataset(info),
                                                  info.get("maxshape"), info["attrs"])
+        for mtype, _, data in rd.messages(rd.root_header):      # attributes of the root group (keras_version, backend, ...)
+            if mtype == 0x0C:
+                try:
+                    k, v = rd._attribute(data)
+                    self.attrs[k] = v
+                except OSError:
+                    pass
         fill(self, rd.root_header)
 
     def flush(self):
@@ -667,10 +683,16 @@ def install_as_h5py():
 
 
 # ---- Keras weight files --------------------------------------------------------------------------
-def load_keras_weights(path, variable_names):
+def load_keras_weights(path, variable_names, report=None):
     """{name: array} for names like 'conv3d_7/kernel' from a Keras HDF5 file: either a weights file
     (<layer>/<layer>/kernel:0) or a full model file (model_weights/<layer>/<layer>/kernel:0), as written by
-    `model.save(path)` / `save_weights` (TrainerController.py:80,356) and read at predictor.py:61."""
+    `model.save(path)` / `save_weights` (TrainerController.py:80,356) and read at predictor.py:61.
+
+    Matching.  (1) By name -- Keras auto-names the Conv3D layers conv3d, conv3d_1, ... in creation order, which is this
+    package's table order.  (2) When the names do not line up (the process that wrote the file had built other Conv3D
+    layers before, so its names start at e.g. conv3d_37 -- Keras' own `load_weights` matches by topology, not by name,
+    and still loads such a file): the file's conv layers are sorted by their numeric suffix (= creation order) and
+    mapped one to one onto the table, every shape checked.  `report` (a dict, optional) receives the scheme used."""
     found = {}
     with open_file(path, "r") as f:
         root = f["model_weights"] if "model_weights" in f else f
@@ -684,9 +706,37 @@ def load_keras_weights(path, variable_names):
             return None
         root.visititems(visit)
     missing = [n for n in variable_names if n not in found]
-    if missing:
-        raise KeyError(f"{path}: missing weights {missing[:4]}{'...' if len(missing) > 4 else ''}")
-    return {n: found[n] for n in variable_names}
+    if not missing:
+        if report is not None:
+            report["scheme"] = "by name"
+        return {n: found[n] for n in variable_names}
+
+    # fallback: creation order by numeric suffix
+    def suffix(layer):
+        tail = layer.rsplit("_", 1)[-1]
+        return int(tail) if tail.isdigit() else 0
+    want_layers = []
+    for n in variable_names:
+        ly = n.split("/")[0]
+        if ly not in want_layers:
+            want_layers.append(ly)
+    have_layers = sorted({k.split("/")[0] for k in found if k.split("/")[0].split("_")[0].startswith("conv3d")}, key=suffix)
+    if len(have_layers) != len(want_layers):
+        raise KeyError(f"{path}: missing weights {missing[:4]}{'...' if len(missing) > 4 else ''} and the file holds "
+                       f"{len(have_layers)} conv layers where {len(want_layers)} are needed")
+    ren = dict(zip(want_layers, have_layers))
+    out = {}
+    for n in variable_names:
+        ly, leaf = n.split("/")
+        key = f"{ren[ly]}/{leaf}"
+        if key not in found:
+            raise KeyError(f"{path}: layer {ren[ly]} (for {ly}) has no {leaf}")
+        out[n] = found[key]
+    if report is not None:
+        report["scheme"] = f"by creation order (file layers {have_layers[0]}..{have_layers[-1]} -> {want_layers[0]}..{want_layers[-1]})"
+    print(f"load_keras_weights: {path}: layer names are offset; matched by creation order "
+          f"({have_layers[0]} -> {want_layers[0]}, ...); shapes are checked when the weights are set")
+    return out
 
 
 def save_keras_weights(path, weights):

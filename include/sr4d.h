@@ -48,14 +48,19 @@ extern "C" {
 #define SR4D_OPT_FUSED_DGRAD 4   /* 1 (default): the tensor-core dgrad folds the clamp-padding halo, adds the skip
                                     gradient and applies the activation derivative in its epilogue where the grid
                                     allows; 0: separate raw dgrad + fold kernel */
-#define SR4D_OPT_DGRAD_SINGLE 5  /* EXPERIMENTAL, default 0, not yet validated on hardware: the tensor-core dgrad consumes
-                                    only the hi plane of the scaled split gradient (one fp16 value per element, weights
-                                    stay split): one MMA per K-step instead of two.  CPU emulation
-                                    (tools/gradient_precision_emulation.py): costs ~0.4e-5 of the flat gradient at
-                                    48^3 voxels (fp32 autograd itself: 1e-5 from float64), ~1/sqrt(#voxels). */
-#define SR4D_OPT_WGRAD_SINGLE 6  /* EXPERIMENTAL, default 0, not yet validated on hardware: the tensor-core wgrad multiplies
-                                    only the hi planes (dYhi x Xhi): per-voxel rounding errors of both operands average
-                                    out over the 10^5..10^6-voxel sum (same emulation: 1.14e-5 vs 1.05e-5 for fp32). */
+#define SR4D_OPT_NVTX        7   /* 1: NVTX ranges around the phases of a step ("sr4d forward", "sr4d loss + backward",
+                                    "sr4d adam") and around every 64->64 layer call, named after its kernel class
+                                    (conv64_fwd_hr, ...); default 0 */
+#define SR4D_OPT_DGRAD_SINGLE 5  /* 1 (default since round 2, validated on B200: profiles/r02_grad_parity.txt): the tensor-core
+                                    dgrad consumes only the hi plane of the power-of-two-scaled split gradient (one fp16
+                                    value per element; the weights stay split): one MMA per K-step instead of two.  Its
+                                    rounding errors are independent per element and average out in the weight-gradient
+                                    sums: flat gradient vs float64 5.97e-5 with it, 6.66e-5 without, at P=24 r=2 8/4 B=8.
+                                    0: both planes (round-1 kernel path). */
+#define SR4D_OPT_WGRAD_SINGLE 6  /* 1 (default since round 2): stacked single-plane weight-gradient kernel (wgrad_tc2.cu): hi
+                                    planes of dY and X, two x-planes of dY on the M rows, accumulator chains cut every 384
+                                    accumulations.  0: two-plane kernel (wgrad_tc.cu, slabs cut at the same chain length);
+                                    2: the two-plane kernel's own hi-only mode (cross-check). */
 
 /* kernel classes timed under SR4D_OPT_PROFILE (index into sr4d_profile_read's arrays):
  * the 64->64 3x3x3 convolution forward / input-gradient / weight-gradient, on the LR
@@ -191,6 +196,12 @@ int  sr4d_conv64_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const
 /* device time (ms, CUDA events on the launch stream) and launch count per kernel class since
  * the last read; synchronises with the last recorded event.  Used by bench.py's roofline. */
 int  sr4d_profile_read(sr4d_t* h, double* ms, int64_t* launches, int nclasses);
+
+/* Activation range.  Feature maps are stored as split fp16 pairs (hi + lo/2048: 22 significant bits), whose range is
+ * +-65504; the fp32 reference has no such limit.  A producer that has to clamp a value (or meets a NaN) sets a
+ * handle-owned device flag instead of saturating silently.  *flag = 1 when that happened since the last reset
+ * (synchronises `stream`).  Venc-normalised inputs keep activations O(1); the flag fires when training diverges. */
+int  sr4d_activation_overflow(sr4d_t* h, int* flag, int reset, void* stream);
 
 /* counters for bench.py: number of kernels this library launched since the last reset */
 int64_t sr4d_launch_count(const sr4d_t* h);

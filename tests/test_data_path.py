@@ -124,6 +124,36 @@ def test_keras_weight_file_layout(h5io, tmp_path):
         h5io.load_keras_weights(p, names + ["conv3d_99/kernel"])
 
 
+@pytest.mark.parametrize("name_offset", [0, 37])
+def test_tf22_model_save_layout_loads(h5io, tmp_path, name_offset):
+    """A file laid out like TF 2.2's `model.save(path)` (root attributes, every layer of model.layers in layer_names,
+    empty weight_names for the weightless ones, nested <layer>/<layer>/kernel:0) is read by name; with a non-zero
+    Conv3D uid offset in the writer process (conv3d_37...) the creation-order fallback maps it -- Keras' own
+    topological `load_weights` loads such files too."""
+    import keras_layout
+    oracle = importlib.import_module("oracle.sr4d_oracle")
+    params = oracle.glorot_params(1, 1, seed=5, bias_scale=0.1)
+    names = [n for n, _ in oracle.param_table(1, 1)]
+    p = str(tmp_path / "4DFlowNet-best.h5")
+    on_disk = keras_layout.write_tf22_model_file(h5io, p, params, name_offset)
+    with h5io.File(p, "r") as f:
+        assert bytes(f.attrs["keras_version"]) == b"2.3.0-tf" and bytes(f.attrs["backend"]) == b"tensorflow"
+        ln = [bytes(x).decode() for x in f["model_weights"].attrs["layer_names"]]
+        assert "u_mag" in ln and "tf_op_layer_MirrorPad" in ln and on_disk["conv3d_4"] in ln
+        assert len(f["model_weights/concatenate"].attrs["weight_names"]) == 0
+        assert f[f"model_weights/{on_disk['conv3d_4']}/{on_disk['conv3d_4']}/kernel:0"].shape == (1, 1, 1, 128, 64)
+    rep = {}
+    back = h5io.load_keras_weights(p, names, report=rep)
+    assert rep["scheme"].startswith("by name" if name_offset == 0 else "by creation order")
+    for n in names:
+        np.testing.assert_array_equal(back[n], params[n])
+    # a file with a different number of conv layers is refused, not mis-mapped
+    few = {k: v for k, v in params.items() if not k.startswith("conv3d_15")}
+    keras_layout.write_tf22_model_file(h5io, p, few, 3)
+    with pytest.raises(KeyError):
+        h5io.load_keras_weights(p, names)
+
+
 def test_rotation_table_matches_reference_golden():
     ph = importlib.import_module("4dflownet_b200.Network.PatchHandler3D")
     z = np.load(GOLD)

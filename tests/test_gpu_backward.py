@@ -16,7 +16,7 @@ def rel_l2(a, b):
 
 @pytest.mark.parametrize("impl", ["simt", "tcgen05_full", "tcgen05", "tcgen05_hi_only_old_kernel"])
 @pytest.mark.parametrize("D,B,dy_scale", [(6, 2, 1.0), (9, 1, 1.0), (24, 1, 3e-7), (26, 1, 1e3), (24, 3, 1.0), (48, 1, 1.0)])
-def test_conv64_layer_bwd(pkg, D, B, dy_scale, impl):
+def test_conv64_layer_bwd(pkg, bars, D, B, dy_scale, impl):
     """Backward kernels of one 64->64 layer given identical inputs, against float64 autograd.
     dy_scale exercises the power-of-two rescaling of the split-fp16 gradient operand: loss gradients of this network
     are ~1e-6, far below the fp16 normal range.
@@ -41,15 +41,20 @@ def test_conv64_layer_bwd(pkg, D, B, dy_scale, impl):
     bt = torch.zeros(64, dtype=torch.float64, requires_grad=True)
     y = oracle.conv3d(xt, kt, bt)
     (y * torch.tensor(dy, dtype=torch.float64)).sum().backward()
-    nvox = B * D ** 3
-    # single gradient plane: every dY element carries an independent fp16 rounding error (rms 2^-11/sqrt(3) = 2.8e-4
-    # relative), and a random-sign sum inherits the relative error of its terms -- the per-voxel input gradient is
-    # 2e-4 off (measured 2.1e-4), independently per voxel; it averages out in the weight gradients downstream,
-    # which is what the reference API exposes (test_backward_kernels_given_identical_gates holds those)
-    tol_dx = 1e-5 if not single[0] else 4e-4
-    tol_dk = 1e-5 if not single[1] else max(1e-5, 6e-4 / nvox ** 0.5)   # both operands rounded: ~2 * 2^-12/sqrt(3) / sqrt(nvox)
-    assert rel_l2(dx.cpu().numpy(), xt.grad.numpy()) < tol_dx
-    assert rel_l2(dk.cpu().numpy(), kt.grad.numpy()) < tol_dk
+    tag = f"layer_bwd/D{D}B{B}s{dy_scale:g}/{impl}"
+    e_dx, e_dk = rel_l2(dx.cpu().numpy(), xt.grad.numpy()), rel_l2(dk.cpu().numpy(), kt.grad.numpy())
+    if single == (0, 0):
+        assert e_dx < 1e-5 and e_dk < 1e-5, (e_dx, e_dk)
+    else:
+        # Single-plane operands: every element carries an independent fp16 rounding error (rms 2^-11/sqrt(3) = 2.8e-4
+        # relative).  x, k and dy are INDEPENDENT random tensors here, so every output is a random-sign sum, and a
+        # random-sign sum inherits the relative error of its terms: ~2e-4 per element of dx, ~3e-4 per element of dk
+        # (both operands rounded), independent from element to element.  This is the worst case by construction: in the
+        # network the weight-gradient sums are not pure noise and the per-voxel errors average out over them, which is
+        # what test_backward_kernels_given_identical_gates and tools/grad_parity.py measure (1e-5 .. 5e-5 on the flat
+        # gradient, the same as the two-plane kernels).
+        bars(tag + "/dx", e_dx, 6e-4)
+        bars(tag + "/dk", e_dk, 1e-3)
     assert rel_l2(db.cpu().numpy(), bt.grad.numpy()) < 1e-5
     eng.close()
 

@@ -127,3 +127,29 @@ def test_trainer_flow_and_restore(pkg, oracle, tmp_path, capsys):
     batch = oracle.synthetic_batch(4, synth.PATCH, synth.R, seed=1)
     net2.train_step(batch)
     assert net2.optimizer.iterations == int(ow[0]) + 1 and np.isfinite(net2.loss_metrics["train_loss"].result())
+
+
+@pytest.mark.parametrize("name_offset", [0, 12])
+def test_load_weights_from_tf22_model_save_layout(pkg, oracle, tmp_path, name_offset):
+    """predictor.py:61 `network.load_weights(model_path)` on a file laid out like TF 2.2's `model.save` (root / group
+    attributes, weightless layers, nested <layer>/<layer>/kernel:0; tests/golden/keras_layout.py), incl. a writer whose
+    Conv3D names are offset: the loaded network predicts exactly what the same weights set directly predict, and the
+    activation-range flag stays clear."""
+    import keras_layout
+    h5io = importlib.import_module("4dflownet_b200.utils.h5io")
+    P, r, low, hi = 8, 2, 1, 1
+    params = oracle.glorot_params(low, hi, seed=40, bias_scale=0.05)
+    path = str(tmp_path / "4DFlowNet.h5")
+    keras_layout.write_tf22_model_file(h5io, path, params, name_offset)
+    net = pkg.prepare_network(P, r, low, hi, max_batch=2)
+    net.load_weights(path)
+    ref = pkg.prepare_network(P, r, low, hi, max_batch=2)
+    ref.set_weights([params[n] for n in ref.variable_names])
+    batch = oracle.synthetic_batch(2, P, r, seed=1)
+    assert np.array_equal(net.predict(list(batch[:6])), ref.predict(list(batch[:6])))
+    assert net.engine.activation_overflow() is False
+    # a diverged network (huge weights) trips the flag instead of saturating silently
+    big = {k: (v * 1e4 if k.endswith("kernel") else v) for k, v in params.items()}
+    ref.set_weights([big[n] for n in ref.variable_names])
+    ref.predict(list(batch[:6]))
+    assert ref.engine.activation_overflow() is True and ref.engine.activation_overflow() is False      # reset on read
