@@ -381,14 +381,25 @@ class TrainerController:
         self.model.load_weights(f"{old_model_dir}/{old_model_file}")
 
     def quicksave(self, testset, epoch_nr):
-        """First batch of the benchmark set -> quicksave_<network_name>.h5 (:415-454)."""
+        """First batch of the benchmark set -> quicksave_<network_name>.h5 (:415-454).  The benchmark iterator yields
+        GLOBAL batches (it is not sharded); rank 0 alone predicts it, in chunks of at most the engine's max_batch (under
+        data parallelism the engine is sized for batch_size / ranks), and writes the file; the other ranks wait."""
         from . import h5util
+        if not parallel.is_main():
+            parallel.barrier()
+            z = np.zeros(1, dtype=np.float32)
+            return z, z, z, z
         for data_pairs in testset:
             u, v, w, u_mag, v_mag, w_mag, u_hr, v_hr, w_hr, venc, mask = data_pairs
-            preds_dev = self.model([u, v, w, u_mag, v_mag, w_mag])
-            per = self.engine.loss_metrics(preds_dev, *[_squeeze_last(a) for a in (u_hr, v_hr, w_hr)], mask)
-            per = per.cpu().numpy()
-            preds = preds_dev.cpu().numpy()
+            n, mb = len(u), self.engine.max_batch
+            preds_l, per_l = [], []
+            for lo in range(0, n, mb):
+                sl = slice(lo, min(lo + mb, n))
+                pd = self.model([a[sl] for a in (u, v, w, u_mag, v_mag, w_mag)])
+                per_l.append(self.engine.loss_metrics(pd, *[_squeeze_last(a[sl]) for a in (u_hr, v_hr, w_hr)], mask[sl]).cpu().numpy())
+                preds_l.append(pd.cpu().numpy())
+            per = np.concatenate(per_l, axis=0)
+            preds = np.concatenate(preds_l, axis=0)
             break
         fn = f"quicksave_{self.network_name}.h5"
         h5util.save_predictions(self.model_dir, fn, "epoch", np.asarray([epoch_nr]), compression='gzip')
@@ -402,4 +413,5 @@ class TrainerController:
                 h5util.save_predictions(self.model_dir, fn, name, np.squeeze(np.asarray(a), -1), compression='gzip')
             h5util.save_predictions(self.model_dir, fn, "venc", np.asarray(venc), compression='gzip')
             h5util.save_predictions(self.model_dir, fn, "mask", np.asarray(mask), compression='gzip')
+        parallel.barrier()
         return per[:, 0], per[:, 2], per[:, 1], np.zeros_like(per[:, 0])

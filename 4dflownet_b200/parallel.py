@@ -27,7 +27,8 @@ def init_from_env(backend=None):
     if cuda:
         torch.cuda.set_device(local)
     if world > 1 and not initialized():
-        backend = backend or ("nccl" if cuda else "gloo")
+        # SR4D_DIST_BACKEND=gloo: several ranks on ONE GPU (NCCL refuses that), used by the single-GPU torchrun smoke test
+        backend = backend or os.environ.get("SR4D_DIST_BACKEND") or ("nccl" if cuda else "gloo")
         kwargs = {"device_id": torch.device("cuda", local)} if backend == "nccl" else {}
         dist.init_process_group(backend, **kwargs)
     return local

@@ -436,6 +436,16 @@ def run_b200(args):
             except Exception:
                 traffic = None
         peak = peaks["tflops_sustained"]
+        # fp16 tensor-core products the kernel class EXECUTES per algorithmic fp32 MAC
+        if "fwd" in dom or args.two_plane_backward:
+            exe, exe_note = 4.0, ("the fp32-accurate split-fp16 path issues 4 fp16 tcgen05 products per fp32 MAC (3 useful + the "
+                                  "64 masked-off rows of the second instruction), so the tensor pipe saturates at frac ~0.25")
+        elif "dgrad" in dom:
+            exe, exe_note = 2.0, ("single-plane dgrad: [Wlo;Whi] x dYhi, 2 fp16 products per fp32 MAC (tensor pipe saturates at frac "
+                                  "~0.5); the launch also folds the halo, adds the skip gradient, applies act' and writes the split copy")
+        else:
+            exe, exe_note = 4.0 / 3.0, ("stacked single-plane wgrad: dYhi x Xhi with two dY planes on M, 8 instructions per 6 useful "
+                                        "tap groups (1.33 fp16 products per fp32 MAC)")
         f_hr_ms, f_hr_n = fprof["conv64_fwd_hr"]
         f_lr_ms, f_lr_n = fprof["conv64_fwd_lr"]
         fwd = {
@@ -466,13 +476,10 @@ def run_b200(args):
                          "traffic_source": "profiles/traffic.json: dram bytes per launch of this kernel class from an "
                                            "ncu --set full capture (not re-measured in this run)",
                          "peak_source": peaks["source"] + ", sustained bf16",
-                         "executed_tflops_fp16": 4.0 * ach, "executed_frac": 4.0 * ach / peak,
+                         "executed_tflops_fp16": exe * ach, "executed_frac": exe * ach / peak,
                          "ms_per_launch": dom_ms / max(dom_n, 1), "launches_per_step": dom_n,
                          "share_of_step": dom_ms / ms_step,
-                         "note": "achieved = algorithmic fp32 FLOPs (2*27*64*64*B*D^3) / event time; the fp32-accurate "
-                                 "split-fp16 path issues 4 fp16 tcgen05 products per fp32 MAC (3 useful + 64 masked-off rows), so the "
-                                 "tensor pipe saturates at frac ~0.25; the dgrad launch also folds the halo, adds the skip "
-                                 "gradient, applies act' and writes the split copy"},
+                         "note": "achieved = algorithmic fp32 FLOPs (2*27*64*64*B*D^3) / event time.  " + exe_note},
             "kernel_classes_ms_per_step": {k: round(v[0], 4) for k, v in prof_step.items()},
             "forward": fwd,
             "other_configs": extra,

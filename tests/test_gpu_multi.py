@@ -86,3 +86,58 @@ def test_two_rank_step_matches_single_gpu():
     assert worst < 2e-5, worst
     assert inf_err == 0.0, inf_err
     assert abs(loss_dp - loss_1) < 1e-5 * abs(loss_1), (loss_dp, loss_1)
+
+
+def _trainer_main_worker(rank, world, port, d, q):
+    """One torchrun-style rank of trainer.main: the environment torchrun exports, gloo so both ranks can share GPU 0."""
+    import contextlib
+    import io
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK="0", SR4D_DIST_BACKEND="gloo")
+    import torch.distributed as dist
+    trainer = importlib.import_module("4dflownet_b200.trainer")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    synth = importlib.import_module("synth")
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            net = trainer.main(data_dir=d, QUICKSAVE=True, initial_learning_rate=1e-3, epochs=2, batch_size=4,
+                               mask_threshold=0.6, network_name="t4d", patch_size=synth.PATCH, res_increase=synth.R,
+                               low_resblock=1, hi_resblock=1, models_root=os.path.join(d, "models"))
+        flat = net.engine.params.cpu()                     # (gloo gathers CPU tensors)
+        other = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(other, flat)
+        q.put((rank, net.model_dir, net.engine.max_batch, net.optimizer.iterations,
+               all(torch.equal(other[0], o) for o in other), float(net.loss_metrics["train_loss"].result())))
+        dist.barrier()
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def test_trainer_main_under_two_ranks(tmp_path):
+    """`torchrun --nproc-per-node 2 trainer.py` in miniature: main() joins the process group from the
+    environment, every rank trains its shard (engine sized for batch_size / ranks), the ranks end with bit-identical
+    weights and the same running means, ONE model directory exists and only rank 0 wrote into it (one loss.csv line
+    per epoch, one quicksave file predicted from the unsharded benchmark batch in chunks of max_batch)."""
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    synth = importlib.import_module("synth")
+    d = str(tmp_path)
+    synth.make_synthetic_h5(d)
+    header = "source,target,index,start_x,start_y,start_z,rotate,rotation_plane,rotation_degree_idx,coverage\n"
+    for name, rows in (("train.csv", synth.ROWS), ("validate.csv", synth.ROWS[:4]), ("benchmark.csv", synth.ROWS[2:6])):
+        with open(os.path.join(d, name), "w") as f:
+            f.write(header + "".join(",".join(r) + "\n" for r in rows))
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    mp.spawn(_trainer_main_worker, args=(2, _free_port(), d, q), nprocs=2, join=True)
+    got = sorted(q.get() for _ in range(2))
+    (r0, dir0, mb0, it0, same0, loss0), (r1, dir1, mb1, it1, same1, loss1) = got
+    assert dir0 == dir1 and mb0 == mb1 == 2 and it0 == it1 and same0 and same1
+    assert abs(loss0 - loss1) <= 1e-6 * abs(loss0)          # both ranks averaged the metrics of the whole global batch
+    models = os.listdir(os.path.join(d, "models"))
+    assert len(models) == 1
+    md = os.path.join(d, "models", models[0])
+    rows = [ln for ln in open(os.path.join(md, "loss.csv")).read().splitlines() if ln[:1].isdigit()]
+    assert len(rows) == 2                                    # not one copy per rank
+    assert os.path.exists(os.path.join(md, "quicksave_t4d.h5")) and os.path.exists(os.path.join(md, "t4d-best.h5"))
