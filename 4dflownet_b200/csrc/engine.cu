@@ -64,6 +64,8 @@ struct sr4d_handle {
     unsigned char* kflag = nullptr;
     unsigned int* ovf = nullptr;       // device: set to 1 when an activation was clamped to the fp16 range
     float* feat = nullptr;
+    float* tapP[3] = {nullptr, nullptr, nullptr};   // tap dot-products of the three heads [maxB (H+2)^3][32] (tensor-core heads)
+    __half* head_wimg = nullptr;                    // their weight images
     std::vector<ActBuf> lr, hr;        // storage slots
     std::vector<int> lr_slot, hr_slot; // tensor index -> slot
     int n_lr_t = 0, n_hr_t = 0;
@@ -397,8 +399,13 @@ int forward_impl(sr4d_t* h, const float* u, const float* v, const float* w, cons
         hd[c] = hr_view(h, 1 + 2 * h->hi + c, B);
         if ((rc = conv64_fwd(h, li + 2 * c, xh, hd[c], nullptr, 0.f, s))) return rc;
     }
-    CK(h, launch_head_out(hd[0], hd[1], hd[2], W(h, li + 1), W(h, li + 3), W(h, li + 5), Bv(h, li + 1),
-                          Bv(h, li + 3), Bv(h, li + 5), out, s), 1);                     // :40,43,46,49
+    static const bool head_simt = getenv("SR4D_HEAD_SIMT") != nullptr;   // debugging aid / A-B: fp32 head_out_kernel
+    if (use_tc(h) && !head_simt)                                                         // :40,43,46,49
+        CK(h, launch_head_out_tc(hd[0], hd[1], hd[2], W(h, li + 1), W(h, li + 3), W(h, li + 5), Bv(h, li + 1), Bv(h, li + 3),
+                                 Bv(h, li + 5), h->head_wimg, h->tapP[0], h->tapP[1], h->tapP[2], out, s), 3);
+    else
+        CK(h, launch_head_out(hd[0], hd[1], hd[2], W(h, li + 1), W(h, li + 3), W(h, li + 5), Bv(h, li + 1),
+                              Bv(h, li + 3), Bv(h, li + 5), out, s), 1);
     h->have_fwd_state = h->training != 0 && out == h->pred;   // backward differentiates h->pred
     h->fwd_batch = B;
     return SR4D_OK;
@@ -635,6 +642,8 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
 void free_all(sr4d_t* h) {
     cudaFree(h->params); cudaFree(h->grads); cudaFree(h->m); cudaFree(h->v); cudaFree(h->kflag); cudaFree(h->ovf);
     cudaFree(h->feat);
+    for (auto t : h->tapP) cudaFree(t);
+    cudaFree(h->head_wimg);
     for (auto& b : h->lr) cudaFree(b.base);
     for (auto& b : h->hr) cudaFree(b.base);
     cudaFree(h->up.lo); cudaFree(h->up.hi); cudaFree(h->up.lerp); cudaFree(h->up.ibeg); cudaFree(h->up.iend);
@@ -688,6 +697,12 @@ int sr4d_create(sr4d_t** out, int patch_size, int res_increase, int low_resblock
         if (dmalloc(&h->ovf, 1)) { rc = SR4D_ENOMEM; break; }
         cudaMemset(h->ovf, 0, sizeof(unsigned int));
         if ((rc = plan_buffers(h))) break;
+        {
+            const size_t prow = (size_t)h->maxB * (h->H + 2) * (h->H + 2) * (h->H + 2);
+            bool bad = dmalloc(&h->head_wimg, head_tc_wimg_halves()) != cudaSuccess;
+            for (auto& t : h->tapP) bad |= dmalloc(&t, prow * 32) != cudaSuccess;
+            if (bad) { rc = SR4D_ENOMEM; break; }
+        }
         if ((rc = build_upsample_tables(h))) break;
         // zero-initialise activations once so halos of never-written regions are defined
         for (auto& b : h->lr) if (b.base) cudaMemset(b.base, 0, 2 * act_plane_elems(h->maxB, b.D) * sizeof(__half));

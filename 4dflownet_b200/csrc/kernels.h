@@ -46,6 +46,13 @@ cudaError_t launch_upsample(ActView in, ActView out, int r, UpsampleTables t, cu
 cudaError_t launch_head_out(ActView h0, ActView h1, ActView h2, const float* w0, const float* w1,
                             const float* w2, const float* b0, const float* b1, const float* b2, float* out,
                             cudaStream_t s);
+// the same three heads on the tensor cores (head_tc.cu): tap-dot GEMM over the voxel rows of the padded Acts into
+// P0..P2 [B (D+2)^3][32] fp32, then the 27-point re-indexed sum; wimg: head_tc_wimg_halves() halves of scratch for the
+// weight images (rebuilt per call)
+size_t head_tc_wimg_halves();
+cudaError_t launch_head_out_tc(ActView h0, ActView h1, ActView h2, const float* w0, const float* w1, const float* w2,
+                               const float* b0, const float* b1, const float* b2, __half* wimg, float* P0, float* P1,
+                               float* P2, float* out, cudaStream_t s);
 // fp32 channels-last (B,D,D,D,64) <-> Act
 cudaError_t launch_pack_act(const float* x, ActView out, cudaStream_t s);
 cudaError_t launch_unpack_act(ActView in, float* y, cudaStream_t s);

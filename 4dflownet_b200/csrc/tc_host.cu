@@ -80,6 +80,27 @@ bool tc_make_act_map(CUtensorMap* map, const __half* base, int B, int E, int by,
     return true;
 }
 
+bool tc_make_rows_map(CUtensorMap* map, const __half* base, long long nrows, long long plane_elems, int box_rows) {
+    // cached under the same key type: (device, base, B := nrows low bits, E := nrows high bits, by := box_rows, bz := -3, bx := plane stride hash)
+    const MapKey key(cur_dev(), base, (int)(nrows & 0x7fffffff), (int)(nrows >> 31), box_rows, -3, (int)(plane_elems & 0x7fffffff));
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *map = it->second; return true; }
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {64, (cuuint64_t)nrows, 2};
+    cuuint64_t strides[2] = {128, (cuuint64_t)plane_elems * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps[key] = *map;
+    return true;
+}
+
 void tc_forget_maps(const void* base, size_t bytes) {
     const char* lo = static_cast<const char*>(base);
     const char* hi = lo + bytes;

@@ -15,3 +15,6 @@ bool tc_make_act_map(CUtensorMap* map, const __half* base, int B, int E, int by,
 // drop every cached descriptor that points into [base, base + bytes) (call before freeing device memory that was
 // used as a TMA source, so a recycled address never meets a stale descriptor with another geometry)
 void tc_forget_maps(const void* base, size_t bytes);
+// 3-D tiled map over the two packed planes of an Act viewed as a matrix of voxel rows: {64 channels, nrows, 2 planes},
+// box {64, box_rows, 1}, SWIZZLE_128B (plane 0 = hi, plane 1 = lo; `plane_elems` = distance between the planes in halves)
+bool tc_make_rows_map(CUtensorMap* map, const __half* base, long long nrows, long long plane_elems, int box_rows);
