@@ -55,6 +55,7 @@ SYMBOLS = {
     "sr4d_conv64_layer": (C.c_int, [_P, _P, _P, _P, _P, _F, _P, C.c_int, C.c_int, C.c_int, _P]),
     "sr4d_upsample_layer": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "sr4d_conv64_layer_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "sr4d_head_layer_bwd": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "sr4d_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
     "sr4d_activation_overflow": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int, _P]),
     "sr4d_launch_count": (C.c_int64, [_P]),

@@ -66,6 +66,11 @@ struct sr4d_handle {
     float* feat = nullptr;
     float* tapP[3] = {nullptr, nullptr, nullptr};   // tap dot-products of the three heads [maxB (H+2)^3][32] (tensor-core heads)
     __half* head_wimg = nullptr;                    // their weight images
+    // tensor-core backward of the heads (head_bwd_tc.cu): per-head scales, weight images, per-CTA partials
+    void* hb_scales = nullptr;
+    __half* hb_wimg = nullptr;
+    float* hb_part = nullptr;
+    size_t hb_part_stride = 0;                      // floats per head
     std::vector<ActBuf> lr, hr;        // storage slots
     std::vector<int> lr_slot, hr_slot; // tensor index -> slot
     int n_lr_t = 0, n_hr_t = 0;
@@ -560,14 +565,23 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
     const float trunk_slope = h->hi > 0 ? 0.2f : (h->r == 1 ? slope_lr_trunk : 1.f);
     const bool fused_heads = dgrad_fused(h, H);
     if (fused_heads) CK(h, cudaMemsetAsync(hb[0]->amax, 0, sizeof(int), s), 0);
+    static const bool head_simt = getenv("SR4D_HEAD_SIMT") != nullptr;   // debugging aid / A-B: fp32 head2_bwd_kernel
+    const bool heads_tc = use_tc(h) && !head_simt && h->hb_part && head_bwd_tc_supported(H);
+    if (heads_tc)
+        CK(h, launch_head_bwd_tc_setup(W(h, l_head + 1), W(h, l_head + 3), W(h, l_head + 5), h->gmax, h->hb_scales,
+                                       h->hb_wimg, s), 1);
     for (int c = 0; c < 3; ++c) {
         ActView hd = hr_view(h, 1 + 2 * h->hi + c, B);
         const int l1 = l_head + 2 * c, l2 = l1 + 1;
         // whole backward of the 64->1 conv, plus what its input gradient needs downstream: the bias gradient of
         // the head's first conv and (tensor-core path) the scaled split copy
         CK(h, cudaMemsetAsync(A.amax, 0, sizeof(int), s), 0);
-        CK(h, launch_head2_bwd(hd, h->gpred, c, W(h, l2), A.f, A.amax, GW(h, l2), GB(h, l2), GB(h, l1),
-                               use_tc(h) ? A.s : nullptr, A.exp, h->gmax, h->scratch, s, lo_plane_dead(h)), 5);
+        if (heads_tc)
+            CK(h, launch_head_bwd_tc(hd, h->gpred, c, h->hb_scales, h->hb_wimg, h->hb_part + c * h->hb_part_stride, A.s, A.exp,
+                                     A.amax, lo_plane_dead(h), s), 1);
+        else
+            CK(h, launch_head2_bwd(hd, h->gpred, c, W(h, l2), A.f, A.amax, GW(h, l2), GB(h, l2), GB(h, l1),
+                                   use_tc(h) ? A.s : nullptr, A.exp, h->gmax, h->scratch, s, lo_plane_dead(h)), 5);
         if ((rc = conv64_wgrad(h, l1, trunk, A, false, s))) return rc;
         if (fused_heads) {
             // the three heads accumulate act'(trunk) * fold(dgrad_c) in place (the activation gradient is linear);
@@ -584,6 +598,15 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
             CK(h, cudaMemcpyAsync(h->head_exp + c, A.exp, sizeof(int), cudaMemcpyDeviceToDevice, s), 0);
             h->raw_hr[c].exp = h->head_exp + c;
         }
+    }
+    if (heads_tc) {
+        const int nc = head_bwd_tc_grid(B, H);
+        const float* part[3] = {h->hb_part, h->hb_part + h->hb_part_stride, h->hb_part + 2 * h->hb_part_stride};
+        const int ncta[3] = {nc, nc, nc};
+        float* dw[3] = {GW(h, l_head + 1), GW(h, l_head + 3), GW(h, l_head + 5)};
+        float* db[3] = {GB(h, l_head + 1), GB(h, l_head + 3), GB(h, l_head + 5)};
+        float* db1[3] = {GB(h, l_head), GB(h, l_head + 2), GB(h, l_head + 4)};
+        CK(h, launch_head_bwd_tc_finish(part, ncta, h->hb_scales, dw, db, db1, s), 1);
     }
     if (!fused_heads) {
         if ((rc = fold_act(h, &h->raw_hr[0], &h->raw_hr[1], &h->raw_hr[2], nullptr, trunk_act ? &trunk : nullptr,
@@ -644,6 +667,7 @@ void free_all(sr4d_t* h) {
     cudaFree(h->feat);
     for (auto t : h->tapP) cudaFree(t);
     cudaFree(h->head_wimg);
+    cudaFree(h->hb_scales); cudaFree(h->hb_wimg); cudaFree(h->hb_part);
     for (auto& b : h->lr) cudaFree(b.base);
     for (auto& b : h->hr) cudaFree(b.base);
     cudaFree(h->up.lo); cudaFree(h->up.hi); cudaFree(h->up.lerp); cudaFree(h->up.ibeg); cudaFree(h->up.iend);
@@ -750,6 +774,12 @@ int sr4d_create(sr4d_t** out, int patch_size, int res_increase, int low_resblock
             size_t need2 = (size_t)1184 * 8192 + 8192;
             if (need2 > h->scratch_floats) h->scratch_floats = need2;
             bad |= dmalloc(&h->scratch, h->scratch_floats) != cudaSuccess;
+            if (head_bwd_tc_supported(h->H)) {
+                h->hb_part_stride = head_bwd_tc_partial_floats(h->maxB, h->H);
+                bad |= cudaMalloc(&h->hb_scales, head_bwd_tc_scales_bytes()) != cudaSuccess;
+                bad |= dmalloc(&h->hb_wimg, head_bwd_tc_wimg_halves()) != cudaSuccess;
+                bad |= dmalloc(&h->hb_part, 3 * h->hb_part_stride) != cudaSuccess;
+            }
             if (bad) { rc = SR4D_ENOMEM; break; }
         }
         if (cudaDeviceSynchronize() != cudaSuccess) { rc = SR4D_ECUDA; break; }
@@ -1071,6 +1101,66 @@ int sr4d_conv64_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const 
     cudaFree(bi.base); cudaFree(g4); cudaFree(raw); cudaFree(g4o); cudaFree(scr); cudaFree(dwb); cudaFree(g4s);
     cudaFree(meta);
     if (tw) tc_free_weights(tw);
+    return rc;
+}
+
+int sr4d_head_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const float* g, int c, float* dx, float* dkernel,
+                        float* dbias, float* dbias_prev, int B, int D, int impl, void* stream) {
+    if (!h || !x || !kernel || !g || !dx || !dkernel || !dbias || !dbias_prev || B < 1 || D < 1 || c < 0 || c > 2)
+        return fail(h, SR4D_EINVAL, "bad argument");
+    const bool tc = impl == SR4D_CONV_TCGEN05;
+    if (tc && !head_bwd_tc_supported(D)) return fail(h, SR4D_EINVAL, "tensor-core head backward: unsupported edge");
+    cudaStream_t s = (cudaStream_t)stream;
+    ActBuf bi;
+    float *g4 = nullptr, *scr = nullptr, *outs = nullptr, *part = nullptr;
+    __half *g4s = nullptr, *wimg = nullptr;
+    void* scales = nullptr;
+    int* meta = nullptr;
+    const size_t n4 = (size_t)B * (D + 4) * (D + 4) * (D + 4) * 64;
+    const size_t ng = (size_t)B * D * D * D * 3;
+    int rc = SR4D_OK;
+    if (alloc_act(bi, B, D) || dmalloc(&g4, n4) || dmalloc(&g4s, 2 * n4) || dmalloc(&scr, (size_t)(592 + 1) * 29 * 64) ||
+        dmalloc(&outs, 27 * 64 + 1 + 64) || dmalloc(&meta, 4) ||
+        (tc && (dmalloc(&part, 3 * head_bwd_tc_partial_floats(B, D)) || dmalloc(&wimg, head_bwd_tc_wimg_halves()) ||
+                cudaMalloc(&scales, head_bwd_tc_scales_bytes()) != cudaSuccess)))
+        rc = SR4D_ENOMEM;
+    if (!rc) {
+        cudaMemsetAsync(g4, 0, n4 * 4, s);
+        cudaMemsetAsync(g4s, 0, 2 * n4 * sizeof(__half), s);
+        cudaMemsetAsync(meta, 0, 4 * sizeof(int), s);
+        ActView vi = bi.view(B);
+        unsigned int* amax = reinterpret_cast<unsigned int*>(meta);
+        unsigned int* gmax = reinterpret_cast<unsigned int*>(meta + 2);
+        cudaError_t e = launch_pack_act(x, vi, s);
+        if (!e) e = launch_absmax(g, ng, gmax, s);
+        float* dw = outs; float* db = outs + 27 * 64; float* db1 = db + 1;
+        if (!e && tc) {
+            e = launch_head_bwd_tc_setup(kernel, kernel, kernel, gmax, scales, wimg, s);
+            const size_t ps = head_bwd_tc_partial_floats(B, D);
+            if (!e) e = launch_head_bwd_tc(vi, g, c, scales, wimg, part + c * ps, g4s, meta + 1, amax, false, s);
+            // the finishing kernel covers three heads: the other two get this head's partials and scratch outputs
+            const float* pp[3] = {part + c * ps, part + c * ps, part + c * ps};
+            const int nc = head_bwd_tc_grid(B, D);
+            const int ncta[3] = {nc, nc, nc};
+            float* odw[3] = {scr, scr, scr}; float* odb[3] = {scr + 2000, scr + 2000, scr + 2000};
+            float* odb1[3] = {scr + 2100, scr + 2100, scr + 2100};
+            odw[c] = dw; odb[c] = db; odb1[c] = db1;
+            if (!e) e = launch_head_bwd_tc_finish(pp, ncta, scales, odw, odb, odb1, s);
+            if (!e) e = launch_dense_from_split(g4s, meta + 1, true, dx, B, D, s);
+            h->launches += 5;
+        } else if (!e) {
+            e = launch_head2_bwd(vi, g, c, kernel, g4, amax, dw, db, db1, nullptr, meta + 1, gmax, scr, s, false);
+            if (!e) e = launch_dense_from_g4(g4, dx, B, D, s);
+            h->launches += 6;
+        }
+        if (!e) e = cudaMemcpyAsync(dkernel, dw, 27 * 64 * 4, cudaMemcpyDeviceToDevice, s);
+        if (!e) e = cudaMemcpyAsync(dbias, db, 4, cudaMemcpyDeviceToDevice, s);
+        if (!e) e = cudaMemcpyAsync(dbias_prev, db1, 64 * 4, cudaMemcpyDeviceToDevice, s);
+        if (!e) e = cudaStreamSynchronize(s);
+        if (e) { rc = SR4D_ECUDA; h->err = cudaGetErrorString(e); }
+    }
+    cudaFree(bi.base); cudaFree(g4); cudaFree(g4s); cudaFree(scr); cudaFree(outs); cudaFree(meta);
+    cudaFree(part); cudaFree(wimg); cudaFree(scales);
     return rc;
 }
 

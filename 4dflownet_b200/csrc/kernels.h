@@ -82,6 +82,25 @@ cudaError_t launch_stitch(const float* pred, int nx, int ny, int nz, int H, int 
 cudaError_t launch_head2_bwd(ActView h, const float* g, int c, const float* w, float* out_g4, unsigned int* amax,
                              float* dw, float* db, float* db1, __half* split_out, int* split_exp,
                              const unsigned int* gmax, float* scratch, cudaStream_t s, bool hi_only = false);
+// the same backward on the tensor cores (head_bwd_tc.cu): setup once per step (scales from *gmax and the weights, weight
+// images), one launch per head (writes the scaled split copy -- hi plane, lo plane unless hi_only -- its exponent and
+// |max|; no fp32 copy), one finishing launch for the three heads (dw[27][64], db, db1[64] from the per-CTA partials)
+bool head_bwd_tc_supported(int D);
+int head_bwd_tc_grid(int B, int D);
+size_t head_bwd_tc_partial_floats(int B, int D);
+size_t head_bwd_tc_scales_bytes();
+size_t head_bwd_tc_wimg_halves();
+cudaError_t launch_head_bwd_tc_setup(const float* w0, const float* w1, const float* w2, const unsigned int* gmax, void* scales,
+                                     __half* wimg, cudaStream_t s);
+cudaError_t launch_head_bwd_tc(ActView h, const float* g, int c, const void* scales, const __half* wimg, float* partial,
+                               __half* split_out, int* split_exp, unsigned int* amax, bool hi_only, cudaStream_t s);
+cudaError_t launch_head_bwd_tc_finish(const float* const part[3], const int ncta[3], const void* scales, float* const dw[3],
+                                      float* const db[3], float* const db1[3], cudaStream_t s);
+// *out_bits = max(*out_bits, bits of max |x|)  (zero it first)
+cudaError_t launch_absmax(const float* x, size_t n, unsigned int* out_bits, cudaStream_t s);
+// scaled split-fp16 gradient (G4 layout) -> dense fp32 (B, D, D, D, 64)
+cudaError_t launch_dense_from_split(const __half* split, const int* exp, bool lo_valid, float* dense, int B, int D,
+                                    cudaStream_t s);
 // out(G4 interior) = (fold(raw0*2^-e0 + raw1*2^-e1 + raw2*2^-e2) + add) * act'(saved); e_i are device
 // exponents (NULL = 0) of the scaled split-fp16 gradients the raws were computed from; amax (optional)
 // receives atomicMax of |out|

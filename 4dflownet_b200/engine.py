@@ -294,3 +294,22 @@ class Engine:
                                                 _stream_ptr(self.device))
         self._check(rc, "sr4d_conv64_layer_bwd")
         return dx, dk, db
+
+    def head_layer_bwd(self, x, kernel, g, c, impl=_lib.CONV_SIMT):
+        """Whole backward of one 64->1 head conv (sr4d_head_layer_bwd): x (B,D,D,D,64) = its saved post-ReLU input,
+        kernel (3,3,3,64,1), g (B,D,D,D,3) loss gradient (channel c is this head's) -> dx, dkernel (27,64), dbias (1),
+        dbias_prev (64)."""
+        x, g = self._dev(x), self._dev(g)
+        B, D = x.shape[0], x.shape[1]
+        k = self._dev(kernel).reshape(27, 64)
+        dx = torch.empty_like(x)
+        dk = torch.empty((27, 64), device=self.device, dtype=torch.float32)
+        db = torch.empty((1,), device=self.device, dtype=torch.float32)
+        db1 = torch.empty((64,), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            rc = self.lib.sr4d_head_layer_bwd(self._h, C.c_void_p(x.data_ptr()), C.c_void_p(k.data_ptr()),
+                                              C.c_void_p(g.data_ptr()), int(c), C.c_void_p(dx.data_ptr()),
+                                              C.c_void_p(dk.data_ptr()), C.c_void_p(db.data_ptr()),
+                                              C.c_void_p(db1.data_ptr()), B, D, impl, _stream_ptr(self.device))
+        self._check(rc, "sr4d_head_layer_bwd")
+        return dx, dk, db, db1

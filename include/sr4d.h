@@ -193,6 +193,14 @@ int  sr4d_conv64_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const
                            float* dx, float* dkernel, float* dbias, int B, int D, int impl,
                            void* stream);
 
+/* whole backward of one 64->1 head convolution (SR4DFlowNet.py:40,43,46: relu -> conv3d(1 filter, 'SYMMETRIC' padding))
+ * given its saved post-ReLU input x (B,D,D,D,64), kernel (3,3,3,64,1) and the loss gradient g (B,D,D,D,3) of which
+ * channel c belongs to this head: dx (B,D,D,D,64) = gradient wrt the PRE-activation of x (ReluGrad applied),
+ * dkernel (27*64), dbias (1), dbias_prev (64) = per-channel sum of dx.  With SR4D_CONV_TCGEN05 dx is what the
+ * tensor-core consumers read: the scaled split-fp16 copy (both planes) converted back to fp32. */
+int  sr4d_head_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const float* g, int c, float* dx,
+                         float* dkernel, float* dbias, float* dbias_prev, int B, int D, int impl, void* stream);
+
 /* device time (ms, CUDA events on the launch stream) and launch count per kernel class since
  * the last read; synchronises with the last recorded event.  Used by bench.py's roofline. */
 int  sr4d_profile_read(sr4d_t* h, double* ms, int64_t* launches, int nclasses);

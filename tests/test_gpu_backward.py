@@ -59,6 +59,37 @@ def test_conv64_layer_bwd(pkg, bars, D, B, dy_scale, impl):
     eng.close()
 
 
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+@pytest.mark.parametrize("D,B,g_scale,c", [(6, 2, 1.0, 0), (12, 1, 1e-6, 1), (16, 2, 1.0, 2), (24, 3, 3e-7, 0), (36, 1, 1e3, 1),
+                                           (48, 2, 1.0, 2), (48, 8, 1e-6, 0)])
+def test_head_layer_bwd(pkg, D, B, g_scale, c, impl):
+    """Whole backward of one 64->1 head (relu -> clamp-padded conv3d with one filter, SR4DFlowNet.py:40-49) given
+    identical inputs, against float64 autograd: input gradient incl. ReluGrad and MirrorPadGrad, kernel gradient, both
+    bias gradients.  tcgen05: the G table, the weights and the saved activations enter the tensor cores as hi + lo fp16
+    pairs (three products), so every output is fp32-accurate; dx is read back from the split-fp16 copy the consumers use."""
+    L = pkg._lib
+    eng = pkg.Engine(8, 2, 0, 0, max_batch=2, training=False, device=0)
+    rng = np.random.default_rng(100 + D + B)
+    x = np.maximum(rng.standard_normal((B, D, D, D, 64)), 0).astype(np.float32)      # a ReLU output: about half zeros
+    k = (rng.standard_normal((3, 3, 3, 64, 1)) * 0.05).astype(np.float32)
+    g = (rng.standard_normal((B, D, D, D, 3)) * g_scale).astype(np.float32)
+    dx, dk, db, db1 = eng.head_layer_bwd(x, k, g, c, impl=L.CONV_SIMT if impl == "simt" else L.CONV_TCGEN05)
+    # float64 reference: the head sees a = relu(pre) with pre > 0 exactly where x > 0; d pre = relu'(x) * d a
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    kt = torch.tensor(k, dtype=torch.float64, requires_grad=True)
+    xp = torch.nn.functional.pad(xt.permute(0, 4, 1, 2, 3), (1, 1, 1, 1, 1, 1), mode="replicate")
+    y = torch.nn.functional.conv3d(xp, kt.permute(4, 3, 0, 1, 2))[:, 0]
+    gt = torch.tensor(g[..., c], dtype=torch.float64)
+    (y * gt).sum().backward()
+    dx_ref = (xt.grad * (xt > 0)).numpy()
+    assert rel_l2(dx.cpu().numpy(), dx_ref) < 2e-6
+    assert rel_l2(dk.cpu().numpy().reshape(-1), kt.grad.numpy().reshape(-1)) < 1e-5
+    np.testing.assert_allclose(db.cpu().numpy()[0], gt.sum().item(), rtol=2e-5, atol=1e-5 * g_scale * np.sqrt(gt.numel()))
+    ref_db1 = dx_ref.sum(axis=(0, 1, 2, 3))
+    assert rel_l2(db1.cpu().numpy(), ref_db1) < 3e-5
+    eng.close()
+
+
 def test_loss_metrics(pkg, oracle):
     P, r, B = 8, 2, 3
     H = P * r
