@@ -70,6 +70,7 @@ struct sr4d_handle {
     void* hb_scales = nullptr;
     __half* hb_wimg = nullptr;
     float* hb_part = nullptr;
+    float* hb_gplanar = nullptr;                    // planar scaled copy of the loss gradient
     size_t hb_part_stride = 0;                      // floats per head
     std::vector<ActBuf> lr, hr;        // storage slots
     std::vector<int> lr_slot, hr_slot; // tensor index -> slot
@@ -569,7 +570,7 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
     const bool heads_tc = use_tc(h) && !head_simt && h->hb_part && head_bwd_tc_supported(H);
     if (heads_tc)
         CK(h, launch_head_bwd_tc_setup(W(h, l_head + 1), W(h, l_head + 3), W(h, l_head + 5), h->gmax, h->hb_scales,
-                                       h->hb_wimg, s), 1);
+                                       h->hb_wimg, h->gpred, h->hb_gplanar, B, H, s), 2);
     for (int c = 0; c < 3; ++c) {
         ActView hd = hr_view(h, 1 + 2 * h->hi + c, B);
         const int l1 = l_head + 2 * c, l2 = l1 + 1;
@@ -577,7 +578,7 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
         // the head's first conv and (tensor-core path) the scaled split copy
         CK(h, cudaMemsetAsync(A.amax, 0, sizeof(int), s), 0);
         if (heads_tc)
-            CK(h, launch_head_bwd_tc(hd, h->gpred, c, h->hb_scales, h->hb_wimg, h->hb_part + c * h->hb_part_stride, A.s, A.exp,
+            CK(h, launch_head_bwd_tc(hd, h->hb_gplanar, c, h->hb_scales, h->hb_wimg, h->hb_part + c * h->hb_part_stride, A.s, A.exp,
                                      A.amax, lo_plane_dead(h), s), 1);
         else
             CK(h, launch_head2_bwd(hd, h->gpred, c, W(h, l2), A.f, A.amax, GW(h, l2), GB(h, l2), GB(h, l1),
@@ -606,7 +607,7 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
         float* dw[3] = {GW(h, l_head + 1), GW(h, l_head + 3), GW(h, l_head + 5)};
         float* db[3] = {GB(h, l_head + 1), GB(h, l_head + 3), GB(h, l_head + 5)};
         float* db1[3] = {GB(h, l_head), GB(h, l_head + 2), GB(h, l_head + 4)};
-        CK(h, launch_head_bwd_tc_finish(part, ncta, h->hb_scales, dw, db, db1, s), 1);
+        CK(h, launch_head_bwd_tc_finish(part, ncta, h->hb_scales, dw, db, db1, lo_plane_dead(h), s), 1);
     }
     if (!fused_heads) {
         if ((rc = fold_act(h, &h->raw_hr[0], &h->raw_hr[1], &h->raw_hr[2], nullptr, trunk_act ? &trunk : nullptr,
@@ -667,7 +668,7 @@ void free_all(sr4d_t* h) {
     cudaFree(h->feat);
     for (auto t : h->tapP) cudaFree(t);
     cudaFree(h->head_wimg);
-    cudaFree(h->hb_scales); cudaFree(h->hb_wimg); cudaFree(h->hb_part);
+    cudaFree(h->hb_scales); cudaFree(h->hb_wimg); cudaFree(h->hb_part); cudaFree(h->hb_gplanar);
     for (auto& b : h->lr) cudaFree(b.base);
     for (auto& b : h->hr) cudaFree(b.base);
     cudaFree(h->up.lo); cudaFree(h->up.hi); cudaFree(h->up.lerp); cudaFree(h->up.ibeg); cudaFree(h->up.iend);
@@ -779,6 +780,7 @@ int sr4d_create(sr4d_t** out, int patch_size, int res_increase, int low_resblock
                 bad |= cudaMalloc(&h->hb_scales, head_bwd_tc_scales_bytes()) != cudaSuccess;
                 bad |= dmalloc(&h->hb_wimg, head_bwd_tc_wimg_halves()) != cudaSuccess;
                 bad |= dmalloc(&h->hb_part, 3 * h->hb_part_stride) != cudaSuccess;
+                bad |= dmalloc(&h->hb_gplanar, head_bwd_tc_gplanar_floats(h->maxB, h->H)) != cudaSuccess;
             }
             if (bad) { rc = SR4D_ENOMEM; break; }
         }
@@ -1112,7 +1114,7 @@ int sr4d_head_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const fl
     if (tc && !head_bwd_tc_supported(D)) return fail(h, SR4D_EINVAL, "tensor-core head backward: unsupported edge");
     cudaStream_t s = (cudaStream_t)stream;
     ActBuf bi;
-    float *g4 = nullptr, *scr = nullptr, *outs = nullptr, *part = nullptr;
+    float *g4 = nullptr, *scr = nullptr, *outs = nullptr, *part = nullptr, *gpl = nullptr;
     __half *g4s = nullptr, *wimg = nullptr;
     void* scales = nullptr;
     int* meta = nullptr;
@@ -1121,7 +1123,7 @@ int sr4d_head_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const fl
     int rc = SR4D_OK;
     if (alloc_act(bi, B, D) || dmalloc(&g4, n4) || dmalloc(&g4s, 2 * n4) || dmalloc(&scr, (size_t)(592 + 1) * 29 * 64) ||
         dmalloc(&outs, 27 * 64 + 1 + 64) || dmalloc(&meta, 4) ||
-        (tc && (dmalloc(&part, 3 * head_bwd_tc_partial_floats(B, D)) || dmalloc(&wimg, head_bwd_tc_wimg_halves()) ||
+        (tc && (dmalloc(&part, 3 * head_bwd_tc_partial_floats(B, D)) || dmalloc(&gpl, head_bwd_tc_gplanar_floats(B, D)) || dmalloc(&wimg, head_bwd_tc_wimg_halves()) ||
                 cudaMalloc(&scales, head_bwd_tc_scales_bytes()) != cudaSuccess)))
         rc = SR4D_ENOMEM;
     if (!rc) {
@@ -1135,9 +1137,10 @@ int sr4d_head_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const fl
         if (!e) e = launch_absmax(g, ng, gmax, s);
         float* dw = outs; float* db = outs + 27 * 64; float* db1 = db + 1;
         if (!e && tc) {
-            e = launch_head_bwd_tc_setup(kernel, kernel, kernel, gmax, scales, wimg, s);
+            e = launch_head_bwd_tc_setup(kernel, kernel, kernel, gmax, scales, wimg, g, gpl, B, D, s);
             const size_t ps = head_bwd_tc_partial_floats(B, D);
-            if (!e) e = launch_head_bwd_tc(vi, g, c, scales, wimg, part + c * ps, g4s, meta + 1, amax, false, s);
+            const bool lean = lo_plane_dead(h);   // the handle's SR4D_OPT_DGRAD_SINGLE / WGRAD_SINGLE pick the kernel, as in training
+            if (!e) e = launch_head_bwd_tc(vi, gpl, c, scales, wimg, part + c * ps, g4s, meta + 1, amax, lean, s);
             // the finishing kernel covers three heads: the other two get this head's partials and scratch outputs
             const float* pp[3] = {part + c * ps, part + c * ps, part + c * ps};
             const int nc = head_bwd_tc_grid(B, D);
@@ -1145,8 +1148,8 @@ int sr4d_head_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const fl
             float* odw[3] = {scr, scr, scr}; float* odb[3] = {scr + 2000, scr + 2000, scr + 2000};
             float* odb1[3] = {scr + 2100, scr + 2100, scr + 2100};
             odw[c] = dw; odb[c] = db; odb1[c] = db1;
-            if (!e) e = launch_head_bwd_tc_finish(pp, ncta, scales, odw, odb, odb1, s);
-            if (!e) e = launch_dense_from_split(g4s, meta + 1, true, dx, B, D, s);
+            if (!e) e = launch_head_bwd_tc_finish(pp, ncta, scales, odw, odb, odb1, lean, s);
+            if (!e) e = launch_dense_from_split(g4s, meta + 1, !lean, dx, B, D, s);
             h->launches += 5;
         } else if (!e) {
             e = launch_head2_bwd(vi, g, c, kernel, g4, amax, dw, db, db1, nullptr, meta + 1, gmax, scr, s, false);
@@ -1160,7 +1163,7 @@ int sr4d_head_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const fl
         if (e) { rc = SR4D_ECUDA; h->err = cudaGetErrorString(e); }
     }
     cudaFree(bi.base); cudaFree(g4); cudaFree(g4s); cudaFree(scr); cudaFree(outs); cudaFree(meta);
-    cudaFree(part); cudaFree(wimg); cudaFree(scales);
+    cudaFree(part); cudaFree(wimg); cudaFree(scales); cudaFree(gpl);
     return rc;
 }
 

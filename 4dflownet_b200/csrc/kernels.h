@@ -90,12 +90,14 @@ int head_bwd_tc_grid(int B, int D);
 size_t head_bwd_tc_partial_floats(int B, int D);
 size_t head_bwd_tc_scales_bytes();
 size_t head_bwd_tc_wimg_halves();
+size_t head_bwd_tc_gplanar_floats(int B, int D);
+// g (B, D^3, 3): the loss gradient; gplanar: head_bwd_tc_gplanar_floats() floats of scratch (planar scaled copy)
 cudaError_t launch_head_bwd_tc_setup(const float* w0, const float* w1, const float* w2, const unsigned int* gmax, void* scales,
-                                     __half* wimg, cudaStream_t s);
-cudaError_t launch_head_bwd_tc(ActView h, const float* g, int c, const void* scales, const __half* wimg, float* partial,
+                                     __half* wimg, const float* g, float* gplanar, int B, int D, cudaStream_t s);
+cudaError_t launch_head_bwd_tc(ActView h, const float* gplanar, int c, const void* scales, const __half* wimg, float* partial,
                                __half* split_out, int* split_exp, unsigned int* amax, bool hi_only, cudaStream_t s);
 cudaError_t launch_head_bwd_tc_finish(const float* const part[3], const int ncta[3], const void* scales, float* const dw[3],
-                                      float* const db[3], float* const db1[3], cudaStream_t s);
+                                      float* const db[3], float* const db1[3], bool hi_only, cudaStream_t s);
 // *out_bits = max(*out_bits, bits of max |x|)  (zero it first)
 cudaError_t launch_absmax(const float* x, size_t n, unsigned int* out_bits, cudaStream_t s);
 // scaled split-fp16 gradient (G4 layout) -> dense fp32 (B, D, D, D, 64)

@@ -101,6 +101,27 @@ bool tc_make_rows_map(CUtensorMap* map, const __half* base, long long nrows, lon
     return true;
 }
 
+bool tc_make_gplanar_map(CUtensorMap* map, const float* base, int B, int D, int by) {
+    const MapKey key(cur_dev(), base, B, D, by, -7, 0);
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *map = it->second; return true; }
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    const cuuint64_t d = (cuuint64_t)D;
+    cuuint64_t dims[5] = {d, d, d, (cuuint64_t)B, 3};
+    cuuint64_t strides[4] = {4 * d, 4 * d * d, 4 * d * d * d, 4 * d * d * d * (cuuint64_t)B};
+    cuuint32_t box[5] = {(cuuint32_t)(D + 8), (cuuint32_t)by, 3, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps[key] = *map;
+    return true;
+}
+
 void tc_forget_maps(const void* base, size_t bytes) {
     const char* lo = static_cast<const char*>(base);
     const char* hi = lo + bytes;

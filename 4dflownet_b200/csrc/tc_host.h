@@ -18,3 +18,6 @@ void tc_forget_maps(const void* base, size_t bytes);
 // 3-D tiled map over the two packed planes of an Act viewed as a matrix of voxel rows: {64 channels, nrows, 2 planes},
 // box {64, box_rows, 1}, SWIZZLE_128B (plane 0 = hi, plane 1 = lo; `plane_elems` = distance between the planes in halves)
 bool tc_make_rows_map(CUtensorMap* map, const __half* base, long long nrows, long long plane_elems, int box_rows);
+// 5-D tiled fp32 map over a planar gradient [3][B][D][D][D] ({z, y, x, b, c}), box {D + 8, by, 3, 1, 1} (z from -4: box starts must be 16-byte aligned), no swizzle: the
+// head backward stages a tile's neighbourhood with it (coordinates may start below 0; out-of-bounds elements arrive as 0)
+bool tc_make_gplanar_map(CUtensorMap* map, const float* base, int B, int D, int by);

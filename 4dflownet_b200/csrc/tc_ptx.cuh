@@ -33,6 +33,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// the same wait for warps that may wait long next to warps that work: mbarrier.try_wait with a suspend-time hint parks
+// the thread in hardware (a tight try_wait / branch loop is always eligible and takes issue slots from the working warps
+// of its scheduler: 16 polling warps cut the others' issue rate by 4x in head_bwd_tc_kernel)
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_P:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_P;\n"
+        "bra WAIT_LOOP_P;\n"
+        "DONE_P:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(100000u)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
                                             int c3, int c4) {
     asm volatile(
@@ -50,6 +66,20 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// true in exactly one lane of a fully converged warp.  A warp that runs its whole issue loop converged and predicates only
+// the tcgen05 instructions on this keeps descriptors in uniform registers; `if (lane == 0)` around the loop makes ptxas
+// wrap every UTCHMMA in an ELECT / BRA.U.ANY loop with R2UR moves (~15 instructions, ~100 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

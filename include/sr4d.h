@@ -197,7 +197,9 @@ int  sr4d_conv64_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const
  * given its saved post-ReLU input x (B,D,D,D,64), kernel (3,3,3,64,1) and the loss gradient g (B,D,D,D,3) of which
  * channel c belongs to this head: dx (B,D,D,D,64) = gradient wrt the PRE-activation of x (ReluGrad applied),
  * dkernel (27*64), dbias (1), dbias_prev (64) = per-channel sum of dx.  With SR4D_CONV_TCGEN05 dx is what the
- * tensor-core consumers read: the scaled split-fp16 copy (both planes) converted back to fp32. */
+ * tensor-core consumers read: the scaled split-fp16 copy converted back to fp32 -- both planes and fp32-accurate
+ * weight / bias gradients when SR4D_OPT_DGRAD_SINGLE = SR4D_OPT_WGRAD_SINGLE = 0, the hi plane and single-plane
+ * arithmetic (the training default) otherwise. */
 int  sr4d_head_layer_bwd(sr4d_t* h, const float* x, const float* kernel, const float* g, int c, float* dx,
                          float* dkernel, float* dbias, float* dbias_prev, int B, int D, int impl, void* stream);
 

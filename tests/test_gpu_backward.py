@@ -59,16 +59,24 @@ def test_conv64_layer_bwd(pkg, bars, D, B, dy_scale, impl):
     eng.close()
 
 
-@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
-@pytest.mark.parametrize("D,B,g_scale,c", [(6, 2, 1.0, 0), (12, 1, 1e-6, 1), (16, 2, 1.0, 2), (24, 3, 3e-7, 0), (36, 1, 1e3, 1),
+@pytest.mark.parametrize("impl", ["simt", "tcgen05_full", "tcgen05"])
+@pytest.mark.parametrize("D,B,g_scale,c", [(6, 2, 1.0, 0), (8, 2, 1.0, 1), (12, 1, 1e-6, 1), (16, 2, 1.0, 2), (24, 3, 3e-7, 0), (36, 1, 1e3, 1),
                                            (48, 2, 1.0, 2), (48, 8, 1e-6, 0)])
-def test_head_layer_bwd(pkg, D, B, g_scale, c, impl):
+def test_head_layer_bwd(pkg, bars, D, B, g_scale, c, impl):
     """Whole backward of one 64->1 head (relu -> clamp-padded conv3d with one filter, SR4DFlowNet.py:40-49) given
     identical inputs, against float64 autograd: input gradient incl. ReluGrad and MirrorPadGrad, kernel gradient, both
-    bias gradients.  tcgen05: the G table, the weights and the saved activations enter the tensor cores as hi + lo fp16
-    pairs (three products), so every output is fp32-accurate; dx is read back from the split-fp16 copy the consumers use."""
+    bias gradients.  tcgen05_full (two-plane backward options): the G table, the weights and the saved activations enter
+    the tensor cores as hi + lo fp16 pairs (three products), so every output is fp32-accurate; dx is read back from the
+    split-fp16 copy the consumers use.  tcgen05 (the training default, single-plane backward): G, the saved activation
+    and the output gradient are single fp16 planes -- independent 2^-12 roundings per element, as in the 64->64 layers'
+    single-plane dgrad / wgrad (test_conv64_layer_bwd explains why random inputs are the worst case for them)."""
     L = pkg._lib
+    if impl != "simt" and D % 4:
+        pytest.skip("tensor-core head backward needs D % 4 == 0 (16-byte strides of the planar gradient); the engine falls back to the SIMT kernel")
     eng = pkg.Engine(8, 2, 0, 0, max_batch=2, training=False, device=0)
+    single = 0 if impl == "tcgen05_full" else 1
+    eng.set_option(L.OPT_DGRAD_SINGLE, single)
+    eng.set_option(L.OPT_WGRAD_SINGLE, single)
     rng = np.random.default_rng(100 + D + B)
     x = np.maximum(rng.standard_normal((B, D, D, D, 64)), 0).astype(np.float32)      # a ReLU output: about half zeros
     k = (rng.standard_normal((3, 3, 3, 64, 1)) * 0.05).astype(np.float32)
@@ -82,11 +90,17 @@ def test_head_layer_bwd(pkg, D, B, g_scale, c, impl):
     gt = torch.tensor(g[..., c], dtype=torch.float64)
     (y * gt).sum().backward()
     dx_ref = (xt.grad * (xt > 0)).numpy()
-    assert rel_l2(dx.cpu().numpy(), dx_ref) < 2e-6
-    assert rel_l2(dk.cpu().numpy().reshape(-1), kt.grad.numpy().reshape(-1)) < 1e-5
-    np.testing.assert_allclose(db.cpu().numpy()[0], gt.sum().item(), rtol=2e-5, atol=1e-5 * g_scale * np.sqrt(gt.numel()))
     ref_db1 = dx_ref.sum(axis=(0, 1, 2, 3))
-    assert rel_l2(db1.cpu().numpy(), ref_db1) < 3e-5
+    e_dx, e_dk = rel_l2(dx.cpu().numpy(), dx_ref), rel_l2(dk.cpu().numpy().reshape(-1), kt.grad.numpy().reshape(-1))
+    e_db1 = rel_l2(db1.cpu().numpy(), ref_db1)
+    np.testing.assert_allclose(db.cpu().numpy()[0], gt.sum().item(), rtol=2e-5, atol=1e-5 * g_scale * np.sqrt(gt.numel()))
+    if impl == "tcgen05":
+        tag = f"head_bwd/D{D}B{B}s{g_scale:g}"
+        bars(tag + "/dx", e_dx, 6e-4)
+        bars(tag + "/dk", e_dk, 1e-3)
+        bars(tag + "/db_prev", e_db1, 1e-3)
+    else:
+        assert e_dx < 2e-6 and e_dk < 1e-5 and e_db1 < 3e-5, (e_dx, e_dk, e_db1)
     eng.close()
 
 
