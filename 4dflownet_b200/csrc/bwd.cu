@@ -4,6 +4,7 @@
 // ResizeBilinearGrad (upsample) -- restated per SURVEY appendix C.  Conv3DBackpropInput for
 // the 64->64 layers is conv64 with dgrad=1 (conv_simt.cu).
 #include "kernels.h"
+#include "tc_host.h"
 
 namespace {
 
@@ -32,6 +33,34 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restric
         for (int k = 1; k < 8; ++k) s += red[k][cx];
         out[j] = s;
     }
+}
+
+// the same reduction for a batch of partial matrices in one launch (blockIdx.y = item): the 30 weight gradients of the
+// 64->64 layers, summed once at the end of the backward pass instead of with one 10-us launch per layer
+__global__ void __launch_bounds__(256) reduce_rows_batched_kernel(const ReduceItem* __restrict__ items, int nrows0, int nrows1,
+                                                                  int ncols) {
+    // one thread per four columns walks the rows in order with seven 16-byte loads in flight (650 MB at B = 8: the first
+    // version -- 32 columns x 8 row phases per block, 4-byte loads -- ran at 2.9 TB/s)
+    const ReduceItem it = items[blockIdx.y];
+    const int nrows = it.cls ? nrows1 : nrows0;
+    const int j = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (j >= ncols) return;
+    const float4* p = reinterpret_cast<const float4*>(it.partial + j);
+    const size_t pitch = (size_t)ncols / 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int r = 0;
+    for (; r + 7 <= nrows; r += 7) {
+        float4 v[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) v[k] = __ldcs(p + (size_t)(r + k) * pitch);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { s.x += v[k].x; s.y += v[k].y; s.z += v[k].z; s.w += v[k].w; }
+    }
+    for (; r < nrows; ++r) {
+        const float4 v = __ldcs(p + (size_t)r * pitch);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(it.out + j) = s;
 }
 
 // the same reduction for short, wide partial matrices (few rows, e.g. the 16 wgrad slabs): one thread per column
@@ -592,10 +621,14 @@ __global__ void __launch_bounds__(256) conv1x1_wgrad_kernel(const float* __restr
 // ---- stem 3->64 weight gradient: dW[t][c][co] = sum_v feat[clamp(v+t)][c] * dY[v][co] ------------
 // A block walks (b,x,y) z-lines: the 3x3 clamped neighbour lines of the 3-channel features are staged in
 // shared memory (float4 per voxel), 64 output channels x 4 z-phases of threads keep dW in registers.
-__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ feat, int ch0,
+// The gradient values of a thread's voxels are requested before the feature lines are staged (one exposed global latency per
+// line instead of one per voxel) and the four z-phases meet once in shared memory at the end (the first version went
+// through 162 block barriers there): 159 -> ~60 us per launch at B = 8, P = 24.
+constexpr int SW_ZMAX = 8;     // voxels per thread and line in registers (P <= 32); longer lines take further passes
+__global__ void __launch_bounds__(256, 2) stem_wgrad_kernel(const float* __restrict__ feat, int ch0,
                                                          const float* __restrict__ dy, int B, int P,
                                                          float* __restrict__ partial) {
-    extern __shared__ __align__(16) float swsm[];      // [9][P+2] float4
+    extern __shared__ __align__(16) float swsm[];      // [9][P+2] float4, later [4][81][64] floats
     float4* fl = reinterpret_cast<float4*>(swsm);
     const int Pz = P + 2;
     const int co = threadIdx.x & 63, q = threadIdx.x >> 6;
@@ -605,38 +638,49 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
     const int nlines = B * P * P;
     for (int line = blockIdx.x; line < nlines; line += gridDim.x) {
         const int y = line % P, x = (line / P) % P, b = line / (P * P);
-        __syncthreads();
-        for (int i = threadIdx.x; i < 9 * Pz; i += 256) {
-            const int r = i / Pz;
-            const int zz = min(max(i % Pz - 1, 0), P - 1);
-            const int xx = min(max(x + r / 3 - 1, 0), P - 1), yy = min(max(y + r % 3 - 1, 0), P - 1);
-            const float* f = feat + ((((size_t)b * P + xx) * P + yy) * P + zz) * 6 + ch0;
-            fl[i] = make_float4(f[0], f[1], f[2], 0.f);
-        }
-        __syncthreads();
-        for (int z = q; z < P; z += 4) {
-            const float d = dy[g4_off(P, b, x, y, z) + co];
+        for (int zb = 0; zb < P; zb += 4 * SW_ZMAX) {
+            float d[SW_ZMAX];
 #pragma unroll
-            for (int r = 0; r < 9; ++r)
-#pragma unroll
-                for (int dz = 0; dz < 3; ++dz) {
-                    const float4 f = fl[r * Pz + z + dz];
-                    const int t = (r * 3 + dz) * 3;
-                    acc[t] = fmaf(f.x, d, acc[t]);
-                    acc[t + 1] = fmaf(f.y, d, acc[t + 1]);
-                    acc[t + 2] = fmaf(f.z, d, acc[t + 2]);
+            for (int u = 0; u < SW_ZMAX; ++u) {
+                const int z = zb + q + 4 * u;
+                d[u] = z < P ? dy[g4_off(P, b, x, y, z) + co] : 0.f;
+            }
+            if (zb == 0) {
+                __syncthreads();
+                for (int i = threadIdx.x; i < 9 * Pz; i += 256) {
+                    const int r = i / Pz;
+                    const int zz = min(max(i % Pz - 1, 0), P - 1);
+                    const int xx = min(max(x + r / 3 - 1, 0), P - 1), yy = min(max(y + r % 3 - 1, 0), P - 1);
+                    const float* f = feat + ((((size_t)b * P + xx) * P + yy) * P + zz) * 6 + ch0;
+                    fl[i] = make_float4(f[0], f[1], f[2], 0.f);
                 }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int u = 0; u < SW_ZMAX; ++u) {
+                const int z = zb + q + 4 * u;
+                if (z < P) {
+#pragma unroll
+                    for (int r = 0; r < 9; ++r)
+#pragma unroll
+                        for (int dz = 0; dz < 3; ++dz) {
+                            const float4 f = fl[r * Pz + z + dz];
+                            const int t = (r * 3 + dz) * 3;
+                            acc[t] = fmaf(f.x, d[u], acc[t]);
+                            acc[t + 1] = fmaf(f.y, d[u], acc[t + 1]);
+                            acc[t + 2] = fmaf(f.z, d[u], acc[t + 2]);
+                        }
+                }
+            }
         }
     }
-    __shared__ float red[4][64];
+    __syncthreads();
+    float* red = swsm;                                 // [4][81][64]
 #pragma unroll
-    for (int t = 0; t < 81; ++t) {
-        __syncthreads();
-        red[q][co] = acc[t];
-        __syncthreads();
-        if (threadIdx.x < 64)
-            partial[(size_t)blockIdx.x * 81 * 64 + t * 64 + co] = red[0][co] + red[1][co] + red[2][co] + red[3][co];
-    }
+    for (int t = 0; t < 81; ++t) red[(q * 81 + t) * 64 + co] = acc[t];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 81 * 64; i += 256)
+        partial[(size_t)blockIdx.x * 81 * 64 + i] = (red[i] + red[81 * 64 + i]) + (red[2 * 81 * 64 + i] + red[3 * 81 * 64 + i]);
 }
 
 __global__ void g4_from_dense_kernel(const float* __restrict__ dense, float* __restrict__ g4, unsigned int* amax,
@@ -716,6 +760,12 @@ cudaError_t launch_reduce_rows(const float* partial, int nrows, int ncols, float
     else reduce_rows_kernel<<<(ncols + 31) / 32, 256, 0, s>>>(partial, nrows, ncols, out);
     return cudaGetLastError();
 }
+cudaError_t launch_reduce_rows_batched(const ReduceItem* items_dev, int nitems, int nrows0, int nrows1, int ncols, cudaStream_t s) {
+    if (nitems <= 0) return cudaSuccess;
+    if (ncols % 4) return cudaErrorInvalidValue;
+    reduce_rows_batched_kernel<<<dim3((ncols / 4 + 255) / 256, nitems), 256, 0, s>>>(items_dev, nrows0, nrows1, ncols);
+    return cudaGetLastError();
+}
 cudaError_t launch_bias_grad(const float* dy_g4, int B, int D, float* db, float* scratch, cudaStream_t s) {
     size_t nvox = (size_t)B * D * D * D;
     unsigned nb = red_blocks(nvox, 64);
@@ -745,8 +795,12 @@ cudaError_t launch_conv1x1_bwd(const float* dy_g4, ActView a, ActView b, const f
 cudaError_t launch_stem_wgrad(const float* feat, int ch0, const float* dy_g4, int B, int P, float* dw,
                               float* db, float* scratch, cudaStream_t s) {
     const int nlines = B * P * P;
-    const unsigned nb = nlines < 592 ? nlines : 592;
-    stem_wgrad_kernel<<<nb, 256, (size_t)9 * (P + 2) * sizeof(float4), s>>>(feat, ch0, dy_g4, B, P, scratch);
+    const unsigned nb = nlines < 296 ? nlines : 296;           // 148 SMs x 2 resident blocks (registers, 81 KB of shared memory)
+    size_t smem = (size_t)9 * (P + 2) * sizeof(float4);
+    if (smem < (size_t)4 * 81 * 64 * sizeof(float)) smem = (size_t)4 * 81 * 64 * sizeof(float);
+    cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(stem_wgrad_kernel), (int)smem);
+    if (ea != cudaSuccess) return ea;
+    stem_wgrad_kernel<<<nb, 256, smem, s>>>(feat, ch0, dy_g4, B, P, scratch);
     reduce_rows_kernel<<<(81 * 64 + 31) / 32, 256, 0, s>>>(scratch, nb, 81 * 64, dw);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -34,6 +34,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "conv_tc.h"
@@ -127,6 +128,23 @@ struct KParams {
     long long* dbg;          // SR4D_TC_DEBUG=1: per-CTA cycles the MMA warp waited on {t_empty, x_full, w_full} and its total
 };
 
+// A chain of forward layers on one grid in ONE launch (n > 0): layer L reads params[L] / maps[L]; the persistent CTAs
+// meet at a grid-wide barrier between layers (bar[0]: arrivals, bar[1]: CTAs that left the kernel -- the last one
+// resets both).  At batch 1 a 24^3 layer is ~7 us of MMAs behind ~12 us of launch, prologue and tail; the chain keeps
+// barriers, TMEM and the pipeline state alive across the 17 low-resolution (11 high-resolution) layers of a forward.
+struct ChainArgs {
+    const KParams* params;
+    const CUtensorMap* maps;
+    int n;
+    unsigned int* bar;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // element offset of channel 0 of interior voxel (x,y,z) of an fp32 G4 tensor [B][D+4]^3[64]
 __device__ __forceinline__ size_t g4_off(int D, int b, int x, int y, int z) {
     const int dp = D + 4;
@@ -143,10 +161,12 @@ __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo) 
     return d;
 }
 
-template <int TY, bool SINGLE>
+template <int TY, bool SINGLE, bool CHAIN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
+conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, const ChainArgs chain) {
     using C = Cfg<TY, SINGLE>;
+    const int nl = CHAIN ? chain.n : 1;
+    const KParams& p = p0;                   // geometry, debug buffer: identical for every layer of a chain
     extern __shared__ uint8_t smem_raw[];
     // align by OFFSET (not by pointer cast) so the compiler keeps the shared address space (STS/LDS, not generic)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -201,7 +221,21 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
             // the weight-group barriers by then, the transfers get half a pass to land and they do not queue the
             // weight images behind one 66 KB burst on the SM's L2 port.
             uint32_t wi = 0;           // running weight-tap counter
+            uint32_t xq = 0;           // running activation-pass counter (stage = xq % NXS)
             const int npass = p.ntiles > (int)blockIdx.x ? ((p.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) * 3 : 0;
+            for (int L = 0; L < nl; ++L) {
+            KParams pl;                              // chained layers: a private copy of the layer's parameter block
+            if (CHAIN) pl = chain.params[L];
+            const KParams& p = CHAIN ? pl : p0;
+            const CUtensorMap* xm = CHAIN ? chain.maps + L : &xmap;
+            // Layers after the first wait for every CTA to have stored its part of the previous layer (release on their
+            // side: __threadfence + CTA barrier + atomic) -- but only before the first ACTIVATION load: the first NWS - WG + 1
+            // weight taps of the new layer do not depend on it and are requested first, so their latency overlaps the wait.
+            auto grid_wait = [&]() {
+                while (ld_acquire_gpu(chain.bar) < (unsigned int)L * gridDim.x) { }
+                asm volatile("fence.proxy.async;" ::: "memory");
+            };
+            const uint32_t xq0 = xq;
             auto x_load = [&](int q, int part) {
                 const int t = blockIdx.x + (q / 3) * gridDim.x, dx = q % 3;
                 const int b = t / tiles_per_b;
@@ -209,7 +243,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                 const int x = rem / tiles_per_x;
                 rem %= tiles_per_x;
                 const int y0 = (rem / p.nzt) * TY, z0 = (rem % p.nzt) * TZ;
-                const uint32_t s = (uint32_t)q % C::NXS;
+                const uint32_t s = (xq0 + (uint32_t)q) % C::NXS;
                 int plane = x + dx;
                 if (p.fused) {
                     // interior plane x of dX: storage planes x+1..x+3 of the zero-haloed dY; at the two boundary
@@ -221,12 +255,13 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                 uint8_t* dst = xs + s * C::XSTAGE_BYTES;
                 if (part == 0) {
                     mbar_expect_tx(&x_full[s], (SINGLE ? 1 : 2) * C::ROWS * 128);
-                    tma_load_5d(dst, &xmap, &x_full[s], 0, z0, y0, plane, b);
+                    tma_load_5d(dst, xm, &x_full[s], 0, z0, y0, plane, b);
                 } else if (!SINGLE) {
-                    tma_load_5d(dst + C::PART_BYTES, &xmap, &x_full[s], 0, z0, y0, plane, p.B + b);
+                    tma_load_5d(dst + C::PART_BYTES, xm, &x_full[s], 0, z0, y0, plane, p.B + b);
                 }
             };
-            if (npass) { x_load(0, 0); x_load(0, 1); }
+            const bool late_x = CHAIN && L > 0;
+            if (npass && !late_x) { x_load(0, 0); x_load(0, 1); }
             for (int q = 0; q < npass; ++q) {
                 const int t = blockIdx.x + (q / 3) * gridDim.x, dx = q % 3;
                 int wsel = dx;
@@ -237,6 +272,9 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                 }
                 for (int tp = 0; tp < 9; ++tp) {
                     const uint32_t ws = wi % C::NWS;
+                    // (a group-start wait at tap counter wi needs taps <= wi - NWS + WG - 1 consumed: from this layer's
+                    // tap NWS - WG + 1 on that includes taps of this layer, which need the activation plane)
+                    if (late_x && q == 0 && tp == C::NWS - C::WG + 1) { grid_wait(); x_load(0, 0); x_load(0, 1); }
                     if (wi % C::WG == 0)                 // first stage of a group: wait until the group's previous round was consumed
                         mbar_wait(&w_empty[(wi / C::WG) % C::NGW], ((wi / C::NWS) & 1) ^ 1);
                     if (q + 1 < npass && p.xsplit) {
@@ -251,6 +289,8 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                 }
                 if (q + 1 < npass && !p.xsplit) { x_load(q + 1, 0); x_load(q + 1, 1); }
             }
+            xq += (uint32_t)npass;
+            }   // layers
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -260,6 +300,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
             uint32_t xi = 0, wi = 0, ti = 0;
             long long wt = 0, wx = 0, ww = 0, c0 = 0;
             const long long tbeg = p.dbg ? clock64() : 0;
+            for (int L = 0; L < nl; ++L)
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
                 const uint32_t buf = ti & 1;
                 const uint32_t dacc = tmem_base + buf * ACC_STRIDE;
@@ -318,13 +359,18 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
         const int gt = threadIdx.x - 64 - grp * C::GT;             // thread within the group
         const bool is_h = e >= 2;
         const int co = 32 * (e & 1) + lane;
+        uint32_t ti = 0;
+        float amax = 0.f;
+        for (int L = 0; L < nl; ++L) {
+        KParams pl;
+        if (CHAIN) pl = chain.params[L];
+        const KParams& p = CHAIN ? pl : p0;
         const float bias = (is_h && p.bias) ? p.bias[co] : 0.f;
         const float s1 = is_h ? 1.f : SR4D_LO_INV;
         const int Do = p.Do;
         const int Di = p.Dint;
         float* gstage = stage + grp * C::GSTAGE_FLOATS;
         float* my_stage = gstage + (is_h ? 0 : C::CV * 64) + co;
-        float amax = 0.f;
         float ksplit = 0.f;
         if (p.fused && p.split_hi) {
             float bound = 8.f * *p.gain * __uint_as_float(*p.dy_amax);
@@ -336,7 +382,6 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
             if (blockIdx.x == 0 && threadIdx.x == 64) *p.split_exp = ex;
         }
         const float ks = (p.fused && p.dy_exp) ? exp2f((float)(-*p.dy_exp)) : 1.f;
-        uint32_t ti = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
             const int b = t / tiles_per_b;
             int rem = t % tiles_per_b;
@@ -527,6 +572,13 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
                 named_bar(1 + grp, C::GT);
             }
         }
+        if (CHAIN && L + 1 < nl) {
+            // layer done in this CTA: make its stores visible device-wide, then one arrival per CTA
+            __threadfence();
+            named_bar(3, NUM_EPI);
+            if (threadIdx.x == 64) atomicAdd(chain.bar, 1u);
+        }
+        }   // layers
         if (p.absmax) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -547,6 +599,14 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, KParams p) {
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                      : "memory");
+    }
+    if (CHAIN && threadIdx.x == 0) {
+        // the last CTA to leave re-arms the barrier words for the next chained launch (nobody polls them any more)
+        if (atomicAdd(chain.bar + 1, 1u) == gridDim.x - 1) {
+            chain.bar[0] = 0u;
+            chain.bar[1] = 0u;
+            __threadfence();
+        }
     }
 }
 
@@ -611,15 +671,33 @@ __global__ void __launch_bounds__(256) weight_gain_kernel(const float* __restric
 template <int TY, bool SINGLE>
 cudaError_t launch_cfg(const CUtensorMap& map, KParams p, cudaStream_t s) {
     using C = Cfg<TY, SINGLE>;
-    cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(conv64_tc_kernel<TY, SINGLE>), C::SMEM_BYTES);
+    cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(conv64_tc_kernel<TY, SINGLE, false>), C::SMEM_BYTES);
     if (ea != cudaSuccess) return ea;
     p.nyt = (p.Do + TY - 1) / TY;
     p.nzt = (p.Do + TZ - 1) / TZ;
     p.ntiles = p.B * p.nx * p.nyt * p.nzt;
     const int sms = tc_num_sms();
     int grid = p.ntiles < sms ? p.ntiles : sms;
-    conv64_tc_kernel<TY, SINGLE><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(map, p);
+    ChainArgs none;
+    none.params = nullptr; none.maps = nullptr; none.n = 0; none.bar = nullptr;
+    conv64_tc_kernel<TY, SINGLE, false><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(map, p, none);
     return cudaGetLastError();
+}
+
+// chained forward layers: p0 carries the (shared) geometry, the per-layer blocks live in device memory.  The persistent
+// CTAs wait for each other between layers, so all of them must be co-resident: cooperative launch.
+template <int TY>
+cudaError_t launch_chain_cfg(KParams p0, ChainArgs ch, cudaStream_t s) {
+    using C = Cfg<TY, false>;
+    cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(conv64_tc_kernel<TY, false, true>), C::SMEM_BYTES);
+    if (ea != cudaSuccess) return ea;
+    const int sms = tc_num_sms();
+    const int grid = p0.ntiles < sms ? p0.ntiles : sms;
+    CUtensorMap dummy;
+    memset(&dummy, 0, sizeof dummy);
+    void* args[3] = {&dummy, &p0, &ch};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(conv64_tc_kernel<TY, false, true>), dim3(grid), dim3(NUM_THREADS),
+                                       args, C::SMEM_BYTES, s);
 }
 
 }  // namespace
@@ -697,6 +775,11 @@ int pick_ty_fwd(int Do, int B) {
     return best;
 }
 
+long tc_fwd_tiles(int Do, int B) {
+    const int ty = pick_ty_fwd(Do, B);
+    return (long)B * Do * ((Do + ty - 1) / ty) * ((Do + TZ - 1) / TZ);
+}
+
 bool tc_dgrad_fusable(int D) {
     if (D < 2) return false;
     const int ty = pick_ty(D + 2);
@@ -705,11 +788,12 @@ bool tc_dgrad_fusable(int D) {
     return chunk(0) == chunk(1) && chunk(D) == chunk(D + 1) && D / TZ == (D + 1) / TZ;
 }
 
-cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
-    const int Do = a.in.D, B = a.in.B, Dp = a.in.D + 2;
+namespace {
+// the kernel's parameter block of one layer call (everything but the tile geometry and the debug buffer)
+cudaError_t fill_params(TcWeights* w, const TcConvArgs& a, KParams& p) {
+    const int Do = a.in.D, B = a.in.B;
     if (!a.out_raw && !a.fused && a.out.D != Do) return cudaErrorInvalidValue;
     if (a.fused && (!a.dgrad || !a.out_g4 || !tc_dgrad_fusable(Do - 2))) return cudaErrorInvalidValue;
-    KParams p;
     p.w_img = w->img + ((size_t)a.layer * 2 + (a.dgrad ? 1 : 0)) * 27 * 128 * 64;
     p.out_hi = a.out.hi; p.out_lo = a.out.lo;
     p.res_hi = a.res_hi; p.res_lo = a.res_lo;
@@ -727,6 +811,71 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
     static const bool xsplit = !(getenv("SR4D_TC_XSPLIT") && atoi(getenv("SR4D_TC_XSPLIT")) == 0);
     p.xsplit = xsplit;
     p.dbg = nullptr;
+    p.nyt = p.nzt = p.ntiles = 0;
+    if (a.in.lo != a.in.hi + act_plane_elems(B, a.in.D)) return cudaErrorInvalidValue;   // planes must be packed
+    return cudaSuccess;
+}
+}  // namespace
+
+struct TcChain {
+    int n = 0, ty = 0;
+    KParams p0;
+    KParams* dparams = nullptr;
+    CUtensorMap* dmaps = nullptr;
+    unsigned int* bar = nullptr;
+};
+
+cudaError_t tc_chain_build(TcWeights* w, const TcConvArgs* a, int n, TcChain** out) {
+    if (n < 1 || n > 64) return cudaErrorInvalidValue;
+    const int Do = a[0].in.D, B = a[0].in.B, Dp = Do + 2;
+    const int ty = pick_ty_fwd(Do, B);
+    std::vector<KParams> hp(n);
+    std::vector<CUtensorMap> hm(n);
+    for (int i = 0; i < n; ++i) {
+        if (a[i].dgrad || a[i].fused || a[i].out_raw || a[i].in.D != Do || a[i].in.B != B) return cudaErrorInvalidValue;
+        cudaError_t e = fill_params(w, a[i], hp[i]);
+        if (e != cudaSuccess) return e;
+        hp[i].nyt = (Do + ty - 1) / ty;
+        hp[i].nzt = (Do + TZ - 1) / TZ;
+        hp[i].ntiles = B * hp[i].nx * hp[i].nyt * hp[i].nzt;
+        if (!tc_make_act_map(&hm[i], a[i].in.hi, B, Dp, ty + 2, ZP)) return cudaErrorUnknown;
+    }
+    TcChain* c = new TcChain();
+    c->n = n; c->ty = ty; c->p0 = hp[0];
+    cudaError_t e = cudaMalloc((void**)&c->dparams, n * sizeof(KParams));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->dmaps, n * sizeof(CUtensorMap));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->bar, 2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemcpy(c->dparams, hp.data(), n * sizeof(KParams), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(c->dmaps, hm.data(), n * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(c->bar, 0, 2 * sizeof(unsigned int));
+    if (e != cudaSuccess) { tc_chain_free(c); return e; }
+    *out = c;
+    return cudaSuccess;
+}
+void tc_chain_free(TcChain* c) {
+    if (!c) return;
+    cudaFree(c->dparams); cudaFree(c->dmaps); cudaFree(c->bar);
+    delete c;
+}
+int tc_chain_layers(const TcChain* c) { return c ? c->n : 0; }
+cudaError_t tc_chain_launch(TcChain* c, cudaStream_t s) {
+    ChainArgs ch;
+    ch.params = c->dparams; ch.maps = c->dmaps; ch.n = c->n; ch.bar = c->bar;
+    switch (c->ty) {
+        case 8: return launch_chain_cfg<8>(c->p0, ch, s);
+        case 12: return launch_chain_cfg<12>(c->p0, ch, s);
+        case 16: return launch_chain_cfg<16>(c->p0, ch, s);
+        case 24: return launch_chain_cfg<24>(c->p0, ch, s);
+        default: return launch_chain_cfg<26>(c->p0, ch, s);
+    }
+}
+
+cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
+    const int Do = a.in.D, B = a.in.B, Dp = a.in.D + 2;
+    KParams p;
+    cudaError_t ep = fill_params(w, a, p);
+    if (ep != cudaSuccess) return ep;
+    p.dbg = nullptr;
     static const bool debug = getenv("SR4D_TC_DEBUG") != nullptr;
     static long long* dbg_buf = nullptr;
     if (debug) {
@@ -738,7 +887,6 @@ cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s) {
     const int ty = a.dgrad ? pick_ty(Do) : pick_ty_fwd(Do, B);
     CUtensorMap map;
     if (!tc_make_act_map(&map, a.in.hi, B, Dp, ty + 2, ZP)) return cudaErrorUnknown;
-    if (a.in.lo != a.in.hi + act_plane_elems(B, a.in.D)) return cudaErrorInvalidValue;   // planes must be packed
     cudaError_t e;
     if (p.single_b) {
         switch (ty) {

@@ -45,6 +45,15 @@ void tc_free_weights(TcWeights* w);
 cudaError_t tc_prepare_weights(TcWeights* w, const float* params, const int* layers, const long long* offsets, int n,
                                cudaStream_t s);
 cudaError_t tc_conv64(TcWeights* w, const TcConvArgs& a, cudaStream_t s);
+// A chain of forward layers on one grid (same batch and edge, Act -> Act, each with its own weights / bias / residual /
+// slope) as ONE cooperative launch: the persistent CTAs pass a grid-wide barrier between layers instead of the launch
+// boundary.  Built once per (buffers, batch) -- the parameter blocks and tensor maps live in device memory.
+struct TcChain;
+long tc_fwd_tiles(int Do, int B);      // tiles of one forward layer on this grid (persistent grid = min(tiles, SMs))
+cudaError_t tc_chain_build(TcWeights* w, const TcConvArgs* layers, int n, TcChain** out);
+cudaError_t tc_chain_launch(TcChain* c, cudaStream_t s);
+int tc_chain_layers(const TcChain* c);
+void tc_chain_free(TcChain* c);
 // true when the fused dgrad's in-epilogue fold works for interior edge D (the halo line / column pairs
 // (0,1) and (D,D+1) of the padded grid fall into one epilogue chunk and one z tile)
 bool tc_dgrad_fusable(int D);

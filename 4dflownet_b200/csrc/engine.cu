@@ -7,12 +7,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <map>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>
 
 #include "../../include/sr4d.h"
 #include "kernels.h"
+#include "tc_host.h"
 #include "conv_tc.h"
 
 namespace {
@@ -71,6 +73,16 @@ struct sr4d_handle {
     __half* hb_wimg = nullptr;
     float* hb_part = nullptr;
     float* hb_gplanar = nullptr;                    // planar scaled copy of the loss gradient
+    // chained forward launches (conv_tc.h: TcChain), built on first use per (grid, batch); keys: kind * 65536 + B
+    std::map<int, TcChain*> chains;
+    // deferred second stage of the stacked weight gradient: every 64->64 layer keeps its slab partials until one batched
+    // reduction at the end of the backward pass
+    float* wg_part = nullptr;
+    size_t wg_stride = 0;                           // floats per layer
+    ReduceItem* wg_items = nullptr;                 // device, one per 64->64 layer (LR layers: cls 0, HR: cls 1)
+    std::vector<int> wg_slot;                       // layer -> item index (-1: not a 64->64 layer)
+    int wg_nitems = 0;
+    bool wg_pending = false;                        // partials written since the last batched reduction
     size_t hb_part_stride = 0;                      // floats per head
     std::vector<ActBuf> lr, hr;        // storage slots
     std::vector<int> lr_slot, hr_slot; // tensor index -> slot
@@ -110,6 +122,7 @@ struct sr4d_handle {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     std::vector<int> ev_class;        // class of pair i (events 2i, 2i+1)
+    std::vector<int> ev_weight;       // layer calls the pair covers (a chained launch: all its layers)
     std::string err;
 };
 
@@ -137,13 +150,14 @@ const char* const kProfNames[SR4D_PROF_NCLASSES] = {"conv64_fwd_lr", "conv64_fwd
 // range named after the class (SR4D_OPT_NVTX; the ranges show up in Nsight Systems / ncu --nvtx next to the kernels).
 struct ProfScope {
     sr4d_t* h; cudaStream_t s; bool on; bool nvtx;
-    ProfScope(sr4d_t* h_, int cls, cudaStream_t s_) : h(h_), s(s_), on(h_->profile != 0), nvtx(h_->nvtx != 0) {
+    ProfScope(sr4d_t* h_, int cls, cudaStream_t s_, int nlayers = 1) : h(h_), s(s_), on(h_->profile != 0), nvtx(h_->nvtx != 0) {
         if (nvtx) nvtxRangePushA(kProfNames[cls]);
         if (!on) return;
         if (h->ev_used + 2 > h->ev_pool.size()) {
             for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
         }
         h->ev_class.push_back(cls);
+        h->ev_weight.push_back(nlayers);
         cudaEventRecord(h->ev_pool[h->ev_used], s);
     }
     ~ProfScope() {
@@ -361,6 +375,43 @@ int conv64_fwd(sr4d_t* h, int layer, ActView in, ActView out, const ActView* res
     return SR4D_OK;
 }
 
+// A run of consecutive 64->64 forward layers on one grid as one chained launch (tensor-core path; SR4D_NO_CHAIN=1 keeps
+// one launch per layer).  `layers` lists (layer, in, out, residual or NULL, slope).
+struct FwdLayer { int layer; ActView in, out; bool has_res; ActView res; float slope; };
+int conv64_fwd_run(sr4d_t* h, int kind, const std::vector<FwdLayer>& layers, cudaStream_t s) {
+    static const bool no_chain = getenv("SR4D_NO_CHAIN") != nullptr;
+    // chaining pays where a layer is a few tiles per SM (batch 1: launch + prologue + drain are a third of a 24^3 layer);
+    // on large grids the per-layer launches are as fast and keep the per-class timing simple
+    static const int max_tiles_per_sm = getenv("SR4D_CHAIN_TILES_PER_SM") ? atoi(getenv("SR4D_CHAIN_TILES_PER_SM")) : 4;
+    int rc;
+    const bool small = !layers.empty() && tc_fwd_tiles(layers[0].in.D, layers[0].in.B) <= (long)max_tiles_per_sm * tc_num_sms();
+    if (!use_tc(h) || no_chain || layers.size() < 2 || !small) {
+        for (const auto& l : layers)
+            if ((rc = conv64_fwd(h, l.layer, l.in, l.out, l.has_res ? &l.res : nullptr, l.slope, s))) return rc;
+        return SR4D_OK;
+    }
+    const int B = layers[0].in.B;
+    const int key = kind * 65536 + B;
+    auto it = h->chains.find(key);
+    if (it == h->chains.end()) {
+        std::vector<TcConvArgs> args(layers.size());
+        for (size_t i = 0; i < layers.size(); ++i) {
+            TcConvArgs& a = args[i];
+            a.in = layers[i].in; a.out = layers[i].out; a.layer = layers[i].layer; a.dgrad = 0;
+            a.bias = Bv(h, layers[i].layer);
+            a.res_hi = layers[i].has_res ? layers[i].res.hi : nullptr;
+            a.res_lo = layers[i].has_res ? layers[i].res.lo : nullptr;
+            a.slope = layers[i].slope; a.halo = 1;
+        }
+        TcChain* c = nullptr;
+        CK(h, tc_chain_build(h->tcw, args.data(), (int)args.size(), &c), 0);
+        it = h->chains.emplace(key, c).first;
+    }
+    ProfScope prof(h, layers[0].in.D == h->P ? SR4D_PROF_CONV64_FWD_LR : SR4D_PROF_CONV64_FWD_HR, s, (int)layers.size());
+    CK(h, tc_chain_launch(it->second, s), 1);
+    return SR4D_OK;
+}
+
 int forward_impl(sr4d_t* h, const float* u, const float* v, const float* w, const float* um, const float* vm,
                  const float* wm, float* out, int B, cudaStream_t s) {
     if (B < 1 || B > h->maxB) return fail(h, SR4D_EINVAL, "batch size out of range (1..max_batch)");
@@ -376,16 +427,18 @@ int forward_impl(sr4d_t* h, const float* u, const float* v, const float* w, cons
     CK(h, launch_stem_conv(h->feat, 0, W(h, 2), Bv(h, 2), ph1, s), 1);                 // :20
     if ((rc = conv64_fwd(h, 3, ph1, ph2, nullptr, 0.f, s))) return rc;                  // :21
     CK(h, launch_conv1x1_cat(ph2, pc2, W(h, 4), Bv(h, 4), c1, s), 1);                  // :23-24
-    if ((rc = conv64_fwd(h, 5, c1, f, nullptr, 0.f, s))) return rc;                     // :25
+    std::vector<FwdLayer> run;
+    run.push_back(FwdLayer{5, c1, f, false, ActView(), 0.f});                          // :25
     int li = 6;
     ActView x = f;
     for (int k = 0; k < h->low; ++k) {                                                  // :28-30
         ActView t = lr_view(h, lr_t_of_block_t(k), B), xo = lr_view(h, lr_t_of_block_x(k), B);
-        if ((rc = conv64_fwd(h, li, x, t, nullptr, 0.2f, s))) return rc;
-        if ((rc = conv64_fwd(h, li + 1, t, xo, &x, 0.2f, s))) return rc;
+        run.push_back(FwdLayer{li, x, t, false, ActView(), 0.2f});
+        run.push_back(FwdLayer{li + 1, t, xo, true, x, 0.2f});
         x = xo;
         li += 2;
     }
+    if ((rc = conv64_fwd_run(h, 0, run, s))) return rc;
     ActView xh;
     if (h->r == 1) {
         xh = x;                                                                          // :72-74
@@ -393,18 +446,20 @@ int forward_impl(sr4d_t* h, const float* u, const float* v, const float* w, cons
         xh = hr_view(h, 0, B);
         CK(h, launch_upsample(x, xh, h->r, h->up.tables(), s), 1);                      // :32
     }
+    run.clear();
     for (int k = 0; k < h->hi; ++k) {                                                   // :35-36
         ActView t = hr_view(h, hr_t_of_block_t(k), B), xo = hr_view(h, hr_t_of_block_x(k), B);
-        if ((rc = conv64_fwd(h, li, xh, t, nullptr, 0.2f, s))) return rc;
-        if ((rc = conv64_fwd(h, li + 1, t, xo, &xh, 0.2f, s))) return rc;
+        run.push_back(FwdLayer{li, xh, t, false, ActView(), 0.2f});
+        run.push_back(FwdLayer{li + 1, t, xo, true, xh, 0.2f});
         xh = xo;
         li += 2;
     }
     ActView hd[3];
     for (int c = 0; c < 3; ++c) {                                                       // :39-46
         hd[c] = hr_view(h, 1 + 2 * h->hi + c, B);
-        if ((rc = conv64_fwd(h, li + 2 * c, xh, hd[c], nullptr, 0.f, s))) return rc;
+        run.push_back(FwdLayer{li + 2 * c, xh, hd[c], false, ActView(), 0.f});
     }
+    if ((rc = conv64_fwd_run(h, 1, run, s))) return rc;
     static const bool head_simt = getenv("SR4D_HEAD_SIMT") != nullptr;   // debugging aid / A-B: fp32 head_out_kernel
     if (use_tc(h) && !head_simt)                                                         // :40,43,46,49
         CK(h, launch_head_out_tc(hd[0], hd[1], hd[2], W(h, li + 1), W(h, li + 3), W(h, li + 5), Bv(h, li + 1), Bv(h, li + 3),
@@ -452,7 +507,11 @@ int conv64_wgrad(sr4d_t* h, int layer, ActView x, const GBuf& dy, bool bias, cud
     ProfScope prof(h, x.D == h->P ? SR4D_PROF_CONV64_WGRAD_LR : SR4D_PROF_CONV64_WGRAD_HR, s);
     static const bool wgrad_simt = getenv("SR4D_WGRAD_SIMT") != nullptr;   // debugging aid
     if (use_tc(h) && !wgrad_simt) {
-        if (h->wgrad_single == 1) {
+        static const bool immediate = getenv("SR4D_WGRAD_REDUCE_EACH") != nullptr;   // A-B: one reduce launch per layer
+        if (h->wgrad_single == 1 && h->wg_part && !immediate && h->wg_slot[layer] >= 0) {
+            CK(h, tc_wgrad64_single(x, dy.s, dy.exp, h->wg_part + (size_t)h->wg_slot[layer] * h->wg_stride, s), 1);
+            h->wg_pending = true;                      // summed by wgrad_finish() at the end of the backward pass
+        } else if (h->wgrad_single == 1) {
             CK(h, tc_wgrad64_single(x, dy.s, dy.exp, h->scratch, s), 1);
             CK(h, launch_reduce_rows(h->scratch, tc_wgrad2_slabs(x.B, x.D), 27 * 4096, GW(h, layer), s), 1);
         } else {
@@ -463,6 +522,13 @@ int conv64_wgrad(sr4d_t* h, int layer, ActView x, const GBuf& dy, bool bias, cud
         CK(h, launch_wgrad64_simt(x, dy.f, GW(h, layer), h->scratch, h->wgrad_chunks, s), 2);
     }
     if (bias) CK(h, launch_bias_grad(dy.f, x.B, x.D, GB(h, layer), h->scratch, s), 2);
+    return SR4D_OK;
+}
+// one launch sums the slab partials of every 64->64 layer's weight gradient (all layers run in every backward pass)
+int wgrad_finish(sr4d_t* h, int B, cudaStream_t s) {
+    if (!h->wg_pending) return SR4D_OK;
+    h->wg_pending = false;
+    CK(h, launch_reduce_rows_batched(h->wg_items, h->wg_nitems, tc_wgrad2_slabs(B, h->P), tc_wgrad2_slabs(B, h->H), 27 * 4096, s), 1);
     return SR4D_OK;
 }
 // out = (fold(raw0 [+raw1 +raw2]) + add) * act'(saved); then the split copy
@@ -660,7 +726,7 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
     if ((rc = conv64_wgrad(h, 1, pc1, dB, true, s))) return rc;
     if ((rc = dgrad_fold(h, 1, dB, nullptr, &pc1, 0.f, T, h->raw_lr, B, P, s))) return rc;
     CK(h, launch_stem_wgrad(h->feat, 3, T.f, B, P, GW(h, 0), GB(h, 0), h->scratch, s), 4);
-    return SR4D_OK;
+    return wgrad_finish(h, B, s);
 }
 
 void free_all(sr4d_t* h) {
@@ -669,6 +735,9 @@ void free_all(sr4d_t* h) {
     for (auto t : h->tapP) cudaFree(t);
     cudaFree(h->head_wimg);
     cudaFree(h->hb_scales); cudaFree(h->hb_wimg); cudaFree(h->hb_part); cudaFree(h->hb_gplanar);
+    cudaFree(h->wg_part); cudaFree(h->wg_items);
+    for (auto& kv : h->chains) tc_chain_free(kv.second);
+    h->chains.clear();
     for (auto& b : h->lr) cudaFree(b.base);
     for (auto& b : h->hr) cudaFree(b.base);
     cudaFree(h->up.lo); cudaFree(h->up.hi); cudaFree(h->up.lerp); cudaFree(h->up.ibeg); cudaFree(h->up.iend);
@@ -775,6 +844,29 @@ int sr4d_create(sr4d_t** out, int patch_size, int res_increase, int low_resblock
             size_t need2 = (size_t)1184 * 8192 + 8192;
             if (need2 > h->scratch_floats) h->scratch_floats = need2;
             bad |= dmalloc(&h->scratch, h->scratch_floats) != cudaSuccess;
+            {
+                // per-layer slab partials of the stacked weight gradient + the item table of the batched reduction
+                std::vector<ReduceItem> items;
+                h->wg_slot.assign(h->layers.size(), -1);
+                h->wg_stride = (size_t)std::max(tc_wgrad2_slabs(h->maxB, h->P), tc_wgrad2_slabs(h->maxB, h->H)) * 27 * 4096;
+                for (size_t i = 0; i < h->layers.size(); ++i) {
+                    const auto& ly = h->layers[i];
+                    if (ly.k == 3 && ly.cin == 64 && ly.cout == 64) { h->wg_slot[i] = (int)items.size(); items.push_back(ReduceItem{nullptr, nullptr, 0, 0}); }
+                }
+                h->wg_nitems = (int)items.size();
+                if (h->wg_nitems) {
+                    bad |= dmalloc(&h->wg_part, h->wg_stride * h->wg_nitems) != cudaSuccess;
+                    bad |= cudaMalloc(&h->wg_items, sizeof(ReduceItem) * h->wg_nitems) != cudaSuccess;
+                    if (!bad) {
+                        const int l_hr0 = 6 + 2 * h->low;                       // layers from here on run on the HR grid
+                        for (size_t i = 0; i < h->layers.size(); ++i)
+                            if (h->wg_slot[i] >= 0)
+                                items[h->wg_slot[i]] = ReduceItem{h->wg_part + (size_t)h->wg_slot[i] * h->wg_stride, GW(h, (int)i),
+                                                                  (int)i >= l_hr0 ? 1 : 0, 0};
+                        cudaMemcpy(h->wg_items, items.data(), sizeof(ReduceItem) * h->wg_nitems, cudaMemcpyHostToDevice);
+                    }
+                }
+            }
             if (head_bwd_tc_supported(h->H)) {
                 h->hb_part_stride = head_bwd_tc_partial_floats(h->maxB, h->H);
                 bad |= cudaMalloc(&h->hb_scales, head_bwd_tc_scales_bytes()) != cudaSuccess;
@@ -814,11 +906,14 @@ int sr4d_set_option(sr4d_t* h, int option, int value) {
             return SR4D_OK;
         case SR4D_OPT_SAVE_ACTS:
             h->save_acts = value != 0;
+            for (auto& kv : h->chains) tc_chain_free(kv.second);     // the layer -> buffer mapping may differ
+            h->chains.clear();
             return SR4D_OK;
         case SR4D_OPT_PROFILE:
             h->profile = value != 0;
             h->ev_used = 0;
             h->ev_class.clear();
+            h->ev_weight.clear();
             return SR4D_OK;
         case SR4D_OPT_FUSED_DGRAD:
             h->fused_dgrad = value != 0;
@@ -1178,10 +1273,11 @@ int sr4d_profile_read(sr4d_t* h, double* ms, int64_t* launches, int nclasses) {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]) != cudaSuccess) continue;
         ms[h->ev_class[i]] += t;
-        launches[h->ev_class[i]] += 1;
+        launches[h->ev_class[i]] += h->ev_weight[i];
     }
     h->ev_used = 0;
     h->ev_class.clear();
+    h->ev_weight.clear();
     return SR4D_OK;
 }
 

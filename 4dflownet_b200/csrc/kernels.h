@@ -119,6 +119,9 @@ cudaError_t launch_wgrad64_simt(ActView x, const float* dy_g4, float* dw, float*
                                 cudaStream_t s);
 // out[j] = sum_r partial[r][j] (deterministic second stage of the split reductions)
 cudaError_t launch_reduce_rows(const float* partial, int nrows, int ncols, float* out, cudaStream_t s);
+// a batch of such reductions in one launch: item i sums nrows0 (cls 0) or nrows1 (cls 1) rows of its partial matrix
+struct ReduceItem { const float* partial; float* out; int cls; int pad; };
+cudaError_t launch_reduce_rows_batched(const ReduceItem* items_dev, int nitems, int nrows0, int nrows1, int ncols, cudaStream_t s);
 cudaError_t launch_bias_grad(const float* dy_g4, int B, int D, float* db, float* scratch, cudaStream_t s);
 cudaError_t launch_upsample_bwd(const float* dhr_g4, ActView lr_saved, float slope, float* dlr_g4,
                                 unsigned int* amax, int B, int D, int r, UpsampleTables t, cudaStream_t s);
