@@ -27,7 +27,8 @@ __global__ void prep_features_kernel(const float* __restrict__ u, const float* _
 // The kernel is bound by the shared-memory weight fetches (a 16-byte load per 4 FMAs when a thread owns one voxel:
 // 12 LDS.128 per 48 FMAs, 4 LSU cycles each); with four voxels per thread every fetched weight feeds 16 FMAs and the
 // six clamped feature columns of a (dx,dy) row are read once for the three dz taps of all four voxels.
-constexpr int STEM_VZ = 4;
+// Small grids (batch 1: 54 CTAs for 148 SMs with four voxels per thread) take the one-voxel instantiation.
+template <int STEM_VZ>
 __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ feat, int ch0,
                                                         const float* __restrict__ w,
                                                         const float* __restrict__ bias, ActView out) {
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
 // ---- 1x1 conv over concat[a(phase), b(pc)] 128->64 (+bias, ReLU): SR4DFlowNet.py:23-24
 // 4 threads per group of C1_NV consecutive voxels, 16 output channels each: every 16-byte weight fetch from shared
 // memory feeds 4 * C1_NV FMAs (the one-voxel version was bound by those fetches).
-constexpr int C1_NV = 4;
+template <int C1_NV>
 __global__ void __launch_bounds__(256) conv1x1_cat_kernel(ActView a, ActView bq, const float* __restrict__ w,
                                                           const float* __restrict__ bias, ActView out) {
     extern __shared__ __align__(16) float ws[];   // [128][64]
@@ -164,11 +165,14 @@ __global__ void __launch_bounds__(256) conv1x1_cat_kernel(ActView a, ActView bq,
 // fixed, and the LR z index pair (lo, hi) advances by at most one per output voxel (scale <= 1), so the thread keeps the
 // corner values at LR indices i0 and i0+1 in registers and loads every LR voxel of its four columns exactly once:
 // 2 instead of 8 corner loads per output voxel, same lerp expressions and order as the one-voxel-per-thread version.
-__global__ void __launch_bounds__(256) upsample_kernel(ActView in, ActView out, UpsampleTables t) {
+// blockIdx.y = z segment (small grids: a batch-1 volume has only 2304 lines, 124 threads per SM; the segments start with
+// their own corner loads).
+__global__ void __launch_bounds__(256) upsample_kernel(ActView in, ActView out, UpsampleTables t, int zseg) {
     const int H = out.D, D = in.D;
     const size_t nline = (size_t)out.B * H * H;
     const size_t li = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3);
     if (li >= nline) return;
+    const int zbeg = blockIdx.y * zseg, zend = min(H, zbeg + zseg);
     const int c = (threadIdx.x & 7) * 8;
     const int y = (int)(li % H), x = (int)((li / H) % H), b = (int)(li / ((size_t)H * H));
     const int xl = t.lo[x], xh = t.hi[x], yl = t.lo[y], yh = t.hi[y];
@@ -177,13 +181,13 @@ __global__ void __launch_bounds__(256) upsample_kernel(ActView in, ActView out, 
     col[0] = act_off(D, b, xl, yl, 0) + c; col[1] = act_off(D, b, xl, yh, 0) + c;
     col[2] = act_off(D, b, xh, yl, 0) + c; col[3] = act_off(D, b, xh, yh, 0) + c;
     float v0[4][8], v1[4][8];
-    int i0 = 0;
+    int i0 = t.lo[zbeg];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        act_load8(in.hi, in.lo, col[k], v0[k]);
-        act_load8(in.hi, in.lo, col[k] + (size_t)min(1, D - 1) * SR4D_C, v1[k]);
+        act_load8(in.hi, in.lo, col[k] + (size_t)i0 * SR4D_C, v0[k]);
+        act_load8(in.hi, in.lo, col[k] + (size_t)min(i0 + 1, D - 1) * SR4D_C, v1[k]);
     }
-    for (int z = 0; z < H; ++z) {
+    for (int z = zbeg; z < zend; ++z) {
         const int zl = t.lo[z], zh = t.hi[z];
         const float fz = t.lerp[z];
         if (zl > i0) {                               // warp-uniform: every thread of the block walks the same z
@@ -395,21 +399,35 @@ cudaError_t launch_prep_features(const float* u, const float* v, const float* w,
 }
 cudaError_t launch_stem_conv(const float* feat, int ch0, const float* w, const float* bias, ActView out,
                              cudaStream_t s) {
-    const size_t nrun = (size_t)out.B * out.D * out.D * ((out.D + STEM_VZ - 1) / STEM_VZ);
-    const size_t ngrp = (nrun + 63) / 64;
-    stem_conv_kernel<<<(unsigned)(ngrp < 2368 ? ngrp : 2368), 256, 0, s>>>(feat, ch0, w, bias, out);
+    const size_t nrun4 = (size_t)out.B * out.D * out.D * ((out.D + 3) / 4);
+    const size_t ngrp4 = (nrun4 + 63) / 64;
+    if (ngrp4 >= 2 * (size_t)tc_num_sms()) {
+        stem_conv_kernel<4><<<(unsigned)(ngrp4 < 2368 ? ngrp4 : 2368), 256, 0, s>>>(feat, ch0, w, bias, out);
+    } else {
+        const size_t ngrp1 = ((size_t)out.B * out.D * out.D * out.D + 63) / 64;
+        stem_conv_kernel<1><<<(unsigned)(ngrp1 < 2368 ? ngrp1 : 2368), 256, 0, s>>>(feat, ch0, w, bias, out);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_conv1x1_cat(ActView a, ActView b, const float* w, const float* bias, ActView out, cudaStream_t s) {
     size_t nvox = (size_t)out.B * out.D * out.D * out.D;
-    const size_t ngrp = ((nvox + C1_NV - 1) / C1_NV + 63) / 64;
-    conv1x1_cat_kernel<<<(unsigned)(ngrp < 2368 ? ngrp : 2368), 256, 128 * 64 * 4, s>>>(a, b, w, bias, out);
+    const size_t ngrp4 = ((nvox + 3) / 4 + 63) / 64;
+    if (ngrp4 >= 2 * (size_t)tc_num_sms()) {
+        conv1x1_cat_kernel<4><<<(unsigned)(ngrp4 < 2368 ? ngrp4 : 2368), 256, 128 * 64 * 4, s>>>(a, b, w, bias, out);
+    } else {                                       // small grids: one voxel per thread, four times the CTAs
+        const size_t ngrp1 = (nvox + 63) / 64;
+        conv1x1_cat_kernel<1><<<(unsigned)(ngrp1 < 2368 ? ngrp1 : 2368), 256, 128 * 64 * 4, s>>>(a, b, w, bias, out);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_upsample(ActView in, ActView out, int r, UpsampleTables t, cudaStream_t s) {
     (void)r;
     size_t nline = (size_t)out.B * out.D * out.D;
-    upsample_kernel<<<(unsigned)((nline + 31) / 32), 256, 0, s>>>(in, out, t);
+    const unsigned nb = (unsigned)((nline + 31) / 32);
+    int nseg = 1;
+    while (nseg < 4 && (size_t)nb * nseg < 2 * (size_t)tc_num_sms() && out.D / (2 * nseg) >= 8) nseg *= 2;
+    const int zseg = (out.D + nseg - 1) / nseg;
+    upsample_kernel<<<dim3(nb, (unsigned)((out.D + zseg - 1) / zseg)), 256, 0, s>>>(in, out, t, zseg);
     return cudaGetLastError();
 }
 cudaError_t launch_head_out(ActView h0, ActView h1, ActView h2, const float* w0, const float* w1,

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_fwd_b1.csv python tools/fwd_once.py 1 3 > gpurun_out/ncu_b1.log 2>&1; tail -1 gpurun_out/ncu_b1.log
+python tools/ncu_summary.py launches gpurun_out/launches_fwd_b1.csv | head -24
+timeout 120 python tools/time_fwd.py 1 2>&1 | tail -3
