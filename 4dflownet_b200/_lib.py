@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libsr4d.so")
 
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5
 OPT_CONV_IMPL, OPT_SAVE_ACTS, OPT_PROFILE, OPT_FUSED_DGRAD, OPT_DGRAD_SINGLE, OPT_WGRAD_SINGLE, OPT_NVTX = 1, 2, 3, 4, 5, 6, 7
+OPT_FWD_CHAIN = 8
 PROF_CLASSES = ("conv64_fwd_lr", "conv64_fwd_hr", "conv64_dgrad_lr", "conv64_dgrad_hr", "conv64_wgrad_lr",
                 "conv64_wgrad_hr")
 CONV_AUTO, CONV_SIMT, CONV_TCGEN05 = 0, 1, 2

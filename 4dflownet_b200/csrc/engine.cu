@@ -110,6 +110,7 @@ struct sr4d_handle {
     bool tcw_dirty = true;
     int conv_impl = SR4D_CONV_AUTO;
     int save_acts = 0;
+    int fwd_chain = -1;               // SR4D_OPT_FWD_CHAIN: tiles per SM up to which forward runs are chained (-1: default / environment)
     int fused_dgrad = 1;       // SR4D_OPT_FUSED_DGRAD
     int dgrad_single = 1;      // SR4D_OPT_DGRAD_SINGLE
     int wgrad_single = 1;      // SR4D_OPT_WGRAD_SINGLE
@@ -382,10 +383,11 @@ int conv64_fwd_run(sr4d_t* h, int kind, const std::vector<FwdLayer>& layers, cud
     static const bool no_chain = getenv("SR4D_NO_CHAIN") != nullptr;
     // chaining pays where a layer is a few tiles per SM (batch 1: launch + prologue + drain are a third of a 24^3 layer);
     // on large grids the per-layer launches are as fast and keep the per-class timing simple
-    static const int max_tiles_per_sm = getenv("SR4D_CHAIN_TILES_PER_SM") ? atoi(getenv("SR4D_CHAIN_TILES_PER_SM")) : 4;
+    static const int env_tiles_per_sm = getenv("SR4D_CHAIN_TILES_PER_SM") ? atoi(getenv("SR4D_CHAIN_TILES_PER_SM")) : 4;
+    const int max_tiles_per_sm = h->fwd_chain >= 0 ? h->fwd_chain : env_tiles_per_sm;
     int rc;
     const bool small = !layers.empty() && tc_fwd_tiles(layers[0].in.D, layers[0].in.B) <= (long)max_tiles_per_sm * tc_num_sms();
-    if (!use_tc(h) || no_chain || layers.size() < 2 || !small) {
+    if (!use_tc(h) || no_chain || max_tiles_per_sm == 0 || layers.size() < 2 || !small) {
         for (const auto& l : layers)
             if ((rc = conv64_fwd(h, l.layer, l.in, l.out, l.has_res ? &l.res : nullptr, l.slope, s))) return rc;
         return SR4D_OK;
@@ -921,6 +923,10 @@ int sr4d_set_option(sr4d_t* h, int option, int value) {
         case SR4D_OPT_NVTX:
             h->nvtx = value != 0;
             return SR4D_OK;
+        case SR4D_OPT_FWD_CHAIN:
+            if (value < 0 || value > 64) return fail(h, SR4D_EINVAL, "SR4D_OPT_FWD_CHAIN takes 0..64 tiles per SM");
+            h->fwd_chain = value;
+            return SR4D_OK;
         case SR4D_OPT_DGRAD_SINGLE:
             h->dgrad_single = value != 0;
             return SR4D_OK;
@@ -938,6 +944,7 @@ int sr4d_get_option(const sr4d_t* h, int option, int* value) {
     if (option == SR4D_OPT_PROFILE) { *value = h->profile; return SR4D_OK; }
     if (option == SR4D_OPT_FUSED_DGRAD) { *value = h->fused_dgrad; return SR4D_OK; }
     if (option == SR4D_OPT_NVTX) { *value = h->nvtx; return SR4D_OK; }
+    if (option == SR4D_OPT_FWD_CHAIN) { *value = h->fwd_chain >= 0 ? h->fwd_chain : 4; return SR4D_OK; }
     if (option == SR4D_OPT_DGRAD_SINGLE) { *value = h->dgrad_single; return SR4D_OK; }
     if (option == SR4D_OPT_WGRAD_SINGLE) { *value = h->wgrad_single; return SR4D_OK; }
     return SR4D_EINVAL;

@@ -48,6 +48,10 @@ extern "C" {
 #define SR4D_OPT_FUSED_DGRAD 4   /* 1 (default): the tensor-core dgrad folds the clamp-padding halo, adds the skip
                                     gradient and applies the activation derivative in its epilogue where the grid
                                     allows; 0: separate raw dgrad + fold kernel */
+#define SR4D_OPT_FWD_CHAIN   8   /* 0..64 (default 4): runs of consecutive 64->64 forward layers go out as ONE cooperative launch with a
+                                    grid-wide barrier between layers when a layer has at most this many tiles per SM (batch-1 /
+                                    small-grid inference); 0 = one launch per layer.  The arithmetic is the same: outputs are
+                                    bit-identical either way. */
 #define SR4D_OPT_NVTX        7   /* 1: NVTX ranges around the phases of a step ("sr4d forward", "sr4d loss + backward",
                                     "sr4d adam") and around every 64->64 layer call, named after its kernel class
                                     (conv64_fwd_hr, ...); default 0 */

@@ -93,6 +93,26 @@ def test_forward_full_config_vs_oracle(pkg, oracle):
     eng.close()
 
 
+@pytest.mark.parametrize("P,r,low,hi,B", [(8, 2, 1, 1, 3), (12, 2, 2, 1, 2), (24, 2, 8, 4, 1), (24, 2, 2, 1, 4)])
+def test_chained_forward_launches_are_bit_identical(pkg, oracle, P, r, low, hi, B):
+    """SR4D_OPT_FWD_CHAIN: a run of 64->64 layers as one cooperative launch (grid-wide barrier between layers, odd and even
+    tile counts per CTA, 1..4 tiles per SM) must produce exactly the bytes of the per-layer launches -- same kernels, same
+    arithmetic, only the launch boundaries differ.  Three forwards in a row also exercise the barrier re-arming."""
+    L = pkg._lib
+    params = oracle.glorot_params(low, hi, seed=P + B, bias_scale=0.02)
+    batch = oracle.synthetic_batch(B, P, r, seed=3)
+    eng = pkg.Engine(P, r, low, hi, max_batch=B, training=False, device=0)
+    eng.set_weights(params)
+    eng.set_option(L.OPT_FWD_CHAIN, 0)
+    ref = eng.forward(batch[:6]).clone()
+    for tiles_per_sm in (4, 64):
+        eng.set_option(L.OPT_FWD_CHAIN, tiles_per_sm)
+        for _ in range(3):
+            got = eng.forward(batch[:6])
+            assert torch.equal(got, ref)
+    eng.close()
+
+
 def test_model_protocol_and_stitch(pkg, oracle):
     P, r = 8, 2
     model = pkg.prepare_network(P, r, 1, 1, max_batch=4)
