@@ -128,15 +128,20 @@ struct KParams {
     long long* dbg;          // SR4D_TC_DEBUG=1: per-CTA cycles the MMA warp waited on {t_empty, x_full, w_full} and its total
 };
 
-// A chain of forward layers on one grid in ONE launch (n > 0): layer L reads params[L] / maps[L]; the persistent CTAs
-// meet at a grid-wide barrier between layers (bar[0]: arrivals, bar[1]: CTAs that left the kernel -- the last one
-// resets both).  At batch 1 a 24^3 layer is ~7 us of MMAs behind ~12 us of launch, prologue and tail; the chain keeps
-// barriers, TMEM and the pipeline state alive across the 17 low-resolution (11 high-resolution) layers of a forward.
+// A chain of forward layers on one grid in ONE launch (n > 0): layer L reads params[L] / maps[L].  At batch 1 a 24^3 layer
+// is ~7 us of MMAs behind ~12 us of launch, prologue and tail; the chain keeps barriers, TMEM and the pipeline state alive
+// across the 17 low-resolution (11 high-resolution) layers of a forward.  Layers are ordered by PLANE-LEVEL dependencies
+// instead of a grid-wide barrier: done[(L * B + b) * nx + x] counts the finished tiles of x-plane x of layer L, and the
+// activation load of a pass of layer L+1 waits until the plane it reads is complete in layer L -- so the first planes of
+// a layer start while the last planes of the previous one are still in flight (tiles run in plane order on every CTA, and
+// every dependency points to a lower layer: no cycles).  exit_count: CTAs that left the kernel; the last one re-arms `done`.
 struct ChainArgs {
     const KParams* params;
     const CUtensorMap* maps;
     int n;
-    unsigned int* bar;
+    unsigned int* done;          // [(n - 1) * B * nx] tiles done per plane, [n - 1] tiles done per layer, then the exit counter
+    int nplane;                  // (n - 1) * B * nx
+    int ndone;                   // nplane + n - 1
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -228,12 +233,24 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
             if (CHAIN) pl = chain.params[L];
             const KParams& p = CHAIN ? pl : p0;
             const CUtensorMap* xm = CHAIN ? chain.maps + L : &xmap;
-            // Layers after the first wait for every CTA to have stored its part of the previous layer (release on their
-            // side: __threadfence + CTA barrier + atomic) -- but only before the first ACTIVATION load: the first NWS - WG + 1
-            // weight taps of the new layer do not depend on it and are requested first, so their latency overlaps the wait.
-            auto grid_wait = [&]() {
-                while (ld_acquire_gpu(chain.bar) < (unsigned int)L * gridDim.x) { }
-                asm volatile("fence.proxy.async;" ::: "memory");
+            // Activation loads of layers after the first wait for the plane they read to be complete in the previous layer
+            // (release on the writers' side: __threadfence + CTA barrier + atomic per tile).
+            auto plane_of = [&](int q, int& b) {
+                const int t = blockIdx.x + (q / 3) * gridDim.x;
+                b = t / tiles_per_b;
+                const int x = (t % tiles_per_b) / tiles_per_x;
+                return min(max(x + q % 3 - 1, 0), p.nx - 1);
+            };
+            // (an acquire load is an L2 round trip in the middle of the weight stream: once the layer counter says that the
+            // whole previous layer is complete -- after the first round on large grids -- no more flags are read)
+            bool prev_complete = false;
+            auto ready = [&](int q) {
+                if (prev_complete) return true;
+                int b;
+                const int xp = plane_of(q, b);
+                if (ld_acquire_gpu(chain.done + ((size_t)(L - 1) * p.B + b) * p.nx + xp) < (unsigned int)tiles_per_x) return false;
+                prev_complete = ld_acquire_gpu(chain.done + chain.nplane + (L - 1)) >= (unsigned int)p.ntiles;
+                return true;
             };
             const uint32_t xq0 = xq;
             auto x_load = [&](int q, int part) {
@@ -260,8 +277,12 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
                     tma_load_5d(dst + C::PART_BYTES, xm, &x_full[s], 0, z0, y0, plane, p.B + b);
                 }
             };
-            const bool late_x = CHAIN && L > 0;
-            if (npass && !late_x) { x_load(0, 0); x_load(0, 1); }
+            const bool dep = CHAIN && L > 0;
+            // `pend`: the activation load of the current pass has not been issued yet because its plane was not complete at the
+            // prefetch point.  It is issued (after a blocking wait) before tap NWS - WG + 1 of the pass: a group-start wait at tap
+            // counter wi needs taps <= wi - NWS + WG - 1 consumed, which from that tap on includes taps of this pass.
+            bool pend = dep;
+            if (npass && !dep) { x_load(0, 0); x_load(0, 1); }
             for (int q = 0; q < npass; ++q) {
                 const int t = blockIdx.x + (q / 3) * gridDim.x, dx = q % 3;
                 int wsel = dx;
@@ -272,14 +293,20 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
                 }
                 for (int tp = 0; tp < 9; ++tp) {
                     const uint32_t ws = wi % C::NWS;
-                    // (a group-start wait at tap counter wi needs taps <= wi - NWS + WG - 1 consumed: from this layer's
-                    // tap NWS - WG + 1 on that includes taps of this layer, which need the activation plane)
-                    if (late_x && q == 0 && tp == C::NWS - C::WG + 1) { grid_wait(); x_load(0, 0); x_load(0, 1); }
+                    if (pend && tp == C::NWS - C::WG + 1) {
+                        while (!ready(q)) { }
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        x_load(q, 0); x_load(q, 1);
+                        pend = false;
+                    }
                     if (wi % C::WG == 0)                 // first stage of a group: wait until the group's previous round was consumed
                         mbar_wait(&w_empty[(wi / C::WG) % C::NGW], ((wi / C::NWS) & 1) ^ 1);
                     if (q + 1 < npass && p.xsplit) {
-                        if (tp == 4) x_load(q + 1, 0);
-                        if (tp == 6) x_load(q + 1, 1);
+                        if (tp == 4) {
+                            if (dep && !ready(q + 1)) pend = true;           // not yet: issued inside the next pass
+                            else { if (dep) asm volatile("fence.proxy.async;" ::: "memory"); x_load(q + 1, 0); }
+                        }
+                        if (tp == 6 && !pend) x_load(q + 1, 1);
                     }
                     mbar_expect_tx(&w_full[ws], W_TAP_BYTES);
                     bulk_load(wsm + ws * W_STAGE_BYTES,
@@ -287,7 +314,10 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
                               W_TAP_BYTES, &w_full[ws]);
                     ++wi;
                 }
-                if (q + 1 < npass && !p.xsplit) { x_load(q + 1, 0); x_load(q + 1, 1); }
+                if (q + 1 < npass && !p.xsplit) {
+                    if (dep && !ready(q + 1)) pend = true;
+                    else { if (dep) asm volatile("fence.proxy.async;" ::: "memory"); x_load(q + 1, 0); x_load(q + 1, 1); }
+                }
             }
             xq += (uint32_t)npass;
             }   // layers
@@ -436,8 +466,15 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
                         }
                     } else if (p.res_hi && act) {
                         const size_t o = act_off(Do, b, x, y, z) + g8 * 8;
-                        rh[k] = *reinterpret_cast<const uint4*>(p.res_hi + o);
-                        rl[k] = *reinterpret_cast<const uint4*>(p.res_lo + o);
+                        if (CHAIN) {
+                            // the residual was written earlier in THIS launch, possibly into a buffer this SM has read before
+                            // (inference reuses activation slots): bypass the non-coherent L1
+                            rh[k] = __ldcg(reinterpret_cast<const uint4*>(p.res_hi + o));
+                            rl[k] = __ldcg(reinterpret_cast<const uint4*>(p.res_lo + o));
+                        } else {
+                            rh[k] = *reinterpret_cast<const uint4*>(p.res_hi + o);
+                            rl[k] = *reinterpret_cast<const uint4*>(p.res_lo + o);
+                        }
                     }
                 }
                 // ---- phase A: TMEM -> registers -> fp32 staging [part][voxel][channel] ----
@@ -571,12 +608,16 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
                 }
                 named_bar(1 + grp, C::GT);
             }
-        }
-        if (CHAIN && L + 1 < nl) {
-            // layer done in this CTA: make its stores visible device-wide, then one arrival per CTA
-            __threadfence();
-            named_bar(3, NUM_EPI);
-            if (threadIdx.x == 64) atomicAdd(chain.bar, 1u);
+            if (CHAIN && L + 1 < nl) {
+                // tile done: its stores (halo replicas included) are ordered before the CTA barrier, the signalling thread's
+                // device-scope RELEASE after it is cumulative over them (the grid.sync pattern, without its full fence);
+                // the tile then counts for its x-plane.
+                named_bar(3, NUM_EPI);
+                if (threadIdx.x == 64) {
+                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(chain.done + ((size_t)L * p.B + b) * p.nx + x) : "memory");
+                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(chain.done + chain.nplane + L) : "memory");
+                }
+            }
         }
         }   // layers
         if (p.absmax) {
@@ -600,11 +641,13 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                      : "memory");
     }
-    if (CHAIN && threadIdx.x == 0) {
-        // the last CTA to leave re-arms the barrier words for the next chained launch (nobody polls them any more)
-        if (atomicAdd(chain.bar + 1, 1u) == gridDim.x - 1) {
-            chain.bar[0] = 0u;
-            chain.bar[1] = 0u;
+    if (CHAIN) {
+        // the last CTA to leave re-arms the counters for the next chained launch (nobody polls them any more)
+        __shared__ unsigned int is_last;
+        if (threadIdx.x == 0) is_last = atomicAdd(chain.done + chain.ndone, 1u) == gridDim.x - 1 ? 1u : 0u;
+        __syncthreads();
+        if (is_last) {
+            for (int i = threadIdx.x; i <= chain.ndone; i += NUM_THREADS) chain.done[i] = 0u;
             __threadfence();
         }
     }
@@ -679,7 +722,7 @@ cudaError_t launch_cfg(const CUtensorMap& map, KParams p, cudaStream_t s) {
     const int sms = tc_num_sms();
     int grid = p.ntiles < sms ? p.ntiles : sms;
     ChainArgs none;
-    none.params = nullptr; none.maps = nullptr; none.n = 0; none.bar = nullptr;
+    none.params = nullptr; none.maps = nullptr; none.n = 0; none.done = nullptr; none.nplane = 0; none.ndone = 0;
     conv64_tc_kernel<TY, SINGLE, false><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(map, p, none);
     return cudaGetLastError();
 }
@@ -822,7 +865,8 @@ struct TcChain {
     KParams p0;
     KParams* dparams = nullptr;
     CUtensorMap* dmaps = nullptr;
-    unsigned int* bar = nullptr;
+    unsigned int* done = nullptr;
+    int nplane = 0, ndone = 0;
 };
 
 cudaError_t tc_chain_build(TcWeights* w, const TcConvArgs* a, int n, TcChain** out) {
@@ -844,23 +888,25 @@ cudaError_t tc_chain_build(TcWeights* w, const TcConvArgs* a, int n, TcChain** o
     c->n = n; c->ty = ty; c->p0 = hp[0];
     cudaError_t e = cudaMalloc((void**)&c->dparams, n * sizeof(KParams));
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->dmaps, n * sizeof(CUtensorMap));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&c->bar, 2 * sizeof(unsigned int));
+    c->nplane = (n - 1) * B * hp[0].nx;
+    c->ndone = c->nplane + n - 1;
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->done, (size_t)(c->ndone + 1) * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemcpy(c->dparams, hp.data(), n * sizeof(KParams), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(c->dmaps, hm.data(), n * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemset(c->bar, 0, 2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(c->done, 0, (size_t)(c->ndone + 1) * sizeof(unsigned int));
     if (e != cudaSuccess) { tc_chain_free(c); return e; }
     *out = c;
     return cudaSuccess;
 }
 void tc_chain_free(TcChain* c) {
     if (!c) return;
-    cudaFree(c->dparams); cudaFree(c->dmaps); cudaFree(c->bar);
+    cudaFree(c->dparams); cudaFree(c->dmaps); cudaFree(c->done);
     delete c;
 }
 int tc_chain_layers(const TcChain* c) { return c ? c->n : 0; }
 cudaError_t tc_chain_launch(TcChain* c, cudaStream_t s) {
     ChainArgs ch;
-    ch.params = c->dparams; ch.maps = c->dmaps; ch.n = c->n; ch.bar = c->bar;
+    ch.params = c->dparams; ch.maps = c->dmaps; ch.n = c->n; ch.done = c->done; ch.nplane = c->nplane; ch.ndone = c->ndone;
     switch (c->ty) {
         case 8: return launch_chain_cfg<8>(c->p0, ch, s);
         case 12: return launch_chain_cfg<12>(c->p0, ch, s);
