@@ -71,3 +71,11 @@ cudaError_t tc_wgrad64(ActView x, const __half* dy_split, const int* dy_exp, flo
 // accumulations; writes tc_wgrad2_slabs(B, D) partial dW[27][64][64] (slab-major) for a row reduction.
 int tc_wgrad2_slabs(int B, int D);
 cudaError_t tc_wgrad64_single(ActView x, const __half* dy_split, const int* dy_exp, float* partial, cudaStream_t s);
+// The weight gradients of several layers on the same grid (same batch and edge) in ONE launch of the stacked kernel: item i
+// reads the saved input x_i and the split gradient dy_split_i (device exponent dy_exp_i) and writes its slab partials to
+// partial_i.  Built once per set of buffers (tensor maps in device memory), launched once per backward pass.
+struct TcWgradItem { ActView x; const __half* dy_split; const int* dy_exp; float* partial; };
+struct TcWgradBatch;
+cudaError_t tc_wgrad_batch_build(const TcWgradItem* items, int n, TcWgradBatch** out);
+cudaError_t tc_wgrad_batch_launch(TcWgradBatch* b, cudaStream_t s);
+void tc_wgrad_batch_free(TcWgradBatch* b);

@@ -44,6 +44,10 @@ struct GBuf {
     __half* s = nullptr;           // split-fp16 copy scaled by 2^(*exp): [2B][D+4]^3[64]
     unsigned int* amax = nullptr;  // device: max |f| (bit pattern)
     int* exp = nullptr;            // device: exponent of the split copy
+    // s / exp point at the buffer's own storage (s0 / exp0) or, with the batched weight gradient, at the per-layer storage
+    // of the layer whose weight gradient will read this tensor at the end of the backward pass
+    __half* s0 = nullptr;
+    int* exp0 = nullptr;
 };
 struct RawBuf {
     float* p = nullptr;            // fp32 [B][D+2]^3[64]
@@ -83,6 +87,12 @@ struct sr4d_handle {
     std::vector<int> wg_slot;                       // layer -> item index (-1: not a 64->64 layer)
     int wg_nitems = 0;
     bool wg_pending = false;                        // partials written since the last batched reduction
+    // batched weight gradient: every 64->64 layer's dY split copy lives in its own buffer until ONE launch per grid at the
+    // end of the backward pass computes all weight gradients (tc_wgrad_batch_*)
+    std::vector<__half*> lsplit;                    // [layers]; NULL for other layers
+    int* lexp = nullptr;                            // device [layers]
+    std::vector<TcWgradItem> wg_list[2];            // collected during a pass: LR grid, HR grid
+    std::map<long long, TcWgradBatch*> wg_batches;  // (grid class, batch, items) -> device layer table
     size_t hb_part_stride = 0;                      // floats per head
     std::vector<ActBuf> lr, hr;        // storage slots
     std::vector<int> lr_slot, hr_slot; // tensor index -> slot
@@ -505,7 +515,29 @@ int conv64_dgrad(sr4d_t* h, int layer, const GBuf& dy, RawBuf& raw, int B, int D
     CK(h, launch_conv64_simt(a, s), 1);
     return SR4D_OK;
 }
+// batched weight gradient (default): stacked single-plane kernel, per-layer partials, nothing reduced per layer
+bool wgrad_batched(const sr4d_t* h) {
+    static const bool off = getenv("SR4D_WGRAD_REDUCE_EACH") != nullptr || getenv("SR4D_WGRAD_UNBATCHED") != nullptr;
+    static const bool wgrad_simt = getenv("SR4D_WGRAD_SIMT") != nullptr;
+    return !off && !wgrad_simt && h->conv_impl != SR4D_CONV_SIMT && h->wgrad_single == 1 && h->wg_part && h->lexp;
+}
+// the tensor about to be written into g is the dY of `layer` (-1: nobody's, use the buffer's own storage): with the
+// batched weight gradient its split copy must survive until the end of the pass
+void layer_split(sr4d_t* h, GBuf& g, int layer) {
+    if (layer >= 0 && wgrad_batched(h) && h->lsplit[layer]) { g.s = h->lsplit[layer]; g.exp = h->lexp + layer; }
+    else { g.s = g.s0; g.exp = g.exp0; }
+}
 int conv64_wgrad(sr4d_t* h, int layer, ActView x, const GBuf& dy, bool bias, cudaStream_t s) {
+    if (wgrad_batched(h) && h->wg_slot[layer] >= 0 && dy.s == h->lsplit[layer]) {
+        // computed by ONE launch per grid at the end of the pass (wgrad_finish); dY stays in the layer's own buffer
+        TcWgradItem it;
+        it.x = x; it.dy_split = dy.s; it.dy_exp = dy.exp;
+        it.partial = h->wg_part + (size_t)h->wg_slot[layer] * h->wg_stride;
+        h->wg_list[x.D == h->P ? 0 : 1].push_back(it);
+        h->wg_pending = true;
+        if (bias) CK(h, launch_bias_grad(dy.f, x.B, x.D, GB(h, layer), h->scratch, s), 2);
+        return SR4D_OK;
+    }
     ProfScope prof(h, x.D == h->P ? SR4D_PROF_CONV64_WGRAD_LR : SR4D_PROF_CONV64_WGRAD_HR, s);
     static const bool wgrad_simt = getenv("SR4D_WGRAD_SIMT") != nullptr;   // debugging aid
     if (use_tc(h) && !wgrad_simt) {
@@ -530,6 +562,21 @@ int conv64_wgrad(sr4d_t* h, int layer, ActView x, const GBuf& dy, bool bias, cud
 int wgrad_finish(sr4d_t* h, int B, cudaStream_t s) {
     if (!h->wg_pending) return SR4D_OK;
     h->wg_pending = false;
+    for (int cls = 0; cls < 2; ++cls) {
+        auto& list = h->wg_list[cls];
+        if (list.empty()) continue;
+        ProfScope prof(h, cls == 0 ? SR4D_PROF_CONV64_WGRAD_LR : SR4D_PROF_CONV64_WGRAD_HR, s, (int)list.size());
+        const long long key = ((long long)cls << 40) | ((long long)B << 16) | (long long)list.size();
+        auto it = h->wg_batches.find(key);
+        if (it == h->wg_batches.end()) {
+            TcWgradBatch* b = nullptr;
+            CK(h, tc_wgrad_batch_build(list.data(), (int)list.size(), &b), 0);
+            it = h->wg_batches.emplace(key, b).first;
+        }
+        cudaError_t e = tc_wgrad_batch_launch(it->second, s);
+        list.clear();
+        CK(h, e, 1);
+    }
     CK(h, launch_reduce_rows_batched(h->wg_items, h->wg_nitems, tc_wgrad2_slabs(B, h->P), tc_wgrad2_slabs(B, h->H), 27 * 4096, s), 1);
     return SR4D_OK;
 }
@@ -583,8 +630,9 @@ int dgrad_fold(sr4d_t* h, int layer, const GBuf& dy, const GBuf* add, const ActV
 // backward through `nblk` resnet blocks whose first conv is layer `l0`; bufs[0] holds the gradient wrt the
 // pre-activation of the last block output on entry; on exit bufs[*result_idx] holds the gradient wrt the
 // pre-activation (if slope_in >= 0, else the value) of the first block input.
+// next_layer: the 64->64 layer whose dY the final result is (-1: none -- its split copy may live in the rotating buffer)
 int blocks_bwd(sr4d_t* h, int nblk, int l0, bool hr, GBuf* bufs[3], RawBuf& raw, int B, int D,
-               float slope_in, cudaStream_t s, int* result_idx) {
+               float slope_in, cudaStream_t s, int* result_idx, int next_layer) {
     int si = 0;
     int rc;
     for (int k = nblk - 1; k >= 0; --k) {
@@ -597,8 +645,10 @@ int blocks_bwd(sr4d_t* h, int nblk, int l0, bool hr, GBuf* bufs[3], RawBuf& raw,
         GBuf& T = *bufs[(si + 1) % 3];
         GBuf& S2 = *bufs[(si + 2) % 3];
         if ((rc = conv64_wgrad(h, lb, t, S, false, s))) return rc;
+        layer_split(h, T, la);                                   // T becomes dY of conv a
         if ((rc = dgrad_fold(h, lb, S, nullptr, &t, 0.2f, T, raw, B, D, s))) return rc;
         if ((rc = conv64_wgrad(h, la, xin, T, false, s))) return rc;
+        layer_split(h, S2, k > 0 ? la - 1 : next_layer);         // S2 becomes dY of the previous block's conv b
         // gradient wrt x_k (post-activation) = fold + skip path; multiply by its producer's act'
         float slope = k > 0 ? 0.2f : slope_in;
         if (slope >= 0.f) rc = dgrad_fold(h, la, T, &S, &xin, slope, S2, raw, B, D, s);
@@ -633,6 +683,13 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
     const bool trunk_act = h->hi > 0 || h->r == 1;
     const float trunk_slope = h->hi > 0 ? 0.2f : (h->r == 1 ? slope_lr_trunk : 1.f);
     const bool fused_heads = dgrad_fused(h, H);
+    // batched weight gradient: every gradient tensor that is some 64->64 layer's dY gets its split copy written into
+    // that layer's own buffer (layer_split) so that it survives until the single wgrad launch of wgrad_finish
+    for (auto& g : h->g4_lr) layer_split(h, g, -1);
+    for (auto& g : h->g4_hr) layer_split(h, g, -1);
+    h->wg_list[0].clear(); h->wg_list[1].clear();
+    const int lr_top = h->low > 0 ? 6 + 2 * (h->low - 1) + 1 : 5;                       // last 64->64 layer of the LR trunk
+    layer_split(h, *hb[0], h->hi > 0 ? l_hr0 + 2 * (h->hi - 1) + 1 : (h->r == 1 ? lr_top : -1));   // the trunk gradient
     if (fused_heads) CK(h, cudaMemsetAsync(hb[0]->amax, 0, sizeof(int), s), 0);
     static const bool head_simt = getenv("SR4D_HEAD_SIMT") != nullptr;   // debugging aid / A-B: fp32 head2_bwd_kernel
     const bool heads_tc = use_tc(h) && !head_simt && h->hb_part && head_bwd_tc_supported(H);
@@ -645,6 +702,7 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
         // whole backward of the 64->1 conv, plus what its input gradient needs downstream: the bias gradient of
         // the head's first conv and (tensor-core path) the scaled split copy
         CK(h, cudaMemsetAsync(A.amax, 0, sizeof(int), s), 0);
+        layer_split(h, A, l1);
         if (heads_tc)
             CK(h, launch_head_bwd_tc(hd, h->hb_gplanar, c, h->hb_scales, h->hb_wimg, h->hb_part + c * h->hb_part_stride, A.s, A.exp,
                                      A.amax, lo_plane_dead(h), s), 1);
@@ -685,7 +743,7 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
     if (h->hi > 0) {
         int ri = 0;
         float slope_in = h->r == 1 ? slope_lr_trunk : -1.f;
-        if ((rc = blocks_bwd(h, h->hi, l_hr0, true, hb, h->raw_hr[0], B, H, slope_in, s, &ri))) return rc;
+        if ((rc = blocks_bwd(h, h->hi, l_hr0, true, hb, h->raw_hr[0], B, H, slope_in, s, &ri, h->r == 1 ? lr_top : -1))) return rc;
         S = hb[ri];
     } else {
         S = hb[0];
@@ -700,12 +758,13 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
         lb[0] = hb[si]; lb[1] = hb[(si + 1) % 3]; lb[2] = hb[(si + 2) % 3];
     } else {
         CK(h, cudaMemsetAsync(lb[0]->amax, 0, sizeof(int), s), 0);
+        layer_split(h, *lb[0], lr_top);
         CK(h, launch_upsample_bwd(S->f, lr_trunk, slope_lr_trunk, lb[0]->f, lb[0]->amax, B, P, h->r, h->up.tables(), s), 1);
         if ((rc = grad_ready(h, *lb[0], B, P, s))) return rc;
     }
     int ri = 0;
     if (h->low > 0) {
-        if ((rc = blocks_bwd(h, h->low, 6, false, lb, h->raw_lr, B, P, 0.f, s, &ri))) return rc;
+        if ((rc = blocks_bwd(h, h->low, 6, false, lb, h->raw_lr, B, P, 0.f, s, &ri, 5))) return rc;
     }
     GBuf& S5 = *lb[ri];                 // d pre-activation of conv3d_5 (fuse 3x3)
     GBuf& T = *lb[(ri + 1) % 3];
@@ -714,6 +773,9 @@ int backward_impl(sr4d_t* h, const float* hu, const float* hv, const float* hw, 
     ActView pc1 = lr_view(h, 0, B), pc2 = lr_view(h, 1, B), ph1 = lr_view(h, 2, B), ph2 = lr_view(h, 3, B);
     ActView c1 = lr_view(h, 4, B);
     if ((rc = conv64_wgrad(h, 5, c1, S5, true, s))) return rc;
+    layer_split(h, T, -1);
+    layer_split(h, dA, 3);              // dY of the phase branch's second conv
+    layer_split(h, dB, 1);              // dY of the pc branch's second conv
     if ((rc = dgrad_fold(h, 5, S5, nullptr, &c1, 0.f, T, h->raw_lr, B, P, s))) return rc;
     CK(h, cudaMemsetAsync(dA.amax, 0, sizeof(int), s), 0);
     CK(h, cudaMemsetAsync(dB.amax, 0, sizeof(int), s), 0);
@@ -738,13 +800,17 @@ void free_all(sr4d_t* h) {
     cudaFree(h->head_wimg);
     cudaFree(h->hb_scales); cudaFree(h->hb_wimg); cudaFree(h->hb_part); cudaFree(h->hb_gplanar);
     cudaFree(h->wg_part); cudaFree(h->wg_items);
+    for (auto p : h->lsplit) cudaFree(p);
+    cudaFree(h->lexp);
+    for (auto& kv : h->wg_batches) tc_wgrad_batch_free(kv.second);
+    h->wg_batches.clear();
     for (auto& kv : h->chains) tc_chain_free(kv.second);
     h->chains.clear();
     for (auto& b : h->lr) cudaFree(b.base);
     for (auto& b : h->hr) cudaFree(b.base);
     cudaFree(h->up.lo); cudaFree(h->up.hi); cudaFree(h->up.lerp); cudaFree(h->up.ibeg); cudaFree(h->up.iend);
-    for (auto& g : h->g4_lr) { cudaFree(g.f); cudaFree(g.s); }
-    for (auto& g : h->g4_hr) { cudaFree(g.f); cudaFree(g.s); }
+    for (auto& g : h->g4_lr) { cudaFree(g.f); cudaFree(g.s0); }
+    for (auto& g : h->g4_hr) { cudaFree(g.f); cudaFree(g.s0); }
     cudaFree(h->raw_lr.p);
     for (auto& r : h->raw_hr) cudaFree(r.p);
     cudaFree(h->gmeta);
@@ -830,6 +896,7 @@ int sr4d_create(sr4d_t** out, int patch_size, int res_increase, int low_resblock
                 if (!bad) cudaMemset(g.s, 0, 2 * n * sizeof(__half));
                 g.amax = reinterpret_cast<unsigned int*>(h->gmeta + 2 * gi);
                 g.exp = h->gmeta + 2 * gi + 1;
+                g.s0 = g.s; g.exp0 = g.exp;
                 ++gi;
             };
             for (auto& g : h->g4_lr) alloc_g(g, g4l);
@@ -856,6 +923,23 @@ int sr4d_create(sr4d_t** out, int patch_size, int res_increase, int low_resblock
                     if (ly.k == 3 && ly.cin == 64 && ly.cout == 64) { h->wg_slot[i] = (int)items.size(); items.push_back(ReduceItem{nullptr, nullptr, 0, 0}); }
                 }
                 h->wg_nitems = (int)items.size();
+                h->lsplit.assign(h->layers.size(), nullptr);
+                // per-layer dY storage of the batched weight gradient: 4 GB at batch 8, r = 2; geometries where it would
+                // pass 24 GB (r = 4 training at batch 16: 45 GB) keep the per-layer launches instead
+                size_t lbytes = 0;
+                for (size_t i = 0; i < h->layers.size(); ++i)
+                    if (h->wg_slot[i] >= 0) lbytes += 2 * ((int)i >= 6 + 2 * h->low ? g4h : g4l) * sizeof(__half);
+                const bool per_layer = lbytes <= ((size_t)24 << 30);
+                if (per_layer) {
+                    bad |= dmalloc(&h->lexp, h->layers.size()) != cudaSuccess;
+                    if (!bad) cudaMemset(h->lexp, 0, h->layers.size() * sizeof(int));
+                }
+                for (size_t i = 0; i < h->layers.size() && !bad && per_layer; ++i) {
+                    if (h->wg_slot[i] < 0) continue;
+                    const size_t n2 = 2 * ((int)i >= 6 + 2 * h->low ? g4h : g4l);       // hi and lo plane, zero halo
+                    bad |= dmalloc(&h->lsplit[i], n2) != cudaSuccess;
+                    if (!bad) cudaMemset(h->lsplit[i], 0, n2 * sizeof(__half));
+                }
                 if (h->wg_nitems) {
                     bad |= dmalloc(&h->wg_part, h->wg_stride * h->wg_nitems) != cudaSuccess;
                     bad |= cudaMalloc(&h->wg_items, sizeof(ReduceItem) * h->wg_nitems) != cudaSuccess;

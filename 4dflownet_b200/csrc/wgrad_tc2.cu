@@ -37,6 +37,8 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 
 #include "conv_tc.h"
 #include "tc_host.h"
@@ -67,6 +69,18 @@ struct W2Params {
     long long* dbg;          // SR4D_TC_DEBUG=1: per-CTA cycles of the MMA warp {tile waits, acc_empty waits, issue (MMAs + commits), total, iterations}
 };
 
+// Batched launch (BATCH instantiation): the weight gradients of `nlayers` layers on the same grid in one launch.  The
+// layers are independent (every dY and X tensor exists by the end of the backward pass), so the roles simply walk the
+// layers with their ring / chain counters running on: what is saved per layer is the launch, the prologue, the pipeline
+// fill and the drain -- 25 of the 47 us of a 24^3 layer at batch 8.
+struct W2Layer {
+    CUtensorMap xmap, gmap, gmap1;
+    float* partial;
+    const int* exp;
+    long long pad[6];
+};
+static_assert(sizeof(W2Layer) % 64 == 0, "tensor maps in global memory must stay 64-byte aligned");
+
 __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
@@ -85,9 +99,11 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo, uint32
 __device__ __forceinline__ int seg_len(int xa, int remaining, int D) { return min(D + 1 - xa, remaining); }
 __device__ __forceinline__ int seg_groups(int len) { return (len + 2 + GP - 1) / GP; }
 
+template <bool BATCH>
 __global__ void __launch_bounds__(NTHREADS, 1)
-wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap gmap,
-                   const __grid_constant__ CUtensorMap gmap1, W2Params p) {
+wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap0, const __grid_constant__ CUtensorMap gmap0,
+                   const __grid_constant__ CUtensorMap gmap10, W2Params p, const W2Layer* __restrict__ layers, int nlayers) {
+    const int nl = BATCH ? nlayers : 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* ysm = smem;                                   // (NSLOT + 1) x 8 KB; slot NSLOT mirrors slot 0
@@ -112,9 +128,11 @@ wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, NUM_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        prefetch_tmap(&xmap);
-        prefetch_tmap(&gmap);
-        prefetch_tmap(&gmap1);
+        if (!BATCH) {
+            prefetch_tmap(&xmap0);
+            prefetch_tmap(&gmap0);
+            prefetch_tmap(&gmap10);
+        }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -131,6 +149,10 @@ wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
         // ================= TMA producer =================
         if (lane == 0) {
             uint32_t gq = 0;                          // groups issued so far
+            for (int L = 0; L < nl; ++L) {
+            const CUtensorMap* xmapp = BATCH ? &layers[L].xmap : &xmap0;
+            const CUtensorMap* gmapp = BATCH ? &layers[L].gmap : &gmap0;
+            const CUtensorMap* gmap1p = BATCH ? &layers[L].gmap1 : &gmap10;
             int col = t0 / (D + 1);
             int xa = t0 - col * (D + 1);
             for (int t = t0; t < t1;) {
@@ -146,14 +168,15 @@ wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
                     // dY planes xa-1+4g ..+3: interior voxel (plane, y0.., z0..) sits at +2 in the zero-haloed gradient tensor;
                     // Xpad planes xa+4g ..+3 (padded coordinates), lines y0+dy.., rows z0..z0+9.  Planes past the tensor are
                     // zero-filled by the TMA unit and never read.
-                    tma_load_5d(ysm + r * GP * DY_SLOT, &gmap, &full[r], 0, z0 + 2, y0 + 2, xa - 1 + GP * g + 2, b);
-                    if (r == 0) tma_load_5d(ysm + NSLOT * DY_SLOT, &gmap1, &full[r], 0, z0 + 2, y0 + 2, xa - 1 + GP * g + 2, b);
-                    tma_load_5d(xsm + r * GP * X_SLOT, &xmap, &full[r], 0, z0, y0 + dy, xa + GP * g, b);
+                    tma_load_5d(ysm + r * GP * DY_SLOT, gmapp, &full[r], 0, z0 + 2, y0 + 2, xa - 1 + GP * g + 2, b);
+                    if (r == 0) tma_load_5d(ysm + NSLOT * DY_SLOT, gmap1p, &full[r], 0, z0 + 2, y0 + 2, xa - 1 + GP * g + 2, b);
+                    tma_load_5d(xsm + r * GP * X_SLOT, xmapp, &full[r], 0, z0, y0 + dy, xa + GP * g, b);
                 }
                 t += len;
                 xa = 0;                                // every further segment starts a new column
                 ++col;
             }
+            }   // layers
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -168,9 +191,10 @@ wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
             uint32_t wq = 0;                          // groups whose full barrier has been waited for
             int chain_it = 0;                         // iterations issued into the current accumulator chain
             uint32_t nchain = 0;                      // chains completed
-            int xa = t0 % (D + 1);
             long long dwf = 0, dwa = 0, dis = 0;
             const long long tbeg = p.dbg ? clock64() : 0;
+            for (int L = 0; L < nl; ++L) {
+            int xa = t0 % (D + 1);
             for (int t = t0; t < t1;) {
                 const int len = seg_len(xa, t1 - t, D);
                 const int ngrp = seg_groups(len);
@@ -220,6 +244,7 @@ wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
                 t += len;
                 xa = 0;
             }
+            }   // layers (every layer ends its accumulator chain: t + i + 1 == t1 above)
             if (p.dbg) {
                 long long* d = p.dbg + (size_t)(blockIdx.y * 3 + blockIdx.x) * 8;
                 d[0] = dwf; d[1] = dwa; d[2] = dis; d[3] = clock64() - tbeg; d[4] = t1 - t0;
@@ -232,11 +257,14 @@ wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
         const int m = 32 * q + lane;                     // accumulator row
         const int co = m & 63;
         const bool upper = m >= 64;                      // rows 64..127: dY[x] -> taps dx=0 (acc 1) and dx=2 (acc 2); rows 0..63: dx=1
-        const float descale = p.exp ? exp2f(-(float)*p.exp) : 1.f;
-        float* out = p.partial + (size_t)slab * 27 * 4096 + co;
         const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16);
         const int nit = t1 - t0;
         const int nchains = (nit + p.flush_iters - 1) / p.flush_iters;
+        uint32_t cbase = 0;                              // chains drained so far (parity of acc_full runs across layers)
+        for (int L = 0; L < nl; ++L) {
+        const int* expp = BATCH ? layers[L].exp : p.exp;
+        const float descale = expp ? exp2f(-(float)*expp) : 1.f;
+        float* out = (BATCH ? layers[L].partial : p.partial) + (size_t)slab * 27 * 4096 + co;
         auto flush = [&](uint32_t col0, int dx, bool first) {
             // columns n = dz*64 + ci of this accumulator -> partial[(dx*3+dy)*3+dz][ci][co]
 #pragma unroll 1
@@ -263,7 +291,7 @@ wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
             }
         }
         for (int c = 0; c < nchains; ++c) {
-            mbar_wait(acc_full, c & 1);
+            mbar_wait(acc_full, (cbase + c) & 1);
             tc_fence_after();
             flush(0, upper ? 0 : 1, c == 0);
             if (upper) flush(192, 2, c == 0);
@@ -271,6 +299,8 @@ wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty);
         }
+        cbase += (uint32_t)nchains;
+        }   // layers
     }
 
     tc_fence_before();
@@ -293,7 +323,7 @@ int tc_wgrad2_slabs(int B, int D) {
 
 cudaError_t tc_wgrad64_single(ActView x, const __half* dy_split, const int* dy_exp, float* partial, cudaStream_t s) {
     const int B = x.B, D = x.D;
-    cudaError_t e = tc_func_smem(reinterpret_cast<const void*>(wgrad64_tc2_kernel), SMEM_BYTES);
+    cudaError_t e = tc_func_smem(reinterpret_cast<const void*>(wgrad64_tc2_kernel<false>), SMEM_BYTES);
     if (e != cudaSuccess) return e;
     CUtensorMap xmap, gmap, gmap1;
     // hi planes only: the maps cover the packed [2B] plane arrays, the kernel addresses samples b < B
@@ -316,7 +346,7 @@ cudaError_t tc_wgrad64_single(ActView x, const __half* dy_split, const int* dy_e
         cudaMemsetAsync(dbg_buf, 0, 3 * 64 * 8 * sizeof(long long), s);
         p.dbg = dbg_buf;
     }
-    wgrad64_tc2_kernel<<<grid, NTHREADS, SMEM_BYTES, s>>>(xmap, gmap, gmap1, p);
+    wgrad64_tc2_kernel<false><<<grid, NTHREADS, SMEM_BYTES, s>>>(xmap, gmap, gmap1, p, nullptr, 0);
     cudaError_t e2 = cudaGetLastError();
     if (debug && e2 == cudaSuccess) {
         long long hb[3 * 64 * 8];
@@ -329,4 +359,54 @@ cudaError_t tc_wgrad64_single(ActView x, const __half* dy_split, const int* dy_e
                 D, B, a[0], a[1], a[2], a[3], a[4], a[3] / (a[4] > 0 ? a[4] : 1));
     }
     return e2;
+}
+
+// ---- batched launch -----------------------------------------------------------------------------------------------------
+struct TcWgradBatch {
+    int n = 0, B = 0, D = 0;
+    W2Layer* dlayers = nullptr;
+};
+
+cudaError_t tc_wgrad_batch_build(const TcWgradItem* items, int n, TcWgradBatch** out) {
+    if (n < 1) return cudaErrorInvalidValue;
+    const int B = items[0].x.B, D = items[0].x.D;
+    std::vector<W2Layer> hl(n);
+    for (int i = 0; i < n; ++i) {
+        if (items[i].x.B != B || items[i].x.D != D) return cudaErrorInvalidValue;
+        memset(&hl[i], 0, sizeof(W2Layer));
+        if (!tc_make_act_map(&hl[i].xmap, items[i].x.hi, B, D + 2, TY, ZP, GP)) return cudaErrorUnknown;
+        if (!tc_make_act_map(&hl[i].gmap, items[i].dy_split, B, D + 4, TY, TZ, GP)) return cudaErrorUnknown;
+        if (!tc_make_act_map(&hl[i].gmap1, items[i].dy_split, B, D + 4, TY, TZ, 1)) return cudaErrorUnknown;
+        hl[i].partial = items[i].partial;
+        hl[i].exp = items[i].dy_exp;
+    }
+    TcWgradBatch* b = new TcWgradBatch();
+    b->n = n; b->B = B; b->D = D;
+    cudaError_t e = cudaMalloc((void**)&b->dlayers, n * sizeof(W2Layer));
+    if (e == cudaSuccess) e = cudaMemcpy(b->dlayers, hl.data(), n * sizeof(W2Layer), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { tc_wgrad_batch_free(b); return e; }
+    *out = b;
+    return cudaSuccess;
+}
+void tc_wgrad_batch_free(TcWgradBatch* b) {
+    if (!b) return;
+    cudaFree(b->dlayers);
+    delete b;
+}
+cudaError_t tc_wgrad_batch_launch(TcWgradBatch* b, cudaStream_t s) {
+    cudaError_t e = tc_func_smem(reinterpret_cast<const void*>(wgrad64_tc2_kernel<true>), SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    const int B = b->B, D = b->D;
+    W2Params p;
+    p.partial = nullptr; p.exp = nullptr; p.B = B; p.D = D;
+    p.nyt = (D + TY - 1) / TY; p.nzt = (D + TZ - 1) / TZ;
+    p.total = B * p.nyt * p.nzt * (D + 1);
+    p.nslab = tc_wgrad2_slabs(B, D);
+    static const int flush_env = getenv("SR4D_WGRAD_FLUSH") ? atoi(getenv("SR4D_WGRAD_FLUSH")) : 0;
+    p.flush_iters = flush_env > 0 ? flush_env : FLUSH_ITERS;
+    p.dbg = nullptr;
+    CUtensorMap dummy;
+    memset(&dummy, 0, sizeof dummy);
+    wgrad64_tc2_kernel<true><<<dim3(3, p.nslab), NTHREADS, SMEM_BYTES, s>>>(dummy, dummy, dummy, p, b->dlayers, b->n);
+    return cudaGetLastError();
 }
