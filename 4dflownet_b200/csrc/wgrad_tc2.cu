@@ -221,7 +221,9 @@ wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap0, const __grid_const
                         const uint64_t ad = adesc0 | (uint64_t)(a0 + j * (2 * TZ * 128 >> 4));
                         const uint32_t acc = (chain_it | j) != 0;
                         tc_mma_f16(d1, ad, bdesc0 | (uint64_t)(x1 + j * (2 * ZP * 128 >> 4)), idesc, acc);
-                        tc_mma_f16(d2, ad, bdesc0 | (uint64_t)(x2 + j * (2 * ZP * 128 >> 4)), idesc, acc);
+                        // rows 0..63 of this product ("tap 3") are never read: their output lanes are disabled, which the
+                        // power probe prices at -23 % of the instruction's energy (profiles/r02_power_probe.txt)
+                        tc_mma_f16_masked(d2, ad, bdesc0 | (uint64_t)(x2 + j * (2 * ZP * 128 >> 4)), idesc, acc, ~0u, ~0u, 0u, 0u);
                     }
                     // hand a group back after the iteration that read its last plane (dY as "previous", Xpad in MMA-1), the
                     // rest of the segment's groups after its last iteration
