@@ -43,8 +43,9 @@
 
 namespace {
 
-constexpr int W_TAP_BYTES = 128 * 64 * 2;            // 16 KB: [Wlo ; Whi] x 64 ci, fp16, swizzled
-constexpr int W_HI_OFFSET = 64 * 64 * 2;             // the Whi rows start 8 KB into the image
+constexpr int W_TAP_BYTES = 128 * 64 * 2;            // 16 KB: [Wlo half | Whi half], each MN-major: 64 K rows (ci) x 64 co, fp16, swizzled
+constexpr int W_HI_OFFSET = 64 * 64 * 2;             // the Whi half starts 8 KB into the image
+constexpr int W_ZERO_BYTES = 2048;                   // 16 K rows of zeros: the masked rows of the second instruction read them
 constexpr int W_STAGE_BYTES = W_TAP_BYTES;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_EPI = NUM_EPI_WARPS * 32;   // epilogue threads
@@ -85,7 +86,7 @@ struct Cfg {
     static constexpr int COLS = CV / CP;                               // TMEM columns a warp reads per chunk (16 or 32)
     static constexpr int GSTAGE_FLOATS = 2 * CV * 64;                  // per group: [H | L][voxel][channel]
     static constexpr int STAGE_FLOATS = NG * GSTAGE_FLOATS;
-    static constexpr int SMEM_BYTES = 1024 + NXS * XSTAGE_BYTES + NWS * W_STAGE_BYTES + STAGE_FLOATS * 4 + 256;
+    static constexpr int SMEM_BYTES = 1024 + NXS * XSTAGE_BYTES + NWS * W_STAGE_BYTES + W_ZERO_BYTES + STAGE_FLOATS * 4 + 256;
     static_assert(N % 16 == 0 && N >= 16 && N <= 256, "UMMA N constraint for M=128");
     static_assert(IT * GT == CV * 8 && COLS * CP == CV, "epilogue work split");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -166,6 +167,18 @@ __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo) 
     return d;
 }
 
+// MN-major SWIZZLE_128B operand (a shared-memory row = one K index, 64 M elements = 128 B): lbo = distance between the two
+// 64-row atoms of an M = 128 operand, sbo = distance between 8-row K groups
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 template <int TY, bool SINGLE, bool CHAIN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, const ChainArgs chain) {
@@ -177,7 +190,8 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* xs = smem;                                   // NXS x [hi part | lo part]
     uint8_t* wsm = smem + C::NXS * C::XSTAGE_BYTES;       // NWS x 16 KB image
-    float* stage = reinterpret_cast<float*>(wsm + C::NWS * W_STAGE_BYTES);
+    uint8_t* zsm = wsm + C::NWS * W_STAGE_BYTES;          // zeros (behind every weight stage: the LBO of a descriptor is positive)
+    float* stage = reinterpret_cast<float*>(zsm + W_ZERO_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage) + C::STAGE_FLOATS * 4);
     uint64_t* x_full = bars;                 // [NXS]
     uint64_t* w_full = bars + C::NXS;        // [NWS]
@@ -202,6 +216,8 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&xmap);
     }
+    for (int i = threadIdx.x; i < W_ZERO_BYTES / 16; i += NUM_THREADS) reinterpret_cast<uint4*>(zsm)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"((uint32_t)TMEM_COLS)
@@ -325,8 +341,9 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(C::N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // instruction descriptor: D=f32, A=B=f16, A (weights) MN-major, B (voxels) K-major, M=128, N
+            const uint32_t idesc = (1u << 4) | (1u << 15) | ((uint32_t)(C::N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t zaddr = smem_u32(zsm);
             uint32_t xi = 0, wi = 0, ti = 0;
             long long wt = 0, wx = 0, ww = 0, c0 = 0;
             const long long tbeg = p.dbg ? clock64() : 0;
@@ -358,11 +375,15 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint32_t acc = (dx | tp | k) != 0;
-                            // [Wlo ; Whi] x Xhi, then [Whi ; (next 8 KB, lanes 64-127 masked off)] x Xlo into the same accumulator
-                            tc_mma_f16(dacc, make_desc_sbo(wa + k * 32, 1024),
+                            // [Wlo ; Whi] x Xhi, then [Whi ; zeros] x Xlo (lanes 64-127 masked off) into the same accumulator.  The
+                            // weights are MN-major, so the two 64-row halves of the A operand are independent atoms (LBO apart):
+                            // the second instruction pairs the Whi half with the zero block instead of whatever follows it in
+                            // shared memory -- the masked rows are still multiplied, zeros cost less (profiles/r02_power_probe.txt)
+                            const uint32_t wk = wa + k * 2048;
+                            tc_mma_f16(dacc, make_desc_mn(wk, W_HI_OFFSET, 1024),
                                        make_desc_sbo(xhi + boff + k * 32, ZP * 128), idesc, acc);
                             if (!SINGLE)
-                                tc_mma_f16_masked(dacc, make_desc_sbo(wa + W_HI_OFFSET + k * 32, 1024),
+                                tc_mma_f16_masked(dacc, make_desc_mn(wk + W_HI_OFFSET, zaddr - (wk + W_HI_OFFSET), 1024),
                                                   make_desc_sbo(xlo + boff + k * 32, ZP * 128), idesc, 1u, 0u, 0u, ~0u, ~0u);
                         }
                         if (wi % C::WG == C::WG - 1) tc_commit(&w_empty[(wi / C::WG) % C::NGW]);   // hand the group of stages back
@@ -654,7 +675,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
 }
 
 // ------------------------------------------------------------------------------------------
-// weight image: fp32 Keras [27][ci][co] -> fp16 split, rows [Wlo(co 0..63) ; Whi(co 0..63)], swizzled
+// weight image: fp32 Keras [27][ci][co] -> fp16 split, per tap [Wlo half | Whi half], each MN-major (64 K rows x 64 M), swizzled
 // ------------------------------------------------------------------------------------------
 struct PrepList {
     int n;
@@ -675,8 +696,9 @@ __global__ void prep_weights_kernel(const float* __restrict__ params, PrepList l
     const float v = dgrad ? w[((size_t)(26 - tap) * 64 + n) * 64 + k] : w[((size_t)tap * 64 + k) * 64 + n];
     __half h, lo;
     split_f16(v, h, lo);
-    const int grp = row >> 3, rr = row & 7;
-    const size_t off = (size_t)tap * (128 * 64) + grp * 512 + rr * 64 + (((k >> 3) ^ rr) << 3) + (k & 7);
+    // MN-major SWIZZLE_128B: shared-memory row = K index k (64 rows per half), 64 M elements n per row; lo half then hi half
+    const int grp = k >> 3, rr = k & 7;
+    const size_t off = (size_t)tap * (128 * 64) + (is_lo ? 0 : 64 * 64) + grp * 512 + rr * 64 + (((n >> 3) ^ rr) << 3) + (n & 7);
     img[off] = is_lo ? lo : h;
 }
 

@@ -12,4 +12,4 @@ print(sys.argv[1], "step", round(d["ms_per_step"], 3), {a: round(b, 3) for a, b 
 PY
 done; done 2>&1 | tee gpurun_out/ab2.txt
 cp /tmp/new.so 4dflownet_b200/libsr4d.so
-timeout -s KILL 300 python -m pytest tests/test_gpu_backward.py -m gpu -x -q --timeout 100 -k "layer_bwd or identical or train_step" 2>&1 | tail -3
+timeout -s KILL 400 python -m pytest tests/test_gpu_forward.py tests/test_gpu_backward.py -m gpu -x -q --timeout 100 2>&1 | tail -3
