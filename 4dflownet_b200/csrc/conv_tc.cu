@@ -684,22 +684,21 @@ struct PrepList {
 };
 // grid (27*128*64/256, n entries, 2 images): one thread per (tap, row, k) element
 __global__ void prep_weights_kernel(const float* __restrict__ params, PrepList l, __half* __restrict__ images) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // = offset inside the layer's image: coalesced stores
     if (i >= 27 * 128 * 64) return;
     const float* w = params + l.off[blockIdx.y];
     const int dgrad = blockIdx.z;
     __half* img = images + ((size_t)l.layer[blockIdx.y] * 2 + dgrad) * (27 * 128 * 64);
-    const int k = i & 63, row = (i >> 6) & 127, tap = i >> 13;
-    const int n = row & 63;
-    const bool is_lo = row < 64;
+    // MN-major SWIZZLE_128B: per tap [lo half | hi half]; inside a half the shared-memory row is the K index k (8-row groups
+    // of 1024 B), a row holds the 64 M elements n in 16-byte pieces stored at piece ^ (k & 7)
+    const int tap = i >> 13, is_lo = ((i >> 12) & 1) == 0;
+    const int grp = (i >> 9) & 7, rr = (i >> 6) & 7, piece = (i >> 3) & 7, e = i & 7;
+    const int k = grp * 8 + rr, n = ((piece ^ rr) << 3) + e;
     // forward: A[n=co][k=ci] = W[tap][ci][co];  dgrad: A[n=ci][k=co] = W[26-tap][ci][co]
     const float v = dgrad ? w[((size_t)(26 - tap) * 64 + n) * 64 + k] : w[((size_t)tap * 64 + k) * 64 + n];
     __half h, lo;
     split_f16(v, h, lo);
-    // MN-major SWIZZLE_128B: shared-memory row = K index k (64 rows per half), 64 M elements n per row; lo half then hi half
-    const int grp = k >> 3, rr = k & 7;
-    const size_t off = (size_t)tap * (128 * 64) + (is_lo ? 0 : 64 * 64) + grp * 512 + rr * 64 + (((n >> 3) ^ rr) << 3) + (n & 7);
-    img[off] = is_lo ? lo : h;
+    img[i] = is_lo ? lo : h;
 }
 
 // dgrad gain of each listed layer: max over ci of sum_{tap,co} |W[tap][ci][co]| (bounds |dX| <= gain * max|dY|)
