@@ -167,12 +167,14 @@ __global__ void __launch_bounds__(256) conv1x1_cat_kernel(ActView a, ActView bq,
 // 2 instead of 8 corner loads per output voxel, same lerp expressions and order as the one-voxel-per-thread version.
 // blockIdx.y = z segment (small grids: a batch-1 volume has only 2304 lines, 124 threads per SM; the segments start with
 // their own corner loads).
+// (SEG = false is the whole-line kernel as it was: the segmented bounds cost the batch-8 launch 60 % when they were runtime values)
+template <bool SEG>
 __global__ void __launch_bounds__(256) upsample_kernel(ActView in, ActView out, UpsampleTables t, int zseg) {
     const int H = out.D, D = in.D;
     const size_t nline = (size_t)out.B * H * H;
     const size_t li = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3);
     if (li >= nline) return;
-    const int zbeg = blockIdx.y * zseg, zend = min(H, zbeg + zseg);
+    const int zbeg = SEG ? blockIdx.y * zseg : 0, zend = SEG ? min(H, zbeg + zseg) : H;
     const int c = (threadIdx.x & 7) * 8;
     const int y = (int)(li % H), x = (int)((li / H) % H), b = (int)(li / ((size_t)H * H));
     const int xl = t.lo[x], xh = t.hi[x], yl = t.lo[y], yh = t.hi[y];
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(256) upsample_kernel(ActView in, ActView out, 
     col[0] = act_off(D, b, xl, yl, 0) + c; col[1] = act_off(D, b, xl, yh, 0) + c;
     col[2] = act_off(D, b, xh, yl, 0) + c; col[3] = act_off(D, b, xh, yh, 0) + c;
     float v0[4][8], v1[4][8];
-    int i0 = t.lo[zbeg];
+    int i0 = SEG ? t.lo[zbeg] : 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         act_load8(in.hi, in.lo, col[k] + (size_t)i0 * SR4D_C, v0[k]);
@@ -427,7 +429,8 @@ cudaError_t launch_upsample(ActView in, ActView out, int r, UpsampleTables t, cu
     int nseg = 1;
     while (nseg < 4 && (size_t)nb * nseg < 2 * (size_t)tc_num_sms() && out.D / (2 * nseg) >= 8) nseg *= 2;
     const int zseg = (out.D + nseg - 1) / nseg;
-    upsample_kernel<<<dim3(nb, (unsigned)((out.D + zseg - 1) / zseg)), 256, 0, s>>>(in, out, t, zseg);
+    if (nseg == 1) upsample_kernel<false><<<nb, 256, 0, s>>>(in, out, t, zseg);
+    else upsample_kernel<true><<<dim3(nb, (unsigned)((out.D + zseg - 1) / zseg)), 256, 0, s>>>(in, out, t, zseg);
     return cudaGetLastError();
 }
 cudaError_t launch_head_out(ActView h0, ActView h1, ActView h2, const float* w0, const float* w1,
