@@ -32,6 +32,15 @@ def test_library_exports_every_header_symbol(built_lib, pkg):
     assert lib.sr4d_version().decode().startswith("sr4d")
 
 
+def test_option_constants_match_the_header(pkg):
+    """The Python binding's option / implementation constants are the header's #defines (SR4D_OPT_*, SR4D_CONV_*)."""
+    header = open(os.path.join(ROOT, "include", "sr4d.h")).read()
+    defines = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+SR4D_((?:OPT|CONV)_[A-Z0-9_]+)\s+(\d+)", header)}
+    assert len([k for k in defines if k.startswith("OPT_")]) >= 8
+    for name, value in defines.items():
+        assert getattr(pkg._lib, name) == value, name
+
+
 def test_no_cpu_fallback(pkg):
     import torch
     if torch.cuda.is_available():
