@@ -179,10 +179,14 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo, u
     return d;
 }
 
-template <int TY, bool SINGLE, bool CHAIN>
+// CL: the kernel runs as CTA pairs (cluster of 2, consecutive tiles of one x-plane): every weight tap is fetched from L2 by
+// ONE CTA of the pair (taps alternate) and multicast into both CTAs' stages, a stage is handed back when both MMA warps
+// have consumed it (multicast commit, barrier count 2) -- half the L2 -> SM weight traffic, which is 4/5 of the kernel's.
+template <int TY, bool SINGLE, bool CHAIN, bool CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, const ChainArgs chain) {
     using C = Cfg<TY, SINGLE>;
+    const uint32_t crank = CL ? cluster_rank() : 0u;
     const int nl = CHAIN ? chain.n : 1;
     const KParams& p = p0;                   // geometry, debug buffer: identical for every layer of a chain
     extern __shared__ uint8_t smem_raw[];
@@ -211,7 +215,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NXS; ++i) mbar_init(&x_full[i], 1);
         for (int i = 0; i < C::NWS; ++i) mbar_init(&w_full[i], 1);
-        for (int i = 0; i < C::NGW; ++i) mbar_init(&w_empty[i], 1);
+        for (int i = 0; i < C::NGW; ++i) mbar_init(&w_empty[i], CL ? 2 : 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&xmap);
@@ -226,6 +230,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
     }
     tc_fence_before();
     __syncthreads();
+    if (CL) cluster_sync_all();              // the peer's barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 4] = clock64() - t_entry;     // prologue
@@ -325,9 +330,14 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
                         if (tp == 6 && !pend) x_load(q + 1, 1);
                     }
                     mbar_expect_tx(&w_full[ws], W_TAP_BYTES);
-                    bulk_load(wsm + ws * W_STAGE_BYTES,
-                              reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)(wsel * 9 + tp) * W_TAP_BYTES,
-                              W_TAP_BYTES, &w_full[ws]);
+                    if (!CL)
+                        bulk_load(wsm + ws * W_STAGE_BYTES,
+                                  reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)(wsel * 9 + tp) * W_TAP_BYTES,
+                                  W_TAP_BYTES, &w_full[ws]);
+                    else if ((wi & 1u) == crank)       // this CTA's turn: one fetch from L2 lands in both CTAs' stages
+                        bulk_load_mc(wsm + ws * W_STAGE_BYTES,
+                                     reinterpret_cast<const uint8_t*>(p.w_img) + (size_t)(wsel * 9 + tp) * W_TAP_BYTES,
+                                     W_TAP_BYTES, &w_full[ws], (uint16_t)3);
                     ++wi;
                 }
                 if (q + 1 < npass && !p.xsplit) {
@@ -386,7 +396,10 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
                                 tc_mma_f16_masked(dacc, make_desc_mn(wk + W_HI_OFFSET, zaddr - (wk + W_HI_OFFSET), 1024),
                                                   make_desc_sbo(xlo + boff + k * 32, ZP * 128), idesc, 1u, 0u, 0u, ~0u, ~0u);
                         }
-                        if (wi % C::WG == C::WG - 1) tc_commit(&w_empty[(wi / C::WG) % C::NGW]);   // hand the group of stages back
+                        if (wi % C::WG == C::WG - 1) {                      // hand the group of stages back (to both producers of a pair)
+                            if (CL) tc_commit_mc(&w_empty[(wi / C::WG) % C::NGW], (uint16_t)3);
+                            else tc_commit(&w_empty[(wi / C::WG) % C::NGW]);
+                        }
                         ++wi;
                     }
                     ++xi;
@@ -650,6 +663,7 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
 
     tc_fence_before();
     __syncthreads();
+    if (CL) cluster_sync_all();              // the peer may still multicast commits / weight taps into this CTA
     if (p.dbg && threadIdx.x == 64) {
         const long long now = clock64();
         p.dbg[blockIdx.x * 8 + 6] = now - t_entry;                                  // whole CTA lifetime
@@ -735,7 +749,7 @@ __global__ void __launch_bounds__(256) weight_gain_kernel(const float* __restric
 template <int TY, bool SINGLE>
 cudaError_t launch_cfg(const CUtensorMap& map, KParams p, cudaStream_t s) {
     using C = Cfg<TY, SINGLE>;
-    cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(conv64_tc_kernel<TY, SINGLE, false>), C::SMEM_BYTES);
+    cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(conv64_tc_kernel<TY, SINGLE, false, false>), C::SMEM_BYTES);
     if (ea != cudaSuccess) return ea;
     p.nyt = (p.Do + TY - 1) / TY;
     p.nzt = (p.Do + TZ - 1) / TZ;
@@ -744,7 +758,22 @@ cudaError_t launch_cfg(const CUtensorMap& map, KParams p, cudaStream_t s) {
     int grid = p.ntiles < sms ? p.ntiles : sms;
     ChainArgs none;
     none.params = nullptr; none.maps = nullptr; none.n = 0; none.done = nullptr; none.nplane = 0; none.ndone = 0;
-    conv64_tc_kernel<TY, SINGLE, false><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(map, p, none);
+    // CTA pairs: both CTAs of a pair must run the same tap sequence (consecutive tiles of one x-plane: even tiles per plane)
+    // and the same number of tiles (even tile count on an even grid)
+    static const bool cluster_env = !(getenv("SR4D_TC_CLUSTER") != nullptr && atoi(getenv("SR4D_TC_CLUSTER")) == 0);   // default on
+    if (cluster_env && p.ntiles % 2 == 0 && (p.nyt * p.nzt) % 2 == 0 && grid >= 2 && !p.dbg) {
+        ea = tc_func_smem(reinterpret_cast<const void*>(conv64_tc_kernel<TY, SINGLE, false, true>), C::SMEM_BYTES);
+        if (ea != cudaSuccess) return ea;
+        grid &= ~1;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, conv64_tc_kernel<TY, SINGLE, false, true>, map, p, none);
+    }
+    conv64_tc_kernel<TY, SINGLE, false, false><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(map, p, none);
     return cudaGetLastError();
 }
 
@@ -753,14 +782,14 @@ cudaError_t launch_cfg(const CUtensorMap& map, KParams p, cudaStream_t s) {
 template <int TY>
 cudaError_t launch_chain_cfg(KParams p0, ChainArgs ch, cudaStream_t s) {
     using C = Cfg<TY, false>;
-    cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(conv64_tc_kernel<TY, false, true>), C::SMEM_BYTES);
+    cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(conv64_tc_kernel<TY, false, true, false>), C::SMEM_BYTES);
     if (ea != cudaSuccess) return ea;
     const int sms = tc_num_sms();
     const int grid = p0.ntiles < sms ? p0.ntiles : sms;
     CUtensorMap dummy;
     memset(&dummy, 0, sizeof dummy);
     void* args[3] = {&dummy, &p0, &ch};
-    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(conv64_tc_kernel<TY, false, true>), dim3(grid), dim3(NUM_THREADS),
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(conv64_tc_kernel<TY, false, true, false>), dim3(grid), dim3(NUM_THREADS),
                                        args, C::SMEM_BYTES, s);
 }
 
