@@ -761,7 +761,8 @@ cudaError_t launch_cfg(const CUtensorMap& map, KParams p, cudaStream_t s) {
     // CTA pairs: both CTAs of a pair must run the same tap sequence (consecutive tiles of one x-plane: even tiles per plane)
     // and the same number of tiles (even tile count on an even grid)
     static const bool cluster_env = !(getenv("SR4D_TC_CLUSTER") != nullptr && atoi(getenv("SR4D_TC_CLUSTER")) == 0);   // default on
-    if (cluster_env && p.ntiles % 2 == 0 && (p.nyt * p.nzt) % 2 == 0 && grid >= 2 && !p.dbg) {
+    static bool cluster_ok = true;          // cleared when a cluster launch is refused (e.g. a partition that cannot co-schedule pairs)
+    if (cluster_env && cluster_ok && p.ntiles % 2 == 0 && (p.nyt * p.nzt) % 2 == 0 && grid >= 2 && !p.dbg) {
         ea = tc_func_smem(reinterpret_cast<const void*>(conv64_tc_kernel<TY, SINGLE, false, true>), C::SMEM_BYTES);
         if (ea != cudaSuccess) return ea;
         grid &= ~1;
@@ -771,7 +772,11 @@ cudaError_t launch_cfg(const CUtensorMap& map, KParams p, cudaStream_t s) {
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, conv64_tc_kernel<TY, SINGLE, false, true>, map, p, none);
+        cudaError_t ec = cudaLaunchKernelEx(&cfg, conv64_tc_kernel<TY, SINGLE, false, true>, map, p, none);
+        if (ec == cudaSuccess) return ec;
+        (void)cudaGetLastError();           // launch-configuration error (not sticky): run the single-CTA kernel from now on
+        cluster_ok = false;
+        grid = p.ntiles < sms ? p.ntiles : sms;
     }
     conv64_tc_kernel<TY, SINGLE, false, false><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(map, p, none);
     return cudaGetLastError();
