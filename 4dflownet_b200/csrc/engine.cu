@@ -419,8 +419,15 @@ int conv64_fwd_run(sr4d_t* h, int kind, const std::vector<FwdLayer>& layers, cud
         CK(h, tc_chain_build(h->tcw, args.data(), (int)args.size(), &c), 0);
         it = h->chains.emplace(key, c).first;
     }
-    ProfScope prof(h, layers[0].in.D == h->P ? SR4D_PROF_CONV64_FWD_LR : SR4D_PROF_CONV64_FWD_HR, s, (int)layers.size());
-    CK(h, tc_chain_launch(it->second, s), 1);
+    {
+        ProfScope prof(h, layers[0].in.D == h->P ? SR4D_PROF_CONV64_FWD_LR : SR4D_PROF_CONV64_FWD_HR, s, (int)layers.size());
+        if (tc_chain_launch(it->second, s) == cudaSuccess) { h->launches += 1; return SR4D_OK; }
+    }
+    // the cooperative launch was refused (the grid cannot be co-resident here): one launch per layer from now on
+    (void)cudaGetLastError();
+    h->fwd_chain = 0;
+    for (const auto& l : layers)
+        if ((rc = conv64_fwd(h, l.layer, l.in, l.out, l.has_res ? &l.res : nullptr, l.slope, s))) return rc;
     return SR4D_OK;
 }
 
