@@ -166,6 +166,26 @@ def test_backward_kernels_given_identical_gates(pkg, oracle, bars, P, r, low, hi
         bars(f"identical_gates/{tag}/{label}", rel_l2(got, ref), ceiling)
 
 
+@pytest.mark.parametrize("P,r,low,hi,B", [(8, 3, 1, 1, 3), (6, 4, 1, 1, 2), (9, 2, 1, 1, 1), (12, 1, 1, 2, 2), (10, 3, 2, 1, 2)])
+def test_backward_kernels_on_unusual_geometries(pkg, oracle, bars, P, r, low, hi, B):
+    """res_increase 3 / 4 / 1, odd patch edges and batches: grids where the tensor-core head backward is not available
+    (edge % 4 != 0: SIMT head kernel), where tile counts are odd (no CTA pairs) and where the forward is chained -- the same
+    identical-gates comparison as above, every fallback combination against the SIMT backward."""
+    L = pkg._lib
+    params = oracle.glorot_params(low, hi, seed=P * 7 + r, bias_scale=0.05)
+    batch = oracle.synthetic_batch(B, P, r, seed=5)
+    names = [n for n, _ in oracle.param_table(low, hi)]
+    ref = _flat(_engine_grads(pkg, P, r, low, hi, B, params, batch, L.CONV_SIMT, L.CONV_SIMT), names)
+    got = _flat(_engine_grads(pkg, P, r, low, hi, B, params, batch, L.CONV_SIMT, L.CONV_AUTO), names)
+    bars(f"identical_gates_unusual/P{P}r{r}l{low}h{hi}B{B}/default", rel_l2(got, ref), 3e-4)
+    # and the whole tensor-core step (forward included) against the fp64 oracle's gradient
+    full = _flat(_engine_grads(pkg, P, r, low, hi, B, params, batch, L.CONV_AUTO, L.CONV_AUTO), names)
+    grads_ref, _ = oracle.gradients({k: v.astype(np.float64) for k, v in params.items()}, batch, r, low, hi)
+    # (the engine's gradient buffer excludes the L2 term, which its Adam kernel folds in)
+    want = {n: grads_ref[n] - (B * 2 * oracle.L2_COEFF * params[n] if n.endswith("kernel") else 0.0) for n in names}
+    bars(f"train_step_unusual/P{P}r{r}l{low}h{hi}B{B}/flat", rel_l2(full, _flat(want, names)), 1e-3)
+
+
 @pytest.mark.parametrize("impl", ["simt", "auto", "auto_unfused", "auto_full"])
 @pytest.mark.parametrize("P,r,low,hi,B", GEOMS)
 def test_train_step_gradients_vs_oracle(pkg, oracle, bars, P, r, low, hi, B, impl):
