@@ -33,19 +33,27 @@ L2_COEFF = 5e-7    # SR4DFlowNet.py:99 kernel_regularizer=l2(5e-7)
 class Mean:
     """tf.keras.metrics.Mean: running mean over all values passed to update_state."""
 
-    def __init__(self, name=None):
+    def __init__(self, name=None, before_access=None):
         self.name = name
         self.total, self.count = 0.0, 0
+        # hook run before every access: the controller folds the metrics of a step whose read-back is still in flight
+        self._before = before_access
 
     def update_state(self, values):
+        if self._before:
+            self._before()
         v = np.asarray(values, dtype=np.float64).reshape(-1)
         self.total += float(v.sum())
         self.count += v.size
 
     def result(self):
+        if self._before:
+            self._before()
         return self.total / self.count if self.count else 0.0
 
     def reset_states(self):
+        if self._before:
+            self._before()
         self.total, self.count = 0.0, 0
 
 
@@ -142,7 +150,8 @@ class TrainerController:
                                    training=True, device=device, seed=seed)
         self.engine = self.model.engine
 
-        self.loss_metrics = dict((k, Mean(name=k)) for k in (
+        self._pending = None      # token of a train step whose metric read-back has been enqueued but not folded yet
+        self.loss_metrics = dict((k, Mean(name=k, before_access=self._fold_pending)) for k in (
             'train_loss', 'val_loss', 'train_accuracy', 'val_accuracy', 'train_mse', 'val_mse',
             'train_div', 'val_div', 'l2_reg_loss'))
         self.accuracy_metric = 'val_loss'
@@ -191,6 +200,8 @@ class TrainerController:
 
     # ---- steps --------------------------------------------------------------------------------
     def _tail(self):
+        if self._metric_tail is not None and self._metric_tail.world != parallel.world_size():
+            self._fold_pending()             # a read-back of the old tail object is still in flight
         if self._metric_tail is None or self._metric_tail.world != parallel.world_size():
             self._metric_tail = parallel.MetricTail(self.engine.grad_tail, self.engine.max_batch)
         return self._metric_tail
@@ -216,8 +227,19 @@ class TrainerController:
         return per, l2
 
     def train_step(self, data_pairs):
+        """TrainerController.py:209-225.  The step's metrics come back through one small device->host copy that is only
+        waited for when somebody looks at the running means (or at the next train_step, after that step has been
+        enqueued): the GPU never idles while the host folds numbers."""
         self.train_step_async(data_pairs)
-        per, l2, _ = self._tail().read()     # running means cover every sample of the global batch
+        token = self._tail().read_begin()
+        self._fold_pending()                 # the previous step's copy finished long ago
+        self._pending = token
+
+    def _fold_pending(self):
+        if self._pending is None:
+            return
+        token, self._pending = self._pending, None
+        per, l2, _ = self._tail().read_end(token)     # running means cover every sample of the global batch
         self._update_metrics(per, l2, 'train')
 
     def test_step(self, data_pairs):

@@ -174,20 +174,66 @@ class Engine:
         self._check(rc, "sr4d_loss_metrics")
         return per
 
+    @staticmethod
+    def _on_host(a):
+        return isinstance(a, np.ndarray) or (torch.is_tensor(a) and a.device.type == "cpu")
+
+    def _upload_targets(self, hr, mask, B):
+        """Host-resident HR targets / mask (84 % of a step's input bytes) go up on a side stream into engine-owned
+        staging buffers while the forward -- which does not read them -- runs on the caller's stream; returns the four
+        device views and the event the backward has to wait for."""
+        H = self.H
+        if getattr(self, "_tgt_stage", None) is None:
+            self._tgt_stage = torch.empty((4, self.max_batch, H, H, H), device=self.device, dtype=torch.float32)
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._copy_done = torch.cuda.Event()
+        main = torch.cuda.current_stream(self.device)
+        # the staging buffers were last read by the previous step's backward, enqueued on the caller's stream
+        self._copy_stream.wait_stream(main)
+        views = []
+        with torch.cuda.stream(self._copy_stream):
+            for k, a in enumerate(list(hr) + [mask]):
+                if isinstance(a, np.ndarray):
+                    a = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+                dst = self._tgt_stage[k, :B]
+                dst.copy_(a.to(torch.float32).reshape(B, H, H, H), non_blocking=True)
+                views.append(dst)
+            self._copy_done.record(self._copy_stream)
+        return views, self._copy_done
+
     def train_fwd_bwd(self, inputs, hr, mask, want_pred=False, per_out=None, l2_out=None):
         """Returns (per_sample (B,4) [loss, mse, rel_err%, sum mask], l2 (1,), pred or None);
         gradients (sum over the batch, no L2 term) are left in self.grads.  per_out / l2_out: optional
-        preallocated device tensors (e.g. views into self.grad_tail) that receive the metrics."""
+        preallocated device tensors (e.g. views into self.grad_tail) that receive the metrics.
+
+        When the HR targets and the mask arrive in host memory, the low-resolution inputs are uploaded on the
+        caller's stream, the forward is enqueued (sr4d_train_forward), the targets follow on a side stream underneath
+        it, and the backward (sr4d_train_backward) waits for that copy: same kernels as the single
+        sr4d_train_fwd_bwd call, the bulk of the upload off the critical path."""
         P, H = self.patch_size, self.H
+        host_targets = all(self._on_host(a) for a in list(hr) + [mask])
         xs = [self._dev(a).reshape(-1, P, P, P) for a in inputs]
         B = xs[0].shape[0]
-        ys = [self._dev(a).reshape(B, H, H, H) for a in hr]
-        mk = self._dev(mask).reshape(B, H, H, H)
         per = torch.empty((B, 4), device=self.device, dtype=torch.float32) if per_out is None else per_out
         l2 = torch.empty((1,), device=self.device, dtype=torch.float32) if l2_out is None else l2_out
         if tuple(per.shape) != (B, 4) or not per.is_contiguous() or l2.numel() != 1:
             raise ValueError("per_out must be a contiguous (B,4) tensor and l2_out a single float")
         pred = torch.empty((B, H, H, H, 3), device=self.device, dtype=torch.float32) if want_pred else None
+        if host_targets and B <= self.max_batch:
+            with torch.cuda.device(self.device):
+                rc = self.lib.sr4d_train_forward(self._h, *[C.c_void_p(x.data_ptr()) for x in xs], B,
+                                                 C.c_void_p(pred.data_ptr()) if want_pred else None,
+                                                 _stream_ptr(self.device))
+                self._check(rc, "sr4d_train_forward")
+                tg, done = self._upload_targets(hr, mask, B)
+                torch.cuda.current_stream(self.device).wait_event(done)
+                rc = self.lib.sr4d_train_backward(self._h, *[C.c_void_p(t.data_ptr()) for t in tg], B,
+                                                  C.c_void_p(per.data_ptr()), C.c_void_p(l2.data_ptr()),
+                                                  _stream_ptr(self.device))
+            self._check(rc, "sr4d_train_backward")
+            return per, l2, pred
+        ys = [self._dev(a).reshape(B, H, H, H) for a in hr]
+        mk = self._dev(mask).reshape(B, H, H, H)
         with torch.cuda.device(self.device):
             rc = self.lib.sr4d_train_fwd_bwd(
                 self._h, *[C.c_void_p(x.data_ptr()) for x in xs], *[C.c_void_p(y.data_ptr()) for y in ys],

@@ -134,15 +134,30 @@ class MetricTail:
         if self.world > 1:
             dist.all_reduce(self.tail, op=dist.ReduceOp.SUM)
 
-    def read(self):
-        """After the all-reduce: ((B_global,4) per-sample metrics in rank order == global batch order, l2, B_global).
-        One small device->host copy and one stream synchronisation -- the step's only host round trip."""
+    def read_begin(self):
+        """Enqueue the device->host copy of the all-reduced tail (into one of two pinned buffers) and return a token
+        for read_end -- lets the caller enqueue the NEXT step before waiting for this one's metrics."""
+        if getattr(self, "_ring", None) is None:
+            self._ring = [self._host, torch.empty_like(self._host).pin_memory() if self.tail.is_cuda
+                          else torch.empty_like(self._host)]
+            self._events = [torch.cuda.Event() if self.tail.is_cuda else None for _ in range(2)]
+            self._turn = 0
+        k = self._turn
+        self._turn ^= 1
+        host = self._ring[k]
         n_used = self.world * self.slot
-        self._host[:n_used].copy_(self.tail[:n_used], non_blocking=True)
-        self._host[self.count_index:].copy_(self.tail[self.count_index:], non_blocking=True)
+        host[:n_used].copy_(self.tail[:n_used], non_blocking=True)
+        host[self.count_index:].copy_(self.tail[self.count_index:], non_blocking=True)
         if self.tail.is_cuda:
-            torch.cuda.current_stream(self.tail.device).synchronize()
-        h = self._host.numpy()
+            self._events[k].record(torch.cuda.current_stream(self.tail.device))
+        return k
+
+    def read_end(self, token):
+        """((B_global,4) per-sample metrics in rank order == global batch order, l2, B_global) of the step whose copy
+        read_begin enqueued; waits for that copy only (an event, not the stream)."""
+        if self.tail.is_cuda:
+            self._events[token].synchronize()
+        h = self._ring[token].numpy()
         rows = []
         for r in range(self.world):
             base = r * self.slot
@@ -150,6 +165,11 @@ class MetricTail:
             rows.append(h[base + 2:base + 2 + 4 * n].reshape(n, 4))
         per = np.concatenate(rows, axis=0).copy()
         return per, float(h[self.rank * self.slot + 1]), int(round(float(h[self.count_index])))
+
+    def read(self):
+        """After the all-reduce: the metrics of this step, now (one small device->host copy + one event wait -- the
+        step's only host round trip)."""
+        return self.read_end(self.read_begin())
 
 
 def l2_grad_scale(local_batch, l2_coeff=5e-7):

@@ -368,7 +368,9 @@ def run_b200(args):
         # the call a user makes: TrainerController.train_step on a batch that lives in (pinned) host memory.  The
         # step uploads the 11-tuple, runs forward + loss + backward + the ONE all-reduce + Adam, and reads the
         # all-reduced metric tail back (one small D2H + the step's only stream synchronisation) for the running means.
-        ctl.train_step([h.to(dev, non_blocking=True) for h in host])
+        # (host tensors go in as they are: train_step uploads the low-resolution inputs on its stream and the HR
+        # targets + mask on a side stream underneath the forward, engine.train_fwd_bwd)
+        ctl.train_step(host)
 
     # ---- headline: device-resident train step --------------------------------------------------
     clocks = ClockSampler(local)

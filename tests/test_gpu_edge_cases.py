@@ -229,3 +229,32 @@ def test_training_reduces_the_loss_on_a_fixed_batch(pkg, oracle):
     assert np.isfinite(losses).all()
     assert losses[-1] < 0.5 * losses[0], losses
     assert losses[-1] == min(losses[-5:]) or losses[-1] < 0.6 * losses[0]
+
+
+def test_train_step_from_host_buffers_equals_device_buffers(pkg, oracle):
+    """engine.train_fwd_bwd uploads host-resident HR targets / mask on a side stream underneath the forward
+    (sr4d_train_forward + sr4d_train_backward); the result must be bit-identical to the single sr4d_train_fwd_bwd call on
+    device-resident tensors -- three steps in a row (the staging buffers are reused), pinned and pageable sources."""
+    import contextlib
+    import io
+    import torch
+    tcm = importlib.import_module("4dflownet_b200.Network.TrainerController")
+    P, r, B = 12, 2, 3
+    ctls = []
+    for _ in range(3):
+        with contextlib.redirect_stdout(io.StringIO()):
+            ctls.append(tcm.TrainerController(P, r, 1e-3, False, "t", 2, 1, max_batch=4, seed=5))
+    for step in range(3):
+        batch = [np.ascontiguousarray(a) for a in oracle.synthetic_batch(B, P, r, seed=20 + step)]
+        dev = [torch.from_numpy(a).cuda() for a in batch]
+        pinned = [torch.from_numpy(a).pin_memory() for a in batch]
+        ctls[0].train_step(dev)
+        ctls[1].train_step(pinned)
+        ctls[2].train_step(batch)            # numpy (pageable)
+        torch.cuda.synchronize()
+        for c in ctls[1:]:
+            assert torch.equal(c.engine.grads, ctls[0].engine.grads), f"gradients differ at step {step}"
+            assert torch.equal(c.engine.params, ctls[0].engine.params), f"weights differ at step {step}"
+    for k in ("train_loss", "train_mse", "train_accuracy"):
+        assert ctls[1].loss_metrics[k].result() == ctls[0].loss_metrics[k].result()
+        assert ctls[2].loss_metrics[k].result() == ctls[0].loss_metrics[k].result()
