@@ -787,12 +787,35 @@ cudaError_t launch_cfg(const CUtensorMap& map, KParams p, cudaStream_t s) {
 template <int TY>
 cudaError_t launch_chain_cfg(KParams p0, ChainArgs ch, cudaStream_t s) {
     using C = Cfg<TY, false>;
-    cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(conv64_tc_kernel<TY, false, true, false>), C::SMEM_BYTES);
-    if (ea != cudaSuccess) return ea;
     const int sms = tc_num_sms();
-    const int grid = p0.ntiles < sms ? p0.ntiles : sms;
+    int grid = p0.ntiles < sms ? p0.ntiles : sms;
     CUtensorMap dummy;
     memset(&dummy, 0, sizeof dummy);
+    // CTA pairs with multicast weight taps (see launch_cfg): without them a chained batch-1 HR layer is bound by the L2 -> SM
+    // weight stream (148 CTAs x 432 KB per tile, ~6 TB/s) instead of the tensor pipe.  Both CTAs of a pair must hold the same
+    // number of tiles of every layer: even tile count on an even grid.  Cooperative (co-residency: the CTAs wait for each
+    // other between layers) + cluster launch; a refusal falls back to single CTAs for the rest of the process.
+    static const bool cluster_env = !(getenv("SR4D_CHAIN_CLUSTER") != nullptr && atoi(getenv("SR4D_CHAIN_CLUSTER")) == 0) &&
+                                    !(getenv("SR4D_TC_CLUSTER") != nullptr && atoi(getenv("SR4D_TC_CLUSTER")) == 0);
+    static bool cluster_ok = true;
+    if (cluster_env && cluster_ok && p0.ntiles % 2 == 0 && grid >= 2) {
+        cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(conv64_tc_kernel<TY, false, true, true>), C::SMEM_BYTES);
+        if (ea != cudaSuccess) return ea;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid & ~1); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = s;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeCooperative;
+        attr[1].val.cooperative = 1;
+        cfg.attrs = attr; cfg.numAttrs = 2;
+        cudaError_t ec = cudaLaunchKernelEx(&cfg, conv64_tc_kernel<TY, false, true, true>, dummy, p0, ch);
+        if (ec == cudaSuccess) return ec;
+        (void)cudaGetLastError();
+        cluster_ok = false;
+    }
+    cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(conv64_tc_kernel<TY, false, true, false>), C::SMEM_BYTES);
+    if (ea != cudaSuccess) return ea;
     void* args[3] = {&dummy, &p0, &ch};
     return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(conv64_tc_kernel<TY, false, true, false>), dim3(grid), dim3(NUM_THREADS),
                                        args, C::SMEM_BYTES, s);
