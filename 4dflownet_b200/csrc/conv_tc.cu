@@ -71,7 +71,9 @@ struct Cfg {
     static constexpr int WG = SINGLE ? 3 : 2;
     static constexpr int NGW = 2;
     static constexpr int NWS = NGW * WG;
-    static constexpr int LPC = 4;                                      // y-lines per epilogue chunk
+    // y-lines per epilogue chunk (measured: sending a whole TY = 12 tile through the staging buffer as ONE chunk of three
+    // items per thread is slower -- 357 vs 333 us for the 17 chained 24^3 layers at batch 1, profiles/r02_chain_cluster_ab.txt)
+    static constexpr int LPC = 4;
     static constexpr int CV = LPC * TZ;                                // voxels (TMEM columns) per chunk
     static constexpr int NCHUNK = (TY + LPC - 1) / LPC;
     // Epilogue organisation.  Two-plane kernels (forward, two-plane dgrad) spend >= 22k cycles of MMAs per tile and
@@ -791,12 +793,12 @@ cudaError_t launch_chain_cfg(KParams p0, ChainArgs ch, cudaStream_t s) {
     int grid = p0.ntiles < sms ? p0.ntiles : sms;
     CUtensorMap dummy;
     memset(&dummy, 0, sizeof dummy);
-    // CTA pairs with multicast weight taps (see launch_cfg): without them a chained batch-1 HR layer is bound by the L2 -> SM
-    // weight stream (148 CTAs x 432 KB per tile, ~6 TB/s) instead of the tensor pipe.  Both CTAs of a pair must hold the same
-    // number of tiles of every layer: even tile count on an even grid.  Cooperative (co-residency: the CTAs wait for each
-    // other between layers) + cluster launch; a refusal falls back to single CTAs for the rest of the process.
-    static const bool cluster_env = !(getenv("SR4D_CHAIN_CLUSTER") != nullptr && atoi(getenv("SR4D_CHAIN_CLUSTER")) == 0) &&
-                                    !(getenv("SR4D_TC_CLUSTER") != nullptr && atoi(getenv("SR4D_TC_CLUSTER")) == 0);
+    // Optional CTA pairs with multicast weight taps (see launch_cfg).  Both CTAs of a pair must hold the same number of tiles
+    // of every layer: even tile count on an even grid.  Cooperative (co-residency: the CTAs wait for each other between
+    // layers) + cluster launch; a refusal falls back to single CTAs for the rest of the process.
+    // Measured (profiles/r02_chain_cluster_ab.txt): batch-1 forward 752.7 vs 748.7 patches/s, batch-8 forward 7.42 vs 7.63 ms --
+    // the chained grids are power-limited like the rest, not L2-limited: opt-in only (SR4D_CHAIN_CLUSTER=1).
+    static const bool cluster_env = getenv("SR4D_CHAIN_CLUSTER") != nullptr && atoi(getenv("SR4D_CHAIN_CLUSTER")) != 0;
     static bool cluster_ok = true;
     if (cluster_env && cluster_ok && p0.ntiles % 2 == 0 && grid >= 2) {
         cudaError_t ea = tc_func_smem(reinterpret_cast<const void*>(conv64_tc_kernel<TY, false, true, true>), C::SMEM_BYTES);

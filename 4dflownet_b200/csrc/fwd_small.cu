@@ -28,26 +28,39 @@ __global__ void prep_features_kernel(const float* __restrict__ u, const float* _
 // 12 LDS.128 per 48 FMAs, 4 LSU cycles each); with four voxels per thread every fetched weight feeds 16 FMAs and the
 // six clamped feature columns of a (dx,dy) row are read once for the three dz taps of all four voxels.
 // Small grids (batch 1: 54 CTAs for 148 SMs with four voxels per thread) take the one-voxel instantiation.
-template <int STEM_VZ>
-__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ feat, int ch0,
-                                                        const float* __restrict__ w,
-                                                        const float* __restrict__ bias, ActView out) {
+struct StemArgs {                 // the two stems (pc: feature channels 3..5, phase: 0..2) run as grid.y = 0 / 1 of one launch
+    const float* w[2];
+    const float* bias[2];
+    ActView out[2];
+    int ch0[2];
+};
+// CPT output channels per thread (64 / CPT threads per run): 16 on large grids, 8 on small ones (batch 1: twice the CTAs
+// and half the dependent FMA chain per thread -- the kernel is latency-bound there)
+template <int STEM_VZ, int CPT>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ feat, const StemArgs a) {
     __shared__ __align__(16) float ws[27 * 3 * 64];
+    const int which = blockIdx.y;
+    const float* __restrict__ w = a.w[which];
+    const float* __restrict__ bias = a.bias[which];
+    const ActView out = a.out[which];
+    const int ch0 = a.ch0[which];
     for (int i = threadIdx.x; i < 27 * 3 * 64; i += 256) ws[i] = w[i];
     __syncthreads();
+    constexpr int TPR = 64 / CPT;                                   // threads per run
+    constexpr int RPC = 256 / TPR;                                  // runs per CTA pass
     const int P = out.D;
     const int nzr = (P + STEM_VZ - 1) / STEM_VZ;                    // z runs per line
     const size_t nrun = (size_t)out.B * P * P * nzr;
-    const int cq = (threadIdx.x & 3) * 16;
-    // grid-stride over groups of 64 runs: the weights are staged once per CTA
-    for (size_t ri = (size_t)blockIdx.x * 64 + (threadIdx.x >> 2); ri < nrun; ri += (size_t)gridDim.x * 64) {
+    const int cq = (threadIdx.x % TPR) * CPT;
+    // grid-stride over groups of RPC runs: the weights are staged once per CTA
+    for (size_t ri = (size_t)blockIdx.x * RPC + (threadIdx.x / TPR); ri < nrun; ri += (size_t)gridDim.x * RPC) {
         const int z0 = (int)(ri % nzr) * STEM_VZ, y = (int)((ri / nzr) % P), x = (int)((ri / ((size_t)nzr * P)) % P);
         const int b = (int)(ri / ((size_t)nzr * P * P));
-        float acc[STEM_VZ][16];
+        float acc[STEM_VZ][CPT];
 #pragma unroll
         for (int v = 0; v < STEM_VZ; ++v)
 #pragma unroll
-            for (int n = 0; n < 16; ++n) acc[v][n] = bias[cq + n];
+            for (int n = 0; n < CPT; ++n) acc[v][n] = bias[cq + n];
         for (int dx = -1; dx <= 1; ++dx) {
             const int xx = min(max(x + dx, 0), P - 1);
             for (int dy = -1; dy <= 1; ++dy) {
@@ -63,7 +76,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
                 for (int dz = 0; dz < 3; ++dz) {
                     const float* wp = ws + (((dx + 1) * 3 + (dy + 1)) * 3 + dz) * 192 + cq;
 #pragma unroll
-                    for (int n4 = 0; n4 < 4; ++n4) {
+                    for (int n4 = 0; n4 < CPT / 4; ++n4) {
                         const float4 w0 = *reinterpret_cast<const float4*>(wp + n4 * 4);
                         const float4 w1 = *reinterpret_cast<const float4*>(wp + 64 + n4 * 4);
                         const float4 w2 = *reinterpret_cast<const float4*>(wp + 128 + n4 * 4);
@@ -83,7 +96,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
         for (int v = 0; v < STEM_VZ; ++v) {
             if (z0 + v >= P) break;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < CPT / 4; ++q) {
                 float vv[4];
 #pragma unroll
                 for (int n = 0; n < 4; ++n) vv[n] = fmaxf(acc[v][q * 4 + n], 0.f);
@@ -96,7 +109,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
 // ---- 1x1 conv over concat[a(phase), b(pc)] 128->64 (+bias, ReLU): SR4DFlowNet.py:23-24
 // 4 threads per group of C1_NV consecutive voxels, 16 output channels each: every 16-byte weight fetch from shared
 // memory feeds 4 * C1_NV FMAs (the one-voxel version was bound by those fetches).
-template <int C1_NV>
+template <int C1_NV, int CPT>
 __global__ void __launch_bounds__(256) conv1x1_cat_kernel(ActView a, ActView bq, const float* __restrict__ w,
                                                           const float* __restrict__ bias, ActView out) {
     extern __shared__ __align__(16) float ws[];   // [128][64]
@@ -105,8 +118,10 @@ __global__ void __launch_bounds__(256) conv1x1_cat_kernel(ActView a, ActView bq,
     const int D = out.D;
     const size_t nvox = (size_t)out.B * D * D * D;
     const size_t ngrp = (nvox + C1_NV - 1) / C1_NV;
-    const int cq = (threadIdx.x & 3) * 16;
-    for (size_t gi = (size_t)blockIdx.x * 64 + (threadIdx.x >> 2); gi < ngrp; gi += (size_t)gridDim.x * 64) {
+    constexpr int TPG = 64 / CPT;                  // threads per voxel group (CPT = 16 or 8 output channels each)
+    constexpr int GPC = 256 / TPG;                 // groups per CTA pass
+    const int cq = (threadIdx.x % TPG) * CPT;
+    for (size_t gi = (size_t)blockIdx.x * GPC + (threadIdx.x / TPG); gi < ngrp; gi += (size_t)gridDim.x * GPC) {
         size_t off[C1_NV];
         int vx[C1_NV], vy[C1_NV], vz[C1_NV], vb[C1_NV];
 #pragma unroll
@@ -117,11 +132,11 @@ __global__ void __launch_bounds__(256) conv1x1_cat_kernel(ActView a, ActView bq,
             vb[v] = (int)(vi / ((size_t)D * D * D));
             off[v] = act_off(D, vb[v], vx[v], vy[v], vz[v]);
         }
-        float acc[C1_NV][16];
+        float acc[C1_NV][CPT];
 #pragma unroll
         for (int v = 0; v < C1_NV; ++v)
 #pragma unroll
-            for (int n = 0; n < 16; ++n) acc[v][n] = bias[cq + n];
+            for (int n = 0; n < CPT; ++n) acc[v][n] = bias[cq + n];
         for (int half = 0; half < 2; ++half) {
             const __half* hi = half ? bq.hi : a.hi;
             const __half* lo = half ? bq.lo : a.lo;
@@ -133,7 +148,7 @@ __global__ void __launch_bounds__(256) conv1x1_cat_kernel(ActView a, ActView bq,
                 for (int k = 0; k < 8; ++k) {
                     const float4* wp = reinterpret_cast<const float4*>(ws + (half * 64 + c8 * 8 + k) * 64 + cq);
 #pragma unroll
-                    for (int n4 = 0; n4 < 4; ++n4) {
+                    for (int n4 = 0; n4 < CPT / 4; ++n4) {
                         const float4 wv = wp[n4];
 #pragma unroll
                         for (int v = 0; v < C1_NV; ++v) {
@@ -150,7 +165,7 @@ __global__ void __launch_bounds__(256) conv1x1_cat_kernel(ActView a, ActView bq,
         for (int v = 0; v < C1_NV; ++v) {
             if (gi * C1_NV + v >= nvox) break;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < CPT / 4; ++q) {
                 float vv[4];
 #pragma unroll
                 for (int n = 0; n < 4; ++n) vv[n] = fmaxf(acc[v][q * 4 + n], 0.f);
@@ -399,15 +414,19 @@ cudaError_t launch_prep_features(const float* u, const float* v, const float* w,
     prep_features_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(u, v, w, um, vm, wm, feat, n);
     return cudaGetLastError();
 }
-cudaError_t launch_stem_conv(const float* feat, int ch0, const float* w, const float* bias, ActView out,
-                             cudaStream_t s) {
+cudaError_t launch_stem_convs(const float* feat, const float* w_pc, const float* b_pc, ActView out_pc, const float* w_ph,
+                              const float* b_ph, ActView out_ph, cudaStream_t s) {
+    StemArgs a;
+    a.w[0] = w_pc; a.bias[0] = b_pc; a.out[0] = out_pc; a.ch0[0] = 3;      // pc = concat[pcmr, mag, speed]   (SR4DFlowNet.py:15,17)
+    a.w[1] = w_ph; a.bias[1] = b_ph; a.out[1] = out_ph; a.ch0[1] = 0;      // phase = concat[u, v, w]           (:14,20)
+    const ActView& out = out_pc;
     const size_t nrun4 = (size_t)out.B * out.D * out.D * ((out.D + 3) / 4);
     const size_t ngrp4 = (nrun4 + 63) / 64;
-    if (ngrp4 >= 2 * (size_t)tc_num_sms()) {
-        stem_conv_kernel<4><<<(unsigned)(ngrp4 < 2368 ? ngrp4 : 2368), 256, 0, s>>>(feat, ch0, w, bias, out);
+    if (ngrp4 >= (size_t)tc_num_sms()) {
+        stem_conv_kernel<4, 16><<<dim3((unsigned)(ngrp4 < 1184 ? ngrp4 : 1184), 2), 256, 0, s>>>(feat, a);
     } else {
-        const size_t ngrp1 = ((size_t)out.B * out.D * out.D * out.D + 63) / 64;
-        stem_conv_kernel<1><<<(unsigned)(ngrp1 < 2368 ? ngrp1 : 2368), 256, 0, s>>>(feat, ch0, w, bias, out);
+        const size_t ngrp1 = ((size_t)out.B * out.D * out.D * out.D + 31) / 32;
+        stem_conv_kernel<1, 8><<<dim3((unsigned)(ngrp1 < 1184 ? ngrp1 : 1184), 2), 256, 0, s>>>(feat, a);
     }
     return cudaGetLastError();
 }
@@ -415,10 +434,10 @@ cudaError_t launch_conv1x1_cat(ActView a, ActView b, const float* w, const float
     size_t nvox = (size_t)out.B * out.D * out.D * out.D;
     const size_t ngrp4 = ((nvox + 3) / 4 + 63) / 64;
     if (ngrp4 >= 2 * (size_t)tc_num_sms()) {
-        conv1x1_cat_kernel<4><<<(unsigned)(ngrp4 < 2368 ? ngrp4 : 2368), 256, 128 * 64 * 4, s>>>(a, b, w, bias, out);
-    } else {                                       // small grids: one voxel per thread, four times the CTAs
-        const size_t ngrp1 = (nvox + 63) / 64;
-        conv1x1_cat_kernel<1><<<(unsigned)(ngrp1 < 2368 ? ngrp1 : 2368), 256, 128 * 64 * 4, s>>>(a, b, w, bias, out);
+        conv1x1_cat_kernel<4, 16><<<(unsigned)(ngrp4 < 2368 ? ngrp4 : 2368), 256, 128 * 64 * 4, s>>>(a, b, w, bias, out);
+    } else {                                       // small grids: one voxel and 8 channels per thread, eight times the CTAs
+        const size_t ngrp1 = (nvox + 31) / 32;
+        conv1x1_cat_kernel<1, 8><<<(unsigned)(ngrp1 < 2368 ? ngrp1 : 2368), 256, 128 * 64 * 4, s>>>(a, b, w, bias, out);
     }
     return cudaGetLastError();
 }

@@ -184,7 +184,7 @@ template <int YT>
 __global__ void __launch_bounds__(256) head_sum_kernel(const float* __restrict__ P0, const float* __restrict__ P1,
                                                        const float* __restrict__ P2, const float* __restrict__ b0,
                                                        const float* __restrict__ b1, const float* __restrict__ b2,
-                                                       float* __restrict__ out, int B, int D) {
+                                                       float* __restrict__ out, int B, int D, int xseg) {
     extern __shared__ float hs_sm[];
     constexpr int ROWS = (YT + 2) * (HS_ZT + 2);
     const int Dp = D + 2;
@@ -234,13 +234,15 @@ __global__ void __launch_bounds__(256) head_sum_kernel(const float* __restrict__
                 if ((w4 >> k) & 1u) d[3] = v[k].w;     // taps 0..26
             }
     };
-    fetch(0); stash(0);
-    fetch(1); stash(1);
-    fetch(2);
-    for (int x = 0; x < D; ++x) {
+    // blockIdx.y: segment of xseg output planes (small batches: more, shorter marches instead of 48 latency-bound steps)
+    const int xs0 = blockIdx.y * xseg, xs1 = min(D, xs0 + xseg);
+    fetch(xs0); stash(xs0);
+    fetch(xs0 + 1); stash(xs0 + 1);
+    fetch(xs0 + 2);
+    for (int x = xs0; x < xs1; ++x) {
         stash(x + 2);                                  // slot (x+2)%3 held plane x-1: its readers passed the barrier below
         __syncthreads();
-        if (x + 3 <= D + 1) fetch(x + 3);
+        if (x + 3 <= xs1 + 1) fetch(x + 3);
         const float* pl[3] = {hs_sm + (x % 3) * ROWS * HS_PITCH, hs_sm + ((x + 1) % 3) * ROWS * HS_PITCH,
                               hs_sm + ((x + 2) % 3) * ROWS * HS_PITCH};
         for (int i = threadIdx.x; i < ny * nz; i += 256) {
@@ -286,14 +288,18 @@ cudaError_t launch_head_out_tc(ActView h0, ActView h1, ActView h2, const float* 
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // tile height of the sum kernel: the largest of 8 / 4 / 2 / 1 lines that still gives (90 % of) the SMs a CTA
+    // and, before the tiles get flat, the march along x is cut into up to 8 segments of >= 6 planes (batch 1: 8 lines x 8
+    // segments instead of 1 line x 48 planes: a step of the march is one exposed memory latency)
     const int nzt = (D + HS_ZT - 1) / HS_ZT;
-    int yt = 8;
-    while (yt > 1 && (long)B * 3 * ((D + yt - 1) / yt) * nzt * 10 < (long)sms * 9) yt >>= 1;
-    const unsigned sgrid = (unsigned)(B * 3 * ((D + yt - 1) / yt) * nzt);
+    int yt = 8, nseg = 1;
+    while (nseg < 8 && D / (nseg * 2) >= 6 && (long)B * 3 * ((D + yt - 1) / yt) * nzt * nseg * 10 < (long)sms * 9) nseg *= 2;
+    while (yt > 1 && (long)B * 3 * ((D + yt - 1) / yt) * nzt * nseg * 10 < (long)sms * 9) yt >>= 1;
+    const int xseg = (D + nseg - 1) / nseg;
+    const dim3 sgrid((unsigned)(B * 3 * ((D + yt - 1) / yt) * nzt), (unsigned)((D + xseg - 1) / xseg));
 #define HS_LAUNCH(YT)                                                                                                 \
     e = tc_func_smem(reinterpret_cast<const void*>(head_sum_kernel<YT>), 3 * (YT + 2) * (HS_ZT + 2) * HS_PITCH * 4);  \
     if (e != cudaSuccess) return e;                                                                                   \
-    head_sum_kernel<YT><<<sgrid, 256, 3 * (YT + 2) * (HS_ZT + 2) * HS_PITCH * 4, s>>>(P0, P1, P2, b0, b1, b2, out, B, D)
+    head_sum_kernel<YT><<<sgrid, 256, 3 * (YT + 2) * (HS_ZT + 2) * HS_PITCH * 4, s>>>(P0, P1, P2, b0, b1, b2, out, B, D, xseg)
     switch (yt) {
         case 8: HS_LAUNCH(8); break;
         case 4: HS_LAUNCH(4); break;

@@ -38,8 +38,8 @@ cudaError_t launch_conv64_simt(const Conv64Args& a, cudaStream_t s);
 cudaError_t launch_prep_features(const float* u, const float* v, const float* w, const float* um,
                                  const float* vm, const float* wm, float* feat, int B, int P, cudaStream_t s);
 // feat [B][P^3][6] = (u,v,w,pcmr,mag,speed); ch0 selects the 3-channel group (0: phase, 3: pc)
-cudaError_t launch_stem_conv(const float* feat, int ch0, const float* w, const float* bias, ActView out,
-                             cudaStream_t s);
+cudaError_t launch_stem_convs(const float* feat, const float* w_pc, const float* b_pc, ActView out_pc, const float* w_ph,
+                              const float* b_ph, ActView out_ph, cudaStream_t s);
 cudaError_t launch_conv1x1_cat(ActView a, ActView b, const float* w, const float* bias, ActView out, cudaStream_t s);
 cudaError_t launch_upsample(ActView in, ActView out, int r, UpsampleTables t, cudaStream_t s);
 // three 64->1 heads: in[c] -> out[b][voxel][c]
