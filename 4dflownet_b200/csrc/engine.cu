@@ -442,14 +442,9 @@ int forward_impl(sr4d_t* h, const float* u, const float* v, const float* w, cons
     ActView pc1 = lr_view(h, 0, B), pc2 = lr_view(h, 1, B), ph1 = lr_view(h, 2, B), ph2 = lr_view(h, 3, B);
     ActView c1 = lr_view(h, 4, B), f = lr_view(h, 5, B);
     CK(h, launch_stem_convs(h->feat, W(h, 0), Bv(h, 0), pc1, W(h, 2), Bv(h, 2), ph1, s), 1);   // SR4DFlowNet.py:17,20 (one launch)
-    {
-        // the second convs of the two stems (:18, :21) are independent of each other: on small grids they share one chained
-        // launch (the plane-level wait of the second on the first is a false but harmless dependency)
-        std::vector<FwdLayer> stems2;
-        stems2.push_back(FwdLayer{1, pc1, pc2, false, ActView(), 0.f});
-        stems2.push_back(FwdLayer{3, ph1, ph2, false, ActView(), 0.f});
-        if ((rc = conv64_fwd_run(h, 2, stems2, s))) return rc;
-    }
+    if ((rc = conv64_fwd(h, 1, pc1, pc2, nullptr, 0.f, s))) return rc;                  // :18
+    if ((rc = conv64_fwd(h, 3, ph1, ph2, nullptr, 0.f, s))) return rc;                  // :21  (chaining these two independent
+    // layers into one launch was measured slower at batch 1: 61 vs 41 us, profiles/r02_chain_cluster_ab.txt)
     CK(h, launch_conv1x1_cat(ph2, pc2, W(h, 4), Bv(h, 4), c1, s), 1);                  // :23-24
     std::vector<FwdLayer> run;
     run.push_back(FwdLayer{5, c1, f, false, ActView(), 0.f});                          // :25
