@@ -352,7 +352,10 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // The whole warp runs the loop converged and one ELECTED lane issues (elect.sync): with `if (lane == 0)` around the loop
+        // ptxas wraps every UTCHMMA in an ELECT / BRA.U.ANY loop with R2UR moves (~15 instructions per MMA).
+        {
+            const bool leader = elect_one();
             // instruction descriptor: D=f32, A=B=f16, A (weights) MN-major, B (voxels) K-major, M=128, N
             const uint32_t idesc = (1u << 4) | (1u << 15) | ((uint32_t)(C::N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t zaddr = smem_u32(zsm);
@@ -392,23 +395,25 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
                             // the second instruction pairs the Whi half with the zero block instead of whatever follows it in
                             // shared memory -- the masked rows are still multiplied, zeros cost less (profiles/r02_power_probe.txt)
                             const uint32_t wk = wa + k * 2048;
-                            tc_mma_f16(dacc, make_desc_mn(wk, W_HI_OFFSET, 1024),
-                                       make_desc_sbo(xhi + boff + k * 32, ZP * 128), idesc, acc);
-                            if (!SINGLE)
+                            if (leader)
+                                tc_mma_f16(dacc, make_desc_mn(wk, W_HI_OFFSET, 1024),
+                                           make_desc_sbo(xhi + boff + k * 32, ZP * 128), idesc, acc);
+                            if (!SINGLE && leader)
                                 tc_mma_f16_masked(dacc, make_desc_mn(wk + W_HI_OFFSET, zaddr - (wk + W_HI_OFFSET), 1024),
                                                   make_desc_sbo(xlo + boff + k * 32, ZP * 128), idesc, 1u, 0u, 0u, ~0u, ~0u);
                         }
-                        if (wi % C::WG == C::WG - 1) {                      // hand the group of stages back (to both producers of a pair)
+                        if (wi % C::WG == C::WG - 1 && leader) {            // hand the group of stages back (to both producers of a pair)
                             if (CL) tc_commit_mc(&w_empty[(wi / C::WG) % C::NGW], (uint16_t)3);
                             else tc_commit(&w_empty[(wi / C::WG) % C::NGW]);
                         }
+                        __syncwarp();
                         ++wi;
                     }
                     ++xi;
                 }
-                tc_commit(&t_full[buf]);
+                if (leader) tc_commit(&t_full[buf]);
             }
-            if (p.dbg) {
+            if (p.dbg && leader) {
                 p.dbg[blockIdx.x * 8 + 0] = wt; p.dbg[blockIdx.x * 8 + 1] = wx;
                 p.dbg[blockIdx.x * 8 + 2] = ww; p.dbg[blockIdx.x * 8 + 3] = clock64() - tbeg;
                 p.dbg[blockIdx.x * 8 + 5] = clock64();          // MMA issue loop end (absolute)

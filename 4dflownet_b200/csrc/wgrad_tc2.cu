@@ -180,7 +180,11 @@ wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap0, const __grid_const
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // The whole warp runs the loop converged and one ELECTED lane issues: with `if (lane == 0)` around the loop ptxas wraps
+        // every UTCHMMA in an ELECT / BRA.U.ANY loop with R2UR moves (~15 instructions per MMA; eight MMAs per iteration
+        // made the issuing thread the bottleneck: 1114 cycles per iteration against 768 of tensor-pipe time).
+        {
+            const bool leader = elect_one();
             // D=f32, A=B=f16, both MN-major, M=128, N=192
             const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(192 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t d1 = tmem_base, d2 = tmem_base + 192;
@@ -220,26 +224,28 @@ wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap0, const __grid_const
                     for (int j = 0; j < TY / 2; ++j) {
                         const uint64_t ad = adesc0 | (uint64_t)(a0 + j * (2 * TZ * 128 >> 4));
                         const uint32_t acc = (chain_it | j) != 0;
-                        tc_mma_f16(d1, ad, bdesc0 | (uint64_t)(x1 + j * (2 * ZP * 128 >> 4)), idesc, acc);
+                        if (leader) tc_mma_f16(d1, ad, bdesc0 | (uint64_t)(x1 + j * (2 * ZP * 128 >> 4)), idesc, acc);
                         // rows 0..63 of this product ("tap 3") are never read: their output lanes are disabled, which the
                         // power probe prices at -23 % of the instruction's energy (profiles/r02_power_probe.txt)
-                        tc_mma_f16_masked(d2, ad, bdesc0 | (uint64_t)(x2 + j * (2 * ZP * 128 >> 4)), idesc, acc, ~0u, ~0u, 0u, 0u);
+                        if (leader) tc_mma_f16_masked(d2, ad, bdesc0 | (uint64_t)(x2 + j * (2 * ZP * 128 >> 4)), idesc, acc, ~0u, ~0u, 0u, 0u);
                     }
                     // hand a group back after the iteration that read its last plane (dY as "previous", Xpad in MMA-1), the
                     // rest of the segment's groups after its last iteration
-                    if ((i & (GP - 1)) == GP - 1) tc_commit(&empty[(gq + i / GP) % NGR]);
+                    if ((i & (GP - 1)) == GP - 1 && leader) tc_commit(&empty[(gq + i / GP) % NGR]);
                     if (i == len - 1) {
                         // (a trailing group may hold only planes nobody read: see its load land before giving it back)
                         while (wq < gq + (uint32_t)ngrp) { mbar_wait(&full[wq % NGR], (wq / NGR) & 1); ++wq; }
-                        for (int g = len / GP; g < ngrp; ++g) tc_commit(&empty[(gq + g) % NGR]);
+                        for (int g = len / GP; g < ngrp; ++g)
+                            if (leader) tc_commit(&empty[(gq + g) % NGR]);
                     }
                     if (p.dbg) dis += clock64() - c0;
                     ++chain_it;
                     if (chain_it == p.flush_iters || t + i + 1 == t1) {
-                        tc_commit(acc_full);
+                        if (leader) tc_commit(acc_full);
                         chain_it = 0;
                         ++nchain;
                     }
+                    __syncwarp();
                     if (++sprev == NSLOT) sprev = 0;
                 }
                 gq += ngrp;
@@ -247,7 +253,7 @@ wgrad64_tc2_kernel(const __grid_constant__ CUtensorMap xmap0, const __grid_const
                 xa = 0;
             }
             }   // layers (every layer ends its accumulator chain: t + i + 1 == t1 above)
-            if (p.dbg) {
+            if (p.dbg && leader) {
                 long long* d = p.dbg + (size_t)(blockIdx.y * 3 + blockIdx.x) * 8;
                 d[0] = dwf; d[1] = dwa; d[2] = dis; d[3] = clock64() - tbeg; d[4] = t1 - t0;
             }
