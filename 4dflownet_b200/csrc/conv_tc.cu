@@ -94,6 +94,16 @@ struct Cfg {
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
+// what an epilogue thread brings along for its (voxel, 8-channel group) items of one chunk: coordinates and the global-memory
+// operands of the chunk's second phase (skip gradients / saved activation of the fused dgrad, residual of the forward)
+template <int IT>
+struct EpiItems {
+    bool active[IT];
+    int vy[IT], vz[IT];
+    float4 ap0[IT], ap1[IT], aq0[IT], aq1[IT];
+    uint4 rh[IT], rl[IT];
+};
+
 struct KParams {
     const __half* w_img;     // [27][128][64] fp16 pre-swizzled, tap order = Keras (dx*3+dy)*3+dz
     __half* out_hi;
@@ -461,6 +471,58 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
             const int y0 = (rem / p.nzt) * TY, z0 = (rem % p.nzt) * TZ;
             const bool x_edge = p.halo && (x == 0 || x == Do - 1);
             const uint32_t buf = ti & 1;
+            // The loads of a chunk's second phase are issued ONE CHUNK AHEAD (and, outside the chained launches, those of a
+            // tile's first chunk before the wait for its accumulator): the single-plane dgrad has ~11k cycles of MMAs per tile
+            // and its MMA warp spent 15 % of its time waiting for the epilogue, whose chunks were each one exposed memory
+            // latency long (SR4D_TC_DEBUG stamps).
+            auto load_items = [&](int ch, EpiItems<C::IT>& it) {
+#pragma unroll
+                for (int k = 0; k < C::IT; ++k) {
+                    const int item = gt + k * C::GT;
+                    const int vq = item >> 3, g8 = item & 7;
+                    const int line = ch * C::LPC + (vq >> 3);
+                    const int y = y0 + line, z = z0 + (vq & 7);
+                    it.vy[k] = y; it.vz[k] = z;
+                    bool act = line < TY && y < Do && z < Do;
+                    // fused dgrad: (y, z) are padded-grid coordinates; only interior voxels produce output
+                    if (p.fused) act = act && y >= 1 && y <= Di && z >= 1 && z <= Di;
+                    it.active[k] = act;
+                    if (p.fused) {
+                        if (act) {
+                            const size_t go = g4_off(Di, b, x, y - 1, z - 1) + g8 * 8;
+                            if (p.add_pre) {
+                                it.ap0[k] = *reinterpret_cast<const float4*>(p.add_pre + go);
+                                it.ap1[k] = *reinterpret_cast<const float4*>(p.add_pre + go + 4);
+                            }
+                            if (p.add_post) {
+                                it.aq0[k] = *reinterpret_cast<const float4*>(p.add_post + go);
+                                it.aq1[k] = *reinterpret_cast<const float4*>(p.add_post + go + 4);
+                            }
+                            if (p.sav_hi) {
+                                const size_t o = act_off(Di, b, x, y - 1, z - 1) + g8 * 8;
+                                it.rh[k] = *reinterpret_cast<const uint4*>(p.sav_hi + o);
+                                it.rl[k] = *reinterpret_cast<const uint4*>(p.sav_lo + o);
+                            }
+                        }
+                    } else if (p.res_hi && act) {
+                        const size_t o = act_off(Do, b, x, y, z) + g8 * 8;
+                        if (CHAIN) {
+                            // the residual was written earlier in THIS launch, possibly into a buffer this SM has read before
+                            // (inference reuses activation slots): bypass the non-coherent L1
+                            it.rh[k] = __ldcg(reinterpret_cast<const uint4*>(p.res_hi + o));
+                            it.rl[k] = __ldcg(reinterpret_cast<const uint4*>(p.res_lo + o));
+                        } else {
+                            it.rh[k] = *reinterpret_cast<const uint4*>(p.res_hi + o);
+                            it.rl[k] = *reinterpret_cast<const uint4*>(p.res_lo + o);
+                        }
+                    }
+                }
+            };
+            // Only the single-plane dgrad does this: the two-plane kernels have twice the MMA time per tile, their epilogue is
+            // never waited for, and the forward measured 1-2 % slower with the prefetch (profiles/r02_epilogue_prefetch_ab.txt).
+            constexpr bool PREFETCH = SINGLE && !CHAIN;
+            EpiItems<C::IT> nxt;
+            if (PREFETCH && grp < C::NCHUNK) load_items(grp, nxt);
             mbar_wait(&t_full[buf], (ti >> 1) & 1);
             tc_fence_after();
             const uint32_t trow = tmem_base + buf * ACC_STRIDE + ((uint32_t)(32 * e) << 16);
@@ -472,51 +534,12 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
             }
 #pragma unroll 1
             for (int ch = grp; ch < C::NCHUNK; ch += C::NG) {
-                // ---- the (voxel, 8-channel group) items this thread stores, and the prefetch of what they add ----
-                bool active[C::IT];
-                int vy[C::IT], vz[C::IT];
-                float4 ap0[C::IT], ap1[C::IT], aq0[C::IT], aq1[C::IT];
-                uint4 rh[C::IT], rl[C::IT];
-#pragma unroll
-                for (int k = 0; k < C::IT; ++k) {
-                    const int item = gt + k * C::GT;
-                    const int vq = item >> 3, g8 = item & 7;
-                    const int line = ch * C::LPC + (vq >> 3);
-                    const int y = y0 + line, z = z0 + (vq & 7);
-                    vy[k] = y; vz[k] = z;
-                    bool act = line < TY && y < Do && z < Do;
-                    // fused dgrad: (y, z) are padded-grid coordinates; only interior voxels produce output
-                    if (p.fused) act = act && y >= 1 && y <= Di && z >= 1 && z <= Di;
-                    active[k] = act;
-                    if (p.fused) {
-                        if (act) {
-                            const size_t go = g4_off(Di, b, x, y - 1, z - 1) + g8 * 8;
-                            if (p.add_pre) {
-                                ap0[k] = *reinterpret_cast<const float4*>(p.add_pre + go);
-                                ap1[k] = *reinterpret_cast<const float4*>(p.add_pre + go + 4);
-                            }
-                            if (p.add_post) {
-                                aq0[k] = *reinterpret_cast<const float4*>(p.add_post + go);
-                                aq1[k] = *reinterpret_cast<const float4*>(p.add_post + go + 4);
-                            }
-                            if (p.sav_hi) {
-                                const size_t o = act_off(Di, b, x, y - 1, z - 1) + g8 * 8;
-                                rh[k] = *reinterpret_cast<const uint4*>(p.sav_hi + o);
-                                rl[k] = *reinterpret_cast<const uint4*>(p.sav_lo + o);
-                            }
-                        }
-                    } else if (p.res_hi && act) {
-                        const size_t o = act_off(Do, b, x, y, z) + g8 * 8;
-                        if (CHAIN) {
-                            // the residual was written earlier in THIS launch, possibly into a buffer this SM has read before
-                            // (inference reuses activation slots): bypass the non-coherent L1
-                            rh[k] = __ldcg(reinterpret_cast<const uint4*>(p.res_hi + o));
-                            rl[k] = __ldcg(reinterpret_cast<const uint4*>(p.res_lo + o));
-                        } else {
-                            rh[k] = *reinterpret_cast<const uint4*>(p.res_hi + o);
-                            rl[k] = *reinterpret_cast<const uint4*>(p.res_lo + o);
-                        }
-                    }
+                EpiItems<C::IT> cur;
+                if (PREFETCH) {
+                    cur = nxt;
+                    if (ch + C::NG < C::NCHUNK) load_items(ch + C::NG, nxt);
+                } else {
+                    load_items(ch, cur);
                 }
                 // ---- phase A: TMEM -> registers -> fp32 staging [part][voxel][channel] ----
                 const int c0 = ch * C::CV + cpart * C::COLS;           // first accumulator column this warp reads
@@ -540,10 +563,10 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
                 // ---- phase B: coalesced residual / activation / split / store ----
 #pragma unroll
                 for (int k = 0; k < C::IT; ++k) {
-                    if (!active[k]) continue;
+                    if (!cur.active[k]) continue;
                     const int item = gt + k * C::GT;
                     const int vq = item >> 3, g8 = item & 7;
-                    const int y = vy[k], z = vz[k];
+                    const int y = cur.vy[k], z = cur.vz[k];
                     const float* sp = gstage + vq * 64 + g8 * 8;
                     const float4 h0 = *reinterpret_cast<const float4*>(sp);
                     const float4 h1 = *reinterpret_cast<const float4*>(sp + 4);
@@ -570,12 +593,12 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
 #pragma unroll
                         for (int c = 0; c < 8; ++c) val[c] *= ks;
                         if (p.add_pre) {
-                            val[0] += ap0[k].x; val[1] += ap0[k].y; val[2] += ap0[k].z; val[3] += ap0[k].w;
-                            val[4] += ap1[k].x; val[5] += ap1[k].y; val[6] += ap1[k].z; val[7] += ap1[k].w;
+                            val[0] += cur.ap0[k].x; val[1] += cur.ap0[k].y; val[2] += cur.ap0[k].z; val[3] += cur.ap0[k].w;
+                            val[4] += cur.ap1[k].x; val[5] += cur.ap1[k].y; val[6] += cur.ap1[k].z; val[7] += cur.ap1[k].w;
                         }
                         if (p.sav_hi) {
-                            const __half2* hh = reinterpret_cast<const __half2*>(&rh[k]);
-                            const __half2* ll = reinterpret_cast<const __half2*>(&rl[k]);
+                            const __half2* hh = reinterpret_cast<const __half2*>(&cur.rh[k]);
+                            const __half2* ll = reinterpret_cast<const __half2*>(&cur.rl[k]);
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
                                 const float2 ha = __half22float2(hh[c]), la = __half22float2(ll[c]);
@@ -584,8 +607,8 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
                             }
                         }
                         if (p.add_post) {
-                            val[0] += aq0[k].x; val[1] += aq0[k].y; val[2] += aq0[k].z; val[3] += aq0[k].w;
-                            val[4] += aq1[k].x; val[5] += aq1[k].y; val[6] += aq1[k].z; val[7] += aq1[k].w;
+                            val[0] += cur.aq0[k].x; val[1] += cur.aq0[k].y; val[2] += cur.aq0[k].z; val[3] += cur.aq0[k].w;
+                            val[4] += cur.aq1[k].x; val[5] += cur.aq1[k].y; val[6] += cur.aq1[k].z; val[7] += cur.aq1[k].w;
                         }
                         const size_t go = g4_off(Di, b, x, y - 1, z - 1) + g8 * 8;
                         float* o = p.out_g4 + go;
@@ -609,8 +632,8 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
                         for (int c = 0; c < 8; ++c) amax = fmaxf(amax, fabsf(val[c]));
                     } else {
                         if (p.res_hi) {
-                            const __half2* hh = reinterpret_cast<const __half2*>(&rh[k]);
-                            const __half2* ll = reinterpret_cast<const __half2*>(&rl[k]);
+                            const __half2* hh = reinterpret_cast<const __half2*>(&cur.rh[k]);
+                            const __half2* ll = reinterpret_cast<const __half2*>(&cur.rl[k]);
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
                                 float2 ha = __half22float2(hh[c]), la = __half22float2(ll[c]);
