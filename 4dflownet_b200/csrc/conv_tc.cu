@@ -368,8 +368,21 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
             const bool leader = elect_one();
             // instruction descriptor: D=f32, A=B=f16, A (weights) MN-major, B (voxels) K-major, M=128, N
             const uint32_t idesc = (1u << 4) | (1u << 15) | ((uint32_t)(C::N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t zaddr = smem_u32(zsm);
-            uint32_t xi = 0, wi = 0, ti = 0;
+            // Everything the loop needs per tap is a running counter or a compile-time constant: the nine taps of a pass are
+            // unrolled (row shift and accumulate flag fold into immediates), the weight stage / phase / group indices advance
+            // by increments instead of divisions, and a descriptor is its constant part OR-ed with (address >> 4) -- the
+            // bases are masked to the 14-bit field once, the offsets added to them stay inside it.  (The first version spent ~100 uniform-datapath
+            // instructions per tap on this arithmetic: as much issue time as the four MMAs of a single-plane tap execute.)
+            const uint64_t a_const = make_desc_mn(0, W_HI_OFFSET, 1024);           // [Wlo ; Whi] halves 8 KB apart
+            const uint64_t a2_const = make_desc_mn(0, 0, 1024);                    // second instruction: LBO filled in per stage
+            const uint64_t b_const = make_desc_sbo(0, ZP * 128);
+            // (masked to the CTA-local 256 KB window: in a cluster launch the shared address of a CTA carries its rank in the upper
+            // bits, which must not leak into the descriptor fields next to the 14-bit address)
+            const uint32_t wsm4 = (smem_u32(wsm) >> 4) & 0x3FFFu, zaddr4 = (smem_u32(zsm) >> 4) & 0x3FFFu, xs4 = (smem_u32(xs) >> 4) & 0x3FFFu;
+            uint32_t ti = 0, wi = 0;
+            uint32_t xs_i = 0, xph = 0;                  // activation stage and its phase
+            uint32_t ws = 0, wph = 0;                    // weight stage and its phase
+            uint32_t gfill = 0, gidx = 0;                // taps consumed of the current stage group, the group's barrier
             long long wt = 0, wx = 0, ww = 0, c0 = 0;
             const long long tbeg = p.dbg ? clock64() : 0;
             for (int L = 0; L < nl; ++L)
@@ -380,46 +393,82 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
                 mbar_wait(&t_empty[buf], ((ti >> 1) & 1) ^ 1);
                 if (p.dbg) wt += clock64() - c0;
                 tc_fence_after();
+#pragma unroll 1
                 for (int dx = 0; dx < 3; ++dx) {
-                    const uint32_t s = xi % C::NXS, ph = (xi / C::NXS) & 1;
                     if (p.dbg) c0 = clock64();
-                    mbar_wait(&x_full[s], ph);
+                    mbar_wait(&x_full[xs_i], xph);
                     if (p.dbg) wx += clock64() - c0;
                     tc_fence_after();
-                    const uint32_t xhi = smem_u32(xs + s * C::XSTAGE_BYTES);
-                    const uint32_t xlo = xhi + C::PART_BYTES;
+                    const uint32_t xhi4 = xs4 + xs_i * (C::XSTAGE_BYTES >> 4);
+                    const uint32_t xlo4 = xhi4 + (C::PART_BYTES >> 4);
+                    const uint32_t acc0 = dx != 0;                                  // the tile's first MMA overwrites the accumulator
+                    if constexpr (SINGLE) {
+                        // The single-plane dgrad keeps the rolled loop with its index arithmetic: with the lean loop below its HR
+                        // class went from 4.25 to 4.95 ms (same-box A/B, profiles/r02_issue_loop_ab.txt) -- the kernel is bound by
+                        // its epilogue and by weight-stage latency, and an MMA warp that reaches its waits early only spins there,
+                        // on the scheduler it shares with two epilogue warps.
+                        const uint32_t xhi = smem_u32(xs + xs_i * C::XSTAGE_BYTES);
 #pragma unroll 1
+                        for (int tp = 0; tp < 9; ++tp) {
+                            const uint32_t wst = wi % C::NWS, wphase = (wi / C::NWS) & 1;
+                            if (p.dbg) c0 = clock64();
+                            mbar_wait(&w_full[wst], wphase);
+                            if (p.dbg) ww += clock64() - c0;
+                            tc_fence_after();
+                            const uint32_t wa = smem_u32(wsm + wst * W_STAGE_BYTES);
+                            const uint32_t boff = ((tp / 3) * ZP + (tp % 3)) * 128;     // (dy, dz) row shift
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t acc = (dx | tp | k) != 0;
+                                if (leader)
+                                    tc_mma_f16(dacc, make_desc_mn(wa + k * 2048, W_HI_OFFSET, 1024),
+                                               make_desc_sbo(xhi + boff + k * 32, ZP * 128), idesc, acc);
+                            }
+                            if (wi % C::WG == C::WG - 1 && leader) {
+                                if (CL) tc_commit_mc(&w_empty[(wi / C::WG) % C::NGW], (uint16_t)3);
+                                else tc_commit(&w_empty[(wi / C::WG) % C::NGW]);
+                            }
+                            __syncwarp();
+                            ++wi;
+                        }
+                    } else {
+#pragma unroll
                     for (int tp = 0; tp < 9; ++tp) {
-                        const uint32_t ws = wi % C::NWS, wph = (wi / C::NWS) & 1;
                         if (p.dbg) c0 = clock64();
                         mbar_wait(&w_full[ws], wph);
                         if (p.dbg) ww += clock64() - c0;
                         tc_fence_after();
-                        const uint32_t wa = smem_u32(wsm + ws * W_STAGE_BYTES);
-                        const uint32_t boff = ((tp / 3) * ZP + (tp % 3)) * 128;     // (dy, dz) row shift
+                        const uint32_t wk4 = wsm4 + ws * (W_STAGE_BYTES >> 4);
+                        const uint32_t boff4 = ((tp / 3) * ZP + (tp % 3)) * 8;      // (dy, dz) row shift, in 16-byte units (an immediate: tp is unrolled)
+                        // [Wlo ; Whi] x Xhi, then [Whi ; zeros] x Xlo (lanes 64-127 masked off) into the same accumulator.  The
+                        // weights are MN-major, so the two 64-row halves of the A operand are independent atoms (LBO apart):
+                        // the second instruction pairs the Whi half with the zero block instead of whatever follows it in
+                        // shared memory -- the masked rows are still multiplied, zeros cost less (profiles/r02_power_probe.txt)
+                        if (leader) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t acc = (dx | tp | k) != 0;
-                            // [Wlo ; Whi] x Xhi, then [Whi ; zeros] x Xlo (lanes 64-127 masked off) into the same accumulator.  The
-                            // weights are MN-major, so the two 64-row halves of the A operand are independent atoms (LBO apart):
-                            // the second instruction pairs the Whi half with the zero block instead of whatever follows it in
-                            // shared memory -- the masked rows are still multiplied, zeros cost less (profiles/r02_power_probe.txt)
-                            const uint32_t wk = wa + k * 2048;
-                            if (leader)
-                                tc_mma_f16(dacc, make_desc_mn(wk, W_HI_OFFSET, 1024),
-                                           make_desc_sbo(xhi + boff + k * 32, ZP * 128), idesc, acc);
-                            if (!SINGLE && leader)
-                                tc_mma_f16_masked(dacc, make_desc_mn(wk + W_HI_OFFSET, zaddr - (wk + W_HI_OFFSET), 1024),
-                                                  make_desc_sbo(xlo + boff + k * 32, ZP * 128), idesc, 1u, 0u, 0u, ~0u, ~0u);
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t acc = (tp | k) != 0 ? 1u : acc0;
+                                tc_mma_f16(dacc, a_const | (uint64_t)(wk4 + k * 128), b_const | (uint64_t)(xhi4 + boff4 + k * 2), idesc, acc);
+                                if (!SINGLE) {
+                                    const uint32_t a2 = wk4 + (W_HI_OFFSET >> 4) + k * 128;
+                                    tc_mma_f16_masked(dacc, a2_const | (uint64_t)a2 | ((uint64_t)(zaddr4 - a2) << 16),
+                                                      b_const | (uint64_t)(xlo4 + boff4 + k * 2), idesc, 1u, 0u, 0u, ~0u, ~0u);
+                                }
+                            }
                         }
-                        if (wi % C::WG == C::WG - 1 && leader) {            // hand the group of stages back (to both producers of a pair)
-                            if (CL) tc_commit_mc(&w_empty[(wi / C::WG) % C::NGW], (uint16_t)3);
-                            else tc_commit(&w_empty[(wi / C::WG) % C::NGW]);
+                        if (++gfill == C::WG) {                                    // hand the group of stages back (to both producers of a pair)
+                            if (leader) {
+                                if (CL) tc_commit_mc(&w_empty[gidx], (uint16_t)3);
+                                else tc_commit(&w_empty[gidx]);
+                            }
+                            gfill = 0;
+                            gidx = gidx + 1 == C::NGW ? 0 : gidx + 1;
                         }
                         __syncwarp();
-                        ++wi;
+                        if (++ws == C::NWS) { ws = 0; wph ^= 1; }
                     }
-                    ++xi;
+                    }
+                    if (++xs_i == C::NXS) { xs_i = 0; xph ^= 1; }
                 }
                 if (leader) tc_commit(&t_full[buf]);
             }
