@@ -660,9 +660,11 @@ conv64_tc_kernel(const __grid_constant__ CUtensorMap xmap, const KParams p0, con
                             val[4] += cur.aq1[k].x; val[5] += cur.aq1[k].y; val[6] += cur.aq1[k].z; val[7] += cur.aq1[k].w;
                         }
                         const size_t go = g4_off(Di, b, x, y - 1, z - 1) + g8 * 8;
-                        float* o = p.out_g4 + go;
-                        *reinterpret_cast<float4*>(o) = make_float4(val[0], val[1], val[2], val[3]);
-                        *reinterpret_cast<float4*>(o + 4) = make_float4(val[4], val[5], val[6], val[7]);
+                        if (p.out_g4) {                  // NULL when every consumer reads the split copy (mid-block gradients)
+                            float* o = p.out_g4 + go;
+                            *reinterpret_cast<float4*>(o) = make_float4(val[0], val[1], val[2], val[3]);
+                            *reinterpret_cast<float4*>(o + 4) = make_float4(val[4], val[5], val[6], val[7]);
+                        }
                         if (p.split_hi) {
                             __align__(16) __half hv[8];
                             __align__(16) __half lv[8];
@@ -993,7 +995,7 @@ namespace {
 cudaError_t fill_params(TcWeights* w, const TcConvArgs& a, KParams& p) {
     const int Do = a.in.D, B = a.in.B;
     if (!a.out_raw && !a.fused && a.out.D != Do) return cudaErrorInvalidValue;
-    if (a.fused && (!a.dgrad || !a.out_g4 || !tc_dgrad_fusable(Do - 2))) return cudaErrorInvalidValue;
+    if (a.fused && (!a.dgrad || (!a.out_g4 && !a.split_out) || !tc_dgrad_fusable(Do - 2))) return cudaErrorInvalidValue;
     p.w_img = w->img + ((size_t)a.layer * 2 + (a.dgrad ? 1 : 0)) * 27 * 128 * 64;
     p.out_hi = a.out.hi; p.out_lo = a.out.lo;
     p.res_hi = a.res_hi; p.res_lo = a.res_lo;

@@ -603,7 +603,8 @@ bool dgrad_fused(sr4d_t* h, int D) {
 }
 // fused dgrad of `layer`: out.f (interior) = (fold(dgrad(dy)) + add_pre) * act'(saved) + add_post; updates out.amax
 int conv64_dgrad_fused(sr4d_t* h, int layer, const GBuf& dy, const GBuf* add_pre, const float* add_post,
-                       const ActView* saved, float slope, GBuf& out, bool with_split, int B, int D, cudaStream_t s) {
+                       const ActView* saved, float slope, GBuf& out, bool with_split, int B, int D, cudaStream_t s,
+                       bool want_f32 = true) {
     ProfScope prof(h, D == h->P ? SR4D_PROF_CONV64_DGRAD_LR : SR4D_PROF_CONV64_DGRAD_HR, s);
     TcConvArgs a;
     a.in.hi = dy.s; a.in.lo = dy.s + act_plane_elems(B, D + 2); a.in.B = B; a.in.D = D + 2;
@@ -616,19 +617,20 @@ int conv64_dgrad_fused(sr4d_t* h, int layer, const GBuf& dy, const GBuf* add_pre
         a.add_amax = add_pre ? add_pre->amax : (add_post ? h->amax_copy : nullptr);
     }
     a.sav_hi = saved ? saved->hi : nullptr; a.sav_lo = saved ? saved->lo : nullptr;
-    a.slope = slope; a.out_g4 = out.f; a.absmax = out.amax;
+    a.slope = slope; a.out_g4 = (want_f32 || !with_split) ? out.f : nullptr; a.absmax = out.amax;
     CK(h, tc_conv64(h->tcw, a, s), 1);
     return SR4D_OK;
 }
 // gradient wrt the pre-activation of a 64->64 layer's input: out = (MirrorPadGrad(dgrad(dy)) + add) * act'(saved)
 // (saved == NULL: no activation), followed by the split copy for the tensor-core consumers
+// want_f32 = false: nobody reads the fp32 tensor out.f (every consumer takes the scaled split copy), the fused kernel may skip it
 int dgrad_fold(sr4d_t* h, int layer, const GBuf& dy, const GBuf* add, const ActView* saved, float slope, GBuf& out,
-               RawBuf& raw, int B, int D, cudaStream_t s) {
+               RawBuf& raw, int B, int D, cudaStream_t s, bool want_f32 = true) {
     int rc;
     if (dgrad_fused(h, D)) {
         CK(h, cudaMemsetAsync(out.amax, 0, sizeof(int), s), 0);
         // the epilogue also writes the scaled split copy (exponent from a rigorous bound): no g4_split pass
-        return conv64_dgrad_fused(h, layer, dy, add, nullptr, saved, slope, out, true, B, D, s);
+        return conv64_dgrad_fused(h, layer, dy, add, nullptr, saved, slope, out, true, B, D, s, want_f32);
     }
     if ((rc = conv64_dgrad(h, layer, dy, raw, B, D, s))) return rc;
     return fold_act(h, &raw, nullptr, nullptr, add, saved, slope, out, B, D, s);
@@ -653,7 +655,9 @@ int blocks_bwd(sr4d_t* h, int nblk, int l0, bool hr, GBuf* bufs[3], RawBuf& raw,
         GBuf& S2 = *bufs[(si + 2) % 3];
         if ((rc = conv64_wgrad(h, lb, t, S, false, s))) return rc;
         layer_split(h, T, la);                                   // T becomes dY of conv a
-        if ((rc = dgrad_fold(h, lb, S, nullptr, &t, 0.2f, T, raw, B, D, s))) return rc;
+        // T (the gradient inside the block) is read by conv a's weight gradient and dgrad only: as the split copy when the
+        // batched tensor-core weight gradient runs, so its fp32 tensor (256 B per voxel) is not written then
+        if ((rc = dgrad_fold(h, lb, S, nullptr, &t, 0.2f, T, raw, B, D, s, !wgrad_batched(h)))) return rc;
         if ((rc = conv64_wgrad(h, la, xin, T, false, s))) return rc;
         layer_split(h, S2, k > 0 ? la - 1 : next_layer);         // S2 becomes dY of the previous block's conv b
         // gradient wrt x_k (post-activation) = fold + skip path; multiply by its producer's act'
