@@ -441,7 +441,9 @@ def run_b200(args):
         # fp16 tensor-core products the kernel class EXECUTES per algorithmic fp32 MAC
         if "fwd" in dom or args.two_plane_backward:
             exe, exe_note = 4.0, ("the fp32-accurate split-fp16 path issues 4 fp16 tcgen05 products per fp32 MAC (3 useful + the "
-                                  "64 masked-off rows of the second instruction), so the tensor pipe saturates at frac ~0.25")
+                                  "64 masked-off rows of the second instruction): against a pipe that saturates at `peak` the fraction could not exceed 0.25; "
+                                  "`peak` is the MEASURED sustained cuBLAS bf16 rate, which this kernel's executed rate exceeds when "
+                                  "executed_frac > 1")
         elif "dgrad" in dom:
             exe, exe_note = 2.0, ("single-plane dgrad: [Wlo;Whi] x dYhi, 2 fp16 products per fp32 MAC (tensor pipe saturates at frac "
                                   "~0.5); the launch also folds the halo, adds the skip gradient, applies act' and writes the split copy")
