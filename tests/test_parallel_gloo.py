@@ -146,3 +146,32 @@ def test_dp_allreduce_reproduces_full_batch_gradient():
 
 def test_ragged_row_gather():
     _run("_ragged_gather")
+
+
+def test_metric_tail_deferred_read_ring():
+    """read_begin / read_end (TrainerController.train_step folds a step's metrics after the NEXT step has been enqueued):
+    two reads may be in flight; each token returns the values the tail held when its copy was enqueued, also after the
+    tail has been reset and refilled for the following step (single process, CPU tensors)."""
+    import importlib
+    par = importlib.import_module("4dflownet_b200.parallel")
+    tail_buf = torch.zeros(256)
+    tail = par.MetricTail(tail_buf, max_batch=4, rank_=0, world=1)
+
+    def fill(step, B):
+        per, l2 = tail.begin(B)
+        per.copy_(torch.arange(4 * B, dtype=torch.float32).view(B, 4) + 100 * step)
+        l2.fill_(0.5 + step)
+
+    fill(1, 3)
+    t1 = tail.read_begin()
+    fill(2, 2)                                   # the next step overwrites the tail before step 1 has been read
+    t2 = tail.read_begin()
+    assert t1 != t2
+    per1, l2_1, n1 = tail.read_end(t1)
+    per2, l2_2, n2 = tail.read_end(t2)
+    assert n1 == 3 and n2 == 2 and l2_1 == 1.5 and l2_2 == 2.5
+    assert per1.shape == (3, 4) and per1[0, 0] == 100 and per1[2, 3] == 111
+    assert per2.shape == (2, 4) and per2[0, 0] == 200 and per2[1, 3] == 207
+    fill(3, 4)
+    per3, l2_3, n3 = tail.read()                 # the immediate form reuses the ring
+    assert n3 == 4 and l2_3 == 3.5 and per3[3, 3] == 315
